@@ -1,0 +1,48 @@
+"""Compile the CUDA extension in-tree for sm_100a (explicit nvcc; no JIT cache involved)."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libamplipy_b200.so")
+SOURCES = ["amp_abi.cu"]
+HEADERS = ["amp_core.cuh", "amp_kernels.cuh", os.path.join("..", "..", "include", "amplipy_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.isfile(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build amplipy_b200's CUDA extension")
+
+
+def is_stale():
+    if not os.path.isfile(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build_extension(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> amplipy_b200/csrc/libamplipy_b200.so"""
+    if not force and not is_stale():
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    env = dict(os.environ)
+    if os.path.isfile("/usr/bin/g++"):
+        cmd += ["-ccbin", "/usr/bin/g++"]
+    r = subprocess.run(cmd, cwd=CSRC, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building %s" % LIB)
+    with open(os.path.join(CSRC, "ptxas_info.txt"), "w") as f:
+        f.write(r.stdout)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_extension(force=True, verbose=True))

@@ -1,0 +1,544 @@
+// amp_abi.cu -- kernels' __global__ wrappers + the C ABI declared in include/amplipy_b200.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/amplipy_b200.h"
+#include "amp_kernels.cuh"
+
+static_assert(AMP_F_TRIM_START == AMP_FLAG_TRIM_START && AMP_F_KEEP == AMP_FLAG_KEEP && AMP_F_SKIPPED == AMP_FLAG_SKIPPED &&
+                  AMP_F_ERROR == AMP_FLAG_ERROR && AMP_E_ARENA_FULL == AMP_DEVERR_ARENA_FULL,
+              "flag constants out of sync with include/amplipy_b200.h");
+static_assert(sizeof(amp::Seg) == 16 && sizeof(amp::InsSlot) == 16, "layout");
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char* what, const char* detail = "") {
+    g_err = std::string(what) + (detail[0] ? ": " : "") + detail;
+    return code;
+}
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            char buf_[256];                                                                       \
+            snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            g_err = buf_;                                                                         \
+            return AMP_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+constexpr int kThreads = 256;
+constexpr int kCtasPerSm = 2;
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) amp_trim_pileup_kernel(const __grid_constant__ amp::KParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    amp::cta_trim_pileup(P, smem, (int)blockIdx.x, (int)blockDim.x);
+}
+
+__device__ const unsigned char kFixedSyms[8] = {'A', 'C', 'G', 'T', 'N', '-', 0, 0};
+
+__global__ void amp_link_kernel(amp::InsSlot* slots, const unsigned int* entries, const unsigned long long* cursor,
+                                const unsigned char* arena, int* heads) {
+    const unsigned long long n = cursor[1];
+    for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned int s = entries[k];
+        const unsigned char* rec = arena + (slots[s].key & 0xFFFFFFFFFFULL) * 8;
+        const int gpos = ((const int*)rec)[0];
+        slots[s].next = atomicExch(&heads[gpos], (int)s);
+    }
+}
+
+__global__ void amp_call_kernel(const amp::CallParams P) {
+    const long long gp = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (gp < (long long)P.n_samples * P.L) amp::call_position(P, kFixedSyms, gp);
+}
+
+__global__ void amp_gather_entries_kernel(const amp::InsSlot* slots, const unsigned int* entries, unsigned long long n,
+                                          int* count, unsigned long long* off) {
+    for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        const amp::InsSlot s = slots[entries[k]];
+        count[k] = s.count;
+        off[k] = s.key & 0xFFFFFFFFFFULL;
+    }
+}
+
+struct RawText {
+    const char* p;
+    __device__ char operator()(int i) const { return p[i]; }
+};
+__global__ void amp_merge_kernel(amp::InsTable tab, long long n, const int* gpos, const int* count, const long long* str_off,
+                                 const char* chars) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        RawText t{chars + str_off[k]};
+        amp::ins_table_add(tab, gpos[k], (int)(str_off[k + 1] - str_off[k]), t, count[k]);
+    }
+}
+
+struct DevChunk {   // device staging for one in-flight chunk of amp_process_host
+    cudaStream_t stream = nullptr;
+    int32_t* pos = nullptr; uint16_t* flag = nullptr; int32_t* tlen = nullptr;
+    uint32_t *cig_off = nullptr, *seq_off = nullptr, *qual_off = nullptr, *cigar = nullptr;
+    uint8_t *seq = nullptr, *qual = nullptr;
+    int32_t* o_pos = nullptr; uint16_t* o_ncig = nullptr; uint8_t* o_flags = nullptr; uint32_t* o_cigar = nullptr;
+    uint32_t* scratch = nullptr;
+    size_t cap_reads = 0, cap_cig = 0, cap_seq = 0, cap_qual = 0, cap_scratch = 0;
+};
+
+}  // namespace
+
+struct amp_ctx {
+    amp_config cfg;
+    int Lpad = 0, sm_count = 0, max_primer_len = 0;
+    int32_t *d_min_start = nullptr, *d_max_end = nullptr;
+    int* d_counts = nullptr; bool counts_owned = true;
+    amp::InsTable tab{};
+    unsigned long long nslots = 0;
+    unsigned int* d_err = nullptr;
+    int* d_heads = nullptr;
+    uint32_t* d_scratch = nullptr; size_t scratch_words = 0;
+    DevChunk chunk[3];
+    int last_launches = 0;
+    size_t max_dyn_smem = 0;
+    unsigned char* d_ref = nullptr;     // reference characters (amp_set_reference)
+    unsigned char* d_call = nullptr;    // calling outputs (one block, offsets below)
+    size_t o_depth = 0, o_top = 0, o_topc = 0, o_fl = 0, o_refc = 0, o_ff = 0, o_fr = 0, o_alt = 0, o_if = 0, o_ir = 0, o_ia = 0;
+};
+
+namespace {
+
+template <class T>
+int dev_grow(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return AMP_OK;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    size_t n = need + need / 4 + 64;
+    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    *cap = n;
+    return AMP_OK;
+}
+
+int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long long max_cig, long long sum_qual, int mode,
+                   int sample, const amp::TrimOut& o, uint32_t* scratch, cudaStream_t st) {
+    if (b.n <= 0) return AMP_OK;
+    amp::KParams P{};
+    P.b = b; P.o = o;
+    P.tp.L = c->cfg.ref_len; P.tp.min_primer_start = c->d_min_start; P.tp.max_primer_end = c->d_max_end;
+    P.tp.max_primer_len = c->max_primer_len; P.tp.min_quality = c->cfg.min_quality; P.tp.window = c->cfg.sliding_window;
+    P.tp.min_length = c->cfg.min_length; P.tp.include_no_primer = c->cfg.include_no_primer;
+    P.mode = mode;
+    P.counts = c->d_counts + (size_t)sample * AMP_NCH * c->Lpad;
+    P.Lpad = c->Lpad; P.gpos_base = sample * c->Lpad;
+    P.tab = c->tab; P.err = c->d_err;
+    P.scratch = scratch; P.scratch_half = sum_cig + 3 * b.n;
+    (void)max_cig;
+    const amp::TileCfg t = amp::pick_tile_cfg(b.n, sum_cig, sum_qual, mode);
+    P.wt = t.wt; P.maxseg = t.maxseg; P.qbytes = t.qbytes; P.sbytes = t.sbytes; P.reads_per_tile = t.reads_per_tile;
+    P.ntiles = (int)((b.n + t.reads_per_tile - 1) / t.reads_per_tile);
+    int grid = std::min(P.ntiles, c->sm_count * kCtasPerSm);
+    P.tiles_per_cta = (P.ntiles + grid - 1) / grid;
+    grid = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
+    const size_t smem = amp::smem_bytes(P.wt, P.maxseg, P.qbytes, P.sbytes);
+    if (smem > c->max_dyn_smem) {
+        CK(cudaFuncSetAttribute(amp_trim_pileup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->max_dyn_smem = smem;
+    }
+    amp_trim_pileup_kernel<<<grid, kThreads, smem, st>>>(P);
+    CK(cudaGetLastError());
+    c->last_launches += 1;
+    return AMP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* amp_last_error(void) { return g_err.c_str(); }
+int amp_abi_version(void) { return AMP_ABI_VERSION; }
+
+int amp_create(const amp_config* cfg, const int32_t* min_primer_start, const int32_t* max_primer_end, int32_t max_primer_len,
+               amp_ctx** out) {
+    if (!cfg || !out || cfg->ref_len <= 0 || cfg->n_samples <= 0) return fail(AMP_ERR_ARG, "amp_create: bad config");
+    if ((min_primer_start == nullptr) != (max_primer_end == nullptr)) return fail(AMP_ERR_ARG, "amp_create: need both primer tables or none");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(AMP_ERR_ARG, "amp_create: no such CUDA device");
+    CK(cudaSetDevice(cfg->device));
+    amp_ctx* c = new amp_ctx();
+    c->cfg = *cfg;
+    c->Lpad = (cfg->ref_len + 31) & ~31;
+    c->max_primer_len = max_primer_len;
+    CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
+    const size_t L = (size_t)cfg->ref_len;
+    if (min_primer_start) {
+        CK(cudaMalloc((void**)&c->d_min_start, L * 4));
+        CK(cudaMalloc((void**)&c->d_max_end, L * 4));
+        CK(cudaMemcpy(c->d_min_start, min_primer_start, L * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_max_end, max_primer_end, L * 4, cudaMemcpyHostToDevice));
+    }
+    CK(cudaMalloc((void**)&c->d_counts, (size_t)cfg->n_samples * AMP_NCH * c->Lpad * 4));
+    unsigned long long nslots = cfg->ins_slots > 0 ? (unsigned long long)cfg->ins_slots : (1ULL << 21);
+    while (nslots & (nslots - 1)) nslots += nslots & (~nslots + 1);   // round up to a power of two
+    c->nslots = nslots;
+    const unsigned long long arena_bytes = cfg->ins_arena_bytes > 0 ? (unsigned long long)cfg->ins_arena_bytes : (64ULL << 20);
+    CK(cudaMalloc((void**)&c->tab.slots, nslots * sizeof(amp::InsSlot)));
+    CK(cudaMalloc((void**)&c->tab.entries, nslots * 4));
+    CK(cudaMalloc((void**)&c->tab.slot_entry, nslots * 4));
+    CK(cudaMalloc((void**)&c->tab.arena, arena_bytes));
+    CK(cudaMalloc((void**)&c->tab.cursor, 16));
+    CK(cudaMalloc((void**)&c->d_err, 4));
+    CK(cudaMalloc((void**)&c->d_heads, (size_t)cfg->n_samples * c->Lpad * 4));
+    c->tab.mask = nslots - 1; c->tab.arena_words = arena_bytes / 8; c->tab.err = c->d_err;
+    for (auto& ch : c->chunk) CK(cudaStreamCreateWithFlags(&ch.stream, cudaStreamNonBlocking));
+    *out = c;
+    int rc = amp_reset(c);
+    if (rc) { amp_destroy(c); *out = nullptr; }
+    return rc;
+}
+
+int amp_destroy(amp_ctx* c) {
+    if (!c) return AMP_OK;
+    cudaSetDevice(c->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(c->d_min_start); cudaFree(c->d_max_end);
+    if (c->counts_owned) cudaFree(c->d_counts);
+    cudaFree(c->tab.slots); cudaFree(c->tab.entries); cudaFree(c->tab.slot_entry); cudaFree(c->tab.arena); cudaFree(c->tab.cursor);
+    cudaFree(c->d_err); cudaFree(c->d_heads); cudaFree(c->d_scratch); cudaFree(c->d_ref); cudaFree(c->d_call);
+    for (auto& ch : c->chunk) {
+        cudaFree(ch.pos); cudaFree(ch.flag); cudaFree(ch.tlen); cudaFree(ch.cig_off); cudaFree(ch.seq_off); cudaFree(ch.qual_off);
+        cudaFree(ch.cigar); cudaFree(ch.seq); cudaFree(ch.qual); cudaFree(ch.o_pos); cudaFree(ch.o_ncig); cudaFree(ch.o_flags);
+        cudaFree(ch.o_cigar); cudaFree(ch.scratch);
+        if (ch.stream) cudaStreamDestroy(ch.stream);
+    }
+    delete c;
+    return AMP_OK;
+}
+
+int amp_reset(amp_ctx* c) {
+    if (!c) return fail(AMP_ERR_ARG, "amp_reset: null context");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaMemsetAsync(c->d_counts, 0, (size_t)c->cfg.n_samples * AMP_NCH * c->Lpad * 4, 0));
+    CK(cudaMemsetAsync(c->tab.slots, 0, c->nslots * sizeof(amp::InsSlot), 0));
+    CK(cudaMemsetAsync(c->tab.cursor, 0, 16, 0));
+    CK(cudaMemsetAsync(c->d_err, 0, 4, 0));
+    CK(cudaStreamSynchronize(0));
+    return AMP_OK;
+}
+
+int amp_reset_async(amp_ctx* c, void* stream) {
+    if (!c) return fail(AMP_ERR_ARG, "amp_reset_async: null context");
+    CK(cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(c->d_counts, 0, (size_t)c->cfg.n_samples * AMP_NCH * c->Lpad * 4, st));
+    CK(cudaMemsetAsync(c->tab.slots, 0, c->nslots * sizeof(amp::InsSlot), st));
+    CK(cudaMemsetAsync(c->tab.cursor, 0, 16, st));
+    CK(cudaMemsetAsync(c->d_err, 0, 4, st));
+    return AMP_OK;
+}
+
+int amp_error_flags(amp_ctx* c, uint32_t* flags) {
+    if (!c || !flags) return fail(AMP_ERR_ARG, "amp_error_flags: null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(flags, c->d_err, 4, cudaMemcpyDeviceToHost));
+    return AMP_OK;
+}
+
+int amp_lpad(amp_ctx* c) { return c ? c->Lpad : AMP_ERR_ARG; }
+int amp_sm_count(amp_ctx* c) { return c ? c->sm_count : AMP_ERR_ARG; }
+int amp_last_launches(amp_ctx* c) { return c ? c->last_launches : AMP_ERR_ARG; }
+
+int amp_process_device(amp_ctx* c, const amp_batch* b, int64_t sum_cigar_ops, int64_t sum_qual_bytes, int mode, int sample,
+                       const amp_trim_out* o, void* stream) {
+    if (!c || !b) return fail(AMP_ERR_ARG, "amp_process_device: null argument");
+    if (sample < 0 || sample >= c->cfg.n_samples) return fail(AMP_ERR_ARG, "amp_process_device: sample out of range");
+    if ((mode & AMP_MODE_TRIM) && (!o || !c->d_min_start)) return fail(AMP_ERR_ARG, "amp_process_device: trimming needs primer tables and an output block");
+    if (!(mode & (AMP_MODE_TRIM | AMP_MODE_PILEUP))) return fail(AMP_ERR_ARG, "amp_process_device: empty mode");
+    CK(cudaSetDevice(c->cfg.device));
+    c->last_launches = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode & AMP_MODE_TRIM) {
+        // long-CIGAR scratch (2 rows per read); allocated once per high-water mark
+        const size_t need = 2 * ((size_t)sum_cigar_ops + 3 * (size_t)b->n_reads);
+        if (need > c->scratch_words) {
+            CK(cudaStreamSynchronize(st));
+            if (c->d_scratch) CK(cudaFree(c->d_scratch));
+            c->d_scratch = nullptr; c->scratch_words = 0;
+            CK(cudaMalloc((void**)&c->d_scratch, need * 4));
+            c->scratch_words = need;
+        }
+    }
+    amp::BatchPtrs bp{b->first, b->n_reads, b->pos, b->flag, b->tlen, b->cig_off, b->cigar, b->seq_off, b->seq, b->qual_off, b->qual};
+    amp::TrimOut to{};
+    if (o) { to.pos = o->pos; to.ncig = o->ncig; to.flags = o->flags; to.cigar = o->cigar; }
+    uint32_t* scratch = c->d_scratch;
+    if ((mode & AMP_MODE_TRIM) && b->first != 0) {   // scratch rows are addressed like the output rows: shift to the range start
+        uint32_t c_first = 0;
+        CK(cudaMemcpyAsync(&c_first, b->cig_off + b->first, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        scratch -= (size_t)c_first + 3 * (size_t)b->first;
+    }
+    if (sum_qual_bytes <= 0) sum_qual_bytes = (long long)b->n_reads * 150;
+    return launch_process(c, bp, sum_cigar_ops, 0, sum_qual_bytes, mode, sample, to, scratch, st);
+}
+
+int amp_process_host(amp_ctx* c, const amp_batch* b, int mode, int sample, const amp_trim_out* o) {
+    if (!c || !b) return fail(AMP_ERR_ARG, "amp_process_host: null argument");
+    if (sample < 0 || sample >= c->cfg.n_samples) return fail(AMP_ERR_ARG, "amp_process_host: sample out of range");
+    if ((mode & AMP_MODE_TRIM) && (!o || !c->d_min_start)) return fail(AMP_ERR_ARG, "amp_process_host: trimming needs primer tables and an output block");
+    if (!(mode & (AMP_MODE_TRIM | AMP_MODE_PILEUP))) return fail(AMP_ERR_ARG, "amp_process_host: empty mode");
+    CK(cudaSetDevice(c->cfg.device));
+    c->last_launches = 0;
+    const bool trim = mode & AMP_MODE_TRIM, pile = mode & AMP_MODE_PILEUP;
+    const long long first = b->first, last = b->first + b->n_reads;
+    const long long kChunk = 1 << 18;
+    int slot = 0;
+    for (long long a = first; a < last; a += kChunk, slot = (slot + 1) % 3) {
+        const long long e = std::min(last, a + kChunk), n = e - a;
+        DevChunk& d = c->chunk[slot];
+        CK(cudaStreamSynchronize(d.stream));   // previous use of this slot has drained
+        const size_t c0 = b->cig_off[a], c1 = b->cig_off[e];
+        const size_t q0 = b->qual_off[a] & ~(size_t)15, q1 = b->qual_off[e];
+        const size_t s0 = b->seq_off[a] & ~(size_t)15, s1 = b->seq_off[e];
+        if ((size_t)n + 1 > d.cap_reads) {
+            const size_t want = (size_t)n + 1 + 64;
+            void** arrs[9] = {(void**)&d.pos, (void**)&d.flag, (void**)&d.tlen, (void**)&d.cig_off, (void**)&d.seq_off,
+                              (void**)&d.qual_off, (void**)&d.o_pos, (void**)&d.o_ncig, (void**)&d.o_flags};
+            for (void** ap : arrs) {
+                if (*ap) CK(cudaFree(*ap));
+                *ap = nullptr;
+                CK(cudaMalloc(ap, want * 4));
+            }
+            d.cap_reads = want;
+        }
+        {
+            int rc;
+            if ((rc = dev_grow(&d.cigar, &d.cap_cig, (c1 - c0) + 4))) return rc;
+            if ((rc = dev_grow(&d.qual, &d.cap_qual, (q1 - q0) + 32))) return rc;
+            if (pile && (rc = dev_grow(&d.seq, &d.cap_seq, (s1 - s0) + 32))) return rc;
+            if (trim) {
+                const size_t orows = (c1 - c0) + 3 * (size_t)n;
+                size_t ocap = d.cap_scratch / 2;   // o_cigar and scratch grow together
+                if (orows + 4 > ocap) {
+                    if (d.o_cigar) CK(cudaFree(d.o_cigar));
+                    if (d.scratch) CK(cudaFree(d.scratch));
+                    d.o_cigar = nullptr; d.scratch = nullptr; d.cap_scratch = 0;
+                    const size_t want = orows + orows / 4 + 64;
+                    CK(cudaMalloc((void**)&d.o_cigar, want * 4));
+                    CK(cudaMalloc((void**)&d.scratch, 2 * want * 4));
+                    d.cap_scratch = 2 * want;
+                }
+            }
+        }
+        cudaStream_t st = d.stream;
+        CK(cudaMemcpyAsync(d.pos, b->pos + a, n * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d.flag, b->flag + a, n * 2, cudaMemcpyHostToDevice, st));
+        if (trim) CK(cudaMemcpyAsync(d.tlen, b->tlen + a, n * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d.cig_off, b->cig_off + a, (n + 1) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d.qual_off, b->qual_off + a, (n + 1) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d.seq_off, b->seq_off + a, (n + 1) * 4, cudaMemcpyHostToDevice, st));
+        if (c1 > c0) CK(cudaMemcpyAsync(d.cigar, b->cigar + c0, (c1 - c0) * 4, cudaMemcpyHostToDevice, st));
+        if (q1 > q0) CK(cudaMemcpyAsync(d.qual, b->qual + q0, q1 - q0, cudaMemcpyHostToDevice, st));
+        if (pile && s1 > s0) CK(cudaMemcpyAsync(d.seq, b->seq + s0, s1 - s0, cudaMemcpyHostToDevice, st));
+        // pointers are indexed with global read indices / absolute offsets: shift the chunk buffers back
+        amp::BatchPtrs bp{a, n, d.pos - a, d.flag - a, d.tlen - a, d.cig_off - a, d.cigar - c0, d.seq_off - a,
+                          pile ? d.seq - s0 : nullptr, d.qual_off - a, d.qual - q0};
+        amp::TrimOut to{};
+        const size_t orow0 = c0 + 3 * (size_t)a;
+        if (trim) { to.pos = d.o_pos - a; to.ncig = d.o_ncig - a; to.flags = d.o_flags - a; to.cigar = d.o_cigar - orow0; }
+        int rc = launch_process(c, bp, (long long)(c1 - c0), 0, (long long)(b->qual_off[e] - b->qual_off[a]), mode, sample, to,
+                                trim ? d.scratch - orow0 : nullptr, st);
+        if (rc) return rc;
+        if (trim) {
+            CK(cudaMemcpyAsync(o->pos + a, d.o_pos, n * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(o->ncig + a, d.o_ncig, n * 2, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(o->flags + a, d.o_flags, n, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(o->cigar + orow0, d.o_cigar, ((c1 - c0) + 3 * (size_t)n) * 4, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (auto& ch : c->chunk) CK(cudaStreamSynchronize(ch.stream));
+    return AMP_OK;
+}
+
+int amp_counts_device(amp_ctx* c, int32_t** dev_counts) {
+    if (!c || !dev_counts) return fail(AMP_ERR_ARG, "amp_counts_device: null argument");
+    *dev_counts = c->d_counts;
+    return AMP_OK;
+}
+
+int amp_bind_counts(amp_ctx* c, int32_t* dev_counts) {
+    if (!c || !dev_counts) return fail(AMP_ERR_ARG, "amp_bind_counts: null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaDeviceSynchronize());
+    if (c->counts_owned) CK(cudaFree(c->d_counts));
+    c->d_counts = dev_counts; c->counts_owned = false;
+    return AMP_OK;
+}
+
+int amp_counts_host(amp_ctx* c, int sample, int32_t* host) {
+    if (!c || !host || sample < 0 || sample >= c->cfg.n_samples) return fail(AMP_ERR_ARG, "amp_counts_host: bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaDeviceSynchronize());
+    const size_t L = (size_t)c->cfg.ref_len;
+    CK(cudaMemcpy2D(host, L * 4, c->d_counts + (size_t)sample * AMP_NCH * c->Lpad, (size_t)c->Lpad * 4, L * 4, AMP_NCH,
+                    cudaMemcpyDeviceToHost));
+    return AMP_OK;
+}
+
+int amp_ins_count(amp_ctx* c, int64_t* n_alleles, int64_t* n_chars) {
+    if (!c || !n_alleles || !n_chars) return fail(AMP_ERR_ARG, "amp_ins_count: null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaDeviceSynchronize());
+    unsigned long long cur[2];
+    CK(cudaMemcpy(cur, c->tab.cursor, 16, cudaMemcpyDeviceToHost));
+    *n_alleles = (int64_t)cur[1];
+    *n_chars = (int64_t)(cur[0] * 8);   // upper bound (records incl. headers and padding)
+    return AMP_OK;
+}
+
+int amp_ins_export(amp_ctx* c, int32_t* sample, int32_t* pos, int32_t* count, int64_t* str_off, char* chars) {
+    if (!c || !str_off) return fail(AMP_ERR_ARG, "amp_ins_export: null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaDeviceSynchronize());
+    unsigned long long cur[2];
+    CK(cudaMemcpy(cur, c->tab.cursor, 16, cudaMemcpyDeviceToHost));
+    const unsigned long long n = cur[1];
+    str_off[0] = 0;
+    if (n == 0) return AMP_OK;
+    int* d_count = nullptr; unsigned long long* d_off = nullptr;
+    CK(cudaMalloc((void**)&d_count, n * 4));
+    CK(cudaMalloc((void**)&d_off, n * 8));
+    amp_gather_entries_kernel<<<(unsigned)std::min<unsigned long long>((n + 255) / 256, 1184), 256>>>(c->tab.slots, c->tab.entries, n, d_count, d_off);
+    CK(cudaGetLastError());
+    std::vector<unsigned long long> off(n);
+    std::vector<unsigned char> arena(cur[0] * 8);
+    CK(cudaMemcpy(count, d_count, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(off.data(), d_off, n * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(arena.data(), c->tab.arena, cur[0] * 8, cudaMemcpyDeviceToHost));
+    CK(cudaFree(d_count)); CK(cudaFree(d_off));
+    int64_t o = 0;
+    for (unsigned long long k = 0; k < n; ++k) {
+        const unsigned char* rec = arena.data() + off[k] * 8;
+        int gpos; unsigned int len;
+        memcpy(&gpos, rec, 4); memcpy(&len, rec + 4, 4);
+        sample[k] = gpos / c->Lpad; pos[k] = gpos % c->Lpad;
+        memcpy(chars + o, rec + 8, len);
+        o += len; str_off[k + 1] = o;
+    }
+    return AMP_OK;
+}
+
+int amp_ins_merge(amp_ctx* c, int64_t n, const int32_t* sample, const int32_t* pos, const int32_t* count, const int64_t* str_off,
+                  const char* chars) {
+    if (!c || n < 0) return fail(AMP_ERR_ARG, "amp_ins_merge: bad argument");
+    if (n == 0) return AMP_OK;
+    CK(cudaSetDevice(c->cfg.device));
+    std::vector<int> gpos(n);
+    for (int64_t k = 0; k < n; ++k) gpos[k] = sample[k] * c->Lpad + pos[k];
+    int *d_gpos = nullptr, *d_count = nullptr; long long* d_off = nullptr; char* d_chars = nullptr;
+    const size_t nch = (size_t)str_off[n];
+    CK(cudaMalloc((void**)&d_gpos, n * 4)); CK(cudaMalloc((void**)&d_count, n * 4));
+    CK(cudaMalloc((void**)&d_off, (n + 1) * 8)); CK(cudaMalloc((void**)&d_chars, nch + 8));
+    CK(cudaMemcpy(d_gpos, gpos.data(), n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_count, count, n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_off, str_off, (n + 1) * 8, cudaMemcpyHostToDevice));
+    if (nch) CK(cudaMemcpy(d_chars, chars, nch, cudaMemcpyHostToDevice));
+    amp_merge_kernel<<<(unsigned)std::min<int64_t>((n + 127) / 128, 1184), 128>>>(c->tab, n, d_gpos, d_count, d_off, d_chars);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaFree(d_gpos)); CK(cudaFree(d_count)); CK(cudaFree(d_off)); CK(cudaFree(d_chars));
+    return AMP_OK;
+}
+
+int amp_set_reference(amp_ctx* c, const char* ref_seq) {
+    if (!c || !ref_seq) return fail(AMP_ERR_ARG, "amp_set_reference: null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    if (!c->d_ref) CK(cudaMalloc((void**)&c->d_ref, (size_t)c->cfg.ref_len + 16));
+    CK(cudaMemcpy(c->d_ref, ref_seq, (size_t)c->cfg.ref_len, cudaMemcpyHostToDevice));
+    return AMP_OK;
+}
+
+// device-side calling: outputs stay in context-owned HBM buffers; asynchronous on `stream`
+int amp_call_device(amp_ctx* c, const amp_call_params* p, void* stream) {
+    if (!c || !p) return fail(AMP_ERR_ARG, "amp_call_device: null argument");
+    if (!c->d_ref) return fail(AMP_ERR_STATE, "amp_call_device: amp_set_reference has not been called");
+    CK(cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t L = (size_t)c->cfg.ref_len, S = (size_t)c->cfg.n_samples, SL = S * L;
+    if (!c->d_call) {
+        size_t bytes = 0;
+        auto take = [&](size_t n) { size_t o = bytes; bytes += (n + 255) & ~(size_t)255; return o; };
+        c->o_depth = take(SL * 4); c->o_top = take(SL * 4); c->o_topc = take(SL * 4); c->o_fl = take(SL); c->o_refc = take(SL * 4);
+        c->o_ff = take(SL * 6 * 8); c->o_fr = take(SL * 6 * 4); c->o_alt = take(SL);
+        c->o_if = take(c->nslots * 8); c->o_ir = take(c->nslots * 4); c->o_ia = take(c->nslots);
+        CK(cudaMalloc((void**)&c->d_call, bytes + 256));
+    }
+    c->last_launches = 0;
+    CK(cudaMemsetAsync(c->d_heads, 0xFF, S * c->Lpad * 4, st));
+    amp_link_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->tab.slots, c->tab.entries, c->tab.cursor, c->tab.arena, c->d_heads);
+    CK(cudaGetLastError());
+    unsigned char* blk = c->d_call;
+    amp::CallParams P{};
+    P.L = (int)L; P.Lpad = c->Lpad; P.n_samples = (int)S; P.counts = c->d_counts; P.slots = c->tab.slots;
+    P.slot_entry = c->tab.slot_entry; P.arena = c->tab.arena; P.heads = c->d_heads; P.ref_seq = c->d_ref;
+    P.min_depth_consensus = p->min_depth_consensus; P.min_freq_consensus = p->min_freq_consensus;
+    P.min_depth_variants = p->min_depth_variants; P.min_freq_variants = p->min_freq_variants;
+    P.depth = (int*)(blk + c->o_depth); P.top_id = (int*)(blk + c->o_top); P.top_count = (int*)(blk + c->o_topc);
+    P.pos_flags = blk + c->o_fl; P.ref_count = (int*)(blk + c->o_refc); P.fixed_freq = (double*)(blk + c->o_ff);
+    P.fixed_rank = (int*)(blk + c->o_fr); P.alt_mask = blk + c->o_alt; P.ins_freq = (double*)(blk + c->o_if);
+    P.ins_rank = (int*)(blk + c->o_ir); P.ins_alt = blk + c->o_ia;
+    amp_call_kernel<<<(unsigned)((SL + 127) / 128), 128, 0, st>>>(P);
+    CK(cudaGetLastError());
+    c->last_launches = 2;
+    return AMP_OK;
+}
+
+int amp_call(amp_ctx* c, const char* ref_seq, const amp_call_params* p, const amp_call_out* ho, double* ins_freq,
+             int32_t* ins_rank, uint8_t* ins_alt) {
+    if (!c || !p || !ho) return fail(AMP_ERR_ARG, "amp_call: null argument");
+    int rc;
+    if (ref_seq && (rc = amp_set_reference(c, ref_seq))) return rc;
+    CK(cudaDeviceSynchronize());
+    if ((rc = amp_call_device(c, p, nullptr))) return rc;
+    CK(cudaDeviceSynchronize());
+    const size_t L = (size_t)c->cfg.ref_len, S = (size_t)c->cfg.n_samples, SL = S * L;
+    unsigned long long cur[2];
+    CK(cudaMemcpy(cur, c->tab.cursor, 16, cudaMemcpyDeviceToHost));
+    const size_t K = (size_t)cur[1];
+    unsigned char* blk = c->d_call;
+    if (ho->depth) CK(cudaMemcpy(ho->depth, blk + c->o_depth, SL * 4, cudaMemcpyDeviceToHost));
+    if (ho->top_id) CK(cudaMemcpy(ho->top_id, blk + c->o_top, SL * 4, cudaMemcpyDeviceToHost));
+    if (ho->top_count) CK(cudaMemcpy(ho->top_count, blk + c->o_topc, SL * 4, cudaMemcpyDeviceToHost));
+    if (ho->pos_flags) CK(cudaMemcpy(ho->pos_flags, blk + c->o_fl, SL, cudaMemcpyDeviceToHost));
+    if (ho->ref_count) CK(cudaMemcpy(ho->ref_count, blk + c->o_refc, SL * 4, cudaMemcpyDeviceToHost));
+    if (ho->fixed_freq) CK(cudaMemcpy(ho->fixed_freq, blk + c->o_ff, SL * 6 * 8, cudaMemcpyDeviceToHost));
+    if (ho->fixed_rank) CK(cudaMemcpy(ho->fixed_rank, blk + c->o_fr, SL * 6 * 4, cudaMemcpyDeviceToHost));
+    if (ho->alt_mask) CK(cudaMemcpy(ho->alt_mask, blk + c->o_alt, SL, cudaMemcpyDeviceToHost));
+    if (K && ins_freq) CK(cudaMemcpy(ins_freq, blk + c->o_if, K * 8, cudaMemcpyDeviceToHost));
+    if (K && ins_rank) CK(cudaMemcpy(ins_rank, blk + c->o_ir, K * 4, cudaMemcpyDeviceToHost));
+    if (K && ins_alt) CK(cudaMemcpy(ins_alt, blk + c->o_ia, K, cudaMemcpyDeviceToHost));
+    return AMP_OK;
+}
+
+int amp_host_alloc(void** p, int64_t bytes) {
+    if (!p || bytes < 0) return fail(AMP_ERR_ARG, "amp_host_alloc: bad argument");
+    CK(cudaHostAlloc(p, (size_t)std::max<int64_t>(bytes, 16), cudaHostAllocDefault));
+    return AMP_OK;
+}
+int amp_host_free(void* p) {
+    if (p) CK(cudaFreeHost(p));
+    return AMP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,466 @@
+// amp_core.cuh -- per-read device logic of the trim -> pileup path (sm_100a), written as
+// __host__ __device__ code so that tests/emu can execute the very same source on the CPU.
+//
+// Reference behaviour being reproduced (file:line in /root/reference/AmpliPy.py):
+//   get_pos_on_ref 363-386, get_pos_on_query 389-412, fix_cigar 415-423, trim_read 426-687,
+//   update_base_counts 690-753.  pysam-derived quantities (reference_end, query_alignment_start/
+//   end, get_aligned_pairs) follow pysam 0.17 / htslib semantics.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AMP_HD __host__ __device__ __forceinline__
+#define AMP_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define AMP_HD inline
+#define AMP_HD_NOINLINE inline
+#endif
+
+// ---- out_flags bits (include/amplipy_b200.h) -------------------------------------------------
+#define AMP_F_TRIM_START 1
+#define AMP_F_TRIM_END 2
+#define AMP_F_TRIM_QUAL 4
+#define AMP_F_KEEP 8
+#define AMP_F_SKIPPED 16
+#define AMP_F_ERROR 32
+
+// ---- device error word bits -------------------------------------------------------------------
+#define AMP_E_COORD 1        // read outside the genome (IndexError in the reference)
+#define AMP_E_BASE 2         // aligned base not in ACGTN (KeyError in the reference)
+#define AMP_E_INS_END 4      // insertion run reaches the end of the pair list (IndexError, 734)
+#define AMP_E_CIGAR 8        // query-consuming ops exceed l_seq / unsupported op
+#define AMP_E_TABLE_FULL 16  // insertion hash table full
+#define AMP_E_ARENA_FULL 32  // insertion string arena full
+
+#define AMP_NCH 6            // channels A C G T N '-'
+
+#ifndef __CUDACC__
+struct uint4 { unsigned int x, y, z, w; };   // host emulation build only
+#endif
+
+namespace amp {
+
+enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };
+
+// AmpliPy.py:43-44 as bit masks over the op code
+AMP_HD bool cons_q(uint32_t op) { return (0x193u >> op) & 1u; }   // M I S = X
+AMP_HD bool cons_r(uint32_t op) { return (0x18Du >> op) & 1u; }   // M D N = X
+AMP_HD bool cons_qr(uint32_t op) { return (0x181u >> op) & 1u; }  // M = X
+AMP_HD uint32_t c_op(uint32_t w) { return w & 15u; }
+AMP_HD int c_len(uint32_t w) { return (int)(w >> 4); }
+AMP_HD uint32_t c_pack(uint32_t op, int n) { return ((uint32_t)n << 4) | op; }
+
+// ---- atomics: real on the device, plain on the host emulation -----------------------------------
+AMP_HD int atomic_add(int* p, int v) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, v);
+#else
+    int o = *p; *p += v; return o;
+#endif
+}
+AMP_HD unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, v);
+#else
+    unsigned long long o = *p; *p += v; return o;
+#endif
+}
+AMP_HD unsigned long long atomic_cas64(unsigned long long* p, unsigned long long cmp, unsigned long long val) {
+#ifdef __CUDA_ARCH__
+    return atomicCAS(p, cmp, val);
+#else
+    unsigned long long o = *p; if (o == cmp) *p = val; return o;
+#endif
+}
+AMP_HD void atomic_min(int* p, int v) {
+#ifdef __CUDA_ARCH__
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+AMP_HD void atomic_max(int* p, int v) {
+#ifdef __CUDA_ARCH__
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+AMP_HD int atomic_exch(int* p, int v) {
+#ifdef __CUDA_ARCH__
+    return atomicExch(p, v);
+#else
+    int o = *p; *p = v; return o;
+#endif
+}
+AMP_HD void atomic_or(unsigned int* p, unsigned int v) {
+#ifdef __CUDA_ARCH__
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+AMP_HD void fence() {
+#ifdef __CUDA_ARCH__
+    __threadfence();
+#endif
+}
+// L1-bypassing loads for data other SMs may have just published (arena records, table keys)
+AMP_HD unsigned long long ld_cg64(const unsigned long long* p) {
+#ifdef __CUDA_ARCH__
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+AMP_HD unsigned int ld_cg32(const unsigned int* p) {
+#ifdef __CUDA_ARCH__
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+
+// ---- CIGAR helpers on packed ops ---------------------------------------------------------------
+AMP_HD int get_pos_on_ref(const uint32_t* c, int nc, int query_pos, int ref_start) {   // 363-386
+    int cur = 0, ref_pos = ref_start;
+    for (int k = 0; k < nc; ++k) {
+        uint32_t op = c_op(c[k]); int n = c_len(c[k]);
+        if (cons_q(op)) {
+            if (query_pos <= cur + n) { if (cons_r(op)) ref_pos += query_pos - cur; return ref_pos; }
+            cur += n;
+        }
+        if (cons_r(op)) ref_pos += n;
+    }
+    return ref_pos;
+}
+AMP_HD int get_pos_on_query(const uint32_t* c, int nc, int ref_pos, int ref_start) {   // 389-412
+    int qp = 0, cur = ref_start;
+    for (int k = 0; k < nc; ++k) {
+        uint32_t op = c_op(c[k]); int n = c_len(c[k]);
+        if (cons_r(op)) {
+            if (ref_pos <= cur + n) { if (cons_q(op)) qp += ref_pos - cur; return qp; }
+            cur += n;
+        }
+        if (cons_q(op)) qp += n;
+    }
+    return qp;
+}
+// htslib bam_endpos floor of 1
+AMP_HD int ref_len_of(const uint32_t* c, int nc) {
+    int r = 0;
+    for (int k = 0; k < nc; ++k) if (cons_r(c_op(c[k]))) r += c_len(c[k]);
+    return r == 0 ? 1 : r;
+}
+AMP_HD int q_align_start(const uint32_t* c, int nc) {
+    int s = 0;
+    for (int k = 0; k < nc; ++k) {
+        uint32_t op = c_op(c[k]);
+        if (op == OP_H) continue;
+        if (op == OP_S) s += c_len(c[k]); else break;
+    }
+    return s;
+}
+AMP_HD int q_align_end(const uint32_t* c, int nc, int l_seq) {
+    int e = l_seq;
+    for (int k = nc - 1; k >= 1; --k) {   // op 0 is never inspected (pysam getQueryEnd)
+        uint32_t op = c_op(c[k]);
+        if (op == OP_H) continue;
+        if (op == OP_S) e -= c_len(c[k]); else break;
+    }
+    return e;
+}
+// append with fix_cigar's merge of equal neighbours (415-423) folded in
+AMP_HD void push_op(uint32_t* d, int& nd, uint32_t op, int n) {
+    if (nd > 0 && c_op(d[nd - 1]) == op) d[nd - 1] += ((uint32_t)n << 4);
+    else d[nd++] = c_pack(op, n);
+}
+AMP_HD void reverse_ops(uint32_t* d, int nd) {
+    for (int i = 0, j = nd - 1; i < j; ++i, --j) { uint32_t t = d[i]; d[i] = d[j]; d[j] = t; }
+}
+
+struct TrimParams {
+    int L;
+    const int32_t* min_primer_start;   // [L], -1 = uncovered   (find_overlapping_primers, 174-209)
+    const int32_t* max_primer_end;     // [L], -1 = uncovered
+    int max_primer_len, min_quality, window, min_length, include_no_primer;
+};
+
+// shared tail of the primer rewrite loops (467-510 and 524-555): one op, forward or reversed order
+AMP_HD void primer_rewrite_op(uint32_t w, int& del_len, int& pos_start, int& start_pos, uint32_t* d, int& nd) {
+    uint32_t cig = c_op(w); int n = c_len(w);
+    if (del_len == 0 && pos_start) { push_op(d, nd, cig, n); return; }
+    if (del_len == 0 && cons_qr(cig)) { pos_start = 1; push_op(d, nd, cig, n); return; }
+    int ref_add = 0;
+    if (cons_q(cig)) {
+        if (del_len >= n) push_op(d, nd, OP_S, n);
+        else if (0 < del_len && del_len < n) push_op(d, nd, OP_S, del_len);
+        else { push_op(d, nd, OP_S, n); return; }
+        ref_add = del_len < n ? del_len : n;
+        int tmp = n;
+        n = (n - del_len) > 0 ? (n - del_len) : 0;
+        del_len = (del_len - tmp) > 0 ? (del_len - tmp) : 0;
+        uint32_t last = OP_S;
+        if (n > 0) { push_op(d, nd, cig, n); last = cig; }
+        if (del_len == 0 && cons_qr(last)) pos_start = 1;
+    } else if (cons_r(cig)) {
+        ref_add += n;
+    }
+    if (cons_r(cig)) start_pos += ref_add;
+}
+// quality rewrite loops (597-622 and 658-683): one op
+AMP_HD void qual_rewrite_op(uint32_t w, int& del_len, uint32_t* d, int& nd) {
+    uint32_t cig = c_op(w); int n = c_len(w);
+    if (del_len == 0) { push_op(d, nd, cig, n); return; }
+    if (cig == OP_S || cig == OP_H) { push_op(d, nd, cig, n); return; }
+    if (cons_q(cig)) {
+        if (del_len >= n) push_op(d, nd, OP_S, n); else push_op(d, nd, OP_S, del_len);
+        int tmp = n;
+        n = (n - del_len) > 0 ? (n - del_len) : 0;
+        del_len = (del_len - tmp) > 0 ? (del_len - tmp) : 0;
+        if (n > 0) push_op(d, nd, cig, n);
+    }
+}
+
+// Sliding-window search (closed form of 566-587 / 628-649, verified against the literal loops of
+// oracle/amplipy_oracle.c): q = aligned qualities [0, len).  Returns del_len.
+//   forward : first i with sum(q[i:i+w]) < minq*w, w = min(W, len-i)  -> len - i   (0 if none)
+//   reverse : first i from len down to 1 with sum(q[i-w:i]) < minq*w, w = min(W, i) -> i (0 if none)
+AMP_HD int window_del_len_fwd(const uint8_t* q, int len, int W, int minq) {
+    if (len <= 0) return 0;
+    int w = W < len ? W : len;
+    int total = 0;
+    for (int j = 0; j < w; ++j) total += q[j];
+    for (int i = 0; i < len; ++i) {
+        // window [i, i+w)
+        if (total < minq * w) return len - i;
+        total -= q[i];
+        if (i + w < len) total += q[i + w]; else --w;
+    }
+    return 0;
+}
+AMP_HD int window_del_len_rev(const uint8_t* q, int len, int W, int minq) {
+    if (len <= 0) return 0;
+    int w = W < len ? W : len;
+    int total = 0;
+    for (int j = 0; j < w; ++j) total += q[len - 1 - j];
+    for (int i = len; i > 0; --i) {
+        // window [i-w, i)
+        if (total < minq * w) return i;
+        total -= q[i - 1];
+        if (i - 1 - w >= 0) total += q[i - 1 - w]; else --w;
+    }
+    return 0;
+}
+
+// trim_read (426-687).  A holds the input CIGAR (capacity nc+3), B is scratch of the same capacity.
+// On return *res points at the buffer holding the final CIGAR.  Returns AMP_F_* bits.
+AMP_HD int trim_read(uint32_t* A, uint32_t* B, int& nc, int& pos, int flag, int tlen, int l_seq, const uint8_t* qual,
+                     const TrimParams& P, uint32_t** res) {
+    uint32_t* src = A; uint32_t* dst = B;
+    int ref_start = pos;
+    const bool is_paired = flag & 1, is_reverse = (flag & 16) != 0;
+    int ref_end = ref_start + ref_len_of(src, nc);
+    *res = src;
+    if (ref_start < 0 || ref_start >= P.L || ref_end - 1 >= P.L) return AMP_F_ERROR;
+    const int left_max_primer_end = P.max_primer_end[ref_start];        // 450
+    const int right_min_primer_start = P.min_primer_start[ref_end - 1];  // 451
+    const int abs_tlen = tlen < 0 ? -tlen : tlen;
+    const bool isize_flag = (abs_tlen - P.max_primer_len) > l_seq;       // 452
+    int out = 0;
+
+    if (!(is_paired && isize_flag && is_reverse) && left_max_primer_end >= 0) {          // 460
+        out |= AMP_F_TRIM_START;
+        int del_len = get_pos_on_query(src, nc, left_max_primer_end + 1, ref_start);     // 463
+        int nd = 0, pos_start = 0, start_pos = 0;
+        for (int k = 0; k < nc; ++k) primer_rewrite_op(src[k], del_len, pos_start, start_pos, dst, nd);
+        nc = nd; { uint32_t* t = src; src = dst; dst = t; }
+        ref_start += start_pos;                                                          // 514
+    }
+    if (!(is_paired && isize_flag && !is_reverse) && right_min_primer_start >= 0) {      // 517
+        out |= AMP_F_TRIM_END;
+        int del_len = l_seq - get_pos_on_query(src, nc, right_min_primer_start, ref_start);   // 520
+        int nd = 0, pos_start = 0, dummy = 0;
+        for (int k = nc - 1; k >= 0; --k) primer_rewrite_op(src[k], del_len, pos_start, dummy, dst, nd);
+        reverse_ops(dst, nd);
+        nc = nd; { uint32_t* t = src; src = dst; dst = t; }
+    }
+    const int qas = q_align_start(src, nc);
+    int len = q_align_end(src, nc, l_seq) - qas;                                         // 561-563
+    if (len < 0) len = 0;
+    if (is_reverse) {                                                                    // 566-625
+        int del_len = window_del_len_rev(qual + qas, len, P.window, P.min_quality);
+        int sp = get_pos_on_ref(src, nc, del_len + qas - 1, ref_start);                  // 591
+        if (sp > ref_start) {
+            out |= AMP_F_TRIM_QUAL;
+            int nd = 0;
+            for (int k = 0; k < nc; ++k) qual_rewrite_op(src[k], del_len, dst, nd);
+            nc = nd; { uint32_t* t = src; src = dst; dst = t; }
+            // reference_start is NOT advanced (589-625)
+        }
+    } else {                                                                             // 628-686
+        int del_len = window_del_len_fwd(qual + qas, len, P.window, P.min_quality);
+        if (del_len != 0) {
+            out |= AMP_F_TRIM_QUAL;
+            int nd = 0;
+            for (int k = nc - 1; k >= 0; --k) qual_rewrite_op(src[k], del_len, dst, nd);
+            reverse_ops(dst, nd);
+            nc = nd; { uint32_t* t = src; src = dst; dst = t; }
+        }
+    }
+    if (ref_len_of(src, nc) >= P.min_length && ((out & (AMP_F_TRIM_START | AMP_F_TRIM_END)) || P.include_no_primer))
+        out |= AMP_F_KEEP;                                                               // 910
+    pos = ref_start;
+    *res = src;
+    return out;
+}
+
+// ---- sequence access: BAM 4-bit nibbles, high nibble first ---------------------------------------
+AMP_HD uint32_t nib_at(const uint8_t* seq, uint32_t idx) { return (seq[idx >> 1] >> ((~idx & 1u) << 2)) & 15u; }
+AMP_HD char nib_char(uint32_t nib) {
+    // "=ACMGRSVTWYHKDBN"
+    const unsigned long long lo = 0x565352474D43413DULL;  // "=ACMGRSV" little-endian bytes
+    const unsigned long long hi = 0x4E42444B48595754ULL;  // "TWYHKDBN"
+    return (char)(((nib < 8 ? lo : hi) >> ((nib & 7u) * 8u)) & 0xFFu);
+}
+// channel of an aligned base: A C G T N -> 0..4, anything else -> -1
+AMP_HD int nib_channel(uint32_t nib) {
+    switch (nib) { case 1: return 0; case 2: return 1; case 4: return 2; case 8: return 3; case 15: return 4; default: return -1; }
+}
+
+// ---- insertion-allele hash table ------------------------------------------------------------------
+// slot  : key64 = [tag:24 | arena offset in 8-byte words:40] (0 = empty), count32
+// arena : records {int32 gpos; uint32 len; char text[len]} padded to 8 bytes, write-once
+// Lookups compare the full text, so the hash is only a filter: results are exact.
+struct InsSlot { unsigned long long key; int count; int next; };
+struct InsTable {
+    InsSlot* slots; unsigned long long mask;        // capacity - 1 (power of two)
+    unsigned int* entries;                           // dense list: entries[k] = slot of the k-th distinct allele
+    int* slot_entry;                                 // inverse: slot -> k
+    unsigned char* arena; unsigned long long arena_words;
+    unsigned long long* cursor;                      // [0] = arena words used, [1] = entries used
+    unsigned int* err;
+};
+AMP_HD unsigned long long mix64(unsigned long long h) {
+    h ^= h >> 30; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 27; h *= 0x94D049BB133111EBULL; h ^= h >> 31; return h;
+}
+// text getter: ch(i) -> i-th character of the key
+template <class Text>
+AMP_HD void ins_table_add(const InsTable& T, int gpos, int len, const Text& text, int n) {
+    unsigned long long h = 0xCBF29CE484222325ULL ^ (unsigned long long)(unsigned int)gpos;
+    h *= 0x100000001B3ULL;
+    for (int i = 0; i < len; ++i) { h ^= (unsigned char)text(i); h *= 0x100000001B3ULL; }
+    h = mix64(h ^ ((unsigned long long)len << 32));
+    const unsigned long long tag = (h >> 40) | 0x800000ULL;            // never zero
+    unsigned long long slot = h & T.mask;
+    long long my_off = -1;
+    for (unsigned long long probes = 0; probes <= T.mask; ++probes, slot = (slot + 1) & T.mask) {
+        unsigned long long k = ld_cg64(&T.slots[slot].key);
+        if (k == 0) {
+            if (my_off < 0) {
+                unsigned long long words = 1 + ((unsigned long long)len + 7) / 8;
+                unsigned long long off = atomic_add64(&T.cursor[0], words);
+                if (off + words > T.arena_words) { atomic_or(T.err, AMP_E_ARENA_FULL); return; }
+                unsigned char* rec = T.arena + off * 8;
+                ((int*)rec)[0] = gpos; ((unsigned int*)rec)[1] = (unsigned int)len;
+                for (int i = 0; i < len; ++i) rec[8 + i] = (unsigned char)text(i);
+                fence();
+                my_off = (long long)off;
+            }
+            unsigned long long old = atomic_cas64(&T.slots[slot].key, 0ULL, (tag << 40) | (unsigned long long)my_off);
+            if (old == 0) {
+                atomic_add(&T.slots[slot].count, n);
+                const unsigned long long k_new = atomic_add64(&T.cursor[1], 1ULL);
+                T.entries[k_new] = (unsigned int)slot; T.slot_entry[slot] = (int)k_new;
+                return;
+            }
+            k = old;
+        }
+        if ((k >> 40) == tag) {
+            fence();
+            const unsigned char* rec = T.arena + (k & 0xFFFFFFFFFFULL) * 8;
+            const unsigned long long hdr = ld_cg64((const unsigned long long*)rec);
+            if ((int)(hdr & 0xFFFFFFFFu) == gpos && (unsigned int)(hdr >> 32) == (unsigned int)len) {
+                bool same = true;
+                for (int i = 0; i < len && same; i += 4) {
+                    unsigned int w = ld_cg32((const unsigned int*)(rec + 8 + i));
+                    for (int j = 0; j < 4 && i + j < len; ++j)
+                        if ((unsigned char)(w >> (8 * j)) != (unsigned char)text(i + j)) { same = false; break; }
+                }
+                if (same) { atomic_add(&T.slots[slot].count, n); return; }
+            }
+        }
+    }
+    atomic_or(T.err, AMP_E_TABLE_FULL);
+}
+
+// ---- pileup plan: walk the (trimmed) CIGAR exactly as update_base_counts walks get_aligned_pairs() ----
+// Sink interface:  match(rpos, q, len)   aligned run (quality filter applied when counting)
+//                  del(rpos, len)        D / N run -> '-' channel, unconditional (714-715)
+//                  ins(pos, s_begin, s_len)   insertion allele = query_seq[s_begin : s_begin + s_len]
+// Returns AMP_E_* bits (0 = ok).
+template <class Sink>
+AMP_HD int plan_read(const uint32_t* c, int nc, int pos, int l_seq, const uint8_t* qual, int minq, int L, Sink& sink) {
+    const int qs = q_align_start(c, nc);                      // 700
+    const int qe = q_align_end(c, nc, l_seq);                 // 701
+    const int ref_end = pos + ref_len_of(c, nc);              // 705
+    if (pos < 0 || ref_end > L) return AMP_E_COORD;
+    {   // pysam pair list consistency: query-advancing ops (incl. P, as pysam 0.17 does) within l_seq
+        int qt = 0;
+        for (int k = 0; k < nc; ++k) { uint32_t op = c_op(c[k]); if (op > OP_X) return AMP_E_CIGAR; if (cons_q(op) || op == OP_P) qt += c_len(c[k]); }
+        if (qt > l_seq) return AMP_E_CIGAR;
+    }
+    int q = 0, r = pos, q0 = -1;   // q0 >= 0: an insertion event is open (730-734)
+    // key slice [q0-1 : end) with python's negative-index wrap for q0 == 0
+#define AMP_KEY(end_, at_) do { int b_ = q0 - 1; if (b_ < 0) { b_ += l_seq; if (b_ < 0) b_ = 0; } \
+        int e_ = (end_) < l_seq ? (end_) : l_seq; int n_ = e_ - b_; if (n_ < 0) n_ = 0; \
+        int p_ = (at_) - 1; if (p_ < 0) p_ = 0; sink.ins(p_, b_, n_); q0 = -1; } while (0)
+    for (int k = 0; k < nc; ++k) {
+        const uint32_t op = c_op(c[k]); const int n = c_len(c[k]);
+        if (op == OP_H || n == 0) continue;
+        if (cons_qr(op)) {
+            if (q0 >= 0) {                                    // exit (A)/(A'): next pair is a match
+                if (r == 0) { int e_ = q + 1 < l_seq ? q + 1 : l_seq; sink.ins(0, q0, e_ - q0); q0 = -1; }   // 735-736
+                else AMP_KEY(q, r);
+            }
+            sink.match(r, q, n);
+            q += n; r += n;
+        } else if (op == OP_D || op == OP_N) {
+            if (q0 >= 0) {                                    // exit (B): key runs to the end of the read
+                if (r == 0) return AMP_E_INS_END;             // None + 1 -> TypeError in the reference
+                AMP_KEY(l_seq, r);
+            }
+            sink.del(r, n);
+            r += n;
+        } else {                                              // I, S, P: pairs (q, None)
+            int j = q; const int hi = q + n;
+            if (q0 < 0 && j < qs) j = hi < qs ? hi : qs;      // rules 718/722 both skip: leading clip
+            for (; j < hi; ++j) {
+                if (q0 < 0 && j >= qe) return 0;   // trailing clip: every later pair is skipped (718) or breaks (726)
+                if (q0 >= 0) {
+                    if (j >= qe) { AMP_KEY(j, ref_end); }                  // exit (C), pair consumed
+                    else if (qual[j] < minq) { AMP_KEY(j, ref_end); }      // exit (D), pair consumed
+                } else {
+                    if (qual[j] < minq) continue;                          // 718
+                    if (j < qs) continue;                                  // 722
+                    if (j >= qe) return 0;                                 // 726: break
+                    q0 = j;                                                // 732
+                }
+            }
+            q += n;
+        }
+    }
+#undef AMP_KEY
+    if (q0 >= 0) return AMP_E_INS_END;                        // IndexError at 734
+    return 0;
+}
+
+// A unit of counting work produced by plan_read: an aligned run or a deletion run.
+struct Seg {
+    int rpos;            // first reference position
+    int len;             // bases; bit 31 set = deletion run
+    uint32_t qabs;       // absolute index of the first base's quality in the batch qual array
+    uint32_t nibabs;     // absolute nibble index of the first base in the batch seq array
+};
+
+}  // namespace amp

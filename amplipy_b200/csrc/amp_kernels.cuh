@@ -1,0 +1,383 @@
+// amp_kernels.cuh -- CTA-level structure of the fused trim + pileup kernel and the calling kernel.
+//
+// The CTA body is written as barrier-separated phases over AMP_FOR_THREADS so that tests/emu can run
+// the same source on the CPU (one loop over the CTA's threads per phase).  No warp collectives are
+// used inside phases; cross-thread communication is shared-memory atomics + barriers only.
+//
+// Tile = up to `reads_per_tile` consecutive reads.  Per tile:
+//   S  stage the tile's contiguous qual / seq byte ranges into shared memory (128-bit loads)
+//   T  one thread per read: trim_read (AmpliPy.py:426-687), write trim outputs, plan the pileup
+//      (update_base_counts, 690-753) into a shared list of aligned / deleted runs; insertion alleles
+//      go to the global hash table
+//   W  window decision: the CTA keeps a privatised counts tile cnt[6][WT] over reference window
+//      [wbase, wbase+WT); when the tile's reads leave the window it is flushed with global atomics
+//   C  one warp per run, lanes over consecutive bases: quality gate + base channel -> shared atomics
+//      (channel-major tile with WT % 32 == 0 => 32 consecutive positions never bank-conflict)
+#pragma once
+#include "amp_core.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define AMP_FOR_THREADS(tid, nthreads) for (int tid = threadIdx.x, once_ = 1; once_; once_ = 0)
+#define AMP_SYNC() __syncthreads()
+#else
+#define AMP_FOR_THREADS(tid, nthreads) for (int tid = 0; tid < (nthreads); ++tid)
+#define AMP_SYNC() ((void)0)
+#endif
+
+namespace amp {
+
+struct BatchPtrs {
+    long long first;         // global index of the first read to process (pointers are indexed with global indices)
+    long long n;             // number of reads to process
+    const int32_t* pos; const uint16_t* flag; const int32_t* tlen;
+    const uint32_t* cig_off; const uint32_t* cigar;
+    const uint32_t* seq_off; const uint8_t* seq;
+    const uint32_t* qual_off; const uint8_t* qual;
+};
+struct TrimOut { int32_t* pos; uint16_t* ncig; uint8_t* flags; uint32_t* cigar; };
+
+#define AMP_MODE_TRIM 1
+#define AMP_MODE_PILEUP 2
+#define AMP_CMAX 24          // CIGAR ops (+3) handled in per-thread local arrays; longer ones use global scratch
+
+struct KParams {
+    BatchPtrs b;
+    TrimOut o;
+    TrimParams tp;
+    int mode;
+    int* counts;             // [6][Lpad] of the sample being processed
+    int Lpad;
+    int gpos_base;           // sample * Lpad: position key used in the insertion table
+    InsTable tab;
+    unsigned int* err;
+    uint32_t* scratch;       // 2 * (sumC + 3N) words, only touched by reads with n_cigar + 3 > AMP_CMAX
+    long long scratch_half;  // sumC + 3N
+    int reads_per_tile, ntiles, tiles_per_cta;
+    int wt, maxseg, qbytes, sbytes;   // shared-memory carve-up
+};
+
+inline double amp_min_d(double a, double b) { return a < b ? a : b; }
+inline double amp_max_d(double a, double b) { return a > b ? a : b; }
+struct TileCfg { int wt, maxseg, qbytes, sbytes, reads_per_tile; };
+
+// shared-memory carve-up: two CTAs per SM at <= ~100 KB each (227 KB usable per SM)
+inline TileCfg pick_tile_cfg(long long n, long long sum_cig, long long sum_qual, int mode) {
+    TileCfg t;
+    const double avg_len = n ? (double)sum_qual / (double)n : 150.0;
+    const double avg_ops = n ? (double)sum_cig / (double)n : 2.0;
+    if (avg_ops > 8.0) { t.wt = 1024; t.maxseg = 3072; t.qbytes = 20480; t.sbytes = 10240; }   // indel-rich (ONT-like)
+    else { t.wt = 1024; t.maxseg = 1024; t.qbytes = 40960; t.sbytes = 20480; }
+    if (!(mode & AMP_MODE_PILEUP)) { t.wt = 32; t.maxseg = 16; t.sbytes = 16; }
+    double r = 256.0;
+    r = amp_min_d(r, (double)t.qbytes * 0.97 / amp_max_d(avg_len, 1.0));
+    if (mode & AMP_MODE_PILEUP) r = amp_min_d(r, (double)t.maxseg / (1.5 + 0.75 * avg_ops));
+    t.reads_per_tile = (int)amp_max_d(8.0, r);
+    return t;
+}
+
+
+AMP_HD size_t smem_bytes(int wt, int maxseg, int qbytes, int sbytes) {
+    return (size_t)AMP_NCH * wt * 4 + (size_t)maxseg * sizeof(Seg) + 64 + (size_t)qbytes + (size_t)sbytes;
+}
+
+struct Smem {
+    int* cnt; Seg* segs; int* ctrl; uint8_t* qual; uint8_t* seq;
+};
+// ctrl words
+enum { C_NSEG = 0, C_TMIN = 1, C_TMAX = 2 };
+
+AMP_HD Smem carve(unsigned char* base, const KParams& P) {
+    Smem s;
+    s.cnt = (int*)base; base += (size_t)AMP_NCH * P.wt * 4;
+    s.segs = (Seg*)base; base += (size_t)P.maxseg * sizeof(Seg);
+    s.ctrl = (int*)base; base += 64;
+    s.qual = base; base += P.qbytes;
+    s.seq = base;
+    return s;
+}
+
+AMP_HD void count_add(const KParams& P, int* cnt, int wbase, int ch, int p) {
+    const unsigned w = (unsigned)(p - wbase);
+    if (wbase >= 0 && w < (unsigned)P.wt) atomic_add(&cnt[ch * P.wt + (int)w], 1);
+    else atomic_add(&P.counts[(size_t)ch * P.Lpad + p], 1);
+}
+
+// Per-read sink used in phase T.
+struct TileSink {
+    const KParams* P; Smem sm;
+    uint32_t qabs0, nibabs0;           // absolute offsets of this read's first quality / first nibble
+    const uint8_t* seq_read;           // this read's packed sequence (shared or global)
+    const uint8_t* qual_read;
+    unsigned int errs;
+    AMP_HD void push(int rpos, int len_kind, int q) {
+        int idx = atomic_add(&sm.ctrl[C_NSEG], 1);
+        if (idx < P->maxseg) {
+            Seg s; s.rpos = rpos; s.len = len_kind; s.qabs = qabs0 + (uint32_t)q; s.nibabs = nibabs0 + (uint32_t)q;
+            sm.segs[idx] = s;
+        } else {
+            // list full: count this run serially, straight into the global matrix (exact, slow, rare)
+            const int n = len_kind & 0x7FFFFFFF;
+            if (len_kind < 0) { for (int j = 0; j < n; ++j) atomic_add(&P->counts[(size_t)5 * P->Lpad + rpos + j], 1); }
+            else for (int j = 0; j < n; ++j) {
+                if (qual_read[q + j] < P->tp.min_quality) continue;
+                int ch = nib_channel(nib_at(seq_read, (uint32_t)(q + j)));
+                if (ch < 0) { errs |= AMP_E_BASE; continue; }
+                atomic_add(&P->counts[(size_t)ch * P->Lpad + rpos + j], 1);
+            }
+        }
+    }
+    AMP_HD void match(int rpos, int q, int n) { push(rpos, n, q); }
+    AMP_HD void del(int rpos, int n) { push(rpos, (int)(0x80000000u | (unsigned)n), 0); }
+    struct Text {
+        const uint8_t* seq; int b;
+        AMP_HD char operator()(int i) const { return nib_char(nib_at(seq, (uint32_t)(b + i))); }
+    };
+    AMP_HD void ins(int pos, int b, int n) {
+        if (n == 1) {   // one-character key == that base's own dict entry (AmpliPy.py:745-746)
+            int ch = nib_channel(nib_at(seq_read, (uint32_t)b));
+            if (ch >= 0) { atomic_add(&P->counts[(size_t)ch * P->Lpad + pos], 1); return; }
+        }
+        Text t; t.seq = seq_read; t.b = b;
+        ins_table_add(P->tab, P->gpos_base + pos, n, t, 1);
+    }
+};
+
+// The fused CTA body.  `block` / `nthreads` are blockIdx.x / blockDim.x on the device.
+AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int block, int nthreads) {
+    const Smem sm = carve(smem_base, P);
+    const bool do_trim = P.mode & AMP_MODE_TRIM, do_pile = P.mode & AMP_MODE_PILEUP;
+    const int ncnt = AMP_NCH * P.wt;
+    int wbase = -1;                                    // uniform across the CTA
+    if (do_pile) {
+        AMP_FOR_THREADS(tid, nthreads) { for (int i = tid; i < ncnt; i += nthreads) sm.cnt[i] = 0; }
+    }
+    const int tile_lo = block * P.tiles_per_cta;
+    int tile_hi = tile_lo + P.tiles_per_cta; if (tile_hi > P.ntiles) tile_hi = P.ntiles;
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        const long long t0 = P.b.first + (long long)tile * P.reads_per_tile;
+        long long t1 = t0 + P.reads_per_tile; if (t1 > P.b.first + P.b.n) t1 = P.b.first + P.b.n;
+        const int nreads = (int)(t1 - t0);
+        // ---- S: stage qual / seq of the tile ------------------------------------------------------
+        const uint32_t q_lo = P.b.qual_off[t0] & ~15u, q_end = P.b.qual_off[t1];
+        const uint32_t s_lo = P.b.seq_off[t0] & ~15u, s_end = P.b.seq_off[t1];
+        const uint32_t q_hi = (q_end - q_lo <= (uint32_t)P.qbytes) ? q_end : q_lo + (uint32_t)P.qbytes;   // staged [q_lo, q_hi)
+        const uint32_t s_hi = (s_end - s_lo <= (uint32_t)P.sbytes) ? s_end : s_lo + (uint32_t)P.sbytes;
+        AMP_FOR_THREADS(tid, nthreads) {
+            if (tid == 0) { sm.ctrl[C_NSEG] = 0; sm.ctrl[C_TMIN] = 0x7FFFFFFF; sm.ctrl[C_TMAX] = -1; }
+            {
+                const uint32_t nvec = (q_hi - q_lo) >> 4;
+                const uint4* g = (const uint4*)(P.b.qual + q_lo); uint4* s = (uint4*)sm.qual;
+                for (uint32_t v = tid; v < nvec; v += nthreads) s[v] = g[v];
+                for (uint32_t k = (nvec << 4) + tid; k < q_hi - q_lo; k += nthreads) sm.qual[k] = P.b.qual[q_lo + k];
+            }
+            if (do_pile) {
+                const uint32_t nvec = (s_hi - s_lo) >> 4;
+                const uint4* g = (const uint4*)(P.b.seq + s_lo); uint4* s = (uint4*)sm.seq;
+                for (uint32_t v = tid; v < nvec; v += nthreads) s[v] = g[v];
+                for (uint32_t k = (nvec << 4) + tid; k < s_hi - s_lo; k += nthreads) sm.seq[k] = P.b.seq[s_lo + k];
+            }
+        }
+        AMP_SYNC();
+        // ---- T: one thread per read ---------------------------------------------------------------
+        AMP_FOR_THREADS(tid, nthreads) {
+            for (int rr = tid; rr < nreads; rr += nthreads) {
+                const long long i = t0 + rr;
+                const uint32_t c0 = P.b.cig_off[i], c1 = P.b.cig_off[i + 1];
+                const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
+                const uint32_t so0 = P.b.seq_off[i], so1 = P.b.seq_off[i + 1];
+                int nc = (int)(c1 - c0);
+                const int l_seq = (int)(qo1 - qo0);
+                const int flag = P.b.flag[i];
+                int pos = P.b.pos[i];
+                const uint8_t* qual = (qo1 <= q_hi) ? sm.qual + (qo0 - q_lo) : P.b.qual + qo0;
+                const uint8_t* seq = (so1 <= s_hi && do_pile) ? sm.seq + (so0 - s_lo) : P.b.seq + so0;
+                const uint32_t* cig = P.b.cigar + c0;
+                uint32_t la[AMP_CMAX], lb[AMP_CMAX];
+                int f = 0;
+                if ((flag & 4) || nc == 0) f = AMP_F_SKIPPED;                           // AmpliPy.py:902
+                if (do_trim) {
+                    uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
+                    if (f == 0) {
+                        uint32_t *A, *B;
+                        if (nc + 3 <= AMP_CMAX) { A = la; B = lb; }
+                        else { A = P.scratch + (size_t)c0 + 3 * (size_t)i; B = A + P.scratch_half; }
+                        for (int k = 0; k < nc; ++k) A[k] = cig[k];
+                        uint32_t* res;
+                        f = trim_read(A, B, nc, pos, flag, P.b.tlen[i], l_seq, qual, P.tp, &res);
+                        if (f & AMP_F_ERROR) { nc = 0; f = AMP_F_ERROR; atomic_or(P.err, AMP_E_COORD); }
+                        for (int k = 0; k < nc; ++k) orow[k] = res[k];
+                        cig = res;
+                    } else {
+                        for (int k = 0; k < nc; ++k) orow[k] = cig[k];
+                    }
+                    P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)f;
+                }
+                if (do_pile && !(f & (AMP_F_SKIPPED | AMP_F_ERROR))) {
+                    TileSink sink; sink.P = &P; sink.sm = sm; sink.qabs0 = qo0; sink.nibabs0 = so0 * 2u;
+                    sink.seq_read = seq; sink.qual_read = qual; sink.errs = 0;
+                    int e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
+                    e |= (int)sink.errs;
+                    if (e) atomic_or(P.err, (unsigned)e);
+                    if (!(e & (AMP_E_COORD | AMP_E_CIGAR))) {
+                        atomic_min(&sm.ctrl[C_TMIN], pos);
+                        atomic_max(&sm.ctrl[C_TMAX], pos + ref_len_of(cig, nc));
+                    }
+                }
+            }
+        }
+        if (!do_pile) { AMP_SYNC(); continue; }
+        AMP_SYNC();
+        // ---- W: window decision (uniform) -----------------------------------------------------------
+        int nseg = sm.ctrl[C_NSEG]; if (nseg > P.maxseg) nseg = P.maxseg;
+        const int tmin = sm.ctrl[C_TMIN], tmax = sm.ctrl[C_TMAX];
+        if (nseg > 0 && (wbase < 0 || tmin < wbase || tmax > wbase + P.wt)) {
+            if (wbase >= 0) {
+                AMP_FOR_THREADS(tid, nthreads) {
+                    for (int i = tid; i < ncnt; i += nthreads) {
+                        int v = sm.cnt[i];
+                        if (v) { int ch = i / P.wt, w = i - ch * P.wt; atomic_add(&P.counts[(size_t)ch * P.Lpad + wbase + w], v); sm.cnt[i] = 0; }
+                    }
+                }
+                AMP_SYNC();
+            }
+            wbase = tmin & ~31;
+        }
+        // ---- C: one warp per run ----------------------------------------------------------------------
+        AMP_FOR_THREADS(tid, nthreads) {
+            const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+            unsigned errs = 0;
+            for (int s = warp; s < nseg; s += nwarps) {
+                const Seg sg = sm.segs[s];
+                const int n = sg.len & 0x7FFFFFFF;
+                if (sg.len < 0) {
+                    for (int j = lane; j < n; j += 32) count_add(P, sm.cnt, wbase, 5, sg.rpos + j);
+                } else {
+                    const bool qs_ = sg.qabs + (uint32_t)n <= q_hi;
+                    const uint8_t* qp = qs_ ? sm.qual + (sg.qabs - q_lo) : P.b.qual + sg.qabs;
+                    const bool ss_ = ((sg.nibabs + (uint32_t)n + 1u) >> 1) <= s_hi;
+                    const uint8_t* sp = ss_ ? sm.seq : P.b.seq;
+                    const uint32_t sub = ss_ ? s_lo : 0u;
+                    for (int j = lane; j < n; j += 32) {
+                        if (qp[j] < P.tp.min_quality) continue;                              // AmpliPy.py:718, 752
+                        const uint32_t nb = sg.nibabs + (uint32_t)j;
+                        const int ch = nib_channel((sp[(nb >> 1) - sub] >> ((~nb & 1u) << 2)) & 15u);
+                        if (ch < 0) { errs |= AMP_E_BASE; continue; }                       // KeyError at 753
+                        count_add(P, sm.cnt, wbase, ch, sg.rpos + j);
+                    }
+                }
+            }
+            if (errs) atomic_or(P.err, errs);
+        }
+        AMP_SYNC();
+    }
+    if (do_pile && wbase >= 0) {
+        AMP_FOR_THREADS(tid, nthreads) {
+            for (int i = tid; i < ncnt; i += nthreads) {
+                int v = sm.cnt[i];
+                if (v) { int ch = i / P.wt, w = i - ch * P.wt; atomic_add(&P.counts[(size_t)ch * P.Lpad + wbase + w], v); }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Calling (AmpliPy.py:756-771, 919-951).  One thread per (sample, position).
+// ---------------------------------------------------------------------------------------------------
+struct CallParams {
+    int L, Lpad, n_samples;
+    const int* counts;                 // [n_samples][6][Lpad]
+    const InsSlot* slots;              // insertion table (heads[] / next chains built by link_insertions)
+    const int* slot_entry;             // slot -> dense allele index k (amp_ins_export order)
+    const unsigned char* arena;
+    const int* heads;                  // [n_samples * Lpad] slot index of the first insertion allele, -1 = none
+    const unsigned char* ref_seq;      // [L] raw FASTA characters
+    int min_depth_consensus; double min_freq_consensus;
+    int min_depth_variants; double min_freq_variants;
+    // outputs
+    int* depth;                        // [S*L] total depth incl. insertion alleles (767)
+    int* top_id;                       // [S*L] allele id of the top allele: 0..5 = ACGTN-, 6 + k = insertion allele k, -1 none
+    int* top_count;                    // [S*L]
+    unsigned char* pos_flags;          // [S*L] bit0 consensus passes (928), bit1 variant record emitted (940), bit2 GT has ref (948)
+    int* ref_count;                    // [S*L]
+    double* fixed_freq;                // [S*L*6] count/total (float64, IEEE division)
+    int* fixed_rank;                   // [S*L*6] index in the reference's sorted allele list, -1 if count == 0
+    unsigned char* alt_mask;           // [S*L] bit ch: fixed symbol ch is an ALT allele (938)
+    double* ins_freq;                  // [n_alleles] per insertion allele, dense index k
+    int* ins_rank;                     // [n_alleles]
+    unsigned char* ins_alt;            // [n_alleles]
+};
+
+// python string order between two allele symbols (fixed symbols are 1-char strings)
+struct Sym { const unsigned char* p; int len; };
+AMP_HD int sym_cmp(const Sym& a, const Sym& b) {
+    int m = a.len < b.len ? a.len : b.len;
+    for (int i = 0; i < m; ++i) { if (a.p[i] != b.p[i]) return a.p[i] < b.p[i] ? -1 : 1; }
+    return a.len - b.len;
+}
+AMP_HD bool allele_greater(int ca, const Sym& a, int cb, const Sym& b) {   // (count, freq, symbol) descending
+    if (ca != cb) return ca > cb;
+    return sym_cmp(a, b) > 0;
+}
+AMP_HD Sym slot_sym(const CallParams& P, int slot) {
+    const unsigned char* rec = P.arena + (P.slots[slot].key & 0xFFFFFFFFFFULL) * 8;
+    Sym s; s.p = rec + 8; s.len = (int)((const unsigned int*)rec)[1]; return s;
+}
+
+AMP_HD void call_position(const CallParams& P, const unsigned char* fixed_syms, long long gp) {
+    const int sample = (int)(gp / P.L), p = (int)(gp - (long long)sample * P.L);
+    const int* cnt = P.counts + (size_t)sample * AMP_NCH * P.Lpad;
+    int c[AMP_NCH]; long long total = 0;
+    for (int ch = 0; ch < AMP_NCH; ++ch) { c[ch] = cnt[(size_t)ch * P.Lpad + p]; total += c[ch]; }
+    const int head = P.heads[(size_t)sample * P.Lpad + p];
+    for (int s = head; s >= 0; s = P.slots[s].next) total += P.slots[s].count;
+    P.depth[gp] = (int)total;
+    int best_id = -1, best_c = 0; Sym best_s; best_s.p = fixed_syms; best_s.len = 0;
+    int refc = 0; double reff = 0.0; unsigned alt = 0; int n_alt = 0;
+    const unsigned char refsym = P.ref_seq[p];
+    for (int ch = 0; ch < AMP_NCH; ++ch) {
+        double f = total ? (double)c[ch] / (double)total : 0.0;
+        P.fixed_freq[gp * AMP_NCH + ch] = f;
+        int rank = -1;
+        if (c[ch]) {
+            Sym me; me.p = fixed_syms + ch; me.len = 1;
+            rank = 0;
+            for (int o = 0; o < AMP_NCH; ++o) if (o != ch && c[o]) { Sym os; os.p = fixed_syms + o; os.len = 1; if (allele_greater(c[o], os, c[ch], me)) ++rank; }
+            for (int s = head; s >= 0; s = P.slots[s].next) if (P.slots[s].count && allele_greater(P.slots[s].count, slot_sym(P, s), c[ch], me)) ++rank;
+            if (best_id < 0 || allele_greater(c[ch], me, best_c, best_s)) { best_id = ch; best_c = c[ch]; best_s = me; }
+            if (fixed_syms[ch] == refsym) { refc = c[ch]; reff = f; }                  // 936-937
+            else if (f >= P.min_freq_variants) { alt |= 1u << ch; ++n_alt; }           // 938-939
+        }
+        P.fixed_rank[gp * AMP_NCH + ch] = rank;
+    }
+    for (int s = head; s >= 0; s = P.slots[s].next) {
+        const int cs = P.slots[s].count;
+        if (!cs) continue;
+        const Sym me = slot_sym(P, s);
+        const double f = (double)cs / (double)total;
+        int rank = 0;
+        for (int o = 0; o < AMP_NCH; ++o) if (c[o]) { Sym os; os.p = fixed_syms + o; os.len = 1; if (allele_greater(c[o], os, cs, me)) ++rank; }
+        for (int t = head; t >= 0; t = P.slots[t].next) if (t != s && P.slots[t].count && allele_greater(P.slots[t].count, slot_sym(P, t), cs, me)) ++rank;
+        const int kk = P.slot_entry[s];
+        P.ins_freq[kk] = f; P.ins_rank[kk] = rank;
+        if (best_id < 0 || allele_greater(cs, me, best_c, best_s)) { best_id = 6 + kk; best_c = cs; best_s = me; }
+        // an insertion key can never equal the 1-character reference symbol except a 1-char key, which
+        // the pileup already routed to the fixed channels
+        unsigned char is_alt = 0;
+        if (me.len == 1 && me.p[0] == refsym) { refc = cs; reff = f; }
+        else if (f >= P.min_freq_variants) is_alt = 1;
+        P.ins_alt[kk] = is_alt; n_alt += is_alt;
+    }
+    P.top_id[gp] = best_id; P.top_count[gp] = best_c;
+    unsigned char fl = 0;
+    if (best_id >= 0) {
+        const double bf = (double)best_c / (double)total;
+        if (best_c >= P.min_depth_consensus && bf >= P.min_freq_consensus) fl |= 1;     // 928
+    }
+    if (total > 0 && total >= P.min_depth_variants && n_alt != 0) {                    // 940
+        fl |= 2;
+        if (refc >= P.min_depth_variants && reff >= P.min_freq_variants) fl |= 4;      // 948
+    }
+    P.pos_flags[gp] = fl; P.ref_count[gp] = refc; P.alt_mask[gp] = (unsigned char)alt;
+}
+
+}  // namespace amp

@@ -1,0 +1,159 @@
+/*
+ * amplipy_b200.h -- C ABI of the B200-native trim -> pileup -> call path (libamplipy_b200.so).
+ *
+ * The reference (Niema-Lab/AmpliPy, /root/reference/AmpliPy.py) has no FFI: its hot path is three
+ * Python functions called per read / per position.  Each entry point below states which of them it
+ * replaces; INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success or a negative AMP_ERR_* code (message from
+ * amp_last_error(), thread-local); nothing throws; all buffers are caller-owned; no torch types.
+ * "device" pointers are CUDA device pointers on the context's device; `stream` is a cudaStream_t
+ * passed as void* (NULL = default stream).
+ *
+ * Batch layout (struct-of-arrays, one entry per read unless noted; amplipy_b200/batch.py):
+ *   pos i32, flag u16, tlen i32, cig_off u32[N+1], cigar u32[sumC] (BAM: len<<4|op),
+ *   seq_off u32[N+1] (bytes), seq u8 (BAM 4-bit, (l_seq+1)/2 bytes per read),
+ *   qual_off u32[N+1] (bytes; l_seq = diff), qual u8 (phred).
+ *   `seq` and `qual` base addresses must be 16-byte aligned.
+ * Trim output layout: row i of out_cigar starts at cig_off[i] + 3*i (capacity n_cigar[i] + 3).
+ */
+#ifndef AMPLIPY_B200_H
+#define AMPLIPY_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMP_ABI_VERSION 1
+
+/* error codes */
+#define AMP_OK 0
+#define AMP_ERR_CUDA (-1)
+#define AMP_ERR_ARG (-2)
+#define AMP_ERR_NOMEM (-3)
+#define AMP_ERR_STATE (-4)
+
+/* out_flags bits per read (AmpliPy.py:443-447 return tuple of trim_read + write gate 910 + skip 902) */
+#define AMP_FLAG_TRIM_START 1
+#define AMP_FLAG_TRIM_END 2
+#define AMP_FLAG_TRIM_QUAL 4
+#define AMP_FLAG_KEEP 8
+#define AMP_FLAG_SKIPPED 16
+#define AMP_FLAG_ERROR 32
+
+/* device error word bits (amp_error_flags): inputs for which the reference itself crashes */
+#define AMP_DEVERR_COORD 1
+#define AMP_DEVERR_BASE 2
+#define AMP_DEVERR_INS_END 4
+#define AMP_DEVERR_CIGAR 8
+#define AMP_DEVERR_TABLE_FULL 16
+#define AMP_DEVERR_ARENA_FULL 32
+
+/* mode bits for amp_process_* */
+#define AMP_MODE_TRIM 1      /* trim_read, AmpliPy.py:426-687 (+ gate 902/910) */
+#define AMP_MODE_PILEUP 2    /* update_base_counts, AmpliPy.py:690-753 */
+
+typedef struct amp_ctx amp_ctx;
+
+typedef struct {
+    int32_t device;             /* CUDA device ordinal */
+    int32_t ref_len;            /* L: length of the reference genome */
+    int32_t n_samples;          /* number of count matrices kept on the device (1; plate mode: many) */
+    int32_t min_quality;        /* AmpliPy.py:27  */
+    int32_t sliding_window;     /* AmpliPy.py:29  */
+    int32_t min_length;         /* AmpliPy.py:26  */
+    int32_t include_no_primer;  /* -e */
+    int64_t ins_slots;          /* insertion hash table capacity (power of two; 0 = default) */
+    int64_t ins_arena_bytes;    /* insertion string arena (0 = default) */
+} amp_config;
+
+typedef struct {
+    int64_t first;              /* global index of the first read to process */
+    int64_t n_reads;            /* reads to process: [first, first + n_reads) */
+    const int32_t* pos; const uint16_t* flag; const int32_t* tlen;
+    const uint32_t* cig_off; const uint32_t* cigar;
+    const uint32_t* seq_off; const uint8_t* seq;
+    const uint32_t* qual_off; const uint8_t* qual;
+} amp_batch;
+
+typedef struct {
+    int32_t* pos;               /* [N] new reference_start (AmpliPy.py:514) */
+    uint16_t* ncig;             /* [N] number of ops in the rewritten CIGAR */
+    uint8_t* flags;             /* [N] AMP_FLAG_* */
+    uint32_t* cigar;            /* [sumC + 3N] rows at cig_off[i] + 3*i */
+} amp_trim_out;
+
+typedef struct {
+    int32_t min_depth_consensus; double min_freq_consensus;   /* AmpliPy.py:22,24 */
+    int32_t min_depth_variants;  double min_freq_variants;    /* AmpliPy.py:23,25 */
+} amp_call_params;
+
+/* per-(sample, position) outputs of amp_call, host arrays of n_samples*L entries (x6 where noted) */
+typedef struct {
+    int32_t* depth;             /* total depth incl. insertion alleles (AmpliPy.py:767) */
+    int32_t* top_id;            /* top allele: 0..5 = A C G T N '-', 6+k = insertion allele k of amp_ins_export order, -1 none */
+    int32_t* top_count;
+    uint8_t* pos_flags;         /* bit0 consensus passes (928); bit1 variant record emitted (940); bit2 GT includes ref (948) */
+    int32_t* ref_count;         /* REF_DP (937) */
+    double*  fixed_freq;        /* [.. x6] count/total as IEEE float64 */
+    int32_t* fixed_rank;        /* [.. x6] index in the reference's sorted allele list (771), -1 if count 0 */
+    uint8_t* alt_mask;          /* bit ch set: fixed symbol ch is an ALT allele (938) */
+} amp_call_out;
+
+const char* amp_last_error(void);
+int amp_abi_version(void);
+
+/* context: device tables + count matrices + insertion-allele table.  Primer tables are the two lists
+ * returned by find_overlapping_primers (AmpliPy.py:174-209) with None encoded as -1; pass NULL for
+ * pileup-only use (variants / consensus subcommands). */
+int amp_create(const amp_config* cfg, const int32_t* min_primer_start, const int32_t* max_primer_end,
+               int32_t max_primer_len, amp_ctx** out);
+int amp_destroy(amp_ctx* ctx);
+int amp_reset(amp_ctx* ctx);                          /* zero counts + insertion table + error word */
+int amp_reset_async(amp_ctx* ctx, void* stream);      /* same, enqueued on `stream` without synchronising */
+int amp_error_flags(amp_ctx* ctx, uint32_t* flags);   /* AMP_DEVERR_* accumulated since amp_reset */
+int amp_lpad(amp_ctx* ctx);                           /* row stride of the count matrices (L rounded up to 32) */
+int amp_sm_count(amp_ctx* ctx);
+
+/* Replaces the per-read loop AmpliPy.py:896-915 for reads [first, first+n): trim_read + write gate,
+ * and/or update_base_counts into count matrix `sample`.  Device-pointer variant: inputs already
+ * resident in HBM; runs asynchronously on `stream`.  out may be NULL without AMP_MODE_TRIM.
+ * sum_cigar_ops / sum_qual_bytes = totals over the processed range (known to the host that built the
+ * batch); they size the long-CIGAR scratch and pick the shared-memory tile shape. */
+int amp_process_device(amp_ctx* ctx, const amp_batch* dev_batch, int64_t sum_cigar_ops, int64_t sum_qual_bytes, int mode,
+                       int sample, const amp_trim_out* dev_out, void* stream);
+/* Host-buffer variant (the call a reference-side binding makes): chunks the batch, overlaps H2D copy,
+ * kernel and D2H of the trim outputs on internal streams; returns when everything has landed. */
+int amp_process_host(amp_ctx* ctx, const amp_batch* host_batch, int mode, int sample, const amp_trim_out* host_out);
+int amp_last_launches(amp_ctx* ctx);                  /* kernels launched by the last amp_process_* / amp_call */
+
+/* count matrices: device pointer [n_samples][6][lpad] int32 (channel order A C G T N '-'); copy to host */
+int amp_counts_device(amp_ctx* ctx, int32_t** dev_counts);
+int amp_bind_counts(amp_ctx* ctx, int32_t* dev_counts);          /* use a caller-owned device buffer (e.g. a torch tensor for NCCL) */
+int amp_counts_host(amp_ctx* ctx, int sample, int32_t* host_counts /* [6][L] */);
+
+/* insertion alleles (the non-fixed keys of symbol_counts_at_ref_pos, AmpliPy.py:745-748) */
+int amp_ins_count(amp_ctx* ctx, int64_t* n_alleles, int64_t* n_chars);
+int amp_ins_export(amp_ctx* ctx, int32_t* sample, int32_t* pos, int32_t* count, int64_t* str_off /* [n+1] */, char* chars);
+/* add alleles produced elsewhere (another rank's amp_ins_export) into this context's table */
+int amp_ins_merge(amp_ctx* ctx, int64_t n, const int32_t* sample, const int32_t* pos, const int32_t* count,
+                  const int64_t* str_off, const char* chars);
+
+/* Replaces alleles_from_counts + the calling loop (AmpliPy.py:756-771, 921-951) for every sample.
+ * ref_seq: L raw FASTA characters.  Per-insertion-allele outputs are indexed like amp_ins_export. */
+int amp_call(amp_ctx* ctx, const char* ref_seq, const amp_call_params* p, const amp_call_out* host_out,
+             double* ins_freq, int32_t* ins_rank, uint8_t* ins_alt);
+/* the same kernels without the device->host copies: reference characters are uploaded once, results stay
+ * in context-owned HBM buffers; asynchronous on `stream` */
+int amp_set_reference(amp_ctx* ctx, const char* ref_seq);
+int amp_call_device(amp_ctx* ctx, const amp_call_params* p, void* stream);
+
+/* pinned host memory helpers for callers that want full-speed amp_process_host */
+int amp_host_alloc(void** p, int64_t bytes);
+int amp_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,135 @@
+// amp_emu.cpp -- TEST INFRASTRUCTURE: runs the CUDA kernels' own source (amplipy_b200/csrc/*.cuh) on the
+// CPU, one CTA at a time with barrier-separated phases executed as loops over the CTA's threads.
+// It lets the build container (no GPU) check the device logic against the oracle before a GPU run.
+// It is not part of the product and is never loaded by amplipy_b200/.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../amplipy_b200/csrc/amp_kernels.cuh"
+
+struct EmuCtx {
+    int L, Lpad, n_samples;
+    amp::TrimParams tp;
+    std::vector<int32_t> mn, mx;
+    std::vector<int> counts;
+    std::vector<amp::InsSlot> slots;
+    std::vector<unsigned int> entries;
+    std::vector<int> slot_entry;
+    std::vector<unsigned char> arena;
+    unsigned long long cursor[2];
+    unsigned int err;
+    amp::InsTable tab;
+};
+
+extern "C" {
+
+void* emu_create(int L, int n_samples, const int32_t* mn, const int32_t* mx, int max_primer_len, int min_quality, int window,
+                 int min_length, int include_no_primer, long long nslots, long long arena_bytes) {
+    EmuCtx* c = new EmuCtx();
+    c->L = L; c->Lpad = (L + 31) & ~31; c->n_samples = n_samples;
+    if (mn) { c->mn.assign(mn, mn + L); c->mx.assign(mx, mx + L); }
+    c->tp.L = L; c->tp.min_primer_start = mn ? c->mn.data() : nullptr; c->tp.max_primer_end = mn ? c->mx.data() : nullptr;
+    c->tp.max_primer_len = max_primer_len; c->tp.min_quality = min_quality; c->tp.window = window;
+    c->tp.min_length = min_length; c->tp.include_no_primer = include_no_primer;
+    c->counts.assign((size_t)n_samples * AMP_NCH * c->Lpad, 0);
+    c->slots.assign(nslots, amp::InsSlot{0, 0, 0});
+    c->entries.assign(nslots, 0); c->slot_entry.assign(nslots, 0);
+    c->arena.assign(arena_bytes, 0);
+    c->cursor[0] = c->cursor[1] = 0; c->err = 0;
+    c->tab.slots = c->slots.data(); c->tab.mask = (unsigned long long)nslots - 1; c->tab.entries = c->entries.data();
+    c->tab.slot_entry = c->slot_entry.data(); c->tab.arena = c->arena.data(); c->tab.arena_words = arena_bytes / 8;
+    c->tab.cursor = c->cursor; c->tab.err = &c->err;
+    return c;
+}
+void emu_destroy(void* h) { delete (EmuCtx*)h; }
+unsigned int emu_error_flags(void* h) { return ((EmuCtx*)h)->err; }
+
+// grid / threads / reads_per_tile overrides (0 = what the product's launch code would choose)
+int emu_process(void* h, long long first, long long n, const int32_t* pos, const uint16_t* flag, const int32_t* tlen,
+                const uint32_t* cig_off, const uint32_t* cigar, const uint32_t* seq_off, const uint8_t* seq,
+                const uint32_t* qual_off, const uint8_t* qual, int mode, int sample, int32_t* o_pos, uint16_t* o_ncig,
+                uint8_t* o_flags, uint32_t* o_cigar, int grid_override, int threads, int rpt_override, int maxseg_override,
+                int wt_override, int qbytes_override) {
+    EmuCtx* c = (EmuCtx*)h;
+    amp::KParams P{};
+    P.b = amp::BatchPtrs{first, n, pos, flag, tlen, cig_off, cigar, seq_off, seq, qual_off, qual};
+    P.o = amp::TrimOut{o_pos, o_ncig, o_flags, o_cigar};
+    P.tp = c->tp; P.mode = mode;
+    P.counts = c->counts.data() + (size_t)sample * AMP_NCH * c->Lpad; P.Lpad = c->Lpad; P.gpos_base = sample * c->Lpad;
+    P.tab = c->tab; P.err = &c->err;
+    const long long sum_cig = cig_off[first + n] - cig_off[first];
+    std::vector<uint32_t> scratch(2 * (size_t)(sum_cig + 3 * n) + 8);
+    P.scratch = scratch.data() - ((size_t)cig_off[first] + 3 * (size_t)first);
+    P.scratch_half = sum_cig + 3 * n;
+    amp::TileCfg t = amp::pick_tile_cfg(n, sum_cig, (long long)(qual_off[first + n] - qual_off[first]), mode);
+    if (rpt_override) t.reads_per_tile = rpt_override;
+    if (maxseg_override) t.maxseg = maxseg_override;
+    if (wt_override) t.wt = wt_override;
+    if (qbytes_override) { t.qbytes = qbytes_override; t.sbytes = qbytes_override / 2; }
+    P.wt = t.wt; P.maxseg = t.maxseg; P.qbytes = t.qbytes; P.sbytes = t.sbytes; P.reads_per_tile = t.reads_per_tile;
+    P.ntiles = (int)((n + t.reads_per_tile - 1) / t.reads_per_tile);
+    int grid = grid_override ? grid_override : 296;
+    if (grid > P.ntiles) grid = P.ntiles;
+    if (grid < 1) grid = 1;
+    P.tiles_per_cta = (P.ntiles + grid - 1) / grid;
+    grid = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
+    std::vector<unsigned char> smem(amp::smem_bytes(P.wt, P.maxseg, P.qbytes, P.sbytes) + 64);
+    unsigned char* sbase = smem.data();
+    sbase += (16 - ((uintptr_t)sbase & 15)) & 15;
+    for (int b = 0; b < grid; ++b) amp::cta_trim_pileup(P, sbase, b, threads ? threads : 256);
+    return 0;
+}
+
+void emu_counts(void* h, int sample, int32_t* out) {
+    EmuCtx* c = (EmuCtx*)h;
+    for (int ch = 0; ch < AMP_NCH; ++ch)
+        memcpy(out + (size_t)ch * c->L, c->counts.data() + ((size_t)sample * AMP_NCH + ch) * c->Lpad, (size_t)c->L * 4);
+}
+long long emu_ins_count(void* h) { return (long long)((EmuCtx*)h)->cursor[1]; }
+long long emu_ins_chars(void* h) { return (long long)((EmuCtx*)h)->cursor[0] * 8; }
+void emu_ins_export(void* h, int32_t* sample, int32_t* pos, int32_t* count, int64_t* str_off, char* chars) {
+    EmuCtx* c = (EmuCtx*)h;
+    int64_t o = 0; str_off[0] = 0;
+    for (unsigned long long k = 0; k < c->cursor[1]; ++k) {
+        const amp::InsSlot& s = c->slots[c->entries[k]];
+        const unsigned char* rec = c->arena.data() + (s.key & 0xFFFFFFFFFFULL) * 8;
+        int gpos; unsigned len; memcpy(&gpos, rec, 4); memcpy(&len, rec + 4, 4);
+        sample[k] = gpos / c->Lpad; pos[k] = gpos % c->Lpad; count[k] = s.count;
+        memcpy(chars + o, rec + 8, len); o += len; str_off[k + 1] = o;
+    }
+}
+struct RawText { const char* p; char operator()(int i) const { return p[i]; } };
+void emu_ins_merge(void* h, long long n, const int32_t* sample, const int32_t* pos, const int32_t* count, const int64_t* str_off,
+                   const char* chars) {
+    EmuCtx* c = (EmuCtx*)h;
+    for (long long k = 0; k < n; ++k) {
+        RawText t{chars + str_off[k]};
+        amp::ins_table_add(c->tab, sample[k] * c->Lpad + pos[k], (int)(str_off[k + 1] - str_off[k]), t, count[k]);
+    }
+}
+
+void emu_call(void* h, const char* ref_seq, int mdc, double mfc, int mdv, double mfv, int32_t* depth, int32_t* top_id,
+              int32_t* top_count, uint8_t* pos_flags, int32_t* ref_count, double* fixed_freq, int32_t* fixed_rank,
+              uint8_t* alt_mask, double* ins_freq, int32_t* ins_rank, uint8_t* ins_alt) {
+    EmuCtx* c = (EmuCtx*)h;
+    std::vector<int> heads((size_t)c->n_samples * c->Lpad, -1);
+    for (unsigned long long k = 0; k < c->cursor[1]; ++k) {   // amp_link_kernel
+        unsigned int s = c->entries[k];
+        const unsigned char* rec = c->arena.data() + (c->slots[s].key & 0xFFFFFFFFFFULL) * 8;
+        int gpos; memcpy(&gpos, rec, 4);
+        c->slots[s].next = heads[gpos]; heads[gpos] = (int)s;
+    }
+    amp::CallParams P{};
+    P.L = c->L; P.Lpad = c->Lpad; P.n_samples = c->n_samples; P.counts = c->counts.data(); P.slots = c->slots.data();
+    P.slot_entry = c->slot_entry.data(); P.arena = c->arena.data(); P.heads = heads.data(); P.ref_seq = (const unsigned char*)ref_seq;
+    P.min_depth_consensus = mdc; P.min_freq_consensus = mfc; P.min_depth_variants = mdv; P.min_freq_variants = mfv;
+    P.depth = depth; P.top_id = top_id; P.top_count = top_count; P.pos_flags = pos_flags; P.ref_count = ref_count;
+    P.fixed_freq = fixed_freq; P.fixed_rank = fixed_rank; P.alt_mask = alt_mask; P.ins_freq = ins_freq; P.ins_rank = ins_rank;
+    P.ins_alt = ins_alt;
+    static const unsigned char syms[8] = {'A', 'C', 'G', 'T', 'N', '-', 0, 0};
+    for (long long gp = 0; gp < (long long)c->n_samples * c->L; ++gp) amp::call_position(P, syms, gp);
+}
+
+}  // extern "C"

@@ -1,0 +1,218 @@
+"""GPU (B200): parity of the CUDA path, called through the C ABI, against (1) the golden fixtures
+produced by the unmodified reference and (2) the oracle on larger seeded inputs; plus
+size-independent properties at the full config-2 size."""
+import numpy as np
+import pytest
+
+import golden_io
+import parity
+from amplipy_b200 import calling, synth
+from amplipy_b200.batch import ReadBatch
+from amplipy_b200.primers import find_overlapping_primers, max_primer_len
+
+pytestmark = pytest.mark.gpu
+CASES = golden_io.list_cases()
+
+
+def make_engine(**kw):
+    from amplipy_b200.engine import Engine
+    return Engine(**kw)
+
+
+class DeviceEngine:
+    """Engine driven through the device-resident entry point (amp_process_device)."""
+
+    def __init__(self, **kw):
+        self.e = make_engine(**kw)
+
+    def process(self, batch, trim=True, pileup=True, sample=0):
+        import torch
+        d = self.e.upload(batch, trim_out=trim)
+        self.e.process_device(d, trim=trim, pileup=pileup, sample=sample)
+        torch.cuda.synchronize()
+        return self.e.download_trim(batch, d) if trim else None
+
+    def __getattr__(self, k):
+        return getattr(self.e, k)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_aio_host_path(name):
+    parity.check_case_aio(make_engine, name)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_aio_device_path(name):
+    parity.check_case_aio(DeviceEngine, name)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_pileup_only(name):
+    parity.check_case_pileup_only(make_engine, name)
+
+
+@pytest.mark.parametrize("name", ["cfg1_example", "cfg2_illumina", "fuzz1"])
+def test_golden_trim_then_variants_pipeline(name):
+    parity.check_case_pipeline(make_engine, name)
+
+
+def _scheme(L=29903, n_amp=98, seed=2, n_alt=0):
+    g = synth.random_genome(L, 7)
+    primers, amps = synth.make_scheme(L, n_amp, seed=seed, n_alt=n_alt)
+    prim = [(s, e) for s, e, _ in primers]
+    return g, prim, amps
+
+
+def _against_oracle(oracle, b, g, prim, offset=0, mq=20, w=4, ml=30, inc=False, ins_slots=0, arena=0):
+    L = len(g)
+    mn, mx = oracle.find_overlapping_primers(L, prim, offset)
+    tables = find_overlapping_primers(L, prim, offset)
+    assert np.array_equal(tables[0], mn) and np.array_equal(tables[1], mx)
+    mpl = max_primer_len(prim)
+    want = oracle.trim_batch(b, L, mn, mx, mpl, mq, w, ml, inc)
+    wc, wins, nerr = oracle.pileup_batch(b, L, mq, trimmed=want)
+    assert nerr == 0
+    eng = make_engine(ref_len=L, primer_tables=tables, max_primer_len=mpl, min_quality=mq, sliding_window_width=w,
+                      min_length=ml, include_no_primer=inc, ins_slots=ins_slots, ins_arena_bytes=arena)
+    t = eng.process(b, trim=True, pileup=True)
+    assert eng.error_flags() == 0
+    assert np.array_equal(t.flags, want["flags"])
+    assert np.array_equal(t.pos, want["pos"])
+    assert np.array_equal(t.ncig.astype(np.int32), want["ncig"])
+    # rows up to ncig: build a mask of live output words
+    row0 = b.cig_off[:-1].astype(np.int64) + 3 * np.arange(b.n, dtype=np.int64)
+    live = np.repeat(row0, want["ncig"]) + (np.arange(int(want["ncig"].sum())) - np.repeat(np.cumsum(want["ncig"]) - want["ncig"], want["ncig"]))
+    assert np.array_equal(t.cigar[live], want["cigar"][live])
+    counts = eng.counts()
+    assert np.array_equal(counts.astype(np.int64), wc)
+    ins = eng.insertions()
+    assert ins.as_dict() == wins
+    res = eng.call(g)
+    ores = oracle.call(wc, wins, g)
+    assert np.array_equal(res.depth.astype(np.int64), ores["depth"])
+    assert calling.consensus_string(res, ins) == oracle.consensus_string(ores)
+    got = calling.variant_records(res, ins, g, counts)
+    want_v = oracle.variant_records(ores, g)
+    assert len(got) == len(want_v)
+    for a, c in zip(got, want_v):
+        assert tuple(a[:6]) == tuple(c[:6]) and a[6] == c[6] and a[7] == c[7] and tuple(a[8]) == tuple(c[8]), (a, c)
+    return eng, t
+
+
+def test_illumina_300k_vs_oracle(oracle_lib):
+    """> one host chunk (262144 reads), so the chunked H2D/D2H pipeline and pointer rebasing are covered."""
+    g, prim, amps = _scheme()
+    b = synth.illumina_batch(g, amps, 300_000, seed=21, snvs=[(1000, "T", 0.5), (20000, "A", 0.03)])
+    _against_oracle(oracle_lib, b, g, prim)
+
+
+def test_illumina_alt_primers_offset_vs_oracle(oracle_lib):
+    g, prim, amps = _scheme(seed=3, n_alt=20)
+    w = np.zeros(98); w[[10, 11, 50]] = 1 / 3          # deep coverage on three amplicons (atomic contention)
+    b = synth.illumina_batch(g, amps, 120_000, seed=22, amp_weights=w)
+    _against_oracle(oracle_lib, b, g, prim, offset=3, inc=True)
+
+
+def test_ont_40k_vs_oracle(oracle_lib):
+    g, prim, amps = _scheme(seed=4)
+    b = synth.ont_batch(g, amps, 40_000, seed=23)
+    _against_oracle(oracle_lib, b, g, prim, ins_slots=1 << 22, arena=256 << 20)
+
+
+def test_ont_low_min_quality_vs_oracle(oracle_lib):
+    g, prim, amps = _scheme(seed=4)
+    b = synth.ont_batch(g, amps, 15_000, seed=24)
+    _against_oracle(oracle_lib, b, g, prim, mq=7, w=6, ins_slots=1 << 22, arena=256 << 20)
+
+
+def test_unsorted_input_vs_oracle(oracle_lib):
+    """Order-agnostic like the reference: shuffled reads force a window flush on almost every tile."""
+    g, prim, amps = _scheme()
+    b = synth.illumina_batch(g, amps, 60_000, seed=25, sort=False)
+    _against_oracle(oracle_lib, b, g, prim)
+
+
+def test_fuzz_vs_oracle(oracle_lib):
+    L = 4000
+    g = synth.random_genome(L, 5)
+    primers, _ = synth.make_scheme(L, 11, amp_len=350, seed=3, n_alt=3)
+    prim = [(s, e) for s, e, _ in primers]
+    for seed in range(40, 46):
+        b = ReadBatch.from_records(synth.fuzz_records(L, 3000, seed=seed, ont_like=bool(seed & 1)))
+        _against_oracle(oracle_lib, b, g, prim, offset=[0, 2, 7][seed % 3], mq=[20, 0, 33][seed % 3], w=[4, 1, 9][seed % 3],
+                        inc=bool(seed & 2))
+
+
+def test_empty_and_tiny_batches():
+    g, prim, amps = _scheme(L=3000, n_amp=9)
+    tables = find_overlapping_primers(3000, prim, 0)
+    eng = make_engine(ref_len=3000, primer_tables=tables, max_primer_len=max_primer_len(prim))
+    empty = ReadBatch.from_records([])
+    t = eng.process(empty)
+    assert t.pos.shape == (0,) and not eng.counts().any() and eng.insertions().k == 0
+    one = ReadBatch.from_records([(100, 0, 0, [(0, 50)], "ACGTN" * 10, [30] * 50)])
+    eng.process(one)
+    assert int(eng.counts().sum()) == 50
+    res = eng.call(g)
+    assert int(res.depth.sum()) == 50
+
+
+def test_full_size_properties_cfg2():
+    """Config 2 at full size (1M reads): order independence, additivity over read subsets, host path ==
+    device path, and the depth identity sum(counts) + sum(insertion counts) == sum(depth)."""
+    import torch
+    g, prim, amps = _scheme()
+    L = len(g)
+    b = synth.illumina_batch(g, amps, 1_000_000, seed=2)
+    tables = find_overlapping_primers(L, prim, 0)
+    mk = lambda: make_engine(ref_len=L, primer_tables=tables, max_primer_len=max_primer_len(prim))
+    e1 = mk()
+    t1 = e1.process(b)
+    c1 = e1.counts(); i1 = e1.insertions().as_dict()
+    # device-resident path
+    e2 = mk()
+    d = e2.upload(b)
+    e2.process_device(d)
+    torch.cuda.synchronize()
+    t2 = e2.download_trim(b, d)
+    assert np.array_equal(e2.counts(), c1) and e2.insertions().as_dict() == i1
+    assert np.array_equal(t1.pos, t2.pos) and np.array_equal(t1.flags, t2.flags) and np.array_equal(t1.ncig, t2.ncig)
+    # additivity: two halves accumulated into one context, processed in reverse order
+    e3 = mk()
+    h = b.n // 2
+    e3.process(b, first=h, n=b.n - h)
+    e3.process(b, first=0, n=h)
+    assert np.array_equal(e3.counts(), c1) and e3.insertions().as_dict() == i1
+    res = e1.call(g)
+    assert int(res.depth.astype(np.int64).sum()) == int(c1.astype(np.int64).sum()) + sum(i1.values())
+    # every kept read satisfies the write gate on its own outputs
+    assert ((t1.flags & 8) != 0).sum() > 0
+    assert e1.error_flags() == 0
+
+
+def test_multi_sample_context_and_insertion_merge(oracle_lib):
+    """Plate mode: independent count matrices in one context; and merging another context's insertion
+    table (the multi-GPU exchange step) reproduces the single-context result."""
+    g, prim, amps = _scheme(L=6000, n_amp=19)
+    L = len(g)
+    tables = find_overlapping_primers(L, prim, 0)
+    bs = [synth.illumina_batch(g, amps, 20_000, seed=100 + i, p_ins=0.2) for i in range(3)]
+    plate = make_engine(ref_len=L, primer_tables=tables, max_primer_len=max_primer_len(prim), n_samples=3)
+    for i, b in enumerate(bs):
+        plate.process(b, sample=i)
+    pins = plate.insertions()
+    for i, b in enumerate(bs):
+        solo = make_engine(ref_len=L, primer_tables=tables, max_primer_len=max_primer_len(prim))
+        solo.process(b)
+        assert np.array_equal(solo.counts(), plate.counts(i))
+        assert solo.insertions().as_dict() == pins.as_dict(i)
+    # merge: ctx A sees half the reads, ctx B the other half; B's table merged into A equals the whole
+    b = bs[0]
+    a_ = make_engine(ref_len=L, primer_tables=tables, max_primer_len=max_primer_len(prim))
+    b_ = make_engine(ref_len=L, primer_tables=tables, max_primer_len=max_primer_len(prim))
+    a_.process(b, first=0, n=b.n // 2)
+    b_.process(b, first=b.n // 2, n=b.n - b.n // 2)
+    ib = b_.insertions()
+    a_.merge_insertions(ib.sample, ib.pos, ib.count, ib.str_off, ib.chars)
+    assert a_.insertions().as_dict() == pins.as_dict(0)
+    assert a_.error_flags() == 0
