@@ -35,7 +35,7 @@ int fail(int code, const char* what, const char* detail = "") {
     } while (0)
 
 constexpr int kThreads = 256;
-constexpr int kCtasPerSm = 2;
+constexpr int kCtasPerSm = 3;
 
 // ---------------------------------------------------------------------------------------------------
 // kernels

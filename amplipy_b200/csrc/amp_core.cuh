@@ -253,10 +253,62 @@ AMP_HD int window_del_len_rev(const uint8_t* q, int len, int W, int minq) {
     return 0;
 }
 
+// ---- word-at-a-time window search for the default width 4 ----------------------------------------
+AMP_HD unsigned funnel_r(unsigned lo, unsigned hi, unsigned sh) {   // low 32 bits of (hi:lo) >> sh, sh in [0, 31]
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+AMP_HD unsigned byte_perm(unsigned x, unsigned sel) {               // bytes of x picked by the nibbles of sel
+#ifdef __CUDA_ARCH__
+    return __byte_perm(x, 0u, sel);
+#else
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= ((x >> (8u * ((sel >> (4 * i)) & 3u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
+}
+AMP_HD int sum4(unsigned w) {                                       // sum of the four bytes of w
+#ifdef __CUDA_ARCH__
+    return (int)__dp4a(w, 0x01010101u, 0u);
+#else
+    return (int)((w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24));
+#endif
+}
+// Same result as window_del_len_fwd / _rev for W == 4, scanning the logical sequence s[t] = rev ? q[len-1-t] : q[t]
+// four positions per step (one aligned word + funnel shifts + dp4a), identical instruction stream for both
+// strands.  Requires 8 readable bytes on either side of q[0, len) (true inside the staging buffers).
+AMP_HD int window_del_len_w4(const uint8_t* q, int len, int minq, bool rev) {
+    const int thr = 4 * minq;
+    int t = 0;
+    if (len >= 7) {
+        const uint8_t* a0 = rev ? q + len - 4 : q;
+        const unsigned sh = (unsigned)((uintptr_t)a0 & 3u) * 8u;
+        const uint32_t* wp = (const uint32_t*)(a0 - ((uintptr_t)a0 & 3u));
+        const int wstep = rev ? -1 : 1;
+        const unsigned sel = rev ? 0x0123u : 0x3210u;
+        const int ngroups = (len - 7) / 4 + 1;
+        unsigned v0 = byte_perm(funnel_r(wp[0], wp[1], sh), sel);
+        for (int g = 0; g < ngroups; ++g) {
+            wp += wstep;
+            const unsigned v1 = byte_perm(funnel_r(wp[0], wp[1], sh), sel);
+            const int s0 = sum4(v0), s1 = sum4(funnel_r(v0, v1, 8)), s2 = sum4(funnel_r(v0, v1, 16)), s3 = sum4(funnel_r(v0, v1, 24));
+            int m = s0 < s1 ? s0 : s1; const int m2 = s2 < s3 ? s2 : s3; m = m < m2 ? m : m2;
+            if (m < thr) return len - (4 * g + (s0 < thr ? 0 : s1 < thr ? 1 : s2 < thr ? 2 : 3));
+            v0 = v1;
+        }
+        t = 4 * ngroups;
+    }
+    return rev ? window_del_len_rev(q, len - t, 4, minq) : window_del_len_fwd(q + t, len - t, 4, minq);
+}
+
 // trim_read (426-687).  A holds the input CIGAR (capacity nc+3), B is scratch of the same capacity.
 // On return *res points at the buffer holding the final CIGAR.  Returns AMP_F_* bits.
+// qual_padded: the qualities sit in a staging buffer with readable slack around them (enables the word-wise search).
 AMP_HD int trim_read(uint32_t* A, uint32_t* B, int& nc, int& pos, int flag, int tlen, int l_seq, const uint8_t* qual,
-                     const TrimParams& P, uint32_t** res) {
+                     bool qual_padded, const TrimParams& P, uint32_t** res) {
     uint32_t* src = A; uint32_t* dst = B;
     int ref_start = pos;
     const bool is_paired = flag & 1, is_reverse = (flag & 16) != 0;
@@ -288,8 +340,10 @@ AMP_HD int trim_read(uint32_t* A, uint32_t* B, int& nc, int& pos, int flag, int 
     const int qas = q_align_start(src, nc);
     int len = q_align_end(src, nc, l_seq) - qas;                                         // 561-563
     if (len < 0) len = 0;
+    const bool w4 = qual_padded && P.window == 4;
+    const int win_del = w4 ? window_del_len_w4(qual + qas, len, P.min_quality, is_reverse) : 0;
     if (is_reverse) {                                                                    // 566-625
-        int del_len = window_del_len_rev(qual + qas, len, P.window, P.min_quality);
+        int del_len = w4 ? win_del : window_del_len_rev(qual + qas, len, P.window, P.min_quality);
         int sp = get_pos_on_ref(src, nc, del_len + qas - 1, ref_start);                  // 591
         if (sp > ref_start) {
             out |= AMP_F_TRIM_QUAL;
@@ -299,7 +353,7 @@ AMP_HD int trim_read(uint32_t* A, uint32_t* B, int& nc, int& pos, int flag, int 
             // reference_start is NOT advanced (589-625)
         }
     } else {                                                                             // 628-686
-        int del_len = window_del_len_fwd(qual + qas, len, P.window, P.min_quality);
+        int del_len = w4 ? win_del : window_del_len_fwd(qual + qas, len, P.window, P.min_quality);
         if (del_len != 0) {
             out |= AMP_F_TRIM_QUAL;
             int nd = 0;

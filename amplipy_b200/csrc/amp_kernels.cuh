@@ -14,6 +14,9 @@
 //   C  one warp per run, lanes over consecutive bases: quality gate + base channel -> shared atomics
 //      (channel-major tile with WT % 32 == 0 => 32 consecutive positions never bank-conflict)
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "amp_core.cuh"
 
 #if defined(__CUDA_ARCH__)
@@ -60,37 +63,46 @@ inline double amp_min_d(double a, double b) { return a < b ? a : b; }
 inline double amp_max_d(double a, double b) { return a > b ? a : b; }
 struct TileCfg { int wt, maxseg, qbytes, sbytes, reads_per_tile; };
 
-// shared-memory carve-up: two CTAs per SM at <= ~100 KB each (227 KB usable per SM)
+// shared-memory carve-up: three CTAs per SM at <= ~74 KB each (227 KB usable per SM).
+// AMP_TILE="wt,maxseg,qbytes,sbytes,reads_per_tile" overrides it (tuning experiments only).
 inline TileCfg pick_tile_cfg(long long n, long long sum_cig, long long sum_qual, int mode) {
     TileCfg t;
     const double avg_len = n ? (double)sum_qual / (double)n : 150.0;
     const double avg_ops = n ? (double)sum_cig / (double)n : 2.0;
-    if (avg_ops > 8.0) { t.wt = 1024; t.maxseg = 3072; t.qbytes = 20480; t.sbytes = 10240; }   // indel-rich (ONT-like)
-    else { t.wt = 1024; t.maxseg = 1024; t.qbytes = 40960; t.sbytes = 20480; }
-    if (!(mode & AMP_MODE_PILEUP)) { t.wt = 32; t.maxseg = 16; t.sbytes = 16; }
+    if (avg_ops > 8.0) { t.wt = 512; t.maxseg = 2048; t.qbytes = 17408; t.sbytes = 8704; }      // indel-rich (ONT-like)
+    else { t.wt = 512; t.maxseg = 512; t.qbytes = 33792; t.sbytes = 16896; }
+    if (!(mode & AMP_MODE_PILEUP)) { t.wt = 32; t.maxseg = 16; t.sbytes = 16; t.qbytes = 40960; }
     double r = 256.0;
     r = amp_min_d(r, (double)t.qbytes * 0.97 / amp_max_d(avg_len, 1.0));
     if (mode & AMP_MODE_PILEUP) r = amp_min_d(r, (double)t.maxseg / (1.5 + 0.75 * avg_ops));
     t.reads_per_tile = (int)amp_max_d(8.0, r);
+#ifndef __CUDA_ARCH__
+    if (const char* e = getenv("AMP_TILE")) {
+        int a[5];
+        if (sscanf(e, "%d,%d,%d,%d,%d", &a[0], &a[1], &a[2], &a[3], &a[4]) == 5) {
+            t.wt = a[0]; t.maxseg = a[1]; t.qbytes = a[2]; t.sbytes = a[3]; t.reads_per_tile = a[4];
+        }
+    }
+#endif
     return t;
 }
 
-
+#define AMP_ROWS (AMP_NCH + 1)   // counts tile rows: 6 channels + one row that collects non-ACGTN bases (KeyError, 753)
 AMP_HD size_t smem_bytes(int wt, int maxseg, int qbytes, int sbytes) {
-    return (size_t)AMP_NCH * wt * 4 + (size_t)maxseg * sizeof(Seg) + 64 + (size_t)qbytes + (size_t)sbytes;
+    return (size_t)AMP_ROWS * wt * 4 + (size_t)maxseg * sizeof(Seg) + 128 + (size_t)qbytes + (size_t)sbytes + 64;
 }
 
 struct Smem {
     int* cnt; Seg* segs; int* ctrl; uint8_t* qual; uint8_t* seq;
 };
 // ctrl words
-enum { C_NSEG = 0, C_TMIN = 1, C_TMAX = 2 };
+enum { C_NSEG = 0, C_TMIN = 1, C_TMAX = 2, C_LUT = 16 };   // ctrl[C_LUT + nib] = row offset (ints) of nibble `nib`
 
 AMP_HD Smem carve(unsigned char* base, const KParams& P) {
     Smem s;
-    s.cnt = (int*)base; base += (size_t)AMP_NCH * P.wt * 4;
+    s.cnt = (int*)base; base += (size_t)AMP_ROWS * P.wt * 4;
     s.segs = (Seg*)base; base += (size_t)P.maxseg * sizeof(Seg);
-    s.ctrl = (int*)base; base += 64;
+    s.ctrl = (int*)base; base += 128;
     s.qual = base; base += P.qbytes;
     s.seq = base;
     return s;
@@ -100,6 +112,20 @@ AMP_HD void count_add(const KParams& P, int* cnt, int wbase, int ch, int p) {
     const unsigned w = (unsigned)(p - wbase);
     if (wbase >= 0 && w < (unsigned)P.wt) atomic_add(&cnt[ch * P.wt + (int)w], 1);
     else atomic_add(&P.counts[(size_t)ch * P.Lpad + p], 1);
+}
+
+// privatised tile -> global count matrix; the extra row only raises the KeyError flag
+AMP_HD void flush_tile(const KParams& P, int* cnt, int wbase, int tid, int nthreads, bool clear) {
+    for (int ch = 0; ch < AMP_ROWS; ++ch) {
+        for (int w = tid; w < P.wt; w += nthreads) {
+            const int v = cnt[ch * P.wt + w];
+            if (v) {
+                if (ch < AMP_NCH) atomic_add(&P.counts[(size_t)ch * P.Lpad + wbase + w], v);
+                else atomic_or(P.err, AMP_E_BASE);
+                if (clear) cnt[ch * P.wt + w] = 0;
+            }
+        }
+    }
 }
 
 // Per-read sink used in phase T.
@@ -146,10 +172,13 @@ struct TileSink {
 AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int block, int nthreads) {
     const Smem sm = carve(smem_base, P);
     const bool do_trim = P.mode & AMP_MODE_TRIM, do_pile = P.mode & AMP_MODE_PILEUP;
-    const int ncnt = AMP_NCH * P.wt;
+    const int ncnt = AMP_ROWS * P.wt;
     int wbase = -1;                                    // uniform across the CTA
     if (do_pile) {
-        AMP_FOR_THREADS(tid, nthreads) { for (int i = tid; i < ncnt; i += nthreads) sm.cnt[i] = 0; }
+        AMP_FOR_THREADS(tid, nthreads) {
+            for (int i = tid; i < ncnt; i += nthreads) sm.cnt[i] = 0;
+            if (tid < 16) { const int ch = nib_channel((uint32_t)tid); sm.ctrl[C_LUT + tid] = (ch < 0 ? AMP_NCH : ch) * P.wt; }
+        }
     }
     const int tile_lo = block * P.tiles_per_cta;
     int tile_hi = tile_lo + P.tiles_per_cta; if (tile_hi > P.ntiles) tile_hi = P.ntiles;
@@ -203,7 +232,7 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
                         else { A = P.scratch + (size_t)c0 + 3 * (size_t)i; B = A + P.scratch_half; }
                         for (int k = 0; k < nc; ++k) A[k] = cig[k];
                         uint32_t* res;
-                        f = trim_read(A, B, nc, pos, flag, P.b.tlen[i], l_seq, qual, P.tp, &res);
+                        f = trim_read(A, B, nc, pos, flag, P.b.tlen[i], l_seq, qual, qo1 <= q_hi, P.tp, &res);
                         if (f & AMP_F_ERROR) { nc = 0; f = AMP_F_ERROR; atomic_or(P.err, AMP_E_COORD); }
                         for (int k = 0; k < nc; ++k) orow[k] = res[k];
                         cig = res;
@@ -233,10 +262,7 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
         if (nseg > 0 && (wbase < 0 || tmin < wbase || tmax > wbase + P.wt)) {
             if (wbase >= 0) {
                 AMP_FOR_THREADS(tid, nthreads) {
-                    for (int i = tid; i < ncnt; i += nthreads) {
-                        int v = sm.cnt[i];
-                        if (v) { int ch = i / P.wt, w = i - ch * P.wt; atomic_add(&P.counts[(size_t)ch * P.Lpad + wbase + w], v); sm.cnt[i] = 0; }
-                    }
+                    flush_tile(P, sm.cnt, wbase, tid, nthreads, true);
                 }
                 AMP_SYNC();
             }
@@ -245,23 +271,46 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
         // ---- C: one warp per run ----------------------------------------------------------------------
         AMP_FOR_THREADS(tid, nthreads) {
             const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+            const int* lut = sm.ctrl + C_LUT;
+            const int minq = P.tp.min_quality;
             unsigned errs = 0;
             for (int s = warp; s < nseg; s += nwarps) {
                 const Seg sg = sm.segs[s];
                 const int n = sg.len & 0x7FFFFFFF;
+                const int w0 = sg.rpos - wbase;
+                const bool in_win = w0 >= 0 && w0 + n <= P.wt;                     // uniform per run
                 if (sg.len < 0) {
-                    for (int j = lane; j < n; j += 32) count_add(P, sm.cnt, wbase, 5, sg.rpos + j);
+                    if (in_win) { for (int j = lane; j < n; j += 32) atomic_add(&sm.cnt[5 * P.wt + w0 + j], 1); }
+                    else for (int j = lane; j < n; j += 32) count_add(P, sm.cnt, wbase, 5, sg.rpos + j);
+                    continue;
+                }
+                const bool qs_ = sg.qabs + (uint32_t)n <= q_hi;
+                const bool ss_ = ((sg.nibabs + (uint32_t)n + 1u) >> 1) <= s_hi;
+                if (in_win && qs_ && ss_) {
+                    // fast path: everything in shared memory, no per-base branches.  Lanes take consecutive
+                    // bases -> consecutive tile words of one row per lane: bank = position % 32, conflict-free.
+                    const uint8_t* q = sm.qual + (sg.qabs - q_lo) + lane;
+                    const uint32_t nb0 = sg.nibabs + (uint32_t)lane;
+                    const uint32_t shift = (~nb0 & 1u) << 2;
+                    const uint8_t* sb = sm.seq + ((nb0 >> 1) - s_lo);
+                    int* c = sm.cnt + w0 + lane;
+                    // tail lanes (j >= n) read at most 31 bytes past the run, which stays inside the staging buffers
+                    // (smem_bytes() pads the end); their result is discarded by the predicate
+                    for (int j = lane; j - lane < n; j += 32, q += 32, sb += 16, c += 32) {
+                        const int qv = *q;
+                        const uint32_t nib = ((uint32_t)*sb >> shift) & 15u;
+                        const int row = lut[nib];
+                        if (j < n && qv >= minq) atomic_add(c + row, 1);           // AmpliPy.py:718, 752-753
+                    }
                 } else {
-                    const bool qs_ = sg.qabs + (uint32_t)n <= q_hi;
                     const uint8_t* qp = qs_ ? sm.qual + (sg.qabs - q_lo) : P.b.qual + sg.qabs;
-                    const bool ss_ = ((sg.nibabs + (uint32_t)n + 1u) >> 1) <= s_hi;
                     const uint8_t* sp = ss_ ? sm.seq : P.b.seq;
                     const uint32_t sub = ss_ ? s_lo : 0u;
                     for (int j = lane; j < n; j += 32) {
-                        if (qp[j] < P.tp.min_quality) continue;                              // AmpliPy.py:718, 752
+                        if (qp[j] < minq) continue;
                         const uint32_t nb = sg.nibabs + (uint32_t)j;
                         const int ch = nib_channel((sp[(nb >> 1) - sub] >> ((~nb & 1u) << 2)) & 15u);
-                        if (ch < 0) { errs |= AMP_E_BASE; continue; }                       // KeyError at 753
+                        if (ch < 0) { errs |= AMP_E_BASE; continue; }
                         count_add(P, sm.cnt, wbase, ch, sg.rpos + j);
                     }
                 }
@@ -272,10 +321,7 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
     }
     if (do_pile && wbase >= 0) {
         AMP_FOR_THREADS(tid, nthreads) {
-            for (int i = tid; i < ncnt; i += nthreads) {
-                int v = sm.cnt[i];
-                if (v) { int ch = i / P.wt, w = i - ch * P.wt; atomic_add(&P.counts[(size_t)ch * P.Lpad + wbase + w], v); }
-            }
+            flush_tile(P, sm.cnt, wbase, tid, nthreads, false);
         }
     }
 }

@@ -110,6 +110,12 @@ void emu_ins_merge(void* h, long long n, const int32_t* sample, const int32_t* p
     }
 }
 
+// unit hooks for the sliding-window closed forms (q must have 8 readable bytes on both sides for mode 2)
+int emu_window(const uint8_t* q, int len, int W, int minq, int rev, int mode) {
+    if (mode == 2) return amp::window_del_len_w4(q, len, minq, rev != 0);
+    return rev ? amp::window_del_len_rev(q, len, W, minq) : amp::window_del_len_fwd(q, len, W, minq);
+}
+
 void emu_call(void* h, const char* ref_seq, int mdc, double mfc, int mdv, double mfv, int32_t* depth, int32_t* top_id,
               int32_t* top_count, uint8_t* pos_flags, int32_t* ref_count, double* fixed_freq, int32_t* fixed_rank,
               uint8_t* alt_mask, double* ins_freq, int32_t* ins_rank, uint8_t* ins_alt) {
