@@ -44,5 +44,25 @@ def build_extension(force=False, verbose=False):
     return LIB
 
 
+HOSTIO_LIB = os.path.join(CSRC, "libamplipy_hostio.so")
+
+
+def build_hostio(force=False):
+    """g++ -O2 -fopenmp amp_hostio.cpp -lz -> amplipy_b200/csrc/libamplipy_hostio.so (CPU-only BGZF/BAM codec)."""
+    src = os.path.join(CSRC, "amp_hostio.cpp")
+    if not force and os.path.isfile(HOSTIO_LIB) and os.path.getmtime(HOSTIO_LIB) >= os.path.getmtime(src):
+        return HOSTIO_LIB
+    gxx = "/usr/bin/g++" if os.path.isfile("/usr/bin/g++") else "g++"
+    base = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", HOSTIO_LIB, src, "-lz"]
+    r = subprocess.run(base[:1] + ["-fopenmp"] + base[1:], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:   # toolchain without libgomp: single-threaded codec
+        r = subprocess.run(base, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        print(r.stdout)
+        raise RuntimeError("g++ failed building %s" % HOSTIO_LIB)
+    return HOSTIO_LIB
+
+
 if __name__ == "__main__":
+    print(build_hostio(force=True))
     print(build_extension(force=True, verbose=True))

@@ -44,9 +44,11 @@ def _p(a):
 
 class EmuEngine:
     def __init__(self, ref_len, primer_tables=None, max_primer_len=0, min_quality=20, sliding_window_width=4,
-                 min_length=30, include_no_primer=False, n_samples=1, ins_slots=1 << 16, ins_arena_bytes=1 << 22,
+                 min_length=30, include_no_primer=False, n_samples=1, ins_slots=1 << 16, ins_arena_bytes=1 << 22, device=0,
                  grid=0, threads=256, reads_per_tile=0, maxseg=0, wt=0, qbytes=0):
         self.L, self.n_samples = int(ref_len), int(n_samples)
+        ins_slots = min(ins_slots or (1 << 16), 1 << 18)
+        ins_arena_bytes = min(ins_arena_bytes or (1 << 22), 1 << 24)
         mn = mx = None
         if primer_tables is not None:
             mn = np.ascontiguousarray(primer_tables[0], np.int32)
@@ -63,6 +65,9 @@ class EmuEngine:
 
     def error_flags(self):
         return int(lib().emu_error_flags(self._h))
+
+    def raise_on_device_errors(self):
+        assert self.error_flags() == 0, self.error_flags()
 
     def process(self, batch, trim=True, pileup=True, sample=0, first=0, n=None):
         n = batch.n - first if n is None else n

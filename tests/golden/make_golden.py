@@ -177,7 +177,56 @@ def example_case():
     assert rt[i1]["pos"] == 28254 and cigar_string(rt[i1]["cigar"]) == "31S105M15S" and (rt[i1]["ts"], rt[i1]["te"]) == (False, True)
 
 
+def cli_case():
+    """Run the reference's own run_amplipy (AmpliPy.py:774-963) end to end on SAM files: `aio`, and the
+    three-step trim -> variants -> consensus pipeline (config 1's flow).  Outputs are committed as text."""
+    import io
+    import shutil
+    import contextlib
+    ref = ref_loader.load_reference()
+    d = os.path.join(HERE, "cli")
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    L = 4000
+    g = synth.random_genome(L, 31)
+    primers, amps = synth.make_scheme(L, 12, seed=6, n_alt=2)
+    synth.write_bed(os.path.join(d, "primers.bed"), primers, "synth_ref")
+    synth.write_fasta(os.path.join(d, "ref.fas"), "synth_ref some description", g)
+    b1 = synth.illumina_batch(g, amps, 1200, seed=7, snvs=[(900, "T", 0.6), (2500, "G", 0.04)], p_ins=0.05, p_del=0.05)
+    b2 = synth.ont_batch(g, amps, 150, seed=8)
+    b = ReadBatch.concat([b1, b2])
+    b = synth._reorder(b, np.argsort(b.pos, kind="stable")).validate()
+    hdr = "@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:synth_ref\tLN:%d\n@PG\tID:synth\tPN:synth\tVN:1\n" % L
+    with open(os.path.join(d, "in.sam"), "w") as f:
+        f.write(hdr)
+        f.write("\n".join(b.sam_lines(rname="synth_ref")) + "\n")
+    argv_saved = list(sys.argv)
+
+    def run(argv, **kw):
+        sys.argv[:] = argv
+        ref.argv[:] = argv
+        with contextlib.redirect_stderr(io.StringIO()):
+            ref.run_amplipy(**kw)
+    j = lambda n: os.path.join(d, n)
+    run(["AmpliPy.py", "aio"], untrimmed_reads_fn=j("in.sam"), primer_fn=j("primers.bed"), reference_fn=j("ref.fas"),
+        trimmed_reads_fn=j("aio_trimmed.sam"), variants_fn=j("aio_variants.vcf"), consensus_fn=j("aio_consensus.fas"),
+        primer_pos_offset=0, min_length=30, min_quality=20, sliding_window_width=4, min_freq_consensus=0,
+        min_freq_variants=0.03, min_depth_consensus=10, min_depth_variants=1, unknown_symbol="N", include_no_primer=False,
+        run_trim=True, run_variants=True, run_consensus=True)
+    run(["AmpliPy.py", "trim"], untrimmed_reads_fn=j("in.sam"), primer_fn=j("primers.bed"), reference_fn=j("ref.fas"),
+        trimmed_reads_fn=j("step_trimmed.sam"), primer_pos_offset=1, min_length=40, min_quality=15, sliding_window_width=5,
+        include_no_primer=True, run_trim=True)
+    run(["AmpliPy.py", "variants"], trimmed_reads_fn=j("step_trimmed.sam"), reference_fn=j("ref.fas"),
+        variants_fn=j("step_variants.vcf"), min_quality=15, min_freq_variants=0.1, min_depth_variants=5, run_variants=True)
+    run(["AmpliPy.py", "consensus"], trimmed_reads_fn=j("step_trimmed.sam"), reference_fn=j("ref.fas"),
+        consensus_fn=j("step_consensus.fas"), min_quality=15, min_freq_consensus=0.6, min_depth_consensus=4,
+        unknown_symbol="x", run_consensus=True)
+    sys.argv[:] = argv_saved
+    print("cli golden: %d reads -> %s" % (b.n, sorted(os.listdir(d))))
+
+
 def main():
+    cli_case()
     quirk_case()
     example_case()
     L = 6000
