@@ -283,6 +283,22 @@ class Engine:
         _check(self.lib.amp_counts_device(self._ctx, ctypes.byref(p)), "amp_counts_device")
         return p.value
 
+    def counts_tensor(self):
+        """The int32 device tensor [n_samples, 6, lpad] the kernels accumulate into (allocated through torch
+        on first use so that torch.distributed / NCCL can all-reduce it in place)."""
+        if getattr(self, "_bound", None) is None:
+            import torch
+            dev = torch.device("cuda", self.device)
+            t = torch.zeros((self.n_samples, 6, self.lpad), dtype=torch.int32, device=dev)
+            # carry over what has been accumulated so far
+            host = np.zeros((self.n_samples, 6, self.lpad), np.int32)
+            for smp in range(self.n_samples):
+                host[smp, :, :self.L] = self.counts(smp)
+            t.copy_(torch.from_numpy(host))
+            torch.cuda.synchronize(dev)
+            self.bind_counts(t)
+        return self._bound
+
     def bind_counts(self, tensor):
         """Use a caller-owned int32 device tensor [n_samples, 6, lpad] (e.g. to all-reduce it with NCCL)."""
         assert tensor.is_cuda and tensor.is_contiguous() and tensor.numel() == self.n_samples * 6 * self.lpad

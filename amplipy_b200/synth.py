@@ -162,31 +162,45 @@ def _illumina_chunk(rng, ref, amps, n_pairs, read_len, sub_rate, p_ins, p_del, p
     flag = (1 + 2 + np.where(is_rev, 16, 32) + np.where(r1, 64, 128) + np.where(hard, 2048, 0)).astype(np.uint16)
     tlen = np.where(is_rev, -insert, insert).astype(np.int32)
 
-    # query index -> reference index
+    # query index -> reference index (int32 matrices; sparse events are drawn by index, not by full random matrices)
     lmax = int(l.max())
-    j = np.arange(lmax, dtype=np.int64)[None, :]
-    jj = j - s1[:, None]
-    in_m1 = (jj >= 0) & (jj < m1[:, None])
-    jj2 = jj - m1[:, None] - ilen[:, None]
-    in_m2 = (jj2 >= 0) & (jj2 < m2[:, None])
-    R = np.where(in_m1, pos[:, None] + jj, np.where(in_m2, pos[:, None] + m1[:, None] + dlen[:, None] + jj2, -1))
-    base = np.where(R >= 0, ref[np.clip(R, 0, L - 1)], _ACGT[rng.integers(0, 4, (n, lmax))])
+    j = np.arange(lmax, dtype=np.int32)[None, :]
+    s1c, m1c, ilc, m2c, dlc, posc = (x.astype(np.int32)[:, None] for x in (s1, m1, ilen, m2, dlen, pos))
+    jj = j - s1c
+    in_m1 = (jj >= 0) & (jj < m1c)
+    jj2 = jj - m1c - ilc
+    in_m2 = (jj2 >= 0) & (jj2 < m2c)
+    R = np.where(in_m1, posc + jj, np.where(in_m2, posc + m1c + dlc + jj2, -1))
+    rnd = _ACGT[rng.integers(0, 4, (n, lmax), dtype=np.uint8)]
+    base = np.where(R >= 0, ref[np.clip(R, 0, L - 1)], rnd)
     for k in range(len(snv_pos)):
-        m = (R == snv_pos[k]) & carries2[:, k][:, None]
-        base[m] = snv_alt[k]
-    sub = rng.random((n, lmax), dtype=np.float32) < sub_rate
-    base = np.where(sub, _ACGT[rng.integers(0, 4, (n, lmax))], base)
-    isn = rng.random((n, lmax), dtype=np.float32) < 0.001
-    base = np.where(isn, ord("N"), base).astype(np.uint8)
+        cols = snv_pos[k] - pos                       # query column of the SNV if inside M1 (no indel before it)
+        rows = np.flatnonzero(carries2[:, k])
+        m = (R[rows] == snv_pos[k])
+        rr, cc = np.nonzero(m)
+        base[rows[rr], cc] = snv_alt[k]
+    tot = n * lmax
+    flat = base.reshape(-1)
+    ks = rng.binomial(tot, sub_rate)
+    idx = rng.integers(0, tot, ks)
+    flat[idx] = _ACGT[rng.integers(0, 4, ks, dtype=np.uint8)]
+    kn = rng.binomial(tot, 0.001)
+    idxn = rng.integers(0, tot, kn)
+    flat[idxn] = ord("N")
+    base = flat.reshape(n, lmax)
 
-    qual = _quals(rng, (n, lmax))
-    qual[isn] = 2
+    lut = np.empty(256, np.uint8)
+    lut[:179] = 37; lut[179:230] = 25; lut[230:250] = 11; lut[250:] = 2     # ~70 / 20 / 8 / 2 %
+    qual = lut[rng.integers(0, 256, (n, lmax), dtype=np.uint8)]
+    qual.reshape(-1)[idxn] = 2
     tail = rng.random(n) < 0.12
-    tl = np.where(tail, rng.integers(5, 41, n), 0)
+    tl = np.where(tail, rng.integers(5, 41, n), 0).astype(np.int32)
     # 3' end is the right end for forward reads, the left end for reverse reads
-    in_tail = np.where(is_rev[:, None], j < tl[:, None], j >= (l - tl)[:, None])
-    lowq = rng.integers(2, 12, (n, lmax)).astype(np.uint8)
-    qual = np.where(in_tail, lowq, qual)
+    rows = np.flatnonzero(tail)
+    lt = l.astype(np.int32)
+    in_tail = np.where(is_rev[rows, None], j < tl[rows, None], j >= (lt[rows] - tl[rows])[:, None])
+    lowq = rng.integers(2, 12, in_tail.shape, dtype=np.uint8)
+    qual[rows] = np.where(in_tail, lowq, qual[rows])
 
     # CIGAR columns (len, op); zero-length dropped
     ops = np.array([5, 4, 0, 1, 0, 4, 5], np.uint32)

@@ -87,6 +87,8 @@ void emu_counts(void* h, int sample, int32_t* out) {
     for (int ch = 0; ch < AMP_NCH; ++ch)
         memcpy(out + (size_t)ch * c->L, c->counts.data() + ((size_t)sample * AMP_NCH + ch) * c->Lpad, (size_t)c->L * 4);
 }
+int* emu_counts_ptr(void* h) { return ((EmuCtx*)h)->counts.data(); }
+int emu_lpad(void* h) { return ((EmuCtx*)h)->Lpad; }
 long long emu_ins_count(void* h) { return (long long)((EmuCtx*)h)->cursor[1]; }
 long long emu_ins_chars(void* h) { return (long long)((EmuCtx*)h)->cursor[0] * 8; }
 void emu_ins_export(void* h, int32_t* sample, int32_t* pos, int32_t* count, int64_t* str_off, char* chars) {

@@ -89,6 +89,13 @@ class EmuEngine:
         lib().emu_counts(self._h, sample, _p(out))
         return out
 
+    def counts_tensor(self):
+        import torch
+        lib().emu_counts_ptr.restype = ctypes.POINTER(ctypes.c_int)
+        lpad = int(lib().emu_lpad(self._h))
+        arr = np.ctypeslib.as_array(lib().emu_counts_ptr(self._h), shape=(self.n_samples, 6, lpad))
+        return torch.from_numpy(arr)
+
     def insertions(self):
         k = int(lib().emu_ins_count(self._h))
         nch = int(lib().emu_ins_chars(self._h))

@@ -216,3 +216,19 @@ def test_multi_sample_context_and_insertion_merge(oracle_lib):
     a_.merge_insertions(ib.sample, ib.pos, ib.count, ib.str_off, ib.chars)
     assert a_.insertions().as_dict() == pins.as_dict(0)
     assert a_.error_flags() == 0
+
+
+def test_multi_gpu_sharding_nccl():
+    """Needs >= 2 visible GPUs (gpurun --gpus 2); skipped on single-GPU boxes."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("single GPU")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "tests", "dist_gpu_check.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "dist_gpu_check ok" in r.stdout, r.stdout[-3000:]
