@@ -35,7 +35,10 @@ int fail(int code, const char* what, const char* detail = "") {
     } while (0)
 
 constexpr int kThreads = 256;
-constexpr int kCtasPerSm = 3;
+#ifndef AMP_CTAS
+#define AMP_CTAS 3
+#endif
+constexpr int kCtasPerSm = AMP_CTAS;
 
 // ---------------------------------------------------------------------------------------------------
 // kernels
