@@ -512,9 +512,9 @@ AMP_HD int plan_read(const uint32_t* c, int nc, int pos, int l_seq, const uint8_
 // A unit of counting work produced by plan_read: an aligned run or a deletion run.
 struct Seg {
     int rpos;            // first reference position
-    int len;             // bases; bit 31 set = deletion run
-    uint32_t qabs;       // absolute index of the first base's quality in the batch qual array
-    uint32_t nibabs;     // absolute nibble index of the first base in the batch seq array
+    int len;             // bases (30 bits); bit 31 = deletion run; bit 30 = offsets below are staging-buffer relative
+    uint32_t qabs;       // index of the first base's quality (staging buffer or batch qual array)
+    uint32_t nibabs;     // nibble index of the first base (staging buffer or batch seq array)
 };
 
 }  // namespace amp

@@ -131,18 +131,19 @@ AMP_HD void flush_tile(const KParams& P, int* cnt, int wbase, int tid, int nthre
 // Per-read sink used in phase T.
 struct TileSink {
     const KParams* P; Smem sm;
-    uint32_t qabs0, nibabs0;           // absolute offsets of this read's first quality / first nibble
+    uint32_t qabs0, nibabs0;           // first quality byte / first nibble of this read: staging-buffer relative when
+    bool staged;                       // `staged` (both rows fit the staging buffers), else absolute in the batch arrays
     const uint8_t* seq_read;           // this read's packed sequence (shared or global)
     const uint8_t* qual_read;
     unsigned int errs;
     AMP_HD void push(int rpos, int len_kind, int q) {
         int idx = atomic_add(&sm.ctrl[C_NSEG], 1);
         if (idx < P->maxseg) {
-            Seg s; s.rpos = rpos; s.len = len_kind; s.qabs = qabs0 + (uint32_t)q; s.nibabs = nibabs0 + (uint32_t)q;
+            Seg s; s.rpos = rpos; s.len = len_kind | (staged ? 0x40000000 : 0); s.qabs = qabs0 + (uint32_t)q; s.nibabs = nibabs0 + (uint32_t)q;
             sm.segs[idx] = s;
         } else {
             // list full: count this run serially, straight into the global matrix (exact, slow, rare)
-            const int n = len_kind & 0x7FFFFFFF;
+            const int n = len_kind & 0x3FFFFFFF;
             if (len_kind < 0) { for (int j = 0; j < n; ++j) atomic_add(&P->counts[(size_t)5 * P->Lpad + rpos + j], 1); }
             else for (int j = 0; j < n; ++j) {
                 if (qual_read[q + j] < P->tp.min_quality) continue;
@@ -167,6 +168,30 @@ struct TileSink {
         ins_table_add(P->tab, P->gpos_base + pos, n, t, 1);
     }
 };
+
+// Pull the next tile's inputs towards L2 while the current tile is being processed (one 128-byte line per
+// thread and array); purely a hint, so the emulation build leaves it out.
+AMP_HD void prefetch_tile(const KParams& P, long long t0, int tid, int nthreads) {
+#ifdef __CUDA_ARCH__
+    long long t1 = t0 + P.reads_per_tile; if (t1 > P.b.first + P.b.n) t1 = P.b.first + P.b.n;
+    if (t1 <= t0) return;
+    auto pf = [&](const void* base, size_t lo, size_t hi) {
+        const char* p0 = (const char*)base + (lo & ~(size_t)127);
+        const char* p1 = (const char*)base + hi;
+        for (const char* p = p0 + (size_t)tid * 128; p < p1; p += (size_t)nthreads * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    };
+    const size_t q0 = P.b.qual_off[t0], q1 = P.b.qual_off[t1];
+    pf(P.b.qual, q0, q1);
+    if (P.mode & AMP_MODE_PILEUP) pf(P.b.seq, P.b.seq_off[t0], P.b.seq_off[t1]);
+    pf(P.b.cigar, (size_t)P.b.cig_off[t0] * 4, (size_t)P.b.cig_off[t1] * 4);
+    pf(P.b.pos, (size_t)t0 * 4, (size_t)t1 * 4);
+    pf(P.b.tlen, (size_t)t0 * 4, (size_t)t1 * 4);
+    pf(P.b.flag, (size_t)t0 * 2, (size_t)t1 * 2);
+#else
+    (void)P; (void)t0; (void)tid; (void)nthreads;
+#endif
+}
 
 // The fused CTA body.  `block` / `nthreads` are blockIdx.x / blockDim.x on the device.
 AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int block, int nthreads) {
@@ -209,6 +234,7 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
         AMP_SYNC();
         // ---- T: one thread per read ---------------------------------------------------------------
         AMP_FOR_THREADS(tid, nthreads) {
+            if (tile + 1 < tile_hi) prefetch_tile(P, t1, tid, nthreads);   // overlaps this tile's T and C phases
             for (int rr = tid; rr < nreads; rr += nthreads) {
                 const long long i = t0 + rr;
                 const uint32_t c0 = P.b.cig_off[i], c1 = P.b.cig_off[i + 1];
@@ -242,7 +268,10 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
                     P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)f;
                 }
                 if (do_pile && !(f & (AMP_F_SKIPPED | AMP_F_ERROR))) {
-                    TileSink sink; sink.P = &P; sink.sm = sm; sink.qabs0 = qo0; sink.nibabs0 = so0 * 2u;
+                    TileSink sink; sink.P = &P; sink.sm = sm;
+                    sink.staged = qo1 <= q_hi && so1 <= s_hi;
+                    sink.qabs0 = sink.staged ? qo0 - q_lo : qo0;
+                    sink.nibabs0 = sink.staged ? (so0 - s_lo) * 2u : so0 * 2u;
                     sink.seq_read = seq; sink.qual_read = qual; sink.errs = 0;
                     int e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
                     e |= (int)sink.errs;
@@ -276,7 +305,7 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
             unsigned errs = 0;
             for (int s = warp; s < nseg; s += nwarps) {
                 const Seg sg = sm.segs[s];
-                const int n = sg.len & 0x7FFFFFFF;
+                const int n = sg.len & 0x3FFFFFFF;
                 const int w0 = sg.rpos - wbase;
                 const bool in_win = w0 >= 0 && w0 + n <= P.wt;                     // uniform per run
                 if (sg.len < 0) {
@@ -284,32 +313,34 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
                     else for (int j = lane; j < n; j += 32) count_add(P, sm.cnt, wbase, 5, sg.rpos + j);
                     continue;
                 }
-                const bool qs_ = sg.qabs + (uint32_t)n <= q_hi;
-                const bool ss_ = ((sg.nibabs + (uint32_t)n + 1u) >> 1) <= s_hi;
-                if (in_win && qs_ && ss_) {
+                const bool staged = (sg.len & 0x40000000) != 0;
+                if (in_win && staged) {
                     // fast path: everything in shared memory, no per-base branches.  Lanes take consecutive
                     // bases -> consecutive tile words of one row per lane: bank = position % 32, conflict-free.
-                    const uint8_t* q = sm.qual + (sg.qabs - q_lo) + lane;
+                    // Tail lanes (j >= n) read at most 31 bytes past the run, which stays inside the staging
+                    // buffers (smem_bytes() pads the end); the predicate discards them.
+                    const uint8_t* q = sm.qual + sg.qabs + lane;
                     const uint32_t nb0 = sg.nibabs + (uint32_t)lane;
                     const uint32_t shift = (~nb0 & 1u) << 2;
-                    const uint8_t* sb = sm.seq + ((nb0 >> 1) - s_lo);
+                    const uint8_t* sb = sm.seq + (nb0 >> 1);
                     int* c = sm.cnt + w0 + lane;
-                    // tail lanes (j >= n) read at most 31 bytes past the run, which stays inside the staging buffers
-                    // (smem_bytes() pads the end); their result is discarded by the predicate
-                    for (int j = lane; j - lane < n; j += 32, q += 32, sb += 16, c += 32) {
+                    int left = n - lane;                                           // this lane is live while left > 0
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                    for (int it = (n + 31) >> 5; it > 0; --it, q += 32, sb += 16, c += 32, left -= 32) {
                         const int qv = *q;
                         const uint32_t nib = ((uint32_t)*sb >> shift) & 15u;
                         const int row = lut[nib];
-                        if (j < n && qv >= minq) atomic_add(c + row, 1);           // AmpliPy.py:718, 752-753
+                        if (left > 0 && qv >= minq) atomic_add(c + row, 1);        // AmpliPy.py:718, 752-753
                     }
                 } else {
-                    const uint8_t* qp = qs_ ? sm.qual + (sg.qabs - q_lo) : P.b.qual + sg.qabs;
-                    const uint8_t* sp = ss_ ? sm.seq : P.b.seq;
-                    const uint32_t sub = ss_ ? s_lo : 0u;
+                    const uint8_t* qp = staged ? sm.qual + sg.qabs : P.b.qual + sg.qabs;
+                    const uint8_t* sp = staged ? sm.seq : P.b.seq;
                     for (int j = lane; j < n; j += 32) {
                         if (qp[j] < minq) continue;
                         const uint32_t nb = sg.nibabs + (uint32_t)j;
-                        const int ch = nib_channel((sp[(nb >> 1) - sub] >> ((~nb & 1u) << 2)) & 15u);
+                        const int ch = nib_channel((sp[nb >> 1] >> ((~nb & 1u) << 2)) & 15u);
                         if (ch < 0) { errs |= AMP_E_BASE; continue; }
                         count_add(P, sm.cnt, wbase, ch, sg.rpos + j);
                     }
