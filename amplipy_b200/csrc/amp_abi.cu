@@ -157,8 +157,24 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
         CK(cudaFuncSetAttribute(amp_trim_pileup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->max_dyn_smem = smem;
     }
+#ifdef AMP_PHASE_TIMING
+    static long long* d_phase = nullptr;
+    if (!d_phase) CK(cudaMalloc((void**)&d_phase, 4096 * 4 * 8));
+    P.phase_cycles = d_phase;
+#endif
     amp_trim_pileup_kernel<<<grid, kThreads, smem, st>>>(P);
     CK(cudaGetLastError());
+#ifdef AMP_PHASE_TIMING
+    {
+        CK(cudaStreamSynchronize(st));
+        static long long h[4096 * 4];
+        CK(cudaMemcpy(h, d_phase, sizeof(long long) * 4 * grid, cudaMemcpyDeviceToHost));
+        double s4[4] = {0, 0, 0, 0};
+        for (int b = 0; b < grid; ++b) for (int k = 0; k < 4; ++k) s4[k] += (double)h[b * 4 + k];
+        fprintf(stderr, "[phase cycles per CTA, grid %d, tiles/CTA %d] S %.0f  T %.0f  W %.0f  C %.0f\n", grid, P.tiles_per_cta,
+                s4[0] / grid, s4[1] / grid, s4[2] / grid, s4[3] / grid);
+    }
+#endif
     c->last_launches += 1;
     return AMP_OK;
 }

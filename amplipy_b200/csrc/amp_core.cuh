@@ -369,6 +369,70 @@ AMP_HD int trim_read(uint32_t* A, uint32_t* B, int& nc, int& pos, int flag, int 
     return out;
 }
 
+// ---- register-only fast path for the dominant CIGAR shape [S] M [S] --------------------------------------
+// Closed form of trim_read (426-687) for a mapped read whose CIGAR is  S(s1)? (M|=|X)(m) S(s2)?  with
+// s1 + m + s2 == l_seq.  Each step is the generic rewrite loop evaluated symbolically for this shape:
+//   start  : d1 = max_primer_end[pos] + 1 - pos bases leave the aligned run (one past the primer, 463),
+//            pos advances by d1 (514)
+//   end    : d2 = reference_end - min_primer_start[reference_end - 1] bases leave it from the right (520)
+//   quality: the window search result clips from the right (forward) or from the left WITHOUT moving pos
+//            (reverse, 589-625), reverse only when del_len >= 2 (591-594)
+// Anything unusual (offset-induced d1 < 1, a primer swallowing the whole run, coordinates outside the genome,
+// unstaged qualities) returns false and the caller runs the generic trim_read instead -- so this path never has
+// to reproduce the reference's corner cases, only recognise them.
+struct SimpleRead { int s1, m, s2; uint32_t mop; };    // mop = op code of the aligned run (0, 7 or 8)
+AMP_HD bool classify_simple(const uint32_t* cig, int nc, int l_seq, SimpleRead& r) {
+    if (nc < 1 || nc > 3) return false;
+    int k = 0;
+    r.s1 = 0; r.s2 = 0;
+    if (c_op(cig[0]) == OP_S) { r.s1 = c_len(cig[0]); if (r.s1 < 1) return false; k = 1; }
+    if (k >= nc || !cons_qr(c_op(cig[k]))) return false;
+    r.mop = c_op(cig[k]); r.m = c_len(cig[k]); ++k;
+    if (k < nc) { if (c_op(cig[k]) != OP_S) return false; r.s2 = c_len(cig[k]); if (r.s2 < 1) return false; ++k; }
+    return k == nc && r.m >= 1 && r.s1 + r.m + r.s2 == l_seq;
+}
+// On success: r = final shape, pos = final reference_start, returns AMP_F_* bits (incl. KEEP) in *flags_out.
+AMP_HD bool trim_simple(SimpleRead& r, int& pos, int flag, int tlen, int l_seq, const uint8_t* qual, bool qual_padded,
+                        const TrimParams& P, int* flags_out) {
+    const int p = pos, ref_end = p + r.m;
+    if (p < 0 || ref_end > P.L) return false;
+    const bool paired = flag & 1, rev = (flag & 16) != 0;
+    const int L1 = P.max_primer_end[p];                                   // 450
+    const int R1 = P.min_primer_start[ref_end - 1];                       // 451
+    const int abs_tlen = tlen < 0 ? -tlen : tlen;
+    const bool isize = (abs_tlen - P.max_primer_len) > l_seq;             // 452
+    int s1 = r.s1, m = r.m, s2 = r.s2, pp = p, f = 0;
+    if (!(paired && isize && rev) && L1 >= 0) {                           // 460
+        const int d1 = L1 + 1 - p;
+        if (d1 < 1 || d1 >= m) return false;
+        f |= AMP_F_TRIM_START; s1 += d1; m -= d1; pp += d1;
+    }
+    if (!(paired && isize && !rev) && R1 >= 0) {                          // 517
+        const int e = R1 - pp;                                            // aligned bases that stay
+        if (e < 1 || e >= m) return false;
+        f |= AMP_F_TRIM_END; s2 += m - e; m = e;
+    }
+    const bool w4 = qual_padded && P.window == 4;
+    const uint8_t* q = qual + s1;
+    const int del = w4 ? window_del_len_w4(q, m, P.min_quality, rev)
+                       : (rev ? window_del_len_rev(q, m, P.window, P.min_quality) : window_del_len_fwd(q, m, P.window, P.min_quality));
+    if (rev) { if (del >= 2) { f |= AMP_F_TRIM_QUAL; s1 += del; m -= del; } }          // pos stays (F6)
+    else if (del != 0) { f |= AMP_F_TRIM_QUAL; s2 += del; m -= del; }
+    const int ref_len = m > 0 ? m : 1;
+    if (ref_len >= P.min_length && ((f & (AMP_F_TRIM_START | AMP_F_TRIM_END)) || P.include_no_primer)) f |= AMP_F_KEEP;   // 910
+    r.s1 = s1; r.m = m; r.s2 = s2; pos = pp; *flags_out = f;
+    return true;
+}
+// final CIGAR of a simple read: [S] [M] [S]; an emptied aligned run leaves one merged soft clip (fix_cigar)
+AMP_HD int emit_simple(const SimpleRead& r, uint32_t* out) {
+    if (r.m <= 0) { out[0] = c_pack(OP_S, r.s1 + r.s2); return 1; }
+    int n = 0;
+    if (r.s1 > 0) out[n++] = c_pack(OP_S, r.s1);
+    out[n++] = c_pack(r.mop, r.m);
+    if (r.s2 > 0) out[n++] = c_pack(OP_S, r.s2);
+    return n;
+}
+
 // ---- sequence access: BAM 4-bit nibbles, high nibble first ---------------------------------------
 AMP_HD uint32_t nib_at(const uint8_t* seq, uint32_t idx) { return (seq[idx >> 1] >> ((~idx & 1u) << 2)) & 15u; }
 AMP_HD char nib_char(uint32_t nib) {

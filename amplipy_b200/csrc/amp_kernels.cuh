@@ -22,7 +22,13 @@
 #if defined(__CUDA_ARCH__)
 #define AMP_FOR_THREADS(tid, nthreads) for (int tid = threadIdx.x, once_ = 1; once_; once_ = 0)
 #define AMP_SYNC() __syncthreads()
+#ifdef AMP_PHASE_TIMING
+#define AMP_TICK(k) do { if (threadIdx.x == 0) { long long t_ = clock64(); tacc[k] += t_ - tlast; tlast = t_; } } while (0)
 #else
+#define AMP_TICK(k) ((void)0)
+#endif
+#else
+#define AMP_TICK(k) ((void)0)
 #define AMP_FOR_THREADS(tid, nthreads) for (int tid = 0; tid < (nthreads); ++tid)
 #define AMP_SYNC() ((void)0)
 #endif
@@ -41,7 +47,10 @@ struct TrimOut { int32_t* pos; uint16_t* ncig; uint8_t* flags; uint32_t* cigar; 
 
 #define AMP_MODE_TRIM 1
 #define AMP_MODE_PILEUP 2
-#define AMP_CMAX 24          // CIGAR ops (+3) handled in per-thread local arrays; longer ones use global scratch
+#ifndef AMP_CMAX
+#define AMP_CMAX 24
+#endif
+//         // CIGAR ops (+3) handled in per-thread local arrays; longer ones use global scratch
 
 struct KParams {
     BatchPtrs b;
@@ -57,6 +66,7 @@ struct KParams {
     long long scratch_half;  // sumC + 3N
     int reads_per_tile, ntiles, tiles_per_cta;
     int wt, maxseg, qbytes, sbytes;   // shared-memory carve-up
+    long long* phase_cycles;          // debug builds (-DAMP_PHASE_TIMING): per-CTA cycles in S, T, W, C
 };
 
 inline double amp_min_d(double a, double b) { return a < b ? a : b; }
@@ -89,20 +99,20 @@ inline TileCfg pick_tile_cfg(long long n, long long sum_cig, long long sum_qual,
 
 #define AMP_ROWS (AMP_NCH + 1)   // counts tile rows: 6 channels + one row that collects non-ACGTN bases (KeyError, 753)
 AMP_HD size_t smem_bytes(int wt, int maxseg, int qbytes, int sbytes) {
-    return (size_t)AMP_ROWS * wt * 4 + (size_t)maxseg * sizeof(Seg) + 128 + (size_t)qbytes + (size_t)sbytes + 64;
+    return (size_t)AMP_ROWS * wt * 4 + (size_t)maxseg * sizeof(Seg) + 128 + 512 + (size_t)qbytes + (size_t)sbytes + 64;
 }
 
 struct Smem {
     int* cnt; Seg* segs; int* ctrl; uint8_t* qual; uint8_t* seq;
 };
 // ctrl words
-enum { C_NSEG = 0, C_TMIN = 1, C_TMAX = 2, C_LUT = 16 };   // ctrl[C_LUT + nib] = row offset (ints) of nibble `nib`
+enum { C_NSEG = 0, C_TMIN = 1, C_TMAX = 2, C_NCPX = 3, C_LUT = 16, C_CLIST = 32 };   // C_CLIST: u16[256] queue of reads for the generic path;   // ctrl[C_LUT + nib] = row offset (ints) of nibble `nib`
 
 AMP_HD Smem carve(unsigned char* base, const KParams& P) {
     Smem s;
     s.cnt = (int*)base; base += (size_t)AMP_ROWS * P.wt * 4;
     s.segs = (Seg*)base; base += (size_t)P.maxseg * sizeof(Seg);
-    s.ctrl = (int*)base; base += 128;
+    s.ctrl = (int*)base; base += 128 + 512;
     s.qual = base; base += P.qbytes;
     s.seq = base;
     return s;
@@ -193,167 +203,251 @@ AMP_HD void prefetch_tile(const KParams& P, long long t0, int tid, int nthreads)
 #endif
 }
 
+// Everything a thread needs to know about the tile it is working on.
+struct TileCtx {
+    long long t0; int nreads;
+    uint32_t q_lo, q_hi, s_lo, s_hi;   // staged byte ranges [lo, hi) of qual / seq
+    bool do_trim, do_pile;
+};
+
+// Generic per-read path: trim_read loop for loop + plan_read.  Used for every read that is not [S]M[S]
+// (indels, hard clips, ...) and for the corner cases the closed form declines.
+AMP_HD void read_generic(const KParams& P, const Smem& sm, const TileCtx& T, int rr) {
+    const long long i = T.t0 + rr;
+    const uint32_t c0 = P.b.cig_off[i], c1 = P.b.cig_off[i + 1];
+    const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
+    const uint32_t so0 = P.b.seq_off[i], so1 = P.b.seq_off[i + 1];
+    int nc = (int)(c1 - c0);
+    const int l_seq = (int)(qo1 - qo0);
+    const int flag = P.b.flag[i];
+    int pos = P.b.pos[i];
+    const bool q_st = qo1 <= T.q_hi, s_st = T.do_pile && so1 <= T.s_hi;
+    const uint8_t* qual = q_st ? sm.qual + (qo0 - T.q_lo) : P.b.qual + qo0;
+    const uint8_t* seq = s_st ? sm.seq + (so0 - T.s_lo) : P.b.seq + so0;
+    const uint32_t* cig = P.b.cigar + c0;
+    uint32_t la[AMP_CMAX], lb[AMP_CMAX];
+    int f = 0;
+    if (T.do_trim) {
+        uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
+        uint32_t *A, *B;
+        if (nc + 3 <= AMP_CMAX) { A = la; B = lb; }
+        else { A = P.scratch + (size_t)c0 + 3 * (size_t)i; B = A + P.scratch_half; }
+        for (int k = 0; k < nc; ++k) A[k] = cig[k];
+        uint32_t* res;
+        f = trim_read(A, B, nc, pos, flag, P.b.tlen[i], l_seq, qual, q_st, P.tp, &res);
+        if (f & AMP_F_ERROR) { nc = 0; f = AMP_F_ERROR; atomic_or(P.err, AMP_E_COORD); }
+        for (int k = 0; k < nc; ++k) orow[k] = res[k];
+        cig = res;
+        P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)f;
+    }
+    if (T.do_pile && !(f & AMP_F_ERROR)) {
+        TileSink sink; sink.P = &P; sink.sm = sm;
+        sink.staged = q_st && s_st;
+        sink.qabs0 = sink.staged ? qo0 - T.q_lo : qo0;
+        sink.nibabs0 = sink.staged ? (so0 - T.s_lo) * 2u : so0 * 2u;
+        sink.seq_read = seq; sink.qual_read = qual; sink.errs = 0;
+        int e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
+        e |= (int)sink.errs;
+        if (e) atomic_or(P.err, (unsigned)e);
+    }
+}
+
+// Count phase over runs [lo, hi) of the tile's list: one warp per run, lanes over consecutive bases.
+// Warps [0, skip_warps) do not take part (they are busy with the generic path of queued reads).
+AMP_HD void count_runs(const KParams& P, const Smem& sm, int lo, int hi, int wbase, int tid, int nthreads, int skip_warps) {
+    const int lane = tid & 31;
+    int warp = tid >> 5, nwarps = nthreads >> 5 ? nthreads >> 5 : 1;
+    if (skip_warps >= nwarps) skip_warps = 0;
+    if (warp < skip_warps) return;
+    warp -= skip_warps; nwarps -= skip_warps;
+    const int* lut = sm.ctrl + C_LUT;
+    const int minq = P.tp.min_quality;
+    unsigned errs = 0;
+    for (int s = lo + warp % nwarps; s < hi; s += nwarps) {
+        const Seg sg = sm.segs[s];
+        const int n = sg.len & 0x3FFFFFFF;
+        const int w0 = sg.rpos - wbase;
+        const bool in_win = wbase >= 0 && w0 >= 0 && w0 + n <= P.wt;                // uniform per run
+        if (sg.len < 0) {
+            if (in_win) { for (int j = lane; j < n; j += 32) atomic_add(&sm.cnt[5 * P.wt + w0 + j], 1); }
+            else for (int j = lane; j < n; j += 32) count_add(P, sm.cnt, wbase, 5, sg.rpos + j);
+            continue;
+        }
+        const bool staged = (sg.len & 0x40000000) != 0;
+        if (in_win && staged) {
+            // fast path: everything in shared memory, no per-base branches.  Lanes take consecutive bases ->
+            // consecutive tile words of one row per lane: bank = position % 32, conflict-free.  Tail lanes
+            // (j >= n) read at most 31 bytes past the run, which stays inside the padded staging buffers;
+            // the predicate discards them.
+            const uint8_t* q = sm.qual + sg.qabs + lane;
+            const uint32_t nb0 = sg.nibabs + (uint32_t)lane;
+            const uint32_t shift = (~nb0 & 1u) << 2;
+            const uint8_t* sb = sm.seq + (nb0 >> 1);
+            int* c = sm.cnt + w0 + lane;
+            int left = n - lane;                                                   // this lane is live while left > 0
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int it = (n + 31) >> 5; it > 0; --it, q += 32, sb += 16, c += 32, left -= 32) {
+                const int qv = *q;
+                const uint32_t nib = ((uint32_t)*sb >> shift) & 15u;
+                const int row = lut[nib];
+                if (left > 0 && qv >= minq) atomic_add(c + row, 1);                // AmpliPy.py:718, 752-753
+            }
+        } else {
+            const uint8_t* qp = staged ? sm.qual + sg.qabs : P.b.qual + sg.qabs;
+            const uint8_t* sp = staged ? sm.seq : P.b.seq;
+            for (int j = lane; j < n; j += 32) {
+                if (qp[j] < minq) continue;
+                const uint32_t nb = sg.nibabs + (uint32_t)j;
+                const int ch = nib_channel((sp[nb >> 1] >> ((~nb & 1u) << 2)) & 15u);
+                if (ch < 0) { errs |= AMP_E_BASE; continue; }
+                count_add(P, sm.cnt, wbase, ch, sg.rpos + j);
+            }
+        }
+    }
+    if (errs) atomic_or(P.err, errs);
+}
+
 // The fused CTA body.  `block` / `nthreads` are blockIdx.x / blockDim.x on the device.
 AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int block, int nthreads) {
     const Smem sm = carve(smem_base, P);
     const bool do_trim = P.mode & AMP_MODE_TRIM, do_pile = P.mode & AMP_MODE_PILEUP;
     const int ncnt = AMP_ROWS * P.wt;
     int wbase = -1;                                    // uniform across the CTA
+#if defined(__CUDA_ARCH__) && defined(AMP_PHASE_TIMING)
+    long long tacc[4] = {0, 0, 0, 0}, tlast = clock64();
+#endif
     if (do_pile) {
         AMP_FOR_THREADS(tid, nthreads) {
             for (int i = tid; i < ncnt; i += nthreads) sm.cnt[i] = 0;
             if (tid < 16) { const int ch = nib_channel((uint32_t)tid); sm.ctrl[C_LUT + tid] = (ch < 0 ? AMP_NCH : ch) * P.wt; }
         }
     }
+    uint16_t* clist = (uint16_t*)(sm.ctrl + C_CLIST);
     const int tile_lo = block * P.tiles_per_cta;
     int tile_hi = tile_lo + P.tiles_per_cta; if (tile_hi > P.ntiles) tile_hi = P.ntiles;
     for (int tile = tile_lo; tile < tile_hi; ++tile) {
-        const long long t0 = P.b.first + (long long)tile * P.reads_per_tile;
-        long long t1 = t0 + P.reads_per_tile; if (t1 > P.b.first + P.b.n) t1 = P.b.first + P.b.n;
-        const int nreads = (int)(t1 - t0);
+        TileCtx T;
+        T.t0 = P.b.first + (long long)tile * P.reads_per_tile;
+        long long t1 = T.t0 + P.reads_per_tile; if (t1 > P.b.first + P.b.n) t1 = P.b.first + P.b.n;
+        T.nreads = (int)(t1 - T.t0); T.do_trim = do_trim; T.do_pile = do_pile;
         // ---- S: stage qual / seq of the tile ------------------------------------------------------
-        const uint32_t q_lo = P.b.qual_off[t0] & ~15u, q_end = P.b.qual_off[t1];
-        const uint32_t s_lo = P.b.seq_off[t0] & ~15u, s_end = P.b.seq_off[t1];
-        const uint32_t q_hi = (q_end - q_lo <= (uint32_t)P.qbytes) ? q_end : q_lo + (uint32_t)P.qbytes;   // staged [q_lo, q_hi)
-        const uint32_t s_hi = (s_end - s_lo <= (uint32_t)P.sbytes) ? s_end : s_lo + (uint32_t)P.sbytes;
+        const uint32_t q_end = P.b.qual_off[t1], s_end = P.b.seq_off[t1];
+        T.q_lo = P.b.qual_off[T.t0] & ~15u; T.s_lo = P.b.seq_off[T.t0] & ~15u;
+        T.q_hi = (q_end - T.q_lo <= (uint32_t)P.qbytes) ? q_end : T.q_lo + (uint32_t)P.qbytes;   // staged [lo, hi)
+        T.s_hi = (s_end - T.s_lo <= (uint32_t)P.sbytes) ? s_end : T.s_lo + (uint32_t)P.sbytes;
         AMP_FOR_THREADS(tid, nthreads) {
-            if (tid == 0) { sm.ctrl[C_NSEG] = 0; sm.ctrl[C_TMIN] = 0x7FFFFFFF; sm.ctrl[C_TMAX] = -1; }
+            if (tid == 0) { sm.ctrl[C_NSEG] = 0; sm.ctrl[C_TMIN] = 0x7FFFFFFF; sm.ctrl[C_TMAX] = -1; sm.ctrl[C_NCPX] = 0; }
             {
-                const uint32_t nvec = (q_hi - q_lo) >> 4;
-                const uint4* g = (const uint4*)(P.b.qual + q_lo); uint4* s = (uint4*)sm.qual;
+                const uint32_t nvec = (T.q_hi - T.q_lo) >> 4;
+                const uint4* g = (const uint4*)(P.b.qual + T.q_lo); uint4* s = (uint4*)sm.qual;
                 for (uint32_t v = tid; v < nvec; v += nthreads) s[v] = g[v];
-                for (uint32_t k = (nvec << 4) + tid; k < q_hi - q_lo; k += nthreads) sm.qual[k] = P.b.qual[q_lo + k];
+                for (uint32_t k = (nvec << 4) + tid; k < T.q_hi - T.q_lo; k += nthreads) sm.qual[k] = P.b.qual[T.q_lo + k];
             }
             if (do_pile) {
-                const uint32_t nvec = (s_hi - s_lo) >> 4;
-                const uint4* g = (const uint4*)(P.b.seq + s_lo); uint4* s = (uint4*)sm.seq;
+                const uint32_t nvec = (T.s_hi - T.s_lo) >> 4;
+                const uint4* g = (const uint4*)(P.b.seq + T.s_lo); uint4* s = (uint4*)sm.seq;
                 for (uint32_t v = tid; v < nvec; v += nthreads) s[v] = g[v];
-                for (uint32_t k = (nvec << 4) + tid; k < s_hi - s_lo; k += nthreads) sm.seq[k] = P.b.seq[s_lo + k];
+                for (uint32_t k = (nvec << 4) + tid; k < T.s_hi - T.s_lo; k += nthreads) sm.seq[k] = P.b.seq[T.s_lo + k];
             }
         }
-        AMP_SYNC();
-        // ---- T: one thread per read ---------------------------------------------------------------
+        AMP_SYNC(); AMP_TICK(0);
+        // ---- T0: one thread per read.  [S]M[S] reads are finished here in registers (closed-form trim, one
+        // aligned run); everything else is queued for the generic path.
         AMP_FOR_THREADS(tid, nthreads) {
-            if (tile + 1 < tile_hi) prefetch_tile(P, t1, tid, nthreads);   // overlaps this tile's T and C phases
-            for (int rr = tid; rr < nreads; rr += nthreads) {
-                const long long i = t0 + rr;
+            if (tile + 1 < tile_hi) prefetch_tile(P, t1, tid, nthreads);   // overlaps this tile's compute phases
+            for (int rr = tid; rr < T.nreads; rr += nthreads) {
+                const long long i = T.t0 + rr;
                 const uint32_t c0 = P.b.cig_off[i], c1 = P.b.cig_off[i + 1];
                 const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
-                const uint32_t so0 = P.b.seq_off[i], so1 = P.b.seq_off[i + 1];
-                int nc = (int)(c1 - c0);
-                const int l_seq = (int)(qo1 - qo0);
+                const int nc = (int)(c1 - c0), l_seq = (int)(qo1 - qo0);
                 const int flag = P.b.flag[i];
                 int pos = P.b.pos[i];
-                const uint8_t* qual = (qo1 <= q_hi) ? sm.qual + (qo0 - q_lo) : P.b.qual + qo0;
-                const uint8_t* seq = (so1 <= s_hi && do_pile) ? sm.seq + (so0 - s_lo) : P.b.seq + so0;
                 const uint32_t* cig = P.b.cigar + c0;
-                uint32_t la[AMP_CMAX], lb[AMP_CMAX];
-                int f = 0;
-                if ((flag & 4) || nc == 0) f = AMP_F_SKIPPED;                           // AmpliPy.py:902
-                if (do_trim) {
-                    uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
-                    if (f == 0) {
-                        uint32_t *A, *B;
-                        if (nc + 3 <= AMP_CMAX) { A = la; B = lb; }
-                        else { A = P.scratch + (size_t)c0 + 3 * (size_t)i; B = A + P.scratch_half; }
-                        for (int k = 0; k < nc; ++k) A[k] = cig[k];
-                        uint32_t* res;
-                        f = trim_read(A, B, nc, pos, flag, P.b.tlen[i], l_seq, qual, qo1 <= q_hi, P.tp, &res);
-                        if (f & AMP_F_ERROR) { nc = 0; f = AMP_F_ERROR; atomic_or(P.err, AMP_E_COORD); }
-                        for (int k = 0; k < nc; ++k) orow[k] = res[k];
-                        cig = res;
-                    } else {
+                if ((flag & 4) || nc == 0) {                                            // AmpliPy.py:902
+                    if (do_trim) {
+                        uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
                         for (int k = 0; k < nc; ++k) orow[k] = cig[k];
+                        P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)AMP_F_SKIPPED;
                     }
-                    P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)f;
-                }
-                if (do_pile && !(f & (AMP_F_SKIPPED | AMP_F_ERROR))) {
-                    TileSink sink; sink.P = &P; sink.sm = sm;
-                    sink.staged = qo1 <= q_hi && so1 <= s_hi;
-                    sink.qabs0 = sink.staged ? qo0 - q_lo : qo0;
-                    sink.nibabs0 = sink.staged ? (so0 - s_lo) * 2u : so0 * 2u;
-                    sink.seq_read = seq; sink.qual_read = qual; sink.errs = 0;
-                    int e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
-                    e |= (int)sink.errs;
-                    if (e) atomic_or(P.err, (unsigned)e);
-                    if (!(e & (AMP_E_COORD | AMP_E_CIGAR))) {
-                        atomic_min(&sm.ctrl[C_TMIN], pos);
-                        atomic_max(&sm.ctrl[C_TMAX], pos + ref_len_of(cig, nc));
-                    }
-                }
-            }
-        }
-        if (!do_pile) { AMP_SYNC(); continue; }
-        AMP_SYNC();
-        // ---- W: window decision (uniform) -----------------------------------------------------------
-        int nseg = sm.ctrl[C_NSEG]; if (nseg > P.maxseg) nseg = P.maxseg;
-        const int tmin = sm.ctrl[C_TMIN], tmax = sm.ctrl[C_TMAX];
-        if (nseg > 0 && (wbase < 0 || tmin < wbase || tmax > wbase + P.wt)) {
-            if (wbase >= 0) {
-                AMP_FOR_THREADS(tid, nthreads) {
-                    flush_tile(P, sm.cnt, wbase, tid, nthreads, true);
-                }
-                AMP_SYNC();
-            }
-            wbase = tmin & ~31;
-        }
-        // ---- C: one warp per run ----------------------------------------------------------------------
-        AMP_FOR_THREADS(tid, nthreads) {
-            const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-            const int* lut = sm.ctrl + C_LUT;
-            const int minq = P.tp.min_quality;
-            unsigned errs = 0;
-            for (int s = warp; s < nseg; s += nwarps) {
-                const Seg sg = sm.segs[s];
-                const int n = sg.len & 0x3FFFFFFF;
-                const int w0 = sg.rpos - wbase;
-                const bool in_win = w0 >= 0 && w0 + n <= P.wt;                     // uniform per run
-                if (sg.len < 0) {
-                    if (in_win) { for (int j = lane; j < n; j += 32) atomic_add(&sm.cnt[5 * P.wt + w0 + j], 1); }
-                    else for (int j = lane; j < n; j += 32) count_add(P, sm.cnt, wbase, 5, sg.rpos + j);
                     continue;
                 }
-                const bool staged = (sg.len & 0x40000000) != 0;
-                if (in_win && staged) {
-                    // fast path: everything in shared memory, no per-base branches.  Lanes take consecutive
-                    // bases -> consecutive tile words of one row per lane: bank = position % 32, conflict-free.
-                    // Tail lanes (j >= n) read at most 31 bytes past the run, which stays inside the staging
-                    // buffers (smem_bytes() pads the end); the predicate discards them.
-                    const uint8_t* q = sm.qual + sg.qabs + lane;
-                    const uint32_t nb0 = sg.nibabs + (uint32_t)lane;
-                    const uint32_t shift = (~nb0 & 1u) << 2;
-                    const uint8_t* sb = sm.seq + (nb0 >> 1);
-                    int* c = sm.cnt + w0 + lane;
-                    int left = n - lane;                                           // this lane is live while left > 0
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-                    for (int it = (n + 31) >> 5; it > 0; --it, q += 32, sb += 16, c += 32, left -= 32) {
-                        const int qv = *q;
-                        const uint32_t nib = ((uint32_t)*sb >> shift) & 15u;
-                        const int row = lut[nib];
-                        if (left > 0 && qv >= minq) atomic_add(c + row, 1);        // AmpliPy.py:718, 752-753
+                SimpleRead r;
+                const bool q_st = qo1 <= T.q_hi;
+                bool done = q_st && rr < 65536 && classify_simple(cig, nc, l_seq, r);
+                int f = 0;
+                if (done && do_trim) done = trim_simple(r, pos, flag, P.b.tlen[i], l_seq, sm.qual + (qo0 - T.q_lo), true, P.tp, &f);
+                if (done && !do_trim && (pos < 0 || pos + r.m > P.tp.L)) done = false;
+                if (done) {
+                    if (do_trim) {
+                        uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
+                        const int no = emit_simple(r, orow);
+                        P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)no; P.o.flags[i] = (uint8_t)f;
+                    }
+                    if (do_pile && r.m > 0) {
+                        const uint32_t so0 = P.b.seq_off[i], so1 = P.b.seq_off[i + 1];
+                        const bool staged = so1 <= T.s_hi;                            // q_st holds
+                        const int idx = atomic_add(&sm.ctrl[C_NSEG], 1);
+                        if (idx < P.maxseg) {
+                            Seg sgm; sgm.rpos = pos; sgm.len = r.m | (staged ? 0x40000000 : 0);
+                            sgm.qabs = (staged ? qo0 - T.q_lo : qo0) + (uint32_t)r.s1;
+                            sgm.nibabs = (staged ? (so0 - T.s_lo) * 2u : so0 * 2u) + (uint32_t)r.s1;
+                            sm.segs[idx] = sgm;
+                        } else {
+                            TileSink sink; sink.P = &P; sink.sm = sm; sink.staged = false; sink.qabs0 = qo0; sink.nibabs0 = so0 * 2u;
+                            sink.seq_read = P.b.seq + so0; sink.qual_read = P.b.qual + qo0; sink.errs = 0;
+                            sink.push(pos, r.m, r.s1);                                // list full: exact serial path
+                            if (sink.errs) atomic_or(P.err, sink.errs);
+                        }
+                        atomic_min(&sm.ctrl[C_TMIN], pos); atomic_max(&sm.ctrl[C_TMAX], pos + r.m);
                     }
                 } else {
-                    const uint8_t* qp = staged ? sm.qual + sg.qabs : P.b.qual + sg.qabs;
-                    const uint8_t* sp = staged ? sm.seq : P.b.seq;
-                    for (int j = lane; j < n; j += 32) {
-                        if (qp[j] < minq) continue;
-                        const uint32_t nb = sg.nibabs + (uint32_t)j;
-                        const int ch = nib_channel((sp[nb >> 1] >> ((~nb & 1u) << 2)) & 15u);
-                        if (ch < 0) { errs |= AMP_E_BASE; continue; }
-                        count_add(P, sm.cnt, wbase, ch, sg.rpos + j);
+                    const int k = atomic_add(&sm.ctrl[C_NCPX], 1);
+                    clist[k] = (uint16_t)rr;
+                    if (do_pile && pos >= 0) {   // bound where it can pile up: trimming never leaves the input span
+                        atomic_min(&sm.ctrl[C_TMIN], pos); atomic_max(&sm.ctrl[C_TMAX], pos + ref_len_of(cig, nc));
                     }
                 }
             }
-            if (errs) atomic_or(P.err, errs);
         }
-        AMP_SYNC();
-    }
-    if (do_pile && wbase >= 0) {
+        AMP_SYNC(); AMP_TICK(1);
+        // ---- W: window decision (uniform) -----------------------------------------------------------
+        const int ncpx = sm.ctrl[C_NCPX];
+        int nseg0 = sm.ctrl[C_NSEG]; if (nseg0 > P.maxseg) nseg0 = P.maxseg;
+        if (do_pile) {
+            const int tmin = sm.ctrl[C_TMIN], tmax = sm.ctrl[C_TMAX];
+            if (tmax >= 0 && (wbase < 0 || tmin < wbase || tmax > wbase + P.wt)) {
+                if (wbase >= 0) {
+                    AMP_FOR_THREADS(tid, nthreads) { flush_tile(P, sm.cnt, wbase, tid, nthreads, true); }
+                    AMP_SYNC();
+                }
+                wbase = tmin & ~31;
+            }
+        }
+        AMP_TICK(2);
+        // ---- T1 + C: queued reads take the generic path (their runs go to the tail of the list) while the other
+        // warps already count the runs planned in T0.
         AMP_FOR_THREADS(tid, nthreads) {
-            flush_tile(P, sm.cnt, wbase, tid, nthreads, false);
+            for (int k = tid; k < ncpx; k += nthreads) read_generic(P, sm, T, (int)clist[k]);
         }
+        if (do_pile) {
+            AMP_FOR_THREADS(tid, nthreads) { count_runs(P, sm, 0, nseg0, wbase, tid, nthreads, (ncpx + 31) >> 5); }
+        }
+        AMP_SYNC(); AMP_TICK(3);
+        if (do_pile && ncpx > 0) {
+            int nseg = sm.ctrl[C_NSEG]; if (nseg > P.maxseg) nseg = P.maxseg;
+            if (nseg > nseg0) {
+                AMP_FOR_THREADS(tid, nthreads) { count_runs(P, sm, nseg0, nseg, wbase, tid, nthreads, 0); }
+            }
+            AMP_SYNC();
+        }
+    }
+#if defined(__CUDA_ARCH__) && defined(AMP_PHASE_TIMING)
+    if (threadIdx.x == 0 && P.phase_cycles) for (int k = 0; k < 4; ++k) P.phase_cycles[(size_t)block * 4 + k] = tacc[k];
+#endif
+    if (do_pile && wbase >= 0) {
+        AMP_FOR_THREADS(tid, nthreads) { flush_tile(P, sm.cnt, wbase, tid, nthreads, false); }
     }
 }
 
