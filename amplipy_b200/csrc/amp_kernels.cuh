@@ -97,22 +97,28 @@ inline TileCfg pick_tile_cfg(long long n, long long sum_cig, long long sum_qual,
     return t;
 }
 
+#ifndef AMP_DEFER_MAX
+#define AMP_DEFER_MAX 0      // >0: tiles with at most this many generic-path reads defer them to the end of the CTA
+#endif                       // (measured slower on B200: in-tile they overlap with the counting warps; kept for experiments)
+#define AMP_DLIST_CAP 384    // capacity of the per-CTA deferred list
 #define AMP_ROWS (AMP_NCH + 1)   // counts tile rows: 6 channels + one row that collects non-ACGTN bases (KeyError, 753)
 AMP_HD size_t smem_bytes(int wt, int maxseg, int qbytes, int sbytes) {
-    return (size_t)AMP_ROWS * wt * 4 + (size_t)maxseg * sizeof(Seg) + 128 + 512 + (size_t)qbytes + (size_t)sbytes + 64;
+    return (size_t)AMP_ROWS * wt * 4 + (size_t)maxseg * sizeof(Seg) + 128 + 512 + 4 * AMP_DLIST_CAP + (size_t)qbytes + (size_t)sbytes + 64;
 }
 
 struct Smem {
     int* cnt; Seg* segs; int* ctrl; uint8_t* qual; uint8_t* seq;
 };
 // ctrl words
-enum { C_NSEG = 0, C_TMIN = 1, C_TMAX = 2, C_NCPX = 3, C_LUT = 16, C_CLIST = 32 };   // C_CLIST: u16[256] queue of reads for the generic path;   // ctrl[C_LUT + nib] = row offset (ints) of nibble `nib`
+// ctrl words: counters, nibble -> tile row LUT, C_CLIST: u16[256] reads of this tile queued for the generic path,
+// C_DLIST: u32[AMP_DLIST_CAP] reads deferred to the end of the CTA
+enum { C_NSEG = 0, C_TMIN = 1, C_TMAX = 2, C_NCPX = 3, C_LUT = 16, C_CLIST = 32, C_DLIST = 160 };
 
 AMP_HD Smem carve(unsigned char* base, const KParams& P) {
     Smem s;
     s.cnt = (int*)base; base += (size_t)AMP_ROWS * P.wt * 4;
     s.segs = (Seg*)base; base += (size_t)P.maxseg * sizeof(Seg);
-    s.ctrl = (int*)base; base += 128 + 512;
+    s.ctrl = (int*)base; base += 128 + 512 + 4 * AMP_DLIST_CAP;
     s.qual = base; base += P.qbytes;
     s.seq = base;
     return s;
@@ -249,6 +255,7 @@ AMP_HD void read_generic(const KParams& P, const Smem& sm, const TileCtx& T, int
         int e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
         e |= (int)sink.errs;
         if (e) atomic_or(P.err, (unsigned)e);
+        if (!(e & (AMP_E_COORD | AMP_E_CIGAR))) { atomic_min(&sm.ctrl[C_TMIN], pos); atomic_max(&sm.ctrl[C_TMAX], pos + ref_len_of(cig, nc)); }
     }
 }
 
@@ -284,16 +291,22 @@ AMP_HD void count_runs(const KParams& P, const Smem& sm, int lo, int hi, int wba
             const uint32_t shift = (~nb0 & 1u) << 2;
             const uint8_t* sb = sm.seq + (nb0 >> 1);
             int* c = sm.cnt + w0 + lane;
-            int left = n - lane;                                                   // this lane is live while left > 0
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-            for (int it = (n + 31) >> 5; it > 0; --it, q += 32, sb += 16, c += 32, left -= 32) {
-                const int qv = *q;
-                const uint32_t nib = ((uint32_t)*sb >> shift) & 15u;
-                const int row = lut[nib];
-                if (left > 0 && qv >= minq) atomic_add(c + row, 1);                // AmpliPy.py:718, 752-753
+            const int left = n - lane;                                             // this lane has bases lane, lane+32, ... < n
+            const int iters = (n + 31) >> 5;
+#define AMP_COUNT_STEP(u_)                                                                          \
+            {                                                                                       \
+                const int qv = q[32 * (u_)];                                                        \
+                const uint32_t nib = ((uint32_t)sb[16 * (u_)] >> shift) & 15u;                      \
+                const int row = lut[nib];                                                           \
+                if (left > 32 * (u_) && qv >= minq) atomic_add(c + 32 * (u_) + row, 1);             \
             }
+            AMP_COUNT_STEP(0)                                                       /* AmpliPy.py:718, 752-753 */
+            if (iters > 1) AMP_COUNT_STEP(1)
+            if (iters > 2) AMP_COUNT_STEP(2)
+            if (iters > 3) AMP_COUNT_STEP(3)
+            if (iters > 4) AMP_COUNT_STEP(4)
+            for (int u = 5; u < iters; ++u) AMP_COUNT_STEP(u)
+#undef AMP_COUNT_STEP
         } else {
             const uint8_t* qp = staged ? sm.qual + sg.qabs : P.b.qual + sg.qabs;
             const uint8_t* sp = staged ? sm.seq : P.b.seq;
@@ -325,6 +338,8 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
         }
     }
     uint16_t* clist = (uint16_t*)(sm.ctrl + C_CLIST);
+    uint32_t* dlist = (uint32_t*)(sm.ctrl + C_DLIST);   // reads deferred to the end of the CTA (absolute index - P.b.first)
+    int ndef = 0;                                        // uniform
     const int tile_lo = block * P.tiles_per_cta;
     int tile_hi = tile_lo + P.tiles_per_cta; if (tile_hi > P.ntiles) tile_hi = P.ntiles;
     for (int tile = tile_lo; tile < tile_hi; ++tile) {
@@ -413,8 +428,17 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
         }
         AMP_SYNC(); AMP_TICK(1);
         // ---- W: window decision (uniform) -----------------------------------------------------------
-        const int ncpx = sm.ctrl[C_NCPX];
+        int ncpx = sm.ctrl[C_NCPX];
         int nseg0 = sm.ctrl[C_NSEG]; if (nseg0 > P.maxseg) nseg0 = P.maxseg;
+        // A handful of queued reads would keep one warp on the slow generic path for the whole tile: collect them
+        // and run them together at the end of the CTA (unstaged, but with every lane busy).  Tiles that are mostly
+        // generic (indel-rich data) are processed in place, where their rows are staged.
+        if (ncpx > 0 && ncpx <= AMP_DEFER_MAX && ndef + ncpx <= AMP_DLIST_CAP) {
+            AMP_FOR_THREADS(tid, nthreads) {
+                if (tid < ncpx) dlist[ndef + tid] = (uint32_t)(T.t0 - P.b.first) + clist[tid];
+            }
+            ndef += ncpx; ncpx = 0;
+        }
         if (do_pile) {
             const int tmin = sm.ctrl[C_TMIN], tmax = sm.ctrl[C_TMAX];
             if (tmax >= 0 && (wbase < 0 || tmin < wbase || tmax > wbase + P.wt)) {
@@ -446,6 +470,32 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
 #if defined(__CUDA_ARCH__) && defined(AMP_PHASE_TIMING)
     if (threadIdx.x == 0 && P.phase_cycles) for (int k = 0; k < 4; ++k) P.phase_cycles[(size_t)block * 4 + k] = tacc[k];
 #endif
+    // ---- D: deferred reads of the whole CTA, generic path straight from global memory ----------------------------
+    if (ndef > 0) {
+        TileCtx T;
+        T.t0 = P.b.first; T.nreads = 0; T.q_lo = T.q_hi = T.s_lo = T.s_hi = 0; T.do_trim = do_trim; T.do_pile = do_pile;
+        AMP_FOR_THREADS(tid, nthreads) {
+            if (tid == 0) { sm.ctrl[C_NSEG] = 0; sm.ctrl[C_TMIN] = 0x7FFFFFFF; sm.ctrl[C_TMAX] = -1; }
+        }
+        AMP_SYNC();
+        AMP_FOR_THREADS(tid, nthreads) {
+            for (int k = tid; k < ndef; k += nthreads) read_generic(P, sm, T, (int)dlist[k]);
+        }
+        AMP_SYNC();
+        if (do_pile) {
+            int nseg = sm.ctrl[C_NSEG]; if (nseg > P.maxseg) nseg = P.maxseg;
+            const int tmin = sm.ctrl[C_TMIN], tmax = sm.ctrl[C_TMAX];
+            if (tmax >= 0 && (wbase < 0 || tmin < wbase || tmax > wbase + P.wt)) {
+                if (wbase >= 0) {
+                    AMP_FOR_THREADS(tid, nthreads) { flush_tile(P, sm.cnt, wbase, tid, nthreads, true); }
+                    AMP_SYNC();
+                }
+                wbase = tmin & ~31;
+            }
+            AMP_FOR_THREADS(tid, nthreads) { count_runs(P, sm, 0, nseg, wbase, tid, nthreads, 0); }
+            AMP_SYNC();
+        }
+    }
     if (do_pile && wbase >= 0) {
         AMP_FOR_THREADS(tid, nthreads) { flush_tile(P, sm.cnt, wbase, tid, nthreads, false); }
     }
