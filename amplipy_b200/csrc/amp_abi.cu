@@ -43,9 +43,15 @@ constexpr int kCtasPerSm = AMP_CTAS;
 // ---------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------
+// two variants of the fused kernel: short-read batches (runs are counted warp-per-run) and indel-rich batches
+// (generic-path reads count their own runs); see amp::cta_trim_pileup
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) amp_trim_pileup_kernel(const __grid_constant__ amp::KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
-    amp::cta_trim_pileup(P, smem, (int)blockIdx.x, (int)blockDim.x);
+    amp::cta_trim_pileup<false>(P, smem, (int)blockIdx.x, (int)blockDim.x);
+}
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) amp_trim_pileup_indel_kernel(const __grid_constant__ amp::KParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    amp::cta_trim_pileup<true>(P, smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
 __device__ const unsigned char kFixedSyms[8] = {'A', 'C', 'G', 'T', 'N', '-', 0, 0};
@@ -153,8 +159,10 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
     P.tiles_per_cta = (P.ntiles + grid - 1) / grid;
     grid = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
     const size_t smem = amp::smem_bytes(P.wt, P.maxseg, P.qbytes, P.sbytes);
+    P.direct = t.direct;
     if (smem > c->max_dyn_smem) {
         CK(cudaFuncSetAttribute(amp_trim_pileup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(amp_trim_pileup_indel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->max_dyn_smem = smem;
     }
 #ifdef AMP_PHASE_TIMING
@@ -162,7 +170,8 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
     if (!d_phase) CK(cudaMalloc((void**)&d_phase, 4096 * 4 * 8));
     P.phase_cycles = d_phase;
 #endif
-    amp_trim_pileup_kernel<<<grid, kThreads, smem, st>>>(P);
+    if (P.direct) amp_trim_pileup_indel_kernel<<<grid, kThreads, smem, st>>>(P);
+    else amp_trim_pileup_kernel<<<grid, kThreads, smem, st>>>(P);
     CK(cudaGetLastError());
 #ifdef AMP_PHASE_TIMING
     {

@@ -66,12 +66,13 @@ struct KParams {
     long long scratch_half;  // sumC + 3N
     int reads_per_tile, ntiles, tiles_per_cta;
     int wt, maxseg, qbytes, sbytes;   // shared-memory carve-up
+    int direct;                       // 1: launch the indel-rich kernel variant
     long long* phase_cycles;          // debug builds (-DAMP_PHASE_TIMING): per-CTA cycles in S, T, W, C
 };
 
 inline double amp_min_d(double a, double b) { return a < b ? a : b; }
 inline double amp_max_d(double a, double b) { return a > b ? a : b; }
-struct TileCfg { int wt, maxseg, qbytes, sbytes, reads_per_tile; };
+struct TileCfg { int wt, maxseg, qbytes, sbytes, reads_per_tile, direct; };
 
 // shared-memory carve-up: three CTAs per SM at <= ~74 KB each (227 KB usable per SM).
 // AMP_TILE="wt,maxseg,qbytes,sbytes,reads_per_tile" overrides it (tuning experiments only).
@@ -79,12 +80,16 @@ inline TileCfg pick_tile_cfg(long long n, long long sum_cig, long long sum_qual,
     TileCfg t;
     const double avg_len = n ? (double)sum_qual / (double)n : 150.0;
     const double avg_ops = n ? (double)sum_cig / (double)n : 2.0;
-    if (avg_ops > 8.0) { t.wt = 512; t.maxseg = 2048; t.qbytes = 17408; t.sbytes = 8704; }      // indel-rich (ONT-like)
+    const bool indel_rich = avg_ops > 8.0;                                                         // ONT-like
+    t.direct = indel_rich ? 1 : 0;
+    if (indel_rich) { t.wt = 1024; t.maxseg = 512; t.qbytes = 4096; t.sbytes = 2048; }
     else { t.wt = 512; t.maxseg = 512; t.qbytes = 33792; t.sbytes = 16896; }
     if (!(mode & AMP_MODE_PILEUP)) { t.wt = 32; t.maxseg = 16; t.sbytes = 16; t.qbytes = 40960; }
     double r = 256.0;
-    r = amp_min_d(r, (double)t.qbytes * 0.97 / amp_max_d(avg_len, 1.0));
-    if (mode & AMP_MODE_PILEUP) r = amp_min_d(r, (double)t.maxseg / (1.5 + 0.75 * avg_ops));
+    if (!indel_rich) {
+        r = amp_min_d(r, (double)t.qbytes * 0.97 / amp_max_d(avg_len, 1.0));
+        if (mode & AMP_MODE_PILEUP) r = amp_min_d(r, (double)t.maxseg / (1.5 + 0.75 * avg_ops));
+    }
     t.reads_per_tile = (int)amp_max_d(8.0, r);
 #ifndef __CUDA_ARCH__
     if (const char* e = getenv("AMP_TILE")) {
@@ -101,6 +106,7 @@ inline TileCfg pick_tile_cfg(long long n, long long sum_cig, long long sum_qual,
 #define AMP_DEFER_MAX 0      // >0: tiles with at most this many generic-path reads defer them to the end of the CTA
 #endif                       // (measured slower on B200: in-tile they overlap with the counting warps; kept for experiments)
 #define AMP_DLIST_CAP 384    // capacity of the per-CTA deferred list
+#define AMP_DIRECT_MIN 32    // tiles with more generic-path reads than this count them thread-serially (DirectSink)
 #define AMP_ROWS (AMP_NCH + 1)   // counts tile rows: 6 channels + one row that collects non-ACGTN bases (KeyError, 753)
 AMP_HD size_t smem_bytes(int wt, int maxseg, int qbytes, int sbytes) {
     return (size_t)AMP_ROWS * wt * 4 + (size_t)maxseg * sizeof(Seg) + 128 + 512 + 4 * AMP_DLIST_CAP + (size_t)qbytes + (size_t)sbytes + 64;
@@ -209,6 +215,43 @@ AMP_HD void prefetch_tile(const KParams& P, long long t0, int tid, int nthreads)
 #endif
 }
 
+// Sink for tiles that are mostly generic-path reads (indel-rich data, e.g. ONT): the planning thread counts its
+// own runs base by base into the CTA's tile.  A run list would hold tens of short runs per read, and one warp per
+// ~10-base run wastes most lanes; here all lanes of the warp stay busy, each on its own read.
+struct DirectSink {
+    const KParams* P; Smem sm; int wbase;
+    const uint8_t* seq_read; const uint8_t* qual_read;
+    unsigned int errs;
+    AMP_HD void match(int rpos, int q, int n) {
+        const int* lut = sm.ctrl + C_LUT;
+        const int minq = P->tp.min_quality;
+        const int w0 = rpos - wbase;
+        if (wbase >= 0 && w0 >= 0 && w0 + n <= P->wt) {
+            int* c = sm.cnt + w0;
+            for (int j = 0; j < n; ++j) {
+                if (qual_read[q + j] < minq) continue;                                   // AmpliPy.py:718
+                atomic_add(c + j + lut[nib_at(seq_read, (uint32_t)(q + j))], 1);         // 752-753 (row 6 = KeyError flag)
+            }
+        } else {
+            for (int j = 0; j < n; ++j) {
+                if (qual_read[q + j] < minq) continue;
+                const int ch = nib_channel(nib_at(seq_read, (uint32_t)(q + j)));
+                if (ch < 0) { errs |= AMP_E_BASE; continue; }
+                count_add(*P, sm.cnt, wbase, ch, rpos + j);
+            }
+        }
+    }
+    AMP_HD void del(int rpos, int n) { for (int j = 0; j < n; ++j) count_add(*P, sm.cnt, wbase, 5, rpos + j); }   // 714-715
+    AMP_HD void ins(int pos, int b, int n) {
+        if (n == 1) {
+            int ch = nib_channel(nib_at(seq_read, (uint32_t)b));
+            if (ch >= 0) { atomic_add(&P->counts[(size_t)ch * P->Lpad + pos], 1); return; }
+        }
+        TileSink::Text t; t.seq = seq_read; t.b = b;
+        ins_table_add(P->tab, P->gpos_base + pos, n, t, 1);
+    }
+};
+
 // Everything a thread needs to know about the tile it is working on.
 struct TileCtx {
     long long t0; int nreads;
@@ -218,7 +261,8 @@ struct TileCtx {
 
 // Generic per-read path: trim_read loop for loop + plan_read.  Used for every read that is not [S]M[S]
 // (indels, hard clips, ...) and for the corner cases the closed form declines.
-AMP_HD void read_generic(const KParams& P, const Smem& sm, const TileCtx& T, int rr) {
+template <bool DIRECT>
+AMP_HD void read_generic(const KParams& P, const Smem& sm, const TileCtx& T, int rr, bool direct, int wbase) {
     const long long i = T.t0 + rr;
     const uint32_t c0 = P.b.cig_off[i], c1 = P.b.cig_off[i + 1];
     const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
@@ -246,7 +290,12 @@ AMP_HD void read_generic(const KParams& P, const Smem& sm, const TileCtx& T, int
         cig = res;
         P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)f;
     }
-    if (T.do_pile && !(f & AMP_F_ERROR)) {
+    if (DIRECT && T.do_pile && !(f & AMP_F_ERROR) && direct) {
+        DirectSink sink; sink.P = &P; sink.sm = sm; sink.wbase = wbase; sink.seq_read = seq; sink.qual_read = qual; sink.errs = 0;
+        int e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
+        e |= (int)sink.errs;
+        if (e) atomic_or(P.err, (unsigned)e);
+    } else if (T.do_pile && !(f & AMP_F_ERROR)) {
         TileSink sink; sink.P = &P; sink.sm = sm;
         sink.staged = q_st && s_st;
         sink.qabs0 = sink.staged ? qo0 - T.q_lo : qo0;
@@ -322,7 +371,10 @@ AMP_HD void count_runs(const KParams& P, const Smem& sm, int lo, int hi, int wba
     if (errs) atomic_or(P.err, errs);
 }
 
-// The fused CTA body.  `block` / `nthreads` are blockIdx.x / blockDim.x on the device.
+// The fused CTA body.  `block` / `nthreads` are blockIdx.x / blockDim.x on the device.  DIRECT = variant for
+// indel-rich batches (generic-path reads count their own runs, DirectSink); the two variants are separate kernels so
+// that the common short-read kernel does not carry the extra code.
+template <bool DIRECT>
 AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int block, int nthreads) {
     const Smem sm = carve(smem_base, P);
     const bool do_trim = P.mode & AMP_MODE_TRIM, do_pile = P.mode & AMP_MODE_PILEUP;
@@ -340,6 +392,7 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
     uint16_t* clist = (uint16_t*)(sm.ctrl + C_CLIST);
     uint32_t* dlist = (uint32_t*)(sm.ctrl + C_DLIST);   // reads deferred to the end of the CTA (absolute index - P.b.first)
     int ndef = 0;                                        // uniform
+    (void)dlist; (void)ndef;
     const int tile_lo = block * P.tiles_per_cta;
     int tile_hi = tile_lo + P.tiles_per_cta; if (tile_hi > P.ntiles) tile_hi = P.ntiles;
     for (int tile = tile_lo; tile < tile_hi; ++tile) {
@@ -433,12 +486,14 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
         // A handful of queued reads would keep one warp on the slow generic path for the whole tile: collect them
         // and run them together at the end of the CTA (unstaged, but with every lane busy).  Tiles that are mostly
         // generic (indel-rich data) are processed in place, where their rows are staged.
+#if AMP_DEFER_MAX > 0
         if (ncpx > 0 && ncpx <= AMP_DEFER_MAX && ndef + ncpx <= AMP_DLIST_CAP) {
             AMP_FOR_THREADS(tid, nthreads) {
                 if (tid < ncpx) dlist[ndef + tid] = (uint32_t)(T.t0 - P.b.first) + clist[tid];
             }
             ndef += ncpx; ncpx = 0;
         }
+#endif
         if (do_pile) {
             const int tmin = sm.ctrl[C_TMIN], tmax = sm.ctrl[C_TMAX];
             if (tmax >= 0 && (wbase < 0 || tmin < wbase || tmax > wbase + P.wt)) {
@@ -453,7 +508,7 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
         // ---- T1 + C: queued reads take the generic path (their runs go to the tail of the list) while the other
         // warps already count the runs planned in T0.
         AMP_FOR_THREADS(tid, nthreads) {
-            for (int k = tid; k < ncpx; k += nthreads) read_generic(P, sm, T, (int)clist[k]);
+            for (int k = tid; k < ncpx; k += nthreads) read_generic<DIRECT>(P, sm, T, (int)clist[k], DIRECT && ncpx > AMP_DIRECT_MIN, wbase);
         }
         if (do_pile) {
             AMP_FOR_THREADS(tid, nthreads) { count_runs(P, sm, 0, nseg0, wbase, tid, nthreads, (ncpx + 31) >> 5); }
@@ -471,6 +526,7 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
     if (threadIdx.x == 0 && P.phase_cycles) for (int k = 0; k < 4; ++k) P.phase_cycles[(size_t)block * 4 + k] = tacc[k];
 #endif
     // ---- D: deferred reads of the whole CTA, generic path straight from global memory ----------------------------
+#if AMP_DEFER_MAX > 0
     if (ndef > 0) {
         TileCtx T;
         T.t0 = P.b.first; T.nreads = 0; T.q_lo = T.q_hi = T.s_lo = T.s_hi = 0; T.do_trim = do_trim; T.do_pile = do_pile;
@@ -479,7 +535,7 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
         }
         AMP_SYNC();
         AMP_FOR_THREADS(tid, nthreads) {
-            for (int k = tid; k < ndef; k += nthreads) read_generic(P, sm, T, (int)dlist[k]);
+            for (int k = tid; k < ndef; k += nthreads) read_generic<DIRECT>(P, sm, T, (int)dlist[k], false, wbase);
         }
         AMP_SYNC();
         if (do_pile) {
@@ -496,6 +552,7 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
             AMP_SYNC();
         }
     }
+#endif
     if (do_pile && wbase >= 0) {
         AMP_FOR_THREADS(tid, nthreads) { flush_tile(P, sm.cnt, wbase, tid, nthreads, false); }
     }

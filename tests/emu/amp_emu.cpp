@@ -78,7 +78,11 @@ int emu_process(void* h, long long first, long long n, const int32_t* pos, const
     std::vector<unsigned char> smem(amp::smem_bytes(P.wt, P.maxseg, P.qbytes, P.sbytes) + 64);
     unsigned char* sbase = smem.data();
     sbase += (16 - ((uintptr_t)sbase & 15)) & 15;
-    for (int b = 0; b < grid; ++b) amp::cta_trim_pileup(P, sbase, b, threads ? threads : 256);
+    P.direct = t.direct;
+    for (int b = 0; b < grid; ++b) {
+        if (P.direct) amp::cta_trim_pileup<true>(P, sbase, b, threads ? threads : 256);
+        else amp::cta_trim_pileup<false>(P, sbase, b, threads ? threads : 256);
+    }
     return 0;
 }
 
