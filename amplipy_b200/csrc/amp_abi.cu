@@ -34,7 +34,10 @@ int fail(int code, const char* what, const char* detail = "") {
         }                                                                                         \
     } while (0)
 
-constexpr int kThreads = 256;
+#ifndef AMP_THREADS
+#define AMP_THREADS 256
+#endif
+constexpr int kThreads = AMP_THREADS;
 #ifndef AMP_CTAS
 #define AMP_CTAS 3
 #endif

@@ -308,10 +308,17 @@ AMP_HD void read_generic(const KParams& P, const Smem& sm, const TileCtx& T, int
     }
 }
 
-// Count phase over runs [lo, hi) of the tile's list: one warp per run, lanes over consecutive bases.
+// Count phase over runs [lo, hi) of the tile's list.  A warp works on 32/AMP_SUBWARP runs at once: each group of
+// AMP_SUBWARP lanes takes one run and steps over it AMP_SUBWARP consecutive bases at a time.  Runs after trimming
+// average ~75 bases, so narrower groups waste fewer lanes on the last step and share the per-run set-up across
+// several runs; within a group consecutive lanes still hit consecutive banks of one tile row.
 // Warps [0, skip_warps) do not take part (they are busy with the generic path of queued reads).
+#ifndef AMP_SUBWARP
+#define AMP_SUBWARP 8
+#endif
 AMP_HD void count_runs(const KParams& P, const Smem& sm, int lo, int hi, int wbase, int tid, int nthreads, int skip_warps) {
-    const int lane = tid & 31;
+    constexpr int SW = AMP_SUBWARP, GROUPS = 32 / SW;
+    const int lane = tid & 31, l = lane % SW, sub = lane / SW;
     int warp = tid >> 5, nwarps = nthreads >> 5 ? nthreads >> 5 : 1;
     if (skip_warps >= nwarps) skip_warps = 0;
     if (warp < skip_warps) return;
@@ -319,47 +326,40 @@ AMP_HD void count_runs(const KParams& P, const Smem& sm, int lo, int hi, int wba
     const int* lut = sm.ctrl + C_LUT;
     const int minq = P.tp.min_quality;
     unsigned errs = 0;
-    for (int s = lo + warp % nwarps; s < hi; s += nwarps) {
+    for (int s = lo + (warp % nwarps) * GROUPS + sub; s < hi; s += nwarps * GROUPS) {
         const Seg sg = sm.segs[s];
         const int n = sg.len & 0x3FFFFFFF;
         const int w0 = sg.rpos - wbase;
         const bool in_win = wbase >= 0 && w0 >= 0 && w0 + n <= P.wt;                // uniform per run
         if (sg.len < 0) {
-            if (in_win) { for (int j = lane; j < n; j += 32) atomic_add(&sm.cnt[5 * P.wt + w0 + j], 1); }
-            else for (int j = lane; j < n; j += 32) count_add(P, sm.cnt, wbase, 5, sg.rpos + j);
+            if (in_win) { for (int j = l; j < n; j += SW) atomic_add(&sm.cnt[5 * P.wt + w0 + j], 1); }
+            else for (int j = l; j < n; j += SW) count_add(P, sm.cnt, wbase, 5, sg.rpos + j);
             continue;
         }
         const bool staged = (sg.len & 0x40000000) != 0;
         if (in_win && staged) {
-            // fast path: everything in shared memory, no per-base branches.  Lanes take consecutive bases ->
-            // consecutive tile words of one row per lane: bank = position % 32, conflict-free.  Tail lanes
-            // (j >= n) read at most 31 bytes past the run, which stays inside the padded staging buffers;
-            // the predicate discards them.
-            const uint8_t* q = sm.qual + sg.qabs + lane;
-            const uint32_t nb0 = sg.nibabs + (uint32_t)lane;
+            // fast path: everything in shared memory, no per-base branches.  Tail lanes (j >= n) read at most
+            // SW-1 bytes past the run, which stays inside the padded staging buffers; the predicate discards them.
+            const uint8_t* q = sm.qual + sg.qabs + l;
+            const uint32_t nb0 = sg.nibabs + (uint32_t)l;
             const uint32_t shift = (~nb0 & 1u) << 2;
             const uint8_t* sb = sm.seq + (nb0 >> 1);
-            int* c = sm.cnt + w0 + lane;
-            const int left = n - lane;                                             // this lane has bases lane, lane+32, ... < n
-            const int iters = (n + 31) >> 5;
-#define AMP_COUNT_STEP(u_)                                                                          \
-            {                                                                                       \
-                const int qv = q[32 * (u_)];                                                        \
-                const uint32_t nib = ((uint32_t)sb[16 * (u_)] >> shift) & 15u;                      \
-                const int row = lut[nib];                                                           \
-                if (left > 32 * (u_) && qv >= minq) atomic_add(c + 32 * (u_) + row, 1);             \
+            int* c = sm.cnt + w0 + l;
+            const int left = n - l;                                                // this lane has bases l, l+SW, ... < n
+            const int iters = (n + SW - 1) / SW;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+            for (int u = 0; u < iters; ++u) {
+                const int qv = q[SW * u];
+                const uint32_t nib = ((uint32_t)sb[(SW / 2) * u] >> shift) & 15u;
+                const int row = lut[nib];
+                if (left > SW * u && qv >= minq) atomic_add(c + SW * u + row, 1);   // AmpliPy.py:718, 752-753
             }
-            AMP_COUNT_STEP(0)                                                       /* AmpliPy.py:718, 752-753 */
-            if (iters > 1) AMP_COUNT_STEP(1)
-            if (iters > 2) AMP_COUNT_STEP(2)
-            if (iters > 3) AMP_COUNT_STEP(3)
-            if (iters > 4) AMP_COUNT_STEP(4)
-            for (int u = 5; u < iters; ++u) AMP_COUNT_STEP(u)
-#undef AMP_COUNT_STEP
         } else {
             const uint8_t* qp = staged ? sm.qual + sg.qabs : P.b.qual + sg.qabs;
             const uint8_t* sp = staged ? sm.seq : P.b.seq;
-            for (int j = lane; j < n; j += 32) {
+            for (int j = l; j < n; j += SW) {
                 if (qp[j] < minq) continue;
                 const uint32_t nb = sg.nibabs + (uint32_t)j;
                 const int ch = nib_channel((sp[nb >> 1] >> ((~nb & 1u) << 2)) & 15u);
