@@ -92,6 +92,17 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def ncu_traffic(n_reads):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json, taken on the 1M-read config-2 launch); None for other workload sizes."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))
+        return float(d["traffic_bytes_per_launch"]) if n_reads == 1_000_000 else None
+    except Exception:
+        return None
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -134,7 +145,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": workload_config(args, sample),
+            "config": workload_config(args, args.reads),
             "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "port",
                              "sample": "first %d reads of the workload, oracle/amplipy_oracle.c (C+OpenMP restatement of AmpliPy.py), %d threads" % (sample, cores)},
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -300,7 +311,7 @@ def main():
                     "note": "amp_process_host (pinned host SoA -> chunked H2D -> fused kernel -> D2H trim outputs) + amp_call (D2H call outputs)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "amp_trim_pileup_kernel", "kernel_ms": kern_ms,
+                         "traffic": ncu_traffic(b.n) if args.workload == "illumina" else None, "kernel": "amp_trim_pileup_kernel", "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": in_bytes + out_bytes, "bytes_per_read": (in_bytes + out_bytes) / b.n,
                          "peak_source": peak_src, "kernel_share_of_step": kern_ms / ms_per_step},
             "clocks": sampler.summary(), "device_error_flags": flags_dev,
