@@ -232,3 +232,45 @@ def test_multi_gpu_sharding_nccl():
                         "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "tests", "dist_gpu_check.py")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0 and "dist_gpu_check ok" in r.stdout, r.stdout[-3000:]
+
+
+def _long_read_batch(L, n, seed, read_len=(3000, 9000)):
+    """PacBio/ONT-like long reads: rows far larger than the staging buffers, hundreds of CIGAR ops (global scratch
+    rows), deletions/insertions/skips everywhere."""
+    rng = np.random.default_rng(seed)
+    g = synth.random_genome(L, seed)
+    recs = []
+    for _ in range(n):
+        target = int(rng.integers(*read_len))
+        ops = []
+        if rng.random() < 0.5:
+            ops.append((4, int(rng.integers(1, 60))))
+        rl = 0
+        while rl < target:
+            m = int(rng.integers(5, 120))
+            ops.append((0, m)); rl += m
+            r = rng.random()
+            if r < 0.4:
+                ops.append((1, int(rng.integers(1, 6))))
+            elif r < 0.8:
+                d = int(rng.integers(1, 8)); ops.append((2, d)); rl += d
+        if ops[-1][0] != 0:
+            ops.append((0, 10)); rl += 10
+        if rng.random() < 0.5:
+            ops.append((4, int(rng.integers(1, 60))))
+        pos = int(rng.integers(1, L - rl - 2))
+        ql = sum(x for op, x in ops if op in (0, 1, 4))
+        seq = "".join(rng.choice(list("ACGT"), size=ql))
+        qual = rng.integers(5, 40, ql).tolist()
+        recs.append((pos, int(rng.choice([0, 16])), 0, ops, seq, qual))
+    recs.sort(key=lambda r: r[0])
+    return g, ReadBatch.from_records(recs)
+
+
+def test_long_reads_vs_oracle(oracle_lib):
+    L = 30000
+    g, b = _long_read_batch(L, 300, seed=77)
+    primers, _ = synth.make_scheme(L, 60, amp_len=500, seed=9)
+    prim = [(s, e) for s, e, _ in primers]
+    assert int(b.n_cigar.max()) > 100 and int(b.l_seq.max()) > 5000
+    _against_oracle(oracle_lib, b, g, prim, mq=15, ins_slots=1 << 20, arena=64 << 20)
