@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "../../include/amplipy_b200.h"
-#include "amp_kernels.cuh"
+#include "amp_warp.cuh"
 
 static_assert(AMP_F_TRIM_START == AMP_FLAG_TRIM_START && AMP_F_KEEP == AMP_FLAG_KEEP && AMP_F_SKIPPED == AMP_FLAG_SKIPPED &&
                   AMP_F_ERROR == AMP_FLAG_ERROR && AMP_E_ARENA_FULL == AMP_DEVERR_ARENA_FULL,
@@ -55,6 +55,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) amp_trim_pileup_kernel(c
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) amp_trim_pileup_indel_kernel(const __grid_constant__ amp::KParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     amp::cta_trim_pileup<true>(P, smem, (int)blockIdx.x, (int)blockDim.x);
+}
+
+// warp-autonomous kernel for short-read batches (amp_warp.cuh): one CTA per SM, AMP7_WARPS independent warps
+template <bool TRIM, bool PILE>
+__global__ void __launch_bounds__(AMP7_WARPS * 32, 1) amp_trim_pileup_v7_kernel(const __grid_constant__ amp::KParams P) {
+    extern __shared__ __align__(128) unsigned char smem7[];
+    amp::cta_trim_pileup_v7<TRIM, PILE, AMP7_WT>(P, smem7);
 }
 
 __device__ const unsigned char kFixedSyms[8] = {'A', 'C', 'G', 'T', 'N', '-', 0, 0};
@@ -123,6 +130,7 @@ struct amp_ctx {
     DevChunk chunk[3];
     int last_launches = 0;
     size_t max_dyn_smem = 0;
+    bool v7_attr = false;
     unsigned char* d_ref = nullptr;     // reference characters (amp_set_reference)
     unsigned char* d_call = nullptr;    // calling outputs (one block, offsets below)
     size_t o_depth = 0, o_top = 0, o_topc = 0, o_fl = 0, o_refc = 0, o_ff = 0, o_fr = 0, o_alt = 0, o_if = 0, o_ir = 0, o_ia = 0;
@@ -156,6 +164,30 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
     P.scratch = scratch; P.scratch_half = sum_cig + 3 * b.n;
     (void)max_cig;
     const amp::TileCfg t = amp::pick_tile_cfg(b.n, sum_cig, sum_qual, mode);
+    // short-read batches: warp-autonomous kernel.  AMP_KERNEL=tile forces the older CTA-phased kernel (A/B experiments).
+    static const bool force_tile = [] { const char* e = getenv("AMP_KERNEL"); return e && !strcmp(e, "tile"); }();
+    if (!t.direct && !force_tile && sum_qual <= 1000 * b.n) {
+        const amp::V7Cfg v = amp::pick_v7_cfg(b.n, sum_qual, c->sm_count);
+        P.wt = v.wt; P.reads_per_tile = v.batch_reads;
+        P.ntiles = (int)((b.n + v.batch_reads - 1) / v.batch_reads);
+        int grid = std::max(1, std::min(P.ntiles, c->sm_count));
+        P.tiles_per_cta = (P.ntiles + grid - 1) / grid;
+        grid = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
+        const size_t smem = amp::smem_bytes_v7(P.wt, AMP7_WARPS);
+        if (!c->v7_attr) {
+            CK(cudaFuncSetAttribute(amp_trim_pileup_v7_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_v7_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_v7_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            c->v7_attr = true;
+        }
+        const bool tr = mode & AMP_MODE_TRIM, pl = mode & AMP_MODE_PILEUP;
+        if (tr && pl) amp_trim_pileup_v7_kernel<true, true><<<grid, AMP7_WARPS * 32, smem, st>>>(P);
+        else if (tr) amp_trim_pileup_v7_kernel<true, false><<<grid, AMP7_WARPS * 32, smem, st>>>(P);
+        else amp_trim_pileup_v7_kernel<false, true><<<grid, AMP7_WARPS * 32, smem, st>>>(P);
+        CK(cudaGetLastError());
+        c->last_launches += 1;
+        return AMP_OK;
+    }
     P.wt = t.wt; P.maxseg = t.maxseg; P.qbytes = t.qbytes; P.sbytes = t.sbytes; P.reads_per_tile = t.reads_per_tile;
     P.ntiles = (int)((b.n + t.reads_per_tile - 1) / t.reads_per_tile);
     int grid = std::min(P.ntiles, c->sm_count * kCtasPerSm);

@@ -391,9 +391,8 @@ AMP_HD bool classify_simple(const uint32_t* cig, int nc, int l_seq, SimpleRead& 
     if (k < nc) { if (c_op(cig[k]) != OP_S) return false; r.s2 = c_len(cig[k]); if (r.s2 < 1) return false; ++k; }
     return k == nc && r.m >= 1 && r.s1 + r.m + r.s2 == l_seq;
 }
-// On success: r = final shape, pos = final reference_start, returns AMP_F_* bits (incl. KEEP) in *flags_out.
-AMP_HD bool trim_simple(SimpleRead& r, int& pos, int flag, int tlen, int l_seq, const uint8_t* qual, bool qual_padded,
-                        const TrimParams& P, int* flags_out) {
+// Steps 1-2 (primer start / end) of the closed form.  On success r / pos hold the shape after primer clipping.
+AMP_HD bool trim_simple_primers(SimpleRead& r, int& pos, int flag, int tlen, int l_seq, const TrimParams& P, int* flags_out) {
     const int p = pos, ref_end = p + r.m;
     if (p < 0 || ref_end > P.L) return false;
     const bool paired = flag & 1, rev = (flag & 16) != 0;
@@ -412,15 +411,30 @@ AMP_HD bool trim_simple(SimpleRead& r, int& pos, int flag, int tlen, int l_seq, 
         if (e < 1 || e >= m) return false;
         f |= AMP_F_TRIM_END; s2 += m - e; m = e;
     }
-    const bool w4 = qual_padded && P.window == 4;
-    const uint8_t* q = qual + s1;
-    const int del = w4 ? window_del_len_w4(q, m, P.min_quality, rev)
-                       : (rev ? window_del_len_rev(q, m, P.window, P.min_quality) : window_del_len_fwd(q, m, P.window, P.min_quality));
-    if (rev) { if (del >= 2) { f |= AMP_F_TRIM_QUAL; s1 += del; m -= del; } }          // pos stays (F6)
-    else if (del != 0) { f |= AMP_F_TRIM_QUAL; s2 += del; m -= del; }
-    const int ref_len = m > 0 ? m : 1;
-    if (ref_len >= P.min_length && ((f & (AMP_F_TRIM_START | AMP_F_TRIM_END)) || P.include_no_primer)) f |= AMP_F_KEEP;   // 910
     r.s1 = s1; r.m = m; r.s2 = s2; pos = pp; *flags_out = f;
+    return true;
+}
+// Step 3 (quality clip, given the window search result `del` over the aligned run) + the write gate (910).
+AMP_HD void trim_simple_finish(SimpleRead& r, int del, bool rev, const TrimParams& P, int* flags_io) {
+    int f = *flags_io;
+    if (rev) { if (del >= 2) { f |= AMP_F_TRIM_QUAL; r.s1 += del; r.m -= del; } }      // pos stays (F6)
+    else if (del != 0) { f |= AMP_F_TRIM_QUAL; r.s2 += del; r.m -= del; }
+    const int ref_len = r.m > 0 ? r.m : 1;
+    if (ref_len >= P.min_length && ((f & (AMP_F_TRIM_START | AMP_F_TRIM_END)) || P.include_no_primer)) f |= AMP_F_KEEP;   // 910
+    *flags_io = f;
+}
+// On success: r = final shape, pos = final reference_start, returns AMP_F_* bits (incl. KEEP) in *flags_out.
+AMP_HD bool trim_simple(SimpleRead& r, int& pos, int flag, int tlen, int l_seq, const uint8_t* qual, bool qual_padded,
+                        const TrimParams& P, int* flags_out) {
+    int f = 0;
+    if (!trim_simple_primers(r, pos, flag, tlen, l_seq, P, &f)) return false;
+    const bool rev = (flag & 16) != 0;
+    const bool w4 = qual_padded && P.window == 4;
+    const uint8_t* q = qual + r.s1;
+    const int del = w4 ? window_del_len_w4(q, r.m, P.min_quality, rev)
+                       : (rev ? window_del_len_rev(q, r.m, P.window, P.min_quality) : window_del_len_fwd(q, r.m, P.window, P.min_quality));
+    trim_simple_finish(r, del, rev, P, &f);
+    *flags_out = f;
     return true;
 }
 // final CIGAR of a simple read: [S] [M] [S]; an emptied aligned run leaves one merged soft clip (fix_cigar)

@@ -22,7 +22,6 @@
 #if defined(__CUDA_ARCH__)
 #define AMP_FOR_THREADS(tid, nthreads) for (int tid = threadIdx.x, once_ = 1; once_; once_ = 0)
 #define AMP_SYNC() __syncthreads()
-#define AMP_SYNCWARP() __syncwarp()
 #ifdef AMP_PHASE_TIMING
 #define AMP_TICK(k) do { if (threadIdx.x == 0) { long long t_ = clock64(); tacc[k] += t_ - tlast; tlast = t_; } } while (0)
 #else
@@ -32,7 +31,6 @@
 #define AMP_TICK(k) ((void)0)
 #define AMP_FOR_THREADS(tid, nthreads) for (int tid = 0; tid < (nthreads); ++tid)
 #define AMP_SYNC() ((void)0)
-#define AMP_SYNCWARP() ((void)0)
 #endif
 
 namespace amp {
@@ -557,373 +555,6 @@ AMP_HD void cta_trim_pileup(const KParams& P, unsigned char* smem_base, int bloc
 #endif
     if (do_pile && wbase >= 0) {
         AMP_FOR_THREADS(tid, nthreads) { flush_tile(P, sm.cnt, wbase, tid, nthreads, false); }
-    }
-}
-
-// ===================================================================================================
-// Warp-autonomous short-read kernel body (no block barrier in the steady state).
-//
-// One CTA per SM, AMP_WG_WARPS warps.  Every warp owns a slice of shared memory (row staging buffers, a run list, a
-// queue) and loops over its own groups of 32 consecutive reads:
-//   S  stage the group's qual / seq byte ranges (uint4 loads, lanes strided)               -> __syncwarp
-//   T  one lane per read: closed-form trim of [S]M[S] reads, trim outputs, one run descriptor;
-//      any other read is appended to the warp's queue                                       -> __syncwarp
-//   C  count the group's runs into the CTA-wide tile (groups of 8 lanes per run)            -> __syncwarp
-//   G  whenever 32 reads are queued: stage their (scattered) rows into fixed slots, run the generic path with all
-//      32 lanes busy (trim_read + plan_read), count the resulting runs
-// Warps never wait for each other, so a slow generic batch or a long quality scan only delays its own warp.
-// The count tile covers [wbase, wbase + wt) from the first read of the CTA's (coordinate-sorted) chunk; runs
-// that fall outside it use global atomics.  One block barrier before the final flush.
-// ===================================================================================================
-#ifndef AMP_WG_WARPS
-#define AMP_WG_WARPS 20
-#endif
-#define AMP_WG_RUNCAP 96       // run descriptors per warp (32 fast runs, or the runs of one generic batch)
-#define AMP_WG_QCAP 64         // queued generic-path reads per warp
-#define AMP_WG_QSLOT 176       // G phase: bytes per staged quality row slot (150 + alignment slack)
-#define AMP_WG_SSLOT 96        // G phase: bytes per staged sequence row slot
-#define AMP_WG_QBYTES (32 * AMP_WG_QSLOT)
-#define AMP_WG_SBYTES (32 * AMP_WG_SSLOT)
-#define AMP_WG_WARP_BYTES (AMP_WG_RUNCAP * 16 + AMP_WG_QCAP * 4 + 32 + AMP_WG_QBYTES + AMP_WG_SBYTES)
-
-AMP_HD size_t smem_bytes_wg(int wt, int warps) {
-    return (size_t)AMP_ROWS * wt * 4 + 256 + (size_t)warps * AMP_WG_WARP_BYTES + 64;
-}
-
-struct WarpMem {
-    Seg* runs; uint32_t* queue; int* ctr;   // ctr[0] = runs in the list, ctr[1] = queued reads
-    uint8_t* qual; uint8_t* seq;
-};
-AMP_HD WarpMem carve_warp(unsigned char* base, int wt, int w) {
-    unsigned char* b = base + (size_t)AMP_ROWS * wt * 4 + 256 + (size_t)w * AMP_WG_WARP_BYTES;
-    WarpMem m;
-    m.runs = (Seg*)b; b += AMP_WG_RUNCAP * 16;
-    m.queue = (uint32_t*)b; b += AMP_WG_QCAP * 4;
-    m.ctr = (int*)b; b += 32;
-    m.qual = b; b += AMP_WG_QBYTES;
-    m.seq = b;
-    return m;
-}
-
-// sink of the generic path inside a warp: runs go to the warp's list, insertion alleles to the global table
-struct WarpSink {
-    const KParams* P; WarpMem wm;
-    uint32_t qabs0, nibabs0; bool staged;
-    const uint8_t* seq_read; const uint8_t* qual_read;
-    unsigned int errs;
-    AMP_HD void push(int rpos, int len_kind, int q) {
-        const int idx = atomic_add(&wm.ctr[0], 1);
-        if (idx < AMP_WG_RUNCAP) {
-            Seg s; s.rpos = rpos; s.len = len_kind | (staged ? 0x40000000 : 0); s.qabs = qabs0 + (uint32_t)q; s.nibabs = nibabs0 + (uint32_t)q;
-            wm.runs[idx] = s;
-        } else {   // list full: exact serial path into the global matrix
-            const int n = len_kind & 0x3FFFFFFF;
-            if (len_kind < 0) { for (int j = 0; j < n; ++j) atomic_add(&P->counts[(size_t)5 * P->Lpad + rpos + j], 1); }
-            else for (int j = 0; j < n; ++j) {
-                if (qual_read[q + j] < P->tp.min_quality) continue;
-                const int ch = nib_channel(nib_at(seq_read, (uint32_t)(q + j)));
-                if (ch < 0) { errs |= AMP_E_BASE; continue; }
-                atomic_add(&P->counts[(size_t)ch * P->Lpad + rpos + j], 1);
-            }
-        }
-    }
-    AMP_HD void match(int rpos, int q, int n) { push(rpos, n, q); }
-    AMP_HD void del(int rpos, int n) { push(rpos, (int)(0x80000000u | (unsigned)n), 0); }
-    AMP_HD void ins(int pos, int b, int n) {
-        if (n == 1) {
-            const int ch = nib_channel(nib_at(seq_read, (uint32_t)b));
-            if (ch >= 0) { atomic_add(&P->counts[(size_t)ch * P->Lpad + pos], 1); return; }
-        }
-        TileSink::Text t; t.seq = seq_read; t.b = b;
-        ins_table_add(P->tab, P->gpos_base + pos, n, t, 1);
-    }
-};
-
-// count the warp's runs [0, n): groups of AMP_SUBWARP lanes per run (same inner loop as count_runs)
-AMP_HD void count_warp_runs(const KParams& P, int* cnt, const int* lut, const WarpMem& wm, int n_runs, int wbase, int lane) {
-    constexpr int SW = AMP_SUBWARP, GROUPS = 32 / SW;
-    const int l = lane % SW, sub = lane / SW;
-    const int minq = P.tp.min_quality;
-    unsigned errs = 0;
-    for (int s = sub; s < n_runs; s += GROUPS) {
-        const Seg sg = wm.runs[s];
-        const int n = sg.len & 0x3FFFFFFF;
-        const int w0 = sg.rpos - wbase;
-        const bool in_win = wbase >= 0 && w0 >= 0 && w0 + n <= P.wt;
-        if (sg.len < 0) {
-            if (in_win) { for (int j = l; j < n; j += SW) atomic_add(&cnt[5 * P.wt + w0 + j], 1); }
-            else for (int j = l; j < n; j += SW) count_add(P, cnt, wbase, 5, sg.rpos + j);
-            continue;
-        }
-        const bool staged = (sg.len & 0x40000000) != 0;
-        if (in_win && staged) {
-            const uint8_t* q = wm.qual + sg.qabs + l;
-            const uint32_t nb0 = sg.nibabs + (uint32_t)l;
-            const uint32_t shift = (~nb0 & 1u) << 2;
-            const uint8_t* sb = wm.seq + (nb0 >> 1);
-            int* c = cnt + w0 + l;
-            const int left = n - l;
-            const int iters = (n + SW - 1) / SW;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 4
-#endif
-            for (int u = 0; u < iters; ++u) {
-                const int qv = q[SW * u];
-                const uint32_t nib = ((uint32_t)sb[(SW / 2) * u] >> shift) & 15u;
-                const int row = lut[nib];
-                if (left > SW * u && qv >= minq) atomic_add(c + SW * u + row, 1);   // AmpliPy.py:718, 752-753
-            }
-        } else {
-            const uint8_t* qp = staged ? wm.qual + sg.qabs : P.b.qual + sg.qabs;
-            const uint8_t* sp = staged ? wm.seq : P.b.seq;
-            for (int j = l; j < n; j += SW) {
-                if (qp[j] < minq) continue;
-                const uint32_t nb = sg.nibabs + (uint32_t)j;
-                const int ch = nib_channel((sp[nb >> 1] >> ((~nb & 1u) << 2)) & 15u);
-                if (ch < 0) { errs |= AMP_E_BASE; continue; }
-                count_add(P, cnt, wbase, ch, sg.rpos + j);
-            }
-        }
-    }
-    if (errs) atomic_or(P.err, errs);
-}
-
-// generic path for one queued read inside a warp (rows staged in the warp's slot `slot`, or global if they do not fit)
-AMP_HD void warp_read_generic(const KParams& P, const WarpMem& wm, long long i, int slot, bool do_trim, bool do_pile) {
-    const uint32_t c0 = P.b.cig_off[i], c1 = P.b.cig_off[i + 1];
-    const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
-    const uint32_t so0 = P.b.seq_off[i], so1 = P.b.seq_off[i + 1];
-    int nc = (int)(c1 - c0);
-    const int l_seq = (int)(qo1 - qo0);
-    const int flag = P.b.flag[i];
-    int pos = P.b.pos[i];
-    const uint32_t qdst = (uint32_t)slot * AMP_WG_QSLOT + (qo0 & 15u), sdst = (uint32_t)slot * AMP_WG_SSLOT + (so0 & 15u);
-    const bool q_st = (qo0 & 15u) + (qo1 - qo0) + 16u <= AMP_WG_QSLOT;     // row + read-ahead slack fit the slot
-    const bool s_st = do_pile && (so0 & 15u) + (so1 - so0) <= AMP_WG_SSLOT;
-    const uint8_t* qual = q_st ? wm.qual + qdst : P.b.qual + qo0;
-    const uint8_t* seq = s_st ? wm.seq + sdst : P.b.seq + so0;
-    const uint32_t* cig = P.b.cigar + c0;
-    uint32_t la[AMP_CMAX], lb[AMP_CMAX];
-    int f = 0;
-    if (do_trim) {
-        uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
-        uint32_t *A, *B;
-        if (nc + 3 <= AMP_CMAX) { A = la; B = lb; }
-        else { A = P.scratch + (size_t)c0 + 3 * (size_t)i; B = A + P.scratch_half; }
-        for (int k = 0; k < nc; ++k) A[k] = cig[k];
-        uint32_t* res;
-        // the word-wise window search reads up to 8 bytes before the row: slot 0 with a row at offset < 8 would leave
-        // the warp's buffer, so it uses the rolling search there
-        f = trim_read(A, B, nc, pos, flag, P.b.tlen[i], l_seq, qual, q_st && qdst >= 8, P.tp, &res);
-        if (f & AMP_F_ERROR) { nc = 0; f = AMP_F_ERROR; atomic_or(P.err, AMP_E_COORD); }
-        for (int k = 0; k < nc; ++k) orow[k] = res[k];
-        cig = res;
-        P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)f;
-    }
-    if (do_pile && !(f & AMP_F_ERROR)) {
-        WarpSink sink; sink.P = &P; sink.wm = wm;
-        sink.staged = q_st && s_st;
-        sink.qabs0 = sink.staged ? qdst : qo0;
-        sink.nibabs0 = sink.staged ? sdst * 2u : so0 * 2u;
-        sink.seq_read = seq; sink.qual_read = qual; sink.errs = 0;
-        int e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
-        e |= (int)sink.errs;
-        if (e) atomic_or(P.err, (unsigned)e);
-    }
-}
-
-#if defined(__CUDA_ARCH__)
-#define AMP_FOR_WARPS(w, nw) for (int w = threadIdx.x >> 5, once_w_ = 1; once_w_; once_w_ = 0)
-#define AMP_FOR_LANES(lane) for (int lane = threadIdx.x & 31, once_l_ = 1; once_l_; once_l_ = 0)
-#else
-#define AMP_FOR_WARPS(w, nw) for (int w = 0; w < (nw); ++w)
-#define AMP_FOR_LANES(lane) for (int lane = 0; lane < 32; ++lane)
-#endif
-
-AMP_HD void cta_trim_pileup_warps(const KParams& P, unsigned char* smem_base, int block, int nthreads) {
-    const int nw = nthreads >> 5;
-    const bool do_trim = P.mode & AMP_MODE_TRIM, do_pile = P.mode & AMP_MODE_PILEUP;
-    int* cnt = (int*)smem_base;
-    int* ctrl = (int*)(smem_base + (size_t)AMP_ROWS * P.wt * 4);
-    const int* lut = ctrl + C_LUT;
-    const int ncnt = AMP_ROWS * P.wt;
-    const long long g_lo = (long long)block * P.tiles_per_cta;
-    long long g_hi = g_lo + P.tiles_per_cta; if (g_hi > P.ntiles) g_hi = P.ntiles;
-    AMP_FOR_THREADS(tid, nthreads) {
-        if (do_pile) for (int i = tid; i < ncnt; i += nthreads) cnt[i] = 0;
-        if (tid < 16) { const int ch = nib_channel((uint32_t)tid); ctrl[C_LUT + tid] = (ch < 0 ? AMP_NCH : ch) * P.wt; }
-        if (tid == 0) ctrl[C_TMIN] = 0x7FFFFFFF;
-    }
-    AMP_SYNC();
-    // window base: smallest start position among the first reads of the chunk (coordinate-sorted input => of the chunk)
-    AMP_FOR_THREADS(tid, nthreads) {
-        const long long i = P.b.first + g_lo * 32 + tid;
-        if (do_pile && g_lo < g_hi && tid < 64 && i < P.b.first + P.b.n) {
-            const int p0 = P.b.pos[i];
-            if (p0 >= 0 && !(P.b.flag[i] & 4)) atomic_min(&ctrl[C_TMIN], p0);
-        }
-    }
-    AMP_SYNC();
-    const int wmin = ctrl[C_TMIN];
-    const int wbase = (do_pile && wmin != 0x7FFFFFFF) ? (wmin & ~31) : -1;
-
-    AMP_FOR_WARPS(w, nw) {
-        const WarpMem wm = carve_warp(smem_base, P.wt, w);
-        AMP_FOR_LANES(lane) { if (lane < 2) wm.ctr[lane] = 0; }
-        AMP_SYNCWARP();
-        for (long long g = g_lo + w; ; g += nw) {
-            const bool have_group = g < g_hi;
-            if (have_group) {
-                const long long t0 = P.b.first + g * 32;
-                long long t1 = t0 + 32; if (t1 > P.b.first + P.b.n) t1 = P.b.first + P.b.n;
-                const int nreads = (int)(t1 - t0);
-                const uint32_t q_lo = P.b.qual_off[t0] & ~15u, q_end = P.b.qual_off[t1];
-                const uint32_t s_lo = P.b.seq_off[t0] & ~15u, s_end = P.b.seq_off[t1];
-                // staged [lo, hi); 16 bytes of the buffer stay free for the tail lanes' read-ahead
-                const uint32_t q_hi = (q_end - q_lo <= (uint32_t)AMP_WG_QBYTES - 16u) ? q_end : q_lo + (uint32_t)AMP_WG_QBYTES - 16u;
-                const uint32_t s_hi = (s_end - s_lo <= (uint32_t)AMP_WG_SBYTES - 16u) ? s_end : s_lo + (uint32_t)AMP_WG_SBYTES - 16u;
-                // ---- S ----
-                AMP_FOR_LANES(lane) {
-                    {
-                        const uint32_t nvec = (q_hi - q_lo + 15u) >> 4;      // whole vectors: the arrays are padded by the caller? no: clamp below
-                        const uint4* gq = (const uint4*)(P.b.qual + q_lo); uint4* sq = (uint4*)wm.qual;
-                        const uint32_t full = (q_hi - q_lo) >> 4;
-                        for (uint32_t v = lane; v < full; v += 32) sq[v] = gq[v];
-                        for (uint32_t k = (full << 4) + lane; k < q_hi - q_lo; k += 32) wm.qual[k] = P.b.qual[q_lo + k];
-                        (void)nvec;
-                    }
-                    if (do_pile) {
-                        const uint4* gs = (const uint4*)(P.b.seq + s_lo); uint4* ss = (uint4*)wm.seq;
-                        const uint32_t full = (s_hi - s_lo) >> 4;
-                        for (uint32_t v = lane; v < full; v += 32) ss[v] = gs[v];
-                        for (uint32_t k = (full << 4) + lane; k < s_hi - s_lo; k += 32) wm.seq[k] = P.b.seq[s_lo + k];
-                    }
-                }
-                AMP_SYNCWARP();
-                // ---- T ----
-                AMP_FOR_LANES(lane) {
-                    if (lane < nreads) {
-                        const long long i = t0 + lane;
-                        const uint32_t c0 = P.b.cig_off[i], c1 = P.b.cig_off[i + 1];
-                        const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
-                        const int nc = (int)(c1 - c0), l_seq = (int)(qo1 - qo0);
-                        const int flag = P.b.flag[i];
-                        int pos = P.b.pos[i];
-                        const uint32_t* cig = P.b.cigar + c0;
-                        if ((flag & 4) || nc == 0) {                                    // AmpliPy.py:902
-                            if (do_trim) {
-                                uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
-                                for (int k = 0; k < nc; ++k) orow[k] = cig[k];
-                                P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)AMP_F_SKIPPED;
-                            }
-                        } else {
-                            SimpleRead r;
-                            // the word-wise window search reads up to 8 bytes before the row: the first row of the buffer
-                            // may sit closer than that to its start, so require the offset
-                            const bool q_st = qo1 <= q_hi && (qo0 - q_lo) >= 8u;
-                            bool done = q_st && classify_simple(cig, nc, l_seq, r);
-                            int f = 0;
-                            if (done && do_trim) done = trim_simple(r, pos, flag, P.b.tlen[i], l_seq, wm.qual + (qo0 - q_lo), true, P.tp, &f);
-                            if (done && !do_trim && (pos < 0 || pos + r.m > P.tp.L)) done = false;
-                            if (done) {
-                                if (do_trim) {
-                                    uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
-                                    const int no = emit_simple(r, orow);
-                                    P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)no; P.o.flags[i] = (uint8_t)f;
-                                }
-                                if (do_pile && r.m > 0) {
-                                    const uint32_t so0 = P.b.seq_off[i], so1 = P.b.seq_off[i + 1];
-                                    const bool staged = so1 <= s_hi;
-                                    const int idx = atomic_add(&wm.ctr[0], 1);             // < 32 <= AMP_WG_RUNCAP
-                                    Seg sgm; sgm.rpos = pos; sgm.len = r.m | (staged ? 0x40000000 : 0);
-                                    sgm.qabs = (staged ? qo0 - q_lo : qo0) + (uint32_t)r.s1;
-                                    sgm.nibabs = (staged ? (so0 - s_lo) * 2u : so0 * 2u) + (uint32_t)r.s1;
-                                    wm.runs[idx] = sgm;
-                                }
-                            } else {
-                                wm.queue[atomic_add(&wm.ctr[1], 1)] = (uint32_t)(i - P.b.first);   // < 64: drained below once >= 32
-                            }
-                        }
-                    }
-                }
-                AMP_SYNCWARP();
-                // ---- C ----
-                if (do_pile) {
-                    AMP_FOR_LANES(lane) { count_warp_runs(P, cnt, lut, wm, wm.ctr[0], wbase, lane); }
-                    AMP_SYNCWARP();
-                    AMP_FOR_LANES(lane) { if (lane == 0) wm.ctr[0] = 0; }
-                    AMP_SYNCWARP();
-                }
-            }
-            // ---- G: a full batch of queued reads, or whatever is left after the last group ----
-            int nq = wm.ctr[1];
-            while (nq >= 32 || (!have_group && nq > 0)) {
-                const int nb = nq < 32 ? nq : 32;
-                AMP_FOR_LANES(lane) {
-                    // stage the rows of the first nb queued reads into their slots, keeping each row's alignment mod 16
-                    for (int r = 0; r < nb; ++r) {
-                        const long long i = P.b.first + wm.queue[r];
-                        const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
-                        if ((qo0 & 15u) + (qo1 - qo0) + 16u <= AMP_WG_QSLOT) {
-                            const uint4* gq = (const uint4*)(P.b.qual + (qo0 & ~15u));
-                            uint4* sq = (uint4*)(wm.qual + (size_t)r * AMP_WG_QSLOT);
-                            const uint32_t hi = (qo0 & 15u) + (qo1 - qo0);
-                            const uint32_t full = hi >> 4;
-                            for (uint32_t v = lane; v < full; v += 32) sq[v] = gq[v];
-                            for (uint32_t k = (full << 4) + lane; k < hi; k += 32) ((uint8_t*)sq)[k] = ((const uint8_t*)gq)[k];
-                        }
-                        if (do_pile) {
-                            const uint32_t so0 = P.b.seq_off[i], so1 = P.b.seq_off[i + 1];
-                            if ((so0 & 15u) + (so1 - so0) <= AMP_WG_SSLOT) {
-                                const uint4* gs = (const uint4*)(P.b.seq + (so0 & ~15u));
-                                uint4* ss = (uint4*)(wm.seq + (size_t)r * AMP_WG_SSLOT);
-                                const uint32_t hi = (so0 & 15u) + (so1 - so0);
-                                const uint32_t full = hi >> 4;
-                                for (uint32_t v = lane; v < full; v += 32) ss[v] = gs[v];
-                                for (uint32_t k = (full << 4) + lane; k < hi; k += 32) ((uint8_t*)ss)[k] = ((const uint8_t*)gs)[k];
-                            }
-                        }
-                    }
-                }
-                AMP_SYNCWARP();
-                AMP_FOR_LANES(lane) {
-                    if (lane < nb) warp_read_generic(P, wm, P.b.first + wm.queue[lane], lane, do_trim, do_pile);
-                }
-                AMP_SYNCWARP();
-                if (do_pile) {
-                    AMP_FOR_LANES(lane) { int nr = wm.ctr[0]; if (nr > AMP_WG_RUNCAP) nr = AMP_WG_RUNCAP; count_warp_runs(P, cnt, lut, wm, nr, wbase, lane); }
-                    AMP_SYNCWARP();
-                }
-                // drop the processed entries (the queue holds < 64, so one entry per lane moves down)
-                uint32_t moved[1];
-                AMP_FOR_LANES(lane) { (void)moved; }
-                {
-                    // two-step move so that no lane overwrites an entry another lane still has to read
-                    uint32_t tmp_host[32];
-                    AMP_FOR_LANES(lane) {
-                        uint32_t v = (lane + nb < nq) ? wm.queue[lane + nb] : 0u;
-#if defined(__CUDA_ARCH__)
-                        __syncwarp();
-                        if (lane + nb < nq) wm.queue[lane] = v;
-                        (void)tmp_host;
-#else
-                        tmp_host[lane] = v;
-#endif
-                    }
-#if !defined(__CUDA_ARCH__)
-                    for (int lane = 0; lane < 32; ++lane) if (lane + nb < nq) wm.queue[lane] = tmp_host[lane];
-#endif
-                }
-                AMP_FOR_LANES(lane) { if (lane == 0) { wm.ctr[1] = nq - nb; wm.ctr[0] = 0; } }
-                AMP_SYNCWARP();
-                nq -= nb;
-            }
-            if (!have_group) break;
-        }
-    }
-    AMP_SYNC();
-    if (do_pile && wbase >= 0) {
-        AMP_FOR_THREADS(tid, nthreads) { flush_tile(P, cnt, wbase, tid, nthreads, false); }
     }
 }
 

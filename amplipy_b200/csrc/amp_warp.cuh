@@ -1,0 +1,598 @@
+// amp_warp.cuh -- warp-autonomous fused trim + pileup kernel for short-read batches (sm_100a).
+//
+// One CTA per SM; every warp loops on its own over batches of up to 32 consecutive reads and never waits for another
+// warp (one block barrier after set-up, one before the final flush).  Per batch:
+//
+//   A  lane per read : metadata loads, [S]M[S] classification, closed form of the two primer clips
+//                      (trim_read, AmpliPy.py:450-558).  Lane 0 starts ONE bulk async copy (cp.async.bulk, completion on
+//                      an mbarrier) of the batch's contiguous quality / sequence byte ranges into the warp's buffers;
+//                      it lands while the lanes chase cig_off -> cigar -> primer tables.
+//   B  8 lanes per read, four reads per step: lane l owns the aligned 4-byte words l, l+8, l+16, ... of the read's
+//                      aligned quality bytes.
+//        window search (AmpliPy.py:566-587 / 628-649): per word four dp4a window sums against -4*minq; the sign bits are
+//                      funnel-shifted into one 32-bit fail mask per lane; first (forward strand) or last (reverse
+//                      strand) failing window by ffs/clz + three shuffles.  The three shrinking windows at the open end
+//                      are checked from three bytes.
+//        counting (update_base_counts, 690-753): per word a SIMD byte compare q >= minq packed to 4 bits per word,
+//                      AND-ed with the lane's mask of the final aligned range; per base one test + one shared-memory atomic
+//                      on a count tile indexed directly by the BAM nibble (17 rows x WT: rows 1,2,4,8,15 = A,C,G,T,N;
+//                      row 16 = '-'; any other row only raises the KeyError flag).  Lanes of a group hit banks 4 apart.
+//   C  lane per read : quality clip + write gate (589-686, 910), trim outputs.
+//   G  reads that are not [S]M[S] (indels, hard clips, corner cases the closed form declines) are queued per warp and
+//      run 26 at a time through the loop-for-loop generic path (trim_read + plan_read of amp_core.cuh), their runs
+//      counted by 8-lane groups from the warp's run list.
+//
+// tests/emu runs this very source on the CPU with every lane as a fiber (warp collectives = fiber rendezvous).
+#pragma once
+#include <string.h>
+
+#include "amp_kernels.cuh"
+
+namespace amp {
+
+// ---- warp / CTA primitives: hardware on the device, fibers in tests/emu -------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define AMP_WD __device__ __forceinline__
+AMP_WD int c_tid() { return (int)threadIdx.x; }
+AMP_WD int c_nthreads() { return (int)blockDim.x; }
+AMP_WD int c_block() { return (int)blockIdx.x; }
+AMP_WD int w_shfl(int v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
+AMP_WD int w_shfl_xor(int v, int m) { return __shfl_xor_sync(0xFFFFFFFFu, v, m); }
+AMP_WD unsigned w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+AMP_WD int w_max(int v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
+AMP_WD void w_sync() { __syncwarp(); }
+AMP_WD void c_sync() { __syncthreads(); }
+AMP_WD unsigned funnel_l(unsigned lo, unsigned hi, unsigned sh) { return __funnelshift_l(lo, hi, sh); }
+AMP_WD unsigned dp4a_acc(unsigned w, unsigned acc) { return __dp4a(w, 0x01010101u, acc); }
+AMP_WD int ctz32(unsigned x) { return __ffs((int)x) - 1; }
+AMP_WD int msb32(unsigned x) { return 31 - __clz((int)x); }
+AMP_WD int popc32(unsigned x) { return __popc(x); }
+AMP_WD uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+AMP_WD void mbar_init(unsigned long long* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// start the bulk copies of one batch: expect `total` bytes on the barrier, then up to two copies
+AMP_WD void bulk_expect(unsigned long long* bar, uint32_t total) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of the buffers are done
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(total) : "memory");
+}
+AMP_WD void bulk_copy(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+// predicated shared-memory increment (no branch): cnt[idx] += 1 when cond != 0
+AMP_WD void tile_inc_if(int* cnt, int idx, unsigned cond) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.add.u32 [%0], 1; }" ::"r"(smem_addr(cnt) + 4u * (uint32_t)idx), "r"(cond)
+                 : "memory");
+}
+AMP_WD void bulk_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_addr(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+#else
+#define AMP_WD inline
+// implemented by the fiber runtime in tests/emu/amp_emu.cpp
+int c_tid(); int c_nthreads(); int c_block();
+int w_shfl(int v, int src); int w_shfl_xor(int v, int m); unsigned w_ballot(bool p); int w_max(int v);
+void w_sync(); void c_sync();
+AMP_WD unsigned funnel_l(unsigned lo, unsigned hi, unsigned sh) { return sh ? (hi << sh) | (lo >> (32u - sh)) : hi; }
+AMP_WD unsigned dp4a_acc(unsigned w, unsigned acc) { return acc + (w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24); }
+AMP_WD int ctz32(unsigned x) { return __builtin_ctz(x); }
+AMP_WD int msb32(unsigned x) { return 31 - __builtin_clz(x); }
+AMP_WD int popc32(unsigned x) { return __builtin_popcount(x); }
+AMP_WD void mbar_init(unsigned long long*) {}
+AMP_WD void bulk_expect(unsigned long long*, uint32_t) {}
+AMP_WD void bulk_copy(void* dst, const void* src, uint32_t bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+AMP_WD void bulk_wait(unsigned long long*, uint32_t) {}
+AMP_WD void tile_inc_if(int* cnt, int idx, unsigned cond) { if (cond) cnt[idx] += 1; }
+static long long g_v7_stats[2];   // emulation only: reads finished on the cooperative path / reads sent to the generic path
+#endif
+
+// ---- shared-memory layout ------------------------------------------------------------------------------------------
+#ifndef AMP7_WARPS
+#define AMP7_WARPS 16
+#endif
+#define AMP7_WT 512              // count tile width on the device (positions)
+#define AMP7_ROWS 18             // count tile rows: BAM nibble 0..15, row 16 = deleted base, row 17 = sink of masked bases
+#define AMP7_DEL_ROW 16
+#define AMP7_SINK_ROW 17
+#define AMP7_KW 8                // 4-byte words per lane in phase B: aligned runs up to 8 * 32 bytes
+#define AMP7_PAD 16              // bytes in front of the staged data (phase B may address up to 3 nibbles before it)
+#define AMP7_QDATA 5120          // staged quality bytes per batch (32 x 150 + alignment)
+#define AMP7_SDATA 2560
+#define AMP7_QSLACK 272          // idle lanes of phase B read up to KW * 32 + 8 bytes past a row start
+#define AMP7_SSLACK 144
+#define AMP7_QBUF (AMP7_PAD + AMP7_QDATA + AMP7_QSLACK)
+#define AMP7_SBUF (AMP7_PAD + AMP7_SDATA + AMP7_SSLACK)
+#define AMP7_RUNCAP 96           // run descriptors per warp (generic path)
+#define AMP7_QCAP 64             // queued generic-path reads per warp
+#define AMP7_GSLOT_Q 192         // G phase: bytes per staged quality row slot
+#define AMP7_GSLOT_S 96
+#define AMP7_GN 26               // reads per G phase (GN * GSLOT <= DATA)
+#define AMP7_WARP_BYTES (AMP7_QBUF + AMP7_SBUF + AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + 16)
+enum { C7_TMIN = 0, C7_NEXT = 1, C7_WORDS = 16 };
+
+// the sink row is the last one and 32 * KW entries longer: idle slots of a group increment it past the window's end
+AMP_HD size_t tile_bytes_v7(int wt) { return ((size_t)AMP7_ROWS * wt + 32 * AMP7_KW) * 4; }
+AMP_HD size_t smem_bytes_v7(int wt, int warps) { return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_WARP_BYTES; }
+
+// launch shape: reads per batch so that a batch's rows fit the staging buffers; one CTA per SM with a contiguous chunk
+struct V7Cfg { int wt, batch_reads; };
+inline V7Cfg pick_v7_cfg(long long n, long long sum_qual, int sm_count) {
+    (void)sm_count;
+    V7Cfg t;
+    t.wt = AMP7_WT;
+    const double avg_len = n ? (double)sum_qual / (double)n : 150.0;
+    int br = (int)((AMP7_QDATA - 16) / (avg_len * 1.02 + 1.0));
+    t.batch_reads = br < 1 ? 1 : (br > 32 ? 32 : br);
+    return t;
+}
+
+struct WarpMem7 {
+    uint8_t* qbuf; uint8_t* sbuf; Seg* runs; uint32_t* queue; int* ctr; unsigned long long* bar;
+};
+AMP_HD WarpMem7 carve_warp7(unsigned char* base, int wt, int w) {
+    unsigned char* b = base + tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)w * AMP7_WARP_BYTES;
+    WarpMem7 m;
+    m.qbuf = b; b += AMP7_QBUF;
+    m.sbuf = b; b += AMP7_SBUF;
+    m.runs = (Seg*)b; b += AMP7_RUNCAP * 16;
+    m.queue = (uint32_t*)b; b += AMP7_QCAP * 4;
+    m.ctr = (int*)b; b += 32;
+    m.bar = (unsigned long long*)b;
+    return m;
+}
+
+// channel of a tile row (nibble-indexed), -1 = not a countable base
+AMP_HD int row_channel(int row) { return row == AMP7_DEL_ROW ? 5 : nib_channel((uint32_t)row); }
+
+// tile -> global count matrix; rows that are no base only raise the KeyError flag (AmpliPy.py:753)
+AMP_HD void flush_tile7(const KParams& P, const int* cnt, int wbase, int tid, int nthreads) {
+    for (int row = 0; row <= AMP7_DEL_ROW; ++row) {
+        const int ch = row_channel(row);
+        for (int w = tid; w < P.wt; w += nthreads) {
+            const int v = cnt[row * P.wt + w];
+            if (v) {
+                if (ch >= 0) atomic_add(&P.counts[(size_t)ch * P.Lpad + wbase + w], v);
+                else atomic_or(P.err, AMP_E_BASE);
+            }
+        }
+    }
+}
+
+// bits (4j + i), j in [0, 8), i in [0, 4), of the positions b = 32 j + l4 + i with lo <= b < hi
+AMP_HD unsigned below_mask(int h, int l4) {
+    const int x = h - l4;
+    if (x <= 0) return 0u;
+    const int rem = x & 31;
+    const int nb = ((x >> 5) << 2) + (rem < 4 ? rem : 4);
+    return nb >= 32 ? 0xFFFFFFFFu : ((1u << nb) - 1u);
+}
+AMP_HD unsigned lane_range_mask(int lo, int hi, int l4) { return below_mask(hi, l4) & ~below_mask(lo, l4); }
+
+// ---- generic path inside a warp (same logic as TileSink / read_generic, warp-private run list) --------------------
+struct WarpSink7 {
+    const KParams* P; WarpMem7 wm;
+    uint32_t qabs0, nibabs0; bool staged;
+    const uint8_t* seq_read; const uint8_t* qual_read;
+    unsigned int errs;
+    AMP_HD void push(int rpos, int len_kind, int q) {
+        const int idx = atomic_add(&wm.ctr[0], 1);
+        if (idx < AMP7_RUNCAP) {
+            Seg s; s.rpos = rpos; s.len = len_kind | (staged ? 0x40000000 : 0); s.qabs = qabs0 + (uint32_t)q; s.nibabs = nibabs0 + (uint32_t)q;
+            wm.runs[idx] = s;
+        } else {   // list full: exact serial path into the global matrix
+            const int n = len_kind & 0x3FFFFFFF;
+            if (len_kind < 0) { for (int j = 0; j < n; ++j) atomic_add(&P->counts[(size_t)5 * P->Lpad + rpos + j], 1); }
+            else for (int j = 0; j < n; ++j) {
+                if (qual_read[q + j] < P->tp.min_quality) continue;
+                const int ch = nib_channel(nib_at(seq_read, (uint32_t)(q + j)));
+                if (ch < 0) { errs |= AMP_E_BASE; continue; }
+                atomic_add(&P->counts[(size_t)ch * P->Lpad + rpos + j], 1);
+            }
+        }
+    }
+    AMP_HD void match(int rpos, int q, int n) { push(rpos, n, q); }
+    AMP_HD void del(int rpos, int n) { push(rpos, (int)(0x80000000u | (unsigned)n), 0); }
+    AMP_HD void ins(int pos, int b, int n) {
+        if (n == 1) {   // one-character key == that base's own dict entry (AmpliPy.py:745-746)
+            const int ch = nib_channel(nib_at(seq_read, (uint32_t)b));
+            if (ch >= 0) { atomic_add(&P->counts[(size_t)ch * P->Lpad + pos], 1); return; }
+        }
+        TileSink::Text t; t.seq = seq_read; t.b = b;
+        ins_table_add(P->tab, P->gpos_base + pos, n, t, 1);
+    }
+};
+
+// one base outside the tile (or of an unstaged run): straight to the global matrix
+AMP_HD void count_global7(const KParams& P, int* cnt, int wbase, int row, int p, unsigned& errs) {
+    const unsigned w = (unsigned)(p - wbase);
+    if (wbase >= 0 && w < (unsigned)P.wt) { atomic_add(&cnt[row * P.wt + (int)w], 1); return; }
+    const int ch = row_channel(row);
+    if (ch < 0) { errs |= AMP_E_BASE; return; }
+    atomic_add(&P.counts[(size_t)ch * P.Lpad + p], 1);
+}
+
+// count the warp's run list [0, n_runs): groups of 8 lanes per run, consecutive lanes on consecutive bases
+AMP_HD void count_warp_runs7(const KParams& P, int* cnt, const WarpMem7& wm, int n_runs, int wbase, int lane) {
+    const int l = lane & 7, sub = lane >> 3;
+    const int minq = P.tp.min_quality;
+    unsigned errs = 0;
+    for (int s = sub; s < n_runs; s += 4) {
+        const Seg sg = wm.runs[s];
+        const int n = sg.len & 0x3FFFFFFF;
+        const int w0 = sg.rpos - wbase;
+        const bool in_win = wbase >= 0 && w0 >= 0 && w0 + n <= P.wt;
+        if (sg.len < 0) {                                                          // D / N run: unconditional (714-715)
+            if (in_win) { for (int j = l; j < n; j += 8) atomic_add(&cnt[AMP7_DEL_ROW * P.wt + w0 + j], 1); }
+            else for (int j = l; j < n; j += 8) count_global7(P, cnt, wbase, AMP7_DEL_ROW, sg.rpos + j, errs);
+            continue;
+        }
+        const bool staged = (sg.len & 0x40000000) != 0;
+        const uint8_t* qp = staged ? wm.qbuf + sg.qabs : P.b.qual + sg.qabs;
+        const uint8_t* sp = staged ? wm.sbuf : P.b.seq;
+        if (in_win) {
+            for (int j = l; j < n; j += 8) {
+                if (qp[j] < minq) continue;                                        // 718
+                const uint32_t nb = sg.nibabs + (uint32_t)j;
+                atomic_add(&cnt[(int)((sp[nb >> 1] >> ((~nb & 1u) << 2)) & 15u) * P.wt + w0 + j], 1);   // 752-753
+            }
+        } else {
+            for (int j = l; j < n; j += 8) {
+                if (qp[j] < minq) continue;
+                const uint32_t nb = sg.nibabs + (uint32_t)j;
+                count_global7(P, cnt, wbase, (int)((sp[nb >> 1] >> ((~nb & 1u) << 2)) & 15u), sg.rpos + j, errs);
+            }
+        }
+    }
+    if (errs) atomic_or(P.err, errs);
+}
+
+// generic path for one queued read (rows staged in slot `slot` of the warp's buffers, or read from global memory)
+AMP_HD void warp_read_generic7(const KParams& P, const WarpMem7& wm, long long i, int slot, bool do_trim, bool do_pile) {
+    const uint32_t c0 = P.b.cig_off[i], c1 = P.b.cig_off[i + 1];
+    const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
+    int nc = (int)(c1 - c0);
+    const int l_seq = (int)(qo1 - qo0);
+    const int flag = P.b.flag[i];
+    int pos = P.b.pos[i];
+    uint32_t so0 = 0, so1 = 0;
+    if (do_pile) { so0 = P.b.seq_off[i]; so1 = P.b.seq_off[i + 1]; }
+    const uint32_t qdst = AMP7_PAD + (uint32_t)slot * AMP7_GSLOT_Q + (qo0 & 15u), sdst = AMP7_PAD + (uint32_t)slot * AMP7_GSLOT_S + (so0 & 15u);
+    const bool q_st = (qo0 & 15u) + (qo1 - qo0) + 16u <= AMP7_GSLOT_Q;          // row + read-ahead of the word-wise search
+    const bool s_st = do_pile && (so0 & 15u) + (so1 - so0) <= AMP7_GSLOT_S;
+    const uint8_t* qual = q_st ? wm.qbuf + qdst : P.b.qual + qo0;
+    const uint8_t* seq = do_pile ? (s_st ? wm.sbuf + sdst : P.b.seq + so0) : nullptr;
+    const uint32_t* cig = P.b.cigar + c0;
+    uint32_t la[AMP_CMAX], lb[AMP_CMAX];
+    int f = 0;
+    if (do_trim) {
+        uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
+        uint32_t *A, *B;
+        if (nc + 3 <= AMP_CMAX) { A = la; B = lb; }
+        else { A = P.scratch + (size_t)c0 + 3 * (size_t)i; B = A + P.scratch_half; }
+        for (int k = 0; k < nc; ++k) A[k] = cig[k];
+        uint32_t* res;
+        f = trim_read(A, B, nc, pos, flag, P.b.tlen[i], l_seq, qual, q_st, P.tp, &res);   // qdst >= AMP7_PAD >= 8
+        if (f & AMP_F_ERROR) { nc = 0; f = AMP_F_ERROR; atomic_or(P.err, AMP_E_COORD); }
+        for (int k = 0; k < nc; ++k) orow[k] = res[k];
+        cig = res;
+        P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)f;
+    }
+    if (do_pile && !(f & AMP_F_ERROR)) {
+        WarpSink7 sink; sink.P = &P; sink.wm = wm;
+        sink.staged = q_st && s_st;
+        sink.qabs0 = sink.staged ? qdst : qo0;
+        sink.nibabs0 = sink.staged ? sdst * 2u : so0 * 2u;
+        sink.seq_read = seq; sink.qual_read = qual; sink.errs = 0;
+        int e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
+        e |= (int)sink.errs;
+        if (e) atomic_or(P.err, (unsigned)e);
+    }
+}
+
+// G phase: the first nb (<= AMP7_GN) queued reads of the warp
+AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, int wbase, int nb, int nq, int lane, bool do_trim,
+                               bool do_pile) {
+    // stage the (scattered) rows into fixed slots, keeping each row's alignment mod 16
+    for (int r = 0; r < nb; ++r) {
+        const long long i = P.b.first + wm.queue[r];
+        const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
+        if ((qo0 & 15u) + (qo1 - qo0) + 16u <= AMP7_GSLOT_Q) {
+            const uint4* gq = (const uint4*)(P.b.qual + (qo0 & ~15u));
+            uint4* sq = (uint4*)(wm.qbuf + AMP7_PAD + (size_t)r * AMP7_GSLOT_Q);
+            const uint32_t hi = (qo0 & 15u) + (qo1 - qo0);
+            const uint32_t full = hi >> 4;
+            for (uint32_t v = lane; v < full; v += 32) sq[v] = gq[v];
+            for (uint32_t k = (full << 4) + lane; k < hi; k += 32) ((uint8_t*)sq)[k] = ((const uint8_t*)gq)[k];
+        }
+        if (do_pile) {
+            const uint32_t so0 = P.b.seq_off[i], so1 = P.b.seq_off[i + 1];
+            if ((so0 & 15u) + (so1 - so0) <= AMP7_GSLOT_S) {
+                const uint4* gs = (const uint4*)(P.b.seq + (so0 & ~15u));
+                uint4* ss = (uint4*)(wm.sbuf + AMP7_PAD + (size_t)r * AMP7_GSLOT_S);
+                const uint32_t hi = (so0 & 15u) + (so1 - so0);
+                const uint32_t full = hi >> 4;
+                for (uint32_t v = lane; v < full; v += 32) ss[v] = gs[v];
+                for (uint32_t k = (full << 4) + lane; k < hi; k += 32) ((uint8_t*)ss)[k] = ((const uint8_t*)gs)[k];
+            }
+        }
+    }
+    if (lane == 0) wm.ctr[0] = 0;
+    w_sync();
+    if (lane < nb) warp_read_generic7(P, wm, P.b.first + wm.queue[lane], lane, do_trim, do_pile);
+    w_sync();
+    if (do_pile) {
+        int nr = wm.ctr[0]; if (nr > AMP7_RUNCAP) nr = AMP7_RUNCAP;
+        count_warp_runs7(P, cnt, wm, nr, wbase, lane);
+    }
+    // drop the processed entries (the queue holds < 64 entries: at most one move per lane and round)
+    for (int base = 0; base + nb < nq; base += 32) {
+        const bool mv = base + lane + nb < nq;
+        const uint32_t v = mv ? wm.queue[base + lane + nb] : 0u;
+        w_sync();
+        if (mv) wm.queue[base + lane] = v;
+        w_sync();
+    }
+    w_sync();
+}
+
+// ---- the kernel body -------------------------------------------------------------------------------------------------
+// P.reads_per_tile = reads per batch (<= 32), P.ntiles = batches, P.tiles_per_cta = batches per CTA (contiguous chunk).
+// WT = width of the count tile as a compile-time constant (0: P.wt, used by the emulation tests).
+template <bool TRIM, bool PILE, int WT>
+AMP_WD void cta_trim_pileup_v7(const KParams& P, unsigned char* smem_base) {
+    const int wt = WT ? WT : P.wt;
+    const int tid = c_tid(), nthreads = c_nthreads(), block = c_block();
+    const int lane = tid & 31, warp = tid >> 5;
+    const int BR = P.reads_per_tile;
+    int* cnt = (int*)smem_base;
+    int* ctrl = (int*)(smem_base + tile_bytes_v7(wt));
+    const WarpMem7 wm = carve_warp7(smem_base, wt, warp);
+    const long long g_lo = (long long)block * P.tiles_per_cta;
+    long long g_hi = g_lo + P.tiles_per_cta; if (g_hi > P.ntiles) g_hi = P.ntiles;
+    const int n_batches = g_hi > g_lo ? (int)(g_hi - g_lo) : 0;
+    const long long n_end = P.b.first + P.b.n;
+
+    if (PILE) for (int i = tid; i < (AMP7_DEL_ROW + 1) * wt; i += nthreads) cnt[i] = 0;   // the sink row is never read
+    if (tid == 0) { ctrl[C7_TMIN] = 0x7FFFFFFF; ctrl[C7_NEXT] = 0; }
+    if (lane == 0) { wm.ctr[0] = 0; wm.ctr[1] = 0; mbar_init(wm.bar); }
+    c_sync();
+    // window base: smallest start among the first reads of the chunk (coordinate-sorted input => of the whole chunk)
+    if (PILE && n_batches > 0 && tid < 64) {
+        const long long i = P.b.first + g_lo * BR + tid;
+        if (i < n_end) {
+            const int p0 = P.b.pos[i];
+            if (p0 >= 0 && !(P.b.flag[i] & 4)) atomic_min(&ctrl[C7_TMIN], p0);
+        }
+    }
+    c_sync();
+    const int wmin = ctrl[C7_TMIN];
+    // (three positions of slack: a group's position 0 is the aligned word holding the read's first aligned base)
+    const int wbase = (PILE && wmin != 0x7FFFFFFF) ? ((wmin > 3 ? wmin - 3 : 0) & ~31) : -1;
+
+    const int minq = P.tp.min_quality;
+    // the cooperative path needs the default window and a quality threshold that fits the SIMD byte compare
+    const bool fast_ok = minq >= 0 && minq <= 127 && (!TRIM || P.tp.window == 4);
+    const unsigned minq4 = (unsigned)minq * 0x01010101u;
+    const unsigned nthr = (unsigned)(-4 * minq);
+    const int l = lane & 7, sub = lane >> 3, l4 = 4 * l;
+    uint32_t parity = 0;
+    int nq = 0;                                      // queued generic-path reads (uniform across the warp)
+
+    for (;;) {
+        int bi = 0;
+        if (lane == 0) bi = atomic_add(&ctrl[C7_NEXT], 1);
+        bi = w_shfl(bi, 0);
+        if (bi >= n_batches) break;
+        const long long t0 = P.b.first + (g_lo + bi) * BR;
+        long long t1 = t0 + BR; if (t1 > n_end) t1 = n_end;
+        const int nreads = (int)(t1 - t0);
+        const bool have = lane < nreads;
+        const long long i = have ? t0 + lane : t0;
+
+        // ---- A: metadata -----------------------------------------------------------------------------------------
+        const uint32_t c0 = P.b.cig_off[i], c1 = P.b.cig_off[i + 1];
+        const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
+        uint32_t so0 = 0, so1 = 0;
+        if (PILE) { so0 = P.b.seq_off[i]; so1 = P.b.seq_off[i + 1]; }
+        const int flag = P.b.flag[i];
+        int pos = P.b.pos[i];
+        const int tlen = TRIM ? P.b.tlen[i] : 0;
+        // staged byte ranges [lo, hi) of the batch: rows of consecutive reads are contiguous
+        const uint32_t q_lo = (uint32_t)w_shfl((int)qo0, 0) & ~15u, q_end = (uint32_t)w_shfl((int)qo1, nreads - 1);
+        const uint32_t q_hi = (q_end - q_lo <= (uint32_t)AMP7_QDATA) ? q_end : q_lo + (uint32_t)AMP7_QDATA;
+        uint32_t s_lo = 0, s_hi = 0;
+        if (PILE) {
+            s_lo = (uint32_t)w_shfl((int)so0, 0) & ~15u;
+            const uint32_t s_end = (uint32_t)w_shfl((int)so1, nreads - 1);
+            s_hi = (s_end - s_lo <= (uint32_t)AMP7_SDATA) ? s_end : s_lo + (uint32_t)AMP7_SDATA;
+        }
+        const uint32_t q_bulk = (q_hi - q_lo) & ~15u, s_bulk = (s_hi - s_lo) & ~15u;
+        if (lane == 0 && q_bulk + s_bulk > 0) {
+            bulk_expect(wm.bar, q_bulk + s_bulk);
+            if (q_bulk) bulk_copy(wm.qbuf + AMP7_PAD, P.b.qual + q_lo, q_bulk, wm.bar);
+            if (s_bulk) bulk_copy(wm.sbuf + AMP7_PAD, P.b.seq + s_lo, s_bulk, wm.bar);
+        }
+        // the < 16 trailing bytes of each range with ordinary loads
+        if (lane < (int)((q_hi - q_lo) & 15u)) wm.qbuf[AMP7_PAD + q_bulk + lane] = P.b.qual[q_lo + q_bulk + lane];
+        if (PILE && lane < (int)((s_hi - s_lo) & 15u)) wm.sbuf[AMP7_PAD + s_bulk + lane] = P.b.seq[s_lo + s_bulk + lane];
+
+        const int nc = (int)(c1 - c0), l_seq = (int)(qo1 - qo0);
+        const uint32_t* cig = P.b.cigar + c0;
+        const bool skipped = have && ((flag & 4) || nc == 0);                          // AmpliPy.py:902
+        SimpleRead r; r.s1 = 0; r.m = 0; r.s2 = 0; r.mop = 0;
+        int f = 0;
+        bool fast = have && !skipped && fast_ok && qo1 <= q_hi && (!PILE || so1 <= s_hi) && classify_simple(cig, nc, l_seq, r);
+        if (fast && TRIM) fast = trim_simple_primers(r, pos, flag, tlen, l_seq, P.tp, &f);
+        if (fast && !TRIM && (pos < 0 || pos + r.m > P.tp.L)) fast = false;
+        const uint32_t a0 = AMP7_PAD + (qo0 - q_lo) + (uint32_t)r.s1;                  // first aligned quality byte in qbuf
+        if (fast && (r.m < 8 || (int)(a0 & 3u) + r.m > 32 * AMP7_KW)) fast = false;
+        const bool rev = (flag & 16) != 0;
+        // everything else goes to the warp's queue for the generic path
+        {
+            const unsigned qmask = w_ballot(have && !skipped && !fast);
+            if (have && !skipped && !fast) wm.queue[nq + popc32(qmask & ((1u << lane) - 1u))] = (uint32_t)(i - P.b.first);
+            nq += popc32(qmask);
+        }
+        if (skipped && TRIM) {
+            uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
+            for (int k = 0; k < nc; ++k) orow[k] = cig[k];
+            P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)AMP_F_SKIPPED;
+        }
+        // per-read parameters of phase B, fetched by the read's lane group with shuffles
+#if !defined(__CUDA_ARCH__)
+        if (fast) ++g_v7_stats[0]; else if (have && !skipped) ++g_v7_stats[1];
+#endif
+        const int pk0 = fast ? (int)(a0 | ((uint32_t)r.m << 16) | (rev ? 1u << 25 : 0u) | 0x80000000u) : 0;
+        const int pk1 = PILE ? (int)(2u * (AMP7_PAD + so0 - s_lo) + (uint32_t)r.s1) : 0;   // nibble index of the first aligned base in sbuf
+        int del_mine = 0;
+
+        w_sync();
+        if (q_bulk + s_bulk > 0) { bulk_wait(wm.bar, parity); parity ^= 1u; }
+
+        // ---- B: window search + counting, 8 lanes per read --------------------------------------------------------------
+        const int nsteps = (nreads + 3) >> 2;
+        unsigned errs = 0;
+        for (int g = 0; g < nsteps; ++g) {
+            const int src = 4 * g + sub;
+            const int k0 = w_shfl(pk0, src);
+            const int k1s = PILE ? w_shfl(pk1, src) : 0;
+            const int pp = w_shfl(pos, src);
+            const bool valid = k0 < 0;
+            const int k1 = valid ? k1s : 2 * AMP7_PAD;                                    // idle groups address the front of the buffer
+            const int ga0 = k0 & 0xFFFF, m = (k0 >> 16) & 0x1FF;
+            const bool grev = (k0 >> 25) & 1;
+            const int lead = ga0 & 3;
+            const int nsl = valid ? ((lead + m - 1) >> 5) + 1 : 0;                      // slots of 32 positions (per group)
+            unsigned F = 0, Q = 0;
+            {
+                const uint32_t* wq = (const uint32_t*)(wm.qbuf + (ga0 & ~3)) + l;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int j = AMP7_KW - 1; j >= 0; --j) {
+                    if (j < nsl) {
+                        const unsigned v = wq[8 * j];
+                        if (PILE) {   // q >= minq per byte (exact for all byte values, minq <= 127) -> 4 bits
+                            const unsigned t = (v | 0x80808080u) - minq4;
+                            Q = funnel_l(((t | v) & 0x80808080u) * 0x00204081u, Q, 4);
+                        }
+                        if (TRIM) {   // window sums of positions 4k .. 4k+3 minus 4*minq: sign bit = window fails
+                            const unsigned n = wq[8 * j + 1];
+                            F = funnel_l(dp4a_acc(funnel_r(v, n, 24), nthr), F, 1);
+                            F = funnel_l(dp4a_acc(funnel_r(v, n, 16), nthr), F, 1);
+                            F = funnel_l(dp4a_acc(funnel_r(v, n, 8), nthr), F, 1);
+                            F = funnel_l(dp4a_acc(v, nthr), F, 1);
+                        }
+                    }
+                }
+            }
+            int del = 0;
+            if (TRIM) {
+                // full windows start at b in [lead, lead + m - 4]; forward strand: first failing, reverse: last failing
+                const unsigned Fv = F & lane_range_mask(lead, lead + m - 3, l4);
+                int key = -1;
+                if (Fv) {
+                    const int nbit = grev ? msb32(Fv) : ctz32(Fv);
+                    const int b = ((nbit >> 2) << 5) + (nbit & 3) + l4;
+                    key = grev ? b : 0x10000 - b;
+                }
+                { int o = w_shfl_xor(key, 1); key = o > key ? o : key; o = w_shfl_xor(key, 2); key = o > key ? o : key; o = w_shfl_xor(key, 4); key = o > key ? o : key; }
+                if (key >= 0) {
+                    const int b = grev ? key : 0x10000 - key;
+                    del = grev ? b - lead + 4 : m - (b - lead);
+                } else if (valid) {
+                    // the three shrinking windows at the open end (w = 3, 2, 1)
+                    const uint8_t* e3 = wm.qbuf + ga0 + (grev ? 0 : m - 3);
+                    const int x0 = e3[0], x1 = e3[1], x2 = e3[2];
+                    const int e = grev ? x0 : x2;
+                    if (x0 + x1 + x2 < 3 * minq) del = 3;
+                    else if (e + x1 < 2 * minq) del = 2;
+                    else if (e < minq) del = 1;
+                }
+                // hand the result to the read's own lane (lane 4g + s reads group s)
+                const int dsh = w_shfl(del, (lane & 3) << 3);
+                if ((lane >> 2) == g) del_mine = dsh;
+            }
+            if (PILE) {
+                const int dq = TRIM ? (grev ? (del >= 2 ? del : 0) : del) : 0;
+                const int cl = lead + (grev ? dq : 0), ch = valid ? lead + m - (grev ? 0 : dq) : 0;
+                const int rb = pp - lead - (grev ? dq : 0);                               // reference position of b = 0 (pos stays, F6)
+                const unsigned cm = Q & lane_range_mask(cl, ch, l4);
+                const int nn0 = k1 - lead + l4;                                           // nibble index of this lane's first position
+                const int sbyte = nn0 >> 1;
+                const unsigned par4 = (unsigned)(nn0 & 1) << 2, sh8 = (unsigned)(sbyte & 3) << 3;
+                const uint32_t* ws = (const uint32_t*)(wm.sbuf + (sbyte & ~3));
+                const int w0 = rb - wbase;
+                const bool in_win = wbase >= 0 && w0 >= 0 && w0 + ch <= wt;             // uniform per group
+                const int ncs = ch > cl ? ((ch - 1) >> 5) + 1 : 0;                        // slots that hold counted positions
+                if (in_win) {
+                    const int tl = w0 + l4;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int j = 0; j < AMP7_KW; ++j) {
+                        if (j < ncs) {
+                            const unsigned x = funnel_r(ws[4 * j], ws[4 * j + 1], sh8);
+                            const unsigned y = ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);   // nibbles in base order
+                            const unsigned z = y >> par4, zh = z >> 8;
+                            // AmpliPy.py:752-753; the quality gate (718) and the aligned range (722 / 726) are in cm.  A masked
+                            // base increments the sink row at its own position: no branch, and the lanes of a group keep
+                            // hitting banks 4 apart.
+                            const unsigned r0 = (cm & (1u << (4 * j + 0))) ? (z & 15u) : (unsigned)AMP7_SINK_ROW;
+                            const unsigned r1 = (cm & (1u << (4 * j + 1))) ? ((z >> 4) & 15u) : (unsigned)AMP7_SINK_ROW;
+                            const unsigned r2 = (cm & (1u << (4 * j + 2))) ? (zh & 15u) : (unsigned)AMP7_SINK_ROW;
+                            const unsigned r3 = (cm & (1u << (4 * j + 3))) ? ((zh >> 4) & 15u) : (unsigned)AMP7_SINK_ROW;
+                            atomic_add(cnt + tl + 32 * j + 0 + (int)r0 * wt, 1);
+                            atomic_add(cnt + tl + 32 * j + 1 + (int)r1 * wt, 1);
+                            atomic_add(cnt + tl + 32 * j + 2 + (int)r2 * wt, 1);
+                            atomic_add(cnt + tl + 32 * j + 3 + (int)r3 * wt, 1);
+                        }
+                    }
+                } else if (cm) {
+                    for (int j = 0; j < AMP7_KW; ++j) {
+                        if (!((cm >> (4 * j)) & 15u)) continue;
+                        const unsigned x = funnel_r(ws[4 * j], ws[4 * j + 1], sh8);
+                        const unsigned y = ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+                        const unsigned z = y >> par4;
+                        for (int ii = 0; ii < 4; ++ii)
+                            if (cm & (1u << (4 * j + ii))) count_global7(P, cnt, wbase, (int)((z >> (4 * ii)) & 15u), rb + 32 * j + l4 + ii, errs);
+                    }
+                }
+            }
+        }
+        if (errs) atomic_or(P.err, errs);
+
+        // ---- C: quality clip + write gate + outputs, lane per read --------------------------------------------------------
+        if (TRIM && fast) {
+            trim_simple_finish(r, del_mine, rev, P.tp, &f);
+            uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
+            const int no = emit_simple(r, orow);
+            P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)no; P.o.flags[i] = (uint8_t)f;
+        }
+        w_sync();   // every lane is done with the staged rows before the buffers are reused
+
+        // ---- G: a full load of queued reads ----------------------------------------------------------------------------------
+        while (nq >= AMP7_GN) {
+            warp_generic_phase(P, wm, cnt, wbase, AMP7_GN, nq, lane, TRIM, PILE);
+            nq -= AMP7_GN;
+        }
+    }
+    while (nq > 0) {
+        const int nb = nq < AMP7_GN ? nq : AMP7_GN;
+        warp_generic_phase(P, wm, cnt, wbase, nb, nq, lane, TRIM, PILE);
+        nq -= nb;
+    }
+    c_sync();
+    if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);
+}
+
+}  // namespace amp

@@ -2,12 +2,128 @@
 // CPU, one CTA at a time with barrier-separated phases executed as loops over the CTA's threads.
 // It lets the build container (no GPU) check the device logic against the oracle before a GPU run.
 // It is not part of the product and is never loaded by amplipy_b200/.
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
-#include "../../amplipy_b200/csrc/amp_kernels.cuh"
+#include <ucontext.h>
+
+#include <cstdio>
+
+#include "../../amplipy_b200/csrc/amp_warp.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fiber runtime for the warp-autonomous kernel: every CUDA thread of one CTA is a ucontext fiber; warp collectives
+// (shuffle, ballot, reduce, __syncwarp) and the block barrier are rendezvous points handled by a round-robin scheduler.
+// Deterministic and single-threaded, so shared-memory "atomics" can stay plain read-modify-writes.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+enum { FB_READY = 0, FB_WAIT_WARP = 1, FB_WAIT_CTA = 2, FB_DONE = 3 };
+struct Fiber { ucontext_t ctx; int state; };
+struct FiberRt {
+    std::vector<Fiber> f;
+    std::vector<char> stacks;
+    ucontext_t main_ctx;
+    int cur = 0, nthreads = 0, block = 0;
+    int xch[1024];
+    void (*body)(void*) = nullptr;
+    void* arg = nullptr;
+} g_rt;
+const size_t kStack = 256 * 1024;
+
+void fiber_entry() {
+    g_rt.body(g_rt.arg);
+    g_rt.f[g_rt.cur].state = FB_DONE;
+    swapcontext(&g_rt.f[g_rt.cur].ctx, &g_rt.main_ctx);
+}
+void fiber_wait(int kind) {
+    g_rt.f[g_rt.cur].state = kind;
+    swapcontext(&g_rt.f[g_rt.cur].ctx, &g_rt.main_ctx);
+}
+void run_cta(int block, int nthreads, void (*body)(void*), void* arg) {
+    g_rt.block = block; g_rt.nthreads = nthreads; g_rt.body = body; g_rt.arg = arg;
+    g_rt.f.assign(nthreads, Fiber());
+    if (g_rt.stacks.size() < kStack * nthreads) g_rt.stacks.resize(kStack * nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        getcontext(&g_rt.f[t].ctx);
+        g_rt.f[t].ctx.uc_stack.ss_sp = g_rt.stacks.data() + kStack * t;
+        g_rt.f[t].ctx.uc_stack.ss_size = kStack;
+        g_rt.f[t].ctx.uc_link = &g_rt.main_ctx;
+        g_rt.f[t].state = FB_READY;
+        makecontext(&g_rt.f[t].ctx, fiber_entry, 0);
+    }
+    for (;;) {
+        bool progress = false, all_done = true;
+        for (int t = 0; t < nthreads; ++t) {
+            if (g_rt.f[t].state == FB_READY) {
+                g_rt.cur = t;
+                swapcontext(&g_rt.main_ctx, &g_rt.f[t].ctx);
+                progress = true;
+            }
+            if (g_rt.f[t].state != FB_DONE) all_done = false;
+        }
+        if (all_done) break;
+        // release warps whose live lanes all wait at a warp rendezvous
+        for (int w = 0; w * 32 < nthreads; ++w) {
+            int waiting = 0, live = 0;
+            for (int t = w * 32; t < std::min(nthreads, w * 32 + 32); ++t) {
+                if (g_rt.f[t].state != FB_DONE) ++live;
+                if (g_rt.f[t].state == FB_WAIT_WARP) ++waiting;
+            }
+            if (live && waiting == live) {
+                for (int t = w * 32; t < std::min(nthreads, w * 32 + 32); ++t) if (g_rt.f[t].state == FB_WAIT_WARP) g_rt.f[t].state = FB_READY;
+                progress = true;
+            }
+        }
+        {
+            int waiting = 0, live = 0;
+            for (int t = 0; t < nthreads; ++t) {
+                if (g_rt.f[t].state != FB_DONE) ++live;
+                if (g_rt.f[t].state == FB_WAIT_CTA) ++waiting;
+            }
+            if (live && waiting == live) {
+                for (int t = 0; t < nthreads; ++t) g_rt.f[t].state = FB_READY;
+                progress = true;
+            }
+        }
+        if (!progress) { fprintf(stderr, "amp_emu: deadlock in the fiber runtime (divergent collective?)\n"); abort(); }
+    }
+}
+}  // namespace
+
+namespace amp {
+int c_tid() { return g_rt.cur; }
+int c_nthreads() { return g_rt.nthreads; }
+int c_block() { return g_rt.block; }
+void w_sync() { fiber_wait(FB_WAIT_WARP); }
+void c_sync() { fiber_wait(FB_WAIT_CTA); }
+int w_shfl(int v, int src) {
+    g_rt.xch[g_rt.cur] = v;
+    w_sync();
+    const int r = g_rt.xch[(g_rt.cur & ~31) | (src & 31)];
+    w_sync();
+    return r;
+}
+int w_shfl_xor(int v, int m) { return w_shfl(v, (g_rt.cur & 31) ^ m); }
+unsigned w_ballot(bool p) {
+    g_rt.xch[g_rt.cur] = p ? 1 : 0;
+    w_sync();
+    unsigned r = 0;
+    for (int k = 0; k < 32; ++k) if ((g_rt.cur & ~31) + k < g_rt.nthreads && g_rt.xch[(g_rt.cur & ~31) + k]) r |= 1u << k;
+    w_sync();
+    return r;
+}
+int w_max(int v) {
+    g_rt.xch[g_rt.cur] = v;
+    w_sync();
+    int r = v;
+    for (int k = 0; k < 32; ++k) if ((g_rt.cur & ~31) + k < g_rt.nthreads) r = std::max(r, g_rt.xch[(g_rt.cur & ~31) + k]);
+    w_sync();
+    return r;
+}
+}  // namespace amp
 
 struct EmuCtx {
     int L, Lpad, n_samples;
@@ -84,6 +200,51 @@ int emu_process(void* h, long long first, long long n, const int32_t* pos, const
         else amp::cta_trim_pileup<false>(P, sbase, b, threads ? threads : 256);
     }
     return 0;
+}
+
+// the warp-autonomous kernel (amp_warp.cuh): one CTA at a time, every thread a fiber
+struct V7Launch { const amp::KParams* P; unsigned char* smem; int mode; };
+static void v7_body(void* a) {
+    V7Launch* v = (V7Launch*)a;
+    if (v->mode == 3) amp::cta_trim_pileup_v7<true, true, 0>(*v->P, v->smem);
+    else if (v->mode == 1) amp::cta_trim_pileup_v7<true, false, 0>(*v->P, v->smem);
+    else amp::cta_trim_pileup_v7<false, true, 0>(*v->P, v->smem);
+}
+int emu_process_v7(void* h, long long first, long long n, const int32_t* pos, const uint16_t* flag, const int32_t* tlen,
+                   const uint32_t* cig_off, const uint32_t* cigar, const uint32_t* seq_off, const uint8_t* seq,
+                   const uint32_t* qual_off, const uint8_t* qual, int mode, int sample, int32_t* o_pos, uint16_t* o_ncig,
+                   uint8_t* o_flags, uint32_t* o_cigar, int grid_override, int warps, int br_override, int wt_override) {
+    EmuCtx* c = (EmuCtx*)h;
+    if (n <= 0) return 0;
+    amp::KParams P{};
+    P.b = amp::BatchPtrs{first, n, pos, flag, tlen, cig_off, cigar, seq_off, seq, qual_off, qual};
+    P.o = amp::TrimOut{o_pos, o_ncig, o_flags, o_cigar};
+    P.tp = c->tp; P.mode = mode;
+    P.counts = c->counts.data() + (size_t)sample * AMP_NCH * c->Lpad; P.Lpad = c->Lpad; P.gpos_base = sample * c->Lpad;
+    P.tab = c->tab; P.err = &c->err;
+    const long long sum_cig = cig_off[first + n] - cig_off[first];
+    std::vector<uint32_t> scratch(2 * (size_t)(sum_cig + 3 * n) + 8);
+    P.scratch = scratch.data() - ((size_t)cig_off[first] + 3 * (size_t)first);
+    P.scratch_half = sum_cig + 3 * n;
+    const amp::V7Cfg t = amp::pick_v7_cfg(n, (long long)(qual_off[first + n] - qual_off[first]), grid_override ? grid_override : 148);
+    P.wt = wt_override ? wt_override : t.wt;
+    P.reads_per_tile = br_override ? br_override : t.batch_reads;
+    P.ntiles = (int)((n + P.reads_per_tile - 1) / P.reads_per_tile);
+    int grid = std::max(1, std::min(grid_override ? grid_override : 148, P.ntiles));
+    P.tiles_per_cta = (P.ntiles + grid - 1) / grid;
+    grid = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
+    if (!warps) warps = AMP7_WARPS;
+    std::vector<unsigned char> smem(amp::smem_bytes_v7(P.wt, warps) + 64);
+    unsigned char* sbase = smem.data();
+    sbase += (16 - ((uintptr_t)sbase & 15)) & 15;
+    V7Launch v{&P, sbase, mode};
+    for (int b = 0; b < grid; ++b) run_cta(b, warps * 32, v7_body, &v);
+    return 0;
+}
+
+void emu_v7_stats(long long* out, int reset) {
+    out[0] = amp::g_v7_stats[0]; out[1] = amp::g_v7_stats[1];
+    if (reset) amp::g_v7_stats[0] = amp::g_v7_stats[1] = 0;
 }
 
 void emu_counts(void* h, int sample, int32_t* out) {

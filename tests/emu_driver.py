@@ -18,7 +18,8 @@ def build(asan=False):
     name = "libamp_emu_asan.so" if asan else "libamp_emu.so"
     so = os.path.join(_DIR, name)
     srcs = [os.path.join(_DIR, "amp_emu.cpp"), os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_core.cuh"),
-            os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_kernels.cuh")]
+            os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_kernels.cuh"),
+            os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_warp.cuh")]
     if not os.path.isfile(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         gxx = "/usr/bin/g++" if os.path.isfile("/usr/bin/g++") else "g++"
         flags = ["-O1", "-g", "-fsanitize=address,undefined"] if asan else ["-O2"]
@@ -38,6 +39,13 @@ def lib():
     return _lib
 
 
+def v7_stats(reset=True):
+    """(reads finished on the cooperative path, reads sent to the generic path) since the last reset."""
+    out = (ctypes.c_longlong * 2)()
+    lib().emu_v7_stats(out, 1 if reset else 0)
+    return int(out[0]), int(out[1])
+
+
 def _p(a):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
 
@@ -45,7 +53,7 @@ def _p(a):
 class EmuEngine:
     def __init__(self, ref_len, primer_tables=None, max_primer_len=0, min_quality=20, sliding_window_width=4,
                  min_length=30, include_no_primer=False, n_samples=1, ins_slots=1 << 16, ins_arena_bytes=1 << 22, device=0,
-                 grid=0, threads=256, reads_per_tile=0, maxseg=0, wt=0, qbytes=0):
+                 grid=0, threads=256, reads_per_tile=0, maxseg=0, wt=0, qbytes=0, kernel="tile", warps=0, batch_reads=0):
         self.L, self.n_samples = int(ref_len), int(n_samples)
         ins_slots = min(ins_slots or (1 << 16), 1 << 18)
         ins_arena_bytes = min(ins_arena_bytes or (1 << 22), 1 << 24)
@@ -57,6 +65,8 @@ class EmuEngine:
                                                    sliding_window_width, min_length, 1 if include_no_primer else 0,
                                                    ctypes.c_longlong(ins_slots), ctypes.c_longlong(ins_arena_bytes)))
         self.knobs = (grid, threads, reads_per_tile, maxseg, wt, qbytes)
+        # kernel="v7": the warp-autonomous kernel of amp_warp.cuh (every CUDA thread a fiber); "tile": amp_kernels.cuh
+        self.kernel, self.v7_knobs = kernel, (grid, warps, batch_reads, wt)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -77,6 +87,13 @@ class EmuEngine:
         # the staging loops read 16-byte vectors from 16-byte aligned addresses: keep numpy buffers aligned
         qual = _aligned(batch.qual)
         seq = _aligned(batch.seq)
+        if self.kernel == "v7":
+            g, w, br, wt = self.v7_knobs
+            lib().emu_process_v7(self._h, ctypes.c_longlong(first), ctypes.c_longlong(n), _p(batch.pos), _p(batch.flag),
+                                 _p(batch.tlen), _p(batch.cig_off), _p(batch.cigar), _p(batch.seq_off), _p(seq),
+                                 _p(batch.qual_off), _p(qual), mode, sample, _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
+                                 g, w, br, wt)
+            return TrimResult(batch, *out) if trim else None
         g, t, r, ms, wt, qb = self.knobs
         lib().emu_process(self._h, ctypes.c_longlong(first), ctypes.c_longlong(n), _p(batch.pos), _p(batch.flag),
                           _p(batch.tlen), _p(batch.cig_off), _p(batch.cigar), _p(batch.seq_off), _p(seq),

@@ -109,3 +109,40 @@ def check_case_pipeline(make_engine, name):
     eng2.process(tb, trim=False, pileup=True)
     assert np.array_equal(eng2.counts(), arr["counts_kept"])
     assert eng2.insertions().as_dict() == {(int(a), s): int(c) for a, s, c in meta["insertions_kept"]}
+
+
+def check_against_oracle(make_engine, oracle, b, g, prim, offset=0, mq=20, w=4, ml=30, inc=False, ins_slots=0, arena=0):
+    """trim + pileup + call of one engine (CUDA through the C ABI, or the CPU emulation of the kernels) against the oracle."""
+    L = len(g)
+    mn, mx = oracle.find_overlapping_primers(L, prim, offset)
+    tables = find_overlapping_primers(L, prim, offset)
+    assert np.array_equal(tables[0], mn) and np.array_equal(tables[1], mx)
+    mpl = max_primer_len(prim)
+    want = oracle.trim_batch(b, L, mn, mx, mpl, mq, w, ml, inc)
+    wc, wins, nerr = oracle.pileup_batch(b, L, mq, trimmed=want)
+    assert nerr == 0
+    eng = make_engine(ref_len=L, primer_tables=tables, max_primer_len=mpl, min_quality=mq, sliding_window_width=w,
+                      min_length=ml, include_no_primer=inc, ins_slots=ins_slots, ins_arena_bytes=arena)
+    t = eng.process(b, trim=True, pileup=True)
+    assert eng.error_flags() == 0
+    assert np.array_equal(t.flags, want["flags"])
+    assert np.array_equal(t.pos, want["pos"])
+    assert np.array_equal(t.ncig.astype(np.int32), want["ncig"])
+    # rows up to ncig: build a mask of live output words
+    row0 = b.cig_off[:-1].astype(np.int64) + 3 * np.arange(b.n, dtype=np.int64)
+    live = np.repeat(row0, want["ncig"]) + (np.arange(int(want["ncig"].sum())) - np.repeat(np.cumsum(want["ncig"]) - want["ncig"], want["ncig"]))
+    assert np.array_equal(t.cigar[live], want["cigar"][live])
+    counts = eng.counts()
+    assert np.array_equal(counts.astype(np.int64), wc)
+    ins = eng.insertions()
+    assert ins.as_dict() == wins
+    res = eng.call(g)
+    ores = oracle.call(wc, wins, g)
+    assert np.array_equal(res.depth.astype(np.int64), ores["depth"])
+    assert calling.consensus_string(res, ins) == oracle.consensus_string(ores)
+    got = calling.variant_records(res, ins, g, counts)
+    want_v = oracle.variant_records(ores, g)
+    assert len(got) == len(want_v)
+    for a, c in zip(got, want_v):
+        assert tuple(a[:6]) == tuple(c[:6]) and a[6] == c[6] and a[7] == c[7] and tuple(a[8]) == tuple(c[8]), (a, c)
+    return eng, t

@@ -1,0 +1,105 @@
+"""CPU: the warp-autonomous kernel (amplipy_b200/csrc/amp_warp.cuh) run by tests/emu with every CUDA thread as a
+fiber (shuffles / ballots / reductions are rendezvous points) must reproduce the golden fixtures produced by the
+unmodified reference, and the oracle on larger seeded inputs."""
+import numpy as np
+import pytest
+
+import emu_driver
+import golden_io
+import parity
+from amplipy_b200 import synth
+
+CASES = golden_io.list_cases()
+
+
+def v7(**knobs):
+    return lambda **kw: emu_driver.EmuEngine(kernel="v7", **knobs, **kw)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_aio(name):
+    parity.check_case_aio(v7(), name)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pileup_only(name):
+    parity.check_case_pileup_only(v7(), name)
+
+
+@pytest.mark.parametrize("name", ["cfg1_example", "cfg2_illumina", "fuzz1"])
+def test_trim_then_variants_pipeline(name):
+    parity.check_case_pipeline(v7(), name)
+
+
+@pytest.mark.parametrize("knobs", [dict(warps=2, grid=3, batch_reads=5, wt=32), dict(warps=1, grid=1, batch_reads=32, wt=64),
+                                   dict(warps=3, grid=7, batch_reads=17), dict(warps=4, grid=2, batch_reads=1)])
+@pytest.mark.parametrize("name", ["cfg2_illumina", "cfg4_ont", "fuzz3", "quirks"])
+def test_launch_shapes(name, knobs):
+    """Windows narrower than a read (global-atomic path), partial batches, few warps draining long queues."""
+    parity.check_case_aio(v7(**knobs), name)
+
+
+def _scheme(L=29903, n_amp=98, seed=2, n_alt=0):
+    g = synth.random_genome(L, 7)
+    primers, amps = synth.make_scheme(L, n_amp, seed=seed, n_alt=n_alt)
+    return g, [(s, e) for s, e, _ in primers], amps
+
+
+def test_illumina_vs_oracle(oracle_lib):
+    g, prim, amps = _scheme()
+    b = synth.illumina_batch(g, amps, 40_000, seed=31, snvs=[(1000, "T", 0.5), (20000, "A", 0.03)])
+    emu_driver.v7_stats()
+    parity.check_against_oracle(v7(), oracle_lib, b, g, prim)
+    fast, generic = emu_driver.v7_stats()
+    assert fast + generic == b.n and fast > 0.85 * b.n, (fast, generic)   # the cooperative path is the one being tested
+
+
+@pytest.mark.parametrize("mq,w,offset,inc", [(30, 4, 0, False), (11, 4, 3, True), (0, 4, 0, False), (20, 6, 0, False),
+                                             (127, 4, 0, True), (200, 4, 0, True)])
+def test_illumina_parameter_grid_vs_oracle(oracle_lib, mq, w, offset, inc):
+    """Other thresholds; window widths != 4 and thresholds outside the SIMD compare send every read down the generic path."""
+    g, prim, amps = _scheme(seed=3, n_alt=10)
+    b = synth.illumina_batch(g, amps, 6_000, seed=32 + mq)
+    parity.check_against_oracle(v7(grid=4, warps=4), oracle_lib, b, g, prim, offset=offset, mq=mq, w=w, inc=inc)
+
+
+def test_unsorted_vs_oracle(oracle_lib):
+    g, prim, amps = _scheme()
+    b = synth.illumina_batch(g, amps, 12_000, seed=33, sort=False)
+    parity.check_against_oracle(v7(grid=5, warps=4), oracle_lib, b, g, prim)
+
+
+def test_longer_reads_vs_oracle(oracle_lib):
+    """250-bp reads: fewer reads per batch, aligned runs that use all eight words per lane, some beyond them."""
+    g, prim, amps = _scheme(seed=5)
+    b = synth.illumina_batch(g, amps, 8_000, seed=34, read_len=250)
+    parity.check_against_oracle(v7(grid=3, warps=4), oracle_lib, b, g, prim)
+    b = synth.illumina_batch(g, amps, 4_000, seed=35, read_len=301)
+    parity.check_against_oracle(v7(grid=3, warps=4), oracle_lib, b, g, prim)
+
+
+def test_window_edges_vs_oracle(oracle_lib):
+    """Dense low-quality stretches so that failing windows land on every alignment of the run and in the shrinking
+    windows at its open end, on both strands."""
+    g, prim, amps = _scheme(seed=6)
+    rng = np.random.default_rng(7)
+    b = synth.illumina_batch(g, amps, 10_000, seed=36)
+    q = b.qual.copy()
+    for i in range(b.n):
+        lo, hi = int(b.qual_off[i]), int(b.qual_off[i + 1])
+        kind = rng.integers(0, 6)
+        if kind == 0:      # one weak window at a random place
+            p = rng.integers(lo, hi - 4); q[p:p + 4] = rng.integers(0, 25, 4)
+        elif kind == 1:    # weak last / first bases only
+            k = rng.integers(1, 4); q[hi - k:hi] = rng.integers(0, 20, k)
+        elif kind == 2:
+            k = rng.integers(1, 4); q[lo:lo + k] = rng.integers(0, 20, k)
+        elif kind == 3:    # sums right at the threshold
+            p = rng.integers(lo, hi - 4); q[p:p + 4] = [20, 20, 20, rng.integers(19, 22)]
+        elif kind == 4:
+            q[lo:hi] = rng.integers(15, 26, hi - lo)
+    b.qual[:] = q
+    emu_driver.v7_stats()
+    parity.check_against_oracle(v7(grid=3, warps=4), oracle_lib, b, g, prim)
+    fast, generic = emu_driver.v7_stats()
+    assert fast > 0.85 * b.n, (fast, generic)
