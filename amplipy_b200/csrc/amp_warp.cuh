@@ -47,6 +47,7 @@ AMP_WD unsigned dp4a_acc(unsigned w, unsigned acc) { return __dp4a(w, 0x01010101
 AMP_WD int ctz32(unsigned x) { return __ffs((int)x) - 1; }
 AMP_WD int msb32(unsigned x) { return 31 - __clz((int)x); }
 AMP_WD int popc32(unsigned x) { return __popc(x); }
+AMP_WD unsigned byte_perm2(unsigned x, unsigned sel) { return __byte_perm(x, 0u, sel); }
 AMP_WD uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 AMP_WD void mbar_init(unsigned long long* bar) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
@@ -87,6 +88,11 @@ AMP_WD unsigned dp4a_acc(unsigned w, unsigned acc) { return acc + (w & 0xFF) + (
 AMP_WD int ctz32(unsigned x) { return __builtin_ctz(x); }
 AMP_WD int msb32(unsigned x) { return 31 - __builtin_clz(x); }
 AMP_WD int popc32(unsigned x) { return __builtin_popcount(x); }
+AMP_WD unsigned byte_perm2(unsigned x, unsigned sel) {
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) { const unsigned k = (sel >> (4 * i)) & 7u; r |= (k < 4 ? (x >> (8 * k)) & 0xFFu : 0u) << (8 * i); }
+    return r;
+}
 AMP_WD void mbar_init(unsigned long long*) {}
 AMP_WD void bulk_expect(unsigned long long*, uint32_t) {}
 AMP_WD void bulk_copy(void* dst, const void* src, uint32_t bytes, unsigned long long*) { memcpy(dst, src, bytes); }
@@ -167,15 +173,121 @@ AMP_HD void flush_tile7(const KParams& P, const int* cnt, int wbase, int tid, in
     }
 }
 
-// bits (4j + i), j in [0, 8), i in [0, 4), of the positions b = 32 j + l4 + i with lo <= b < hi
-AMP_HD unsigned below_mask(int h, int l4) {
-    const int x = h - l4;
-    if (x <= 0) return 0u;
-    const int rem = x & 31;
-    const int nb = ((x >> 5) << 2) + (rem < 4 ? rem : 4);
-    return nb >= 32 ? 0xFFFFFFFFu : ((1u << nb) - 1u);
+// ---- lane-per-read passes over a staged [S]M[S] read ---------------------------------------------------------------------
+// `buf + a0` = first aligned quality byte (any alignment), m aligned bases, window width 4.  Both passes walk aligned
+// 4-byte words of the staging buffer and funnel-shift them to read-relative words; they read at most 16 bytes past the run.
+
+// (sum - 4*minq) of the 8 windows starting in read-relative words u0, u1 (u2 = look-ahead): sign bit set = window fails
+#define AMP7_WIN8(D, u0, u1, u2, nthr)                                                                              \
+    const unsigned D##0 = dp4a_acc(u0, nthr), D##1 = dp4a_acc(funnel_r(u0, u1, 8), nthr),                           \
+                   D##2 = dp4a_acc(funnel_r(u0, u1, 16), nthr), D##3 = dp4a_acc(funnel_r(u0, u1, 24), nthr),        \
+                   D##4 = dp4a_acc(u1, nthr), D##5 = dp4a_acc(funnel_r(u1, u2, 8), nthr),                           \
+                   D##6 = dp4a_acc(funnel_r(u1, u2, 16), nthr), D##7 = dp4a_acc(funnel_r(u1, u2, 24), nthr)
+AMP_WD unsigned win8_bits(unsigned u0, unsigned u1, unsigned u2, unsigned nthr) {   // bit w = window w of the block fails
+    AMP7_WIN8(D, u0, u1, u2, nthr);
+    unsigned F = funnel_l(D7, 0u, 1);
+    F = funnel_l(D6, F, 1); F = funnel_l(D5, F, 1); F = funnel_l(D4, F, 1);
+    F = funnel_l(D3, F, 1); F = funnel_l(D2, F, 1); F = funnel_l(D1, F, 1); F = funnel_l(D0, F, 1);
+    return F;
 }
-AMP_HD unsigned lane_range_mask(int lo, int hi, int l4) { return below_mask(hi, l4) & ~below_mask(lo, l4); }
+// Sliding-window search (closed form of AmpliPy.py:566-587 / 628-649, same result as window_del_len_fwd / _rev with W = 4)
+// for m >= 8, m + (a0 & 3) <= 256: one pass over blocks of 8 windows keeps one "some window fails" bit per block; the
+// first (forward strand) / last (reverse strand) failing block is then resolved exactly; the three shrinking windows at
+// the open end are checked from three bytes.
+AMP_WD int window_del_blocks(const uint8_t* buf, int a0, int m, bool rev, int minq) {
+    const uint32_t* A = (const uint32_t*)(buf + (a0 & ~3));
+    const unsigned sh = (unsigned)(a0 & 3) << 3;
+    const unsigned nthr = (unsigned)(-4 * minq);
+    const int nwin = m - 3;                       // full windows start at 0 .. nwin - 1
+    const int nb = (nwin + 7) >> 3;               // blocks of 8 windows (<= 32)
+    const unsigned last_mask = (1u << (nwin - 8 * (nb - 1))) - 1u;   // valid windows of the last block (1 .. 8 of them)
+    unsigned Fw = 0;
+    unsigned prev = A[1];
+    unsigned u0 = funnel_r(A[0], prev, sh);
+    for (int i = 0; i < nb - 1; ++i) {
+        const unsigned x1 = A[2 * i + 2], x2 = A[2 * i + 3];
+        const unsigned u1 = funnel_r(prev, x1, sh), u2 = funnel_r(x1, x2, sh);
+        AMP7_WIN8(D, u0, u1, u2, nthr);
+        Fw = funnel_l(D0 | D1 | D2 | D3 | D4 | D5 | D6 | D7, Fw, 1);
+        u0 = u2; prev = x2;
+    }
+    {
+        const unsigned x1 = A[2 * nb], x2 = A[2 * nb + 1];
+        const unsigned bits = win8_bits(u0, funnel_r(prev, x1, sh), funnel_r(x1, x2, sh), nthr) & last_mask;
+        Fw = (Fw << 1) | (bits ? 1u : 0u);
+    }
+    if (Fw) {   // block i sits at bit nb - 1 - i
+        const int i = nb - 1 - (rev ? ctz32(Fw) : msb32(Fw));
+        const unsigned x0 = A[2 * i], x1 = A[2 * i + 1], x2 = A[2 * i + 2], x3 = A[2 * i + 3];
+        unsigned bits = win8_bits(funnel_r(x0, x1, sh), funnel_r(x1, x2, sh), funnel_r(x2, x3, sh), nthr);
+        if (i == nb - 1) bits &= last_mask;
+        const int t = 8 * i + (rev ? msb32(bits) : ctz32(bits));
+        return rev ? t + 4 : m - t;
+    }
+    const uint8_t* e3 = buf + a0 + (rev ? 0 : m - 3);   // shrinking windows w = 3, 2, 1 at the open end
+    const int x0 = e3[0], x1 = e3[1], x2 = e3[2];
+    const int e = rev ? x0 : x2;
+    if (x0 + x1 + x2 < 3 * minq) return 3;
+    if (e + x1 < 2 * minq) return 2;
+    if (e < minq) return 1;
+    return 0;
+}
+
+// Pileup of one aligned run (update_base_counts, AmpliPy.py:718 + 752-753) inside the count tile: quality byte t at
+// qbuf[a0 + t], base t = nibble n0 + t of sbuf, tile position tp0 + t, t in [0, m).  Chunks of 8 bases: two quality words
+// -> SIMD byte compare q >= minq; one sequence word split into pre-scaled high / low nibbles so that one byte permute per
+// base yields the tile row offset; a masked base increments the sink row instead (no branch).  Lanes of a warp that work
+// on reads with the same start hit the same address and are merged by the hardware (ATOMS.POPC.INC).
+template <int WT>
+AMP_WD void count_run_v8(int* cnt, int wt, const uint8_t* qbuf, int a0, const uint8_t* sbuf, int n0, int m, int tp0, unsigned minq4) {
+    const uint32_t* A = (const uint32_t*)(qbuf + (a0 & ~3));
+    const unsigned sh = (unsigned)(a0 & 3) << 3;
+    const int sb = n0 >> 1;
+    const bool par = n0 & 1;
+    const uint32_t* S = (const uint32_t*)(sbuf + (sb & ~3));
+    const unsigned ssh = (unsigned)(sb & 3) << 3;
+    const int nch = (m + 7) >> 3;
+    unsigned qa = A[0];
+    unsigned sa = S[1];
+    unsigned x = funnel_r(S[0], sa, ssh);
+    int* tl = cnt + tp0;
+    for (int c = 0; c < nch; ++c, tl += 8) {
+        const unsigned q1 = A[2 * c + 1], q2 = A[2 * c + 2];
+        const unsigned v0 = funnel_r(qa, q1, sh), v1 = funnel_r(q1, q2, sh);
+        qa = q2;
+        const unsigned s2 = S[c + 2];
+        const unsigned xn = funnel_r(sa, s2, ssh);          // sequence word of the next chunk
+        sa = s2;
+        // q >= minq per byte (exact for every byte value, minq <= 127): bit 7 of each byte
+        unsigned g0 = (((v0 | 0x80808080u) - minq4) | v0) & 0x80808080u;
+        unsigned g1 = (((v1 | 0x80808080u) - minq4) | v1) & 0x80808080u;
+        if (c == nch - 1) {                                  // bases past the run
+            const int left = m - 8 * c;                      // 1 .. 8
+            const unsigned long long keep = left >= 8 ? ~0ULL : ((1ULL << (8 * left)) - 1ULL);
+            g0 &= (unsigned)keep; g1 &= (unsigned)(keep >> 32);
+        }
+        // nibbles scaled by 8, one per byte: E = bases at even nibble positions of x, O = odd ones
+        const unsigned E = (x >> 1) & 0x78787878u, O = (x << 3) & 0x78787878u, En = (xn >> 1) & 0x78787878u;
+        const unsigned a = par ? O : E;                      // bases 0, 2, 4, 6 of the chunk
+        const unsigned b = par ? funnel_r(E, En, 8) : O;     // bases 1, 3, 5, 7
+        x = xn;
+#define AMP7_BASE(ii, src, kb, g)                                                                                      \
+        {                                                                                                              \
+            if (WT == 512) {                                                                                           \
+                const unsigned off = byte_perm2(src, 0x4404u | ((kb) << 4));          /* nibble * 2048 bytes */         \
+                const unsigned o2 = ((g) & (0x80u << (8 * ((ii) & 3)))) ? off : (unsigned)(AMP7_SINK_ROW * 2048 + 64);  \
+                atomic_add((int*)((char*)tl + o2) + (ii), 1);                                                          \
+            } else {                                                                                                   \
+                const unsigned row = ((src) >> (8 * (kb) + 3)) & 15u;                                                  \
+                const int o2 = ((g) & (0x80u << (8 * ((ii) & 3)))) ? (int)row * wt : AMP7_SINK_ROW * wt + 16;            \
+                atomic_add(tl + o2 + (ii), 1);                                                                         \
+            }                                                                                                          \
+        }
+        AMP7_BASE(0, a, 0, g0) AMP7_BASE(1, b, 0, g0) AMP7_BASE(2, a, 1, g0) AMP7_BASE(3, b, 1, g0)
+        AMP7_BASE(4, a, 2, g1) AMP7_BASE(5, b, 2, g1) AMP7_BASE(6, a, 3, g1) AMP7_BASE(7, b, 3, g1)
+#undef AMP7_BASE
+    }
+}
 
 // ---- generic path inside a warp (same logic as TileSink / read_generic, warp-private run list) --------------------
 struct WarpSink7 {
@@ -382,8 +494,6 @@ AMP_WD void cta_trim_pileup_v7(const KParams& P, unsigned char* smem_base) {
     // the cooperative path needs the default window and a quality threshold that fits the SIMD byte compare
     const bool fast_ok = minq >= 0 && minq <= 127 && (!TRIM || P.tp.window == 4);
     const unsigned minq4 = (unsigned)minq * 0x01010101u;
-    const unsigned nthr = (unsigned)(-4 * minq);
-    const int l = lane & 7, sub = lane >> 3, l4 = 4 * l;
     uint32_t parity = 0;
     int nq = 0;                                      // queued generic-path reads (uniform across the warp)
 
@@ -447,136 +557,38 @@ AMP_WD void cta_trim_pileup_v7(const KParams& P, unsigned char* smem_base) {
             for (int k = 0; k < nc; ++k) orow[k] = cig[k];
             P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)AMP_F_SKIPPED;
         }
-        // per-read parameters of phase B, fetched by the read's lane group with shuffles
 #if !defined(__CUDA_ARCH__)
         if (fast) ++g_v7_stats[0]; else if (have && !skipped) ++g_v7_stats[1];
 #endif
-        const int pk0 = fast ? (int)(a0 | ((uint32_t)r.m << 16) | (rev ? 1u << 25 : 0u) | 0x80000000u) : 0;
-        const int pk1 = PILE ? (int)(2u * (AMP7_PAD + so0 - s_lo) + (uint32_t)r.s1) : 0;   // nibble index of the first aligned base in sbuf
-        int del_mine = 0;
-
         w_sync();
         if (q_bulk + s_bulk > 0) { bulk_wait(wm.bar, parity); parity ^= 1u; }
 
-        // ---- B: window search + counting, 8 lanes per read --------------------------------------------------------------
-        const int nsteps = (nreads + 3) >> 2;
-        unsigned errs = 0;
-        for (int g = 0; g < nsteps; ++g) {
-            const int src = 4 * g + sub;
-            const int k0 = w_shfl(pk0, src);
-            const int k1s = PILE ? w_shfl(pk1, src) : 0;
-            const int pp = w_shfl(pos, src);
-            const bool valid = k0 < 0;
-            const int k1 = valid ? k1s : 2 * AMP7_PAD;                                    // idle groups address the front of the buffer
-            const int ga0 = k0 & 0xFFFF, m = (k0 >> 16) & 0x1FF;
-            const bool grev = (k0 >> 25) & 1;
-            const int lead = ga0 & 3;
-            const int nsl = valid ? ((lead + m - 1) >> 5) + 1 : 0;                      // slots of 32 positions (per group)
-            unsigned F = 0, Q = 0;
-            {
-                const uint32_t* wq = (const uint32_t*)(wm.qbuf + (ga0 & ~3)) + l;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                for (int j = AMP7_KW - 1; j >= 0; --j) {
-                    if (j < nsl) {
-                        const unsigned v = wq[8 * j];
-                        if (PILE) {   // q >= minq per byte (exact for all byte values, minq <= 127) -> 4 bits
-                            const unsigned t = (v | 0x80808080u) - minq4;
-                            Q = funnel_l(((t | v) & 0x80808080u) * 0x00204081u, Q, 4);
-                        }
-                        if (TRIM) {   // window sums of positions 4k .. 4k+3 minus 4*minq: sign bit = window fails
-                            const unsigned n = wq[8 * j + 1];
-                            F = funnel_l(dp4a_acc(funnel_r(v, n, 24), nthr), F, 1);
-                            F = funnel_l(dp4a_acc(funnel_r(v, n, 16), nthr), F, 1);
-                            F = funnel_l(dp4a_acc(funnel_r(v, n, 8), nthr), F, 1);
-                            F = funnel_l(dp4a_acc(v, nthr), F, 1);
-                        }
-                    }
-                }
-            }
-            int del = 0;
+        // ---- B: lane per read: window search, quality clip + write gate + outputs, pileup of the aligned run ------------
+        if (fast) {
             if (TRIM) {
-                // full windows start at b in [lead, lead + m - 4]; forward strand: first failing, reverse: last failing
-                const unsigned Fv = F & lane_range_mask(lead, lead + m - 3, l4);
-                int key = -1;
-                if (Fv) {
-                    const int nbit = grev ? msb32(Fv) : ctz32(Fv);
-                    const int b = ((nbit >> 2) << 5) + (nbit & 3) + l4;
-                    key = grev ? b : 0x10000 - b;
-                }
-                { int o = w_shfl_xor(key, 1); key = o > key ? o : key; o = w_shfl_xor(key, 2); key = o > key ? o : key; o = w_shfl_xor(key, 4); key = o > key ? o : key; }
-                if (key >= 0) {
-                    const int b = grev ? key : 0x10000 - key;
-                    del = grev ? b - lead + 4 : m - (b - lead);
-                } else if (valid) {
-                    // the three shrinking windows at the open end (w = 3, 2, 1)
-                    const uint8_t* e3 = wm.qbuf + ga0 + (grev ? 0 : m - 3);
-                    const int x0 = e3[0], x1 = e3[1], x2 = e3[2];
-                    const int e = grev ? x0 : x2;
-                    if (x0 + x1 + x2 < 3 * minq) del = 3;
-                    else if (e + x1 < 2 * minq) del = 2;
-                    else if (e < minq) del = 1;
-                }
-                // hand the result to the read's own lane (lane 4g + s reads group s)
-                const int dsh = w_shfl(del, (lane & 3) << 3);
-                if ((lane >> 2) == g) del_mine = dsh;
+                const int del = window_del_blocks(wm.qbuf, (int)a0, r.m, rev, minq);
+                trim_simple_finish(r, del, rev, P.tp, &f);                            // 589-686 (pos stays on the reverse strand, F6), 910
+                uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
+                const int no = emit_simple(r, orow);
+                P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)no; P.o.flags[i] = (uint8_t)f;
             }
-            if (PILE) {
-                const int dq = TRIM ? (grev ? (del >= 2 ? del : 0) : del) : 0;
-                const int cl = lead + (grev ? dq : 0), ch = valid ? lead + m - (grev ? 0 : dq) : 0;
-                const int rb = pp - lead - (grev ? dq : 0);                               // reference position of b = 0 (pos stays, F6)
-                const unsigned cm = Q & lane_range_mask(cl, ch, l4);
-                const int nn0 = k1 - lead + l4;                                           // nibble index of this lane's first position
-                const int sbyte = nn0 >> 1;
-                const unsigned par4 = (unsigned)(nn0 & 1) << 2, sh8 = (unsigned)(sbyte & 3) << 3;
-                const uint32_t* ws = (const uint32_t*)(wm.sbuf + (sbyte & ~3));
-                const int w0 = rb - wbase;
-                const bool in_win = wbase >= 0 && w0 >= 0 && w0 + ch <= wt;             // uniform per group
-                const int ncs = ch > cl ? ((ch - 1) >> 5) + 1 : 0;                        // slots that hold counted positions
-                if (in_win) {
-                    const int tl = w0 + l4;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                    for (int j = 0; j < AMP7_KW; ++j) {
-                        if (j < ncs) {
-                            const unsigned x = funnel_r(ws[4 * j], ws[4 * j + 1], sh8);
-                            const unsigned y = ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);   // nibbles in base order
-                            const unsigned z = y >> par4, zh = z >> 8;
-                            // AmpliPy.py:752-753; the quality gate (718) and the aligned range (722 / 726) are in cm.  A masked
-                            // base increments the sink row at its own position: no branch, and the lanes of a group keep
-                            // hitting banks 4 apart.
-                            const unsigned r0 = (cm & (1u << (4 * j + 0))) ? (z & 15u) : (unsigned)AMP7_SINK_ROW;
-                            const unsigned r1 = (cm & (1u << (4 * j + 1))) ? ((z >> 4) & 15u) : (unsigned)AMP7_SINK_ROW;
-                            const unsigned r2 = (cm & (1u << (4 * j + 2))) ? (zh & 15u) : (unsigned)AMP7_SINK_ROW;
-                            const unsigned r3 = (cm & (1u << (4 * j + 3))) ? ((zh >> 4) & 15u) : (unsigned)AMP7_SINK_ROW;
-                            atomic_add(cnt + tl + 32 * j + 0 + (int)r0 * wt, 1);
-                            atomic_add(cnt + tl + 32 * j + 1 + (int)r1 * wt, 1);
-                            atomic_add(cnt + tl + 32 * j + 2 + (int)r2 * wt, 1);
-                            atomic_add(cnt + tl + 32 * j + 3 + (int)r3 * wt, 1);
-                        }
+            if (PILE && r.m > 0) {
+                // final shape S(s1) M(m) S(s2) at pos: query base s1 + t sits on reference position pos + t
+                const int qa0 = (int)(AMP7_PAD + (qo0 - q_lo)) + r.s1;
+                const int n0 = (int)(2u * (AMP7_PAD + so0 - s_lo)) + r.s1;
+                const int w0 = pos - wbase;
+                if (wbase >= 0 && w0 >= 0 && w0 + r.m <= wt) {
+                    count_run_v8<WT>(cnt, wt, wm.qbuf, qa0, wm.sbuf, n0, r.m, w0, minq4);
+                } else {   // outside the tile: base by base into the global matrix (exact, rare on sorted input)
+                    unsigned errs = 0;
+                    for (int t = 0; t < r.m; ++t) {
+                        if (wm.qbuf[qa0 + t] < minq) continue;
+                        const uint32_t nb = (uint32_t)(n0 + t);
+                        count_global7(P, cnt, wbase, (int)((wm.sbuf[nb >> 1] >> ((~nb & 1u) << 2)) & 15u), pos + t, errs);
                     }
-                } else if (cm) {
-                    for (int j = 0; j < AMP7_KW; ++j) {
-                        if (!((cm >> (4 * j)) & 15u)) continue;
-                        const unsigned x = funnel_r(ws[4 * j], ws[4 * j + 1], sh8);
-                        const unsigned y = ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
-                        const unsigned z = y >> par4;
-                        for (int ii = 0; ii < 4; ++ii)
-                            if (cm & (1u << (4 * j + ii))) count_global7(P, cnt, wbase, (int)((z >> (4 * ii)) & 15u), rb + 32 * j + l4 + ii, errs);
-                    }
+                    if (errs) atomic_or(P.err, errs);
                 }
             }
-        }
-        if (errs) atomic_or(P.err, errs);
-
-        // ---- C: quality clip + write gate + outputs, lane per read --------------------------------------------------------
-        if (TRIM && fast) {
-            trim_simple_finish(r, del_mine, rev, P.tp, &f);
-            uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
-            const int no = emit_simple(r, orow);
-            P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)no; P.o.flags[i] = (uint8_t)f;
         }
         w_sync();   // every lane is done with the staged rows before the buffers are reused
 
