@@ -57,11 +57,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) amp_trim_pileup_indel_ke
     amp::cta_trim_pileup<true>(P, smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
-// warp-autonomous kernel for short-read batches (amp_warp.cuh): one CTA per SM, AMP7_WARPS independent warps
+// warp-autonomous kernels for short-read batches (amp_warp.cuh): one CTA per SM, independent warps.
+// fast: [S]M[S] reads, lane per read; generic: every other mapped read, from the per-CTA lists the fast kernel wrote.
 template <bool TRIM, bool PILE>
-__global__ void __launch_bounds__(AMP7_WARPS * 32, 1) amp_trim_pileup_v7_kernel(const __grid_constant__ amp::KParams P) {
+__global__ void __launch_bounds__(AMP7_WARPS * 32, 1) amp_trim_pileup_fast_kernel(const __grid_constant__ amp::KParams P) {
     extern __shared__ __align__(128) unsigned char smem7[];
-    amp::cta_trim_pileup_v7<TRIM, PILE, AMP7_WT>(P, smem7);
+    amp::cta_fast_v8<TRIM, PILE, AMP7_WT>(P, smem7);
+}
+template <bool TRIM, bool PILE>
+__global__ void __launch_bounds__(AMP7_GWARPS * 32, 1) amp_trim_pileup_generic_kernel(const __grid_constant__ amp::KParams P) {
+    extern __shared__ __align__(128) unsigned char smem7[];
+    amp::cta_generic_v8<TRIM, PILE>(P, smem7);
 }
 
 __device__ const unsigned char kFixedSyms[8] = {'A', 'C', 'G', 'T', 'N', '-', 0, 0};
@@ -112,6 +118,7 @@ struct DevChunk {   // device staging for one in-flight chunk of amp_process_hos
     uint8_t *seq = nullptr, *qual = nullptr;
     int32_t* o_pos = nullptr; uint16_t* o_ncig = nullptr; uint8_t* o_flags = nullptr; uint32_t* o_cigar = nullptr;
     uint32_t* scratch = nullptr;
+    uint32_t* glist = nullptr; size_t cap_glist = 0;
     size_t cap_reads = 0, cap_cig = 0, cap_seq = 0, cap_qual = 0, cap_scratch = 0;
 };
 
@@ -127,6 +134,7 @@ struct amp_ctx {
     unsigned int* d_err = nullptr;
     int* d_heads = nullptr;
     uint32_t* d_scratch = nullptr; size_t scratch_words = 0;
+    uint32_t* d_glist = nullptr; size_t glist_words = 0;   // per-CTA generic-read lists of the warp-autonomous kernels
     DevChunk chunk[3];
     int last_launches = 0;
     size_t max_dyn_smem = 0;
@@ -149,8 +157,11 @@ int dev_grow(T** p, size_t* cap, size_t need) {
     return AMP_OK;
 }
 
+// words of the per-CTA generic-read lists + their counters for a launch over n reads
+size_t glist_words_for(const amp_ctx* c, long long n) { return (size_t)n + 33 * ((size_t)c->sm_count + 1) + (size_t)c->sm_count + 64; }
+
 int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long long max_cig, long long sum_qual, int mode,
-                   int sample, const amp::TrimOut& o, uint32_t* scratch, cudaStream_t st) {
+                   int sample, const amp::TrimOut& o, uint32_t* scratch, uint32_t* glist, cudaStream_t st) {
     if (b.n <= 0) return AMP_OK;
     amp::KParams P{};
     P.b = b; P.o = o;
@@ -173,19 +184,29 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
         int grid = std::max(1, std::min(P.ntiles, c->sm_count));
         P.tiles_per_cta = (P.ntiles + grid - 1) / grid;
         grid = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
-        const size_t smem = amp::smem_bytes_v7(P.wt, AMP7_WARPS);
+        const size_t smem_f = amp::smem_bytes_fast(P.wt, AMP7_WARPS), smem_g = amp::smem_bytes_v7(P.wt, AMP7_GWARPS);
         if (!c->v7_attr) {
-            CK(cudaFuncSetAttribute(amp_trim_pileup_v7_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(amp_trim_pileup_v7_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(amp_trim_pileup_v7_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_generic_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_generic_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_generic_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
             c->v7_attr = true;
         }
+        // per-CTA lists of the reads that need the generic kernel
+        P.gcap = (long long)P.tiles_per_cta * P.reads_per_tile;
+        P.glist = glist; P.gcount = (int*)(glist + (size_t)grid * (size_t)P.gcap);
         const bool tr = mode & AMP_MODE_TRIM, pl = mode & AMP_MODE_PILEUP;
-        if (tr && pl) amp_trim_pileup_v7_kernel<true, true><<<grid, AMP7_WARPS * 32, smem, st>>>(P);
-        else if (tr) amp_trim_pileup_v7_kernel<true, false><<<grid, AMP7_WARPS * 32, smem, st>>>(P);
-        else amp_trim_pileup_v7_kernel<false, true><<<grid, AMP7_WARPS * 32, smem, st>>>(P);
+        if (tr && pl) amp_trim_pileup_fast_kernel<true, true><<<grid, AMP7_WARPS * 32, smem_f, st>>>(P);
+        else if (tr) amp_trim_pileup_fast_kernel<true, false><<<grid, AMP7_WARPS * 32, smem_f, st>>>(P);
+        else amp_trim_pileup_fast_kernel<false, true><<<grid, AMP7_WARPS * 32, smem_f, st>>>(P);
         CK(cudaGetLastError());
-        c->last_launches += 1;
+        if (tr && pl) amp_trim_pileup_generic_kernel<true, true><<<grid, AMP7_GWARPS * 32, smem_g, st>>>(P);
+        else if (tr) amp_trim_pileup_generic_kernel<true, false><<<grid, AMP7_GWARPS * 32, smem_g, st>>>(P);
+        else amp_trim_pileup_generic_kernel<false, true><<<grid, AMP7_GWARPS * 32, smem_g, st>>>(P);
+        CK(cudaGetLastError());
+        c->last_launches += 2;
         return AMP_OK;
     }
     P.wt = t.wt; P.maxseg = t.maxseg; P.qbytes = t.qbytes; P.sbytes = t.sbytes; P.reads_per_tile = t.reads_per_tile;
@@ -277,11 +298,11 @@ int amp_destroy(amp_ctx* c) {
     cudaFree(c->d_min_start); cudaFree(c->d_max_end);
     if (c->counts_owned) cudaFree(c->d_counts);
     cudaFree(c->tab.slots); cudaFree(c->tab.entries); cudaFree(c->tab.slot_entry); cudaFree(c->tab.arena); cudaFree(c->tab.cursor);
-    cudaFree(c->d_err); cudaFree(c->d_heads); cudaFree(c->d_scratch); cudaFree(c->d_ref); cudaFree(c->d_call);
+    cudaFree(c->d_err); cudaFree(c->d_heads); cudaFree(c->d_scratch); cudaFree(c->d_glist); cudaFree(c->d_ref); cudaFree(c->d_call);
     for (auto& ch : c->chunk) {
         cudaFree(ch.pos); cudaFree(ch.flag); cudaFree(ch.tlen); cudaFree(ch.cig_off); cudaFree(ch.seq_off); cudaFree(ch.qual_off);
         cudaFree(ch.cigar); cudaFree(ch.seq); cudaFree(ch.qual); cudaFree(ch.o_pos); cudaFree(ch.o_ncig); cudaFree(ch.o_flags);
-        cudaFree(ch.o_cigar); cudaFree(ch.scratch);
+        cudaFree(ch.o_cigar); cudaFree(ch.scratch); cudaFree(ch.glist);
         if (ch.stream) cudaStreamDestroy(ch.stream);
     }
     delete c;
@@ -342,6 +363,16 @@ int amp_process_device(amp_ctx* c, const amp_batch* b, int64_t sum_cigar_ops, in
             c->scratch_words = need;
         }
     }
+    {
+        const size_t need = glist_words_for(c, b->n_reads);
+        if (need > c->glist_words) {
+            CK(cudaStreamSynchronize(st));
+            if (c->d_glist) CK(cudaFree(c->d_glist));
+            c->d_glist = nullptr; c->glist_words = 0;
+            CK(cudaMalloc((void**)&c->d_glist, need * 4));
+            c->glist_words = need;
+        }
+    }
     amp::BatchPtrs bp{b->first, b->n_reads, b->pos, b->flag, b->tlen, b->cig_off, b->cigar, b->seq_off, b->seq, b->qual_off, b->qual};
     amp::TrimOut to{};
     if (o) { to.pos = o->pos; to.ncig = o->ncig; to.flags = o->flags; to.cigar = o->cigar; }
@@ -353,7 +384,7 @@ int amp_process_device(amp_ctx* c, const amp_batch* b, int64_t sum_cigar_ops, in
         scratch -= (size_t)c_first + 3 * (size_t)b->first;
     }
     if (sum_qual_bytes <= 0) sum_qual_bytes = (long long)b->n_reads * 150;
-    return launch_process(c, bp, sum_cigar_ops, 0, sum_qual_bytes, mode, sample, to, scratch, st);
+    return launch_process(c, bp, sum_cigar_ops, 0, sum_qual_bytes, mode, sample, to, scratch, c->d_glist, st);
 }
 
 int amp_process_host(amp_ctx* c, const amp_batch* b, int mode, int sample, const amp_trim_out* o) {
@@ -389,6 +420,7 @@ int amp_process_host(amp_ctx* c, const amp_batch* b, int mode, int sample, const
             int rc;
             if ((rc = dev_grow(&d.cigar, &d.cap_cig, (c1 - c0) + 4))) return rc;
             if ((rc = dev_grow(&d.qual, &d.cap_qual, (q1 - q0) + 32))) return rc;
+            if ((rc = dev_grow(&d.glist, &d.cap_glist, glist_words_for(c, n)))) return rc;
             if (pile && (rc = dev_grow(&d.seq, &d.cap_seq, (s1 - s0) + 32))) return rc;
             if (trim) {
                 const size_t orows = (c1 - c0) + 3 * (size_t)n;
@@ -421,7 +453,7 @@ int amp_process_host(amp_ctx* c, const amp_batch* b, int mode, int sample, const
         const size_t orow0 = c0 + 3 * (size_t)a;
         if (trim) { to.pos = d.o_pos - a; to.ncig = d.o_ncig - a; to.flags = d.o_flags - a; to.cigar = d.o_cigar - orow0; }
         int rc = launch_process(c, bp, (long long)(c1 - c0), 0, (long long)(b->qual_off[e] - b->qual_off[a]), mode, sample, to,
-                                trim ? d.scratch - orow0 : nullptr, st);
+                                trim ? d.scratch - orow0 : nullptr, d.glist, st);
         if (rc) return rc;
         if (trim) {
             CK(cudaMemcpyAsync(o->pos + a, d.o_pos, n * 4, cudaMemcpyDeviceToHost, st));

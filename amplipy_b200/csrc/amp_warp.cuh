@@ -103,7 +103,10 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 
 // ---- shared-memory layout ------------------------------------------------------------------------------------------
 #ifndef AMP7_WARPS
-#define AMP7_WARPS 16
+#define AMP7_WARPS 16            // warps per CTA of the fast kernel
+#endif
+#ifndef AMP7_GWARPS
+#define AMP7_GWARPS 16           // warps per CTA of the generic kernel
 #endif
 #define AMP7_WT 512              // count tile width on the device (positions)
 #define AMP7_ROWS 18             // count tile rows: BAM nibble 0..15, row 16 = deleted base, row 17 = sink of masked bases
@@ -123,7 +126,7 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_GSLOT_S 96
 #define AMP7_GN 26               // reads per G phase (GN * GSLOT <= DATA)
 #define AMP7_WARP_BYTES (AMP7_QBUF + AMP7_SBUF + AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + 16)
-enum { C7_TMIN = 0, C7_NEXT = 1, C7_WORDS = 16 };
+enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_WORDS = 16 };
 
 // the sink row is the last one and 32 * KW entries longer: idle slots of a group increment it past the window's end
 AMP_HD size_t tile_bytes_v7(int wt) { return ((size_t)AMP7_ROWS * wt + 32 * AMP7_KW) * 4; }
@@ -139,6 +142,23 @@ inline V7Cfg pick_v7_cfg(long long n, long long sum_qual, int sm_count) {
     int br = (int)((AMP7_QDATA - 16) / (avg_len * 1.02 + 1.0));
     t.batch_reads = br < 1 ? 1 : (br > 32 ? 32 : br);
     return t;
+}
+
+// fast kernel: per-warp staging buffers, the per-read parameters of the count pass, and the bulk-copy barrier
+struct Par4 { int x, y, z, w; };   // x = qbuf offset | aligned bases << 16, y = first nibble in sbuf, z = tile position, w = first chunk
+AMP_HD Par4 make_par(int x, int y, int z, int w) { Par4 p; p.x = x; p.y = y; p.z = z; p.w = w; return p; }
+#define AMP7_FAST_BYTES (AMP7_QBUF + AMP7_SBUF + 32 * 16 + 32 + 16)
+struct FastMem { uint8_t* qbuf; uint8_t* sbuf; Par4* par; uint8_t* own; unsigned long long* bar; };
+AMP_HD size_t smem_bytes_fast(int wt, int warps) { return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_FAST_BYTES; }
+AMP_HD FastMem carve_fast(unsigned char* base, int wt, int w) {
+    unsigned char* b = base + tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)w * AMP7_FAST_BYTES;
+    FastMem m;
+    m.qbuf = b; b += AMP7_QBUF;
+    m.sbuf = b; b += AMP7_SBUF;
+    m.par = (Par4*)b; b += 32 * 16;
+    m.own = b; b += 32;
+    m.bar = (unsigned long long*)b;
+    return m;
 }
 
 struct WarpMem7 {
@@ -234,12 +254,14 @@ AMP_WD int window_del_blocks(const uint8_t* buf, int a0, int m, bool rev, int mi
 }
 
 // Pileup of one aligned run (update_base_counts, AmpliPy.py:718 + 752-753) inside the count tile: quality byte t at
-// qbuf[a0 + t], base t = nibble n0 + t of sbuf, tile position tp0 + t, t in [0, m).  Chunks of 8 bases: two quality words
+// qbuf[a0 + t], base t = nibble n0 + t of sbuf, tile position tp0 + t, t in [0, m); this call covers the 8-base chunks
+// [c_lo, c_hi).  Per chunk: two quality words
 // -> SIMD byte compare q >= minq; one sequence word split into pre-scaled high / low nibbles so that one byte permute per
 // base yields the tile row offset; a masked base increments the sink row instead (no branch).  Lanes of a warp that work
 // on reads with the same start hit the same address and are merged by the hardware (ATOMS.POPC.INC).
 template <int WT>
-AMP_WD void count_run_v8(int* cnt, int wt, const uint8_t* qbuf, int a0, const uint8_t* sbuf, int n0, int m, int tp0, unsigned minq4) {
+AMP_WD void count_run_v8(int* cnt, int wt, const uint8_t* qbuf, int a0, const uint8_t* sbuf, int n0, int m, int tp0, int c_lo, int c_hi,
+                          unsigned minq4) {
     const uint32_t* A = (const uint32_t*)(qbuf + (a0 & ~3));
     const unsigned sh = (unsigned)(a0 & 3) << 3;
     const int sb = n0 >> 1;
@@ -247,11 +269,11 @@ AMP_WD void count_run_v8(int* cnt, int wt, const uint8_t* qbuf, int a0, const ui
     const uint32_t* S = (const uint32_t*)(sbuf + (sb & ~3));
     const unsigned ssh = (unsigned)(sb & 3) << 3;
     const int nch = (m + 7) >> 3;
-    unsigned qa = A[0];
-    unsigned sa = S[1];
-    unsigned x = funnel_r(S[0], sa, ssh);
-    int* tl = cnt + tp0;
-    for (int c = 0; c < nch; ++c, tl += 8) {
+    unsigned qa = A[2 * c_lo];
+    unsigned sa = S[c_lo + 1];
+    unsigned x = funnel_r(S[c_lo], sa, ssh);
+    int* tl = cnt + tp0 + 8 * c_lo;
+    for (int c = c_lo; c < c_hi; ++c, tl += 8) {
         const unsigned q1 = A[2 * c + 1], q2 = A[2 * c + 2];
         const unsigned v0 = funnel_r(qa, q1, sh), v1 = funnel_r(q1, q2, sh);
         qa = q2;
@@ -456,30 +478,22 @@ AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, i
     w_sync();
 }
 
-// ---- the kernel body -------------------------------------------------------------------------------------------------
+// ---- the kernels -----------------------------------------------------------------------------------------------------
 // P.reads_per_tile = reads per batch (<= 32), P.ntiles = batches, P.tiles_per_cta = batches per CTA (contiguous chunk).
 // WT = width of the count tile as a compile-time constant (0: P.wt, used by the emulation tests).
-template <bool TRIM, bool PILE, int WT>
-AMP_WD void cta_trim_pileup_v7(const KParams& P, unsigned char* smem_base) {
-    const int wt = WT ? WT : P.wt;
-    const int tid = c_tid(), nthreads = c_nthreads(), block = c_block();
-    const int lane = tid & 31, warp = tid >> 5;
-    const int BR = P.reads_per_tile;
-    int* cnt = (int*)smem_base;
-    int* ctrl = (int*)(smem_base + tile_bytes_v7(wt));
-    const WarpMem7 wm = carve_warp7(smem_base, wt, warp);
-    const long long g_lo = (long long)block * P.tiles_per_cta;
-    long long g_hi = g_lo + P.tiles_per_cta; if (g_hi > P.ntiles) g_hi = P.ntiles;
-    const int n_batches = g_hi > g_lo ? (int)(g_hi - g_lo) : 0;
-    const long long n_end = P.b.first + P.b.n;
+//
+// Two launches per batch of reads, same grid, CTA c owns the same chunk of reads in both:
+//   fast kernel    : [S]M[S] reads, lane per read (phases A and B above); every other mapped read is appended to the
+//                    CTA's segment of P.glist
+//   generic kernel : the reads of that list, AMP7_GN at a time per warp (phase G)
+// Keeping the loop-for-loop generic code out of the fast kernel keeps the latter's instruction footprint small.
 
-    if (PILE) for (int i = tid; i < (AMP7_DEL_ROW + 1) * wt; i += nthreads) cnt[i] = 0;   // the sink row is never read
-    if (tid == 0) { ctrl[C7_TMIN] = 0x7FFFFFFF; ctrl[C7_NEXT] = 0; }
-    if (lane == 0) { wm.ctr[0] = 0; wm.ctr[1] = 0; mbar_init(wm.bar); }
+// window base of a CTA's chunk: smallest start among its first reads (coordinate-sorted input => of the whole chunk)
+AMP_WD int chunk_window_base(const KParams& P, int* ctrl, long long first_read, long long n_end, int tid, bool any) {
+    if (tid == 0) ctrl[C7_TMIN] = 0x7FFFFFFF;
     c_sync();
-    // window base: smallest start among the first reads of the chunk (coordinate-sorted input => of the whole chunk)
-    if (PILE && n_batches > 0 && tid < 64) {
-        const long long i = P.b.first + g_lo * BR + tid;
+    if (any && tid < 64) {
+        const long long i = first_read + tid;
         if (i < n_end) {
             const int p0 = P.b.pos[i];
             if (p0 >= 0 && !(P.b.flag[i] & 4)) atomic_min(&ctrl[C7_TMIN], p0);
@@ -487,15 +501,35 @@ AMP_WD void cta_trim_pileup_v7(const KParams& P, unsigned char* smem_base) {
     }
     c_sync();
     const int wmin = ctrl[C7_TMIN];
-    // (three positions of slack: a group's position 0 is the aligned word holding the read's first aligned base)
-    const int wbase = (PILE && wmin != 0x7FFFFFFF) ? ((wmin > 3 ? wmin - 3 : 0) & ~31) : -1;
+    return wmin != 0x7FFFFFFF ? (wmin & ~31) : -1;
+}
+
+template <bool TRIM, bool PILE, int WT>
+AMP_WD void cta_fast_v8(const KParams& P, unsigned char* smem_base) {
+    const int wt = WT ? WT : P.wt;
+    const int tid = c_tid(), nthreads = c_nthreads(), block = c_block();
+    const int lane = tid & 31, warp = tid >> 5;
+    const int BR = P.reads_per_tile;
+    int* cnt = (int*)smem_base;
+    int* ctrl = (int*)(smem_base + tile_bytes_v7(wt));
+    const FastMem wm = carve_fast(smem_base, wt, warp);
+    const long long g_lo = (long long)block * P.tiles_per_cta;
+    long long g_hi = g_lo + P.tiles_per_cta; if (g_hi > P.ntiles) g_hi = P.ntiles;
+    const int n_batches = g_hi > g_lo ? (int)(g_hi - g_lo) : 0;
+    const long long n_end = P.b.first + P.b.n;
+    uint32_t* glist = P.glist + (size_t)block * P.gcap;
+
+    if (PILE) for (int i = tid; i < (AMP7_DEL_ROW + 1) * wt; i += nthreads) cnt[i] = 0;   // the sink row is never read
+    if (tid == 0) { ctrl[C7_NEXT] = 0; ctrl[C7_NGEN] = 0; }
+    if (lane == 0) mbar_init(wm.bar);
+    const int wb = chunk_window_base(P, ctrl, P.b.first + g_lo * BR, n_end, tid, n_batches > 0);
+    const int wbase = PILE ? wb : -1;
 
     const int minq = P.tp.min_quality;
-    // the cooperative path needs the default window and a quality threshold that fits the SIMD byte compare
+    // the word-wise passes need the default window and a quality threshold that fits the SIMD byte compare
     const bool fast_ok = minq >= 0 && minq <= 127 && (!TRIM || P.tp.window == 4);
     const unsigned minq4 = (unsigned)minq * 0x01010101u;
     uint32_t parity = 0;
-    int nq = 0;                                      // queued generic-path reads (uniform across the warp)
 
     for (;;) {
         int bi = 0;
@@ -544,13 +578,18 @@ AMP_WD void cta_trim_pileup_v7(const KParams& P, unsigned char* smem_base) {
         if (fast && TRIM) fast = trim_simple_primers(r, pos, flag, tlen, l_seq, P.tp, &f);
         if (fast && !TRIM && (pos < 0 || pos + r.m > P.tp.L)) fast = false;
         const uint32_t a0 = AMP7_PAD + (qo0 - q_lo) + (uint32_t)r.s1;                  // first aligned quality byte in qbuf
-        if (fast && (r.m < 8 || (int)(a0 & 3u) + r.m > 32 * AMP7_KW)) fast = false;
+        if (fast && (r.m < 8 || (int)(a0 & 3u) + r.m > 256)) fast = false;
         const bool rev = (flag & 16) != 0;
-        // everything else goes to the warp's queue for the generic path
+        // everything else goes to the CTA's list for the generic kernel
         {
-            const unsigned qmask = w_ballot(have && !skipped && !fast);
-            if (have && !skipped && !fast) wm.queue[nq + popc32(qmask & ((1u << lane) - 1u))] = (uint32_t)(i - P.b.first);
-            nq += popc32(qmask);
+            const bool gen = have && !skipped && !fast;
+            const unsigned gmask = w_ballot(gen);
+            if (gmask) {
+                int base = 0;
+                if (lane == 0) base = atomic_add(&ctrl[C7_NGEN], popc32(gmask));
+                base = w_shfl(base, 0);
+                if (gen) glist[base + popc32(gmask & ((1u << lane) - 1u))] = (uint32_t)(i - P.b.first);
+            }
         }
         if (skipped && TRIM) {
             uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
@@ -563,7 +602,9 @@ AMP_WD void cta_trim_pileup_v7(const KParams& P, unsigned char* smem_base) {
         w_sync();
         if (q_bulk + s_bulk > 0) { bulk_wait(wm.bar, parity); parity ^= 1u; }
 
-        // ---- B: lane per read: window search, quality clip + write gate + outputs, pileup of the aligned run ------------
+        // ---- B1: lane per read: window search, quality clip + write gate + outputs ---------------------------------------
+        int nchk = 0;                                                  // 8-base chunks of this lane's read to count in the tile
+        int qa0 = 0, n0 = 0, w0 = 0;
         if (fast) {
             if (TRIM) {
                 const int del = window_del_blocks(wm.qbuf, (int)a0, r.m, rev, minq);
@@ -574,11 +615,11 @@ AMP_WD void cta_trim_pileup_v7(const KParams& P, unsigned char* smem_base) {
             }
             if (PILE && r.m > 0) {
                 // final shape S(s1) M(m) S(s2) at pos: query base s1 + t sits on reference position pos + t
-                const int qa0 = (int)(AMP7_PAD + (qo0 - q_lo)) + r.s1;
-                const int n0 = (int)(2u * (AMP7_PAD + so0 - s_lo)) + r.s1;
-                const int w0 = pos - wbase;
+                qa0 = (int)(AMP7_PAD + (qo0 - q_lo)) + r.s1;
+                n0 = (int)(2u * (AMP7_PAD + so0 - s_lo)) + r.s1;
+                w0 = pos - wbase;
                 if (wbase >= 0 && w0 >= 0 && w0 + r.m <= wt) {
-                    count_run_v8<WT>(cnt, wt, wm.qbuf, qa0, wm.sbuf, n0, r.m, w0, minq4);
+                    nchk = (r.m + 7) >> 3;
                 } else {   // outside the tile: base by base into the global matrix (exact, rare on sorted input)
                     unsigned errs = 0;
                     for (int t = 0; t < r.m; ++t) {
@@ -590,18 +631,69 @@ AMP_WD void cta_trim_pileup_v7(const KParams& P, unsigned char* smem_base) {
                 }
             }
         }
-        w_sync();   // every lane is done with the staged rows before the buffers are reused
-
-        // ---- G: a full load of queued reads ----------------------------------------------------------------------------------
-        while (nq >= AMP7_GN) {
-            warp_generic_phase(P, wm, cnt, wbase, AMP7_GN, nq, lane, TRIM, PILE);
-            nq -= AMP7_GN;
+        // ---- B2: pileup.  Quality clipping leaves aligned runs of very different lengths, so the chunks of the whole
+        // batch are dealt out evenly: lane l takes chunks [l*q, (l+1)*q) of the concatenation of all runs.
+        if (PILE) {
+            int incl = nchk;
+            for (int d = 1; d < 32; d <<= 1) { const int t = w_shfl(incl, lane - d); if (lane >= d) incl += t; }
+            const int start = incl - nchk, total = w_shfl(incl, 31);
+            if (total > 0) {
+                const int q = (total + 31) >> 5;
+                wm.par[lane] = make_par(qa0 | ((nchk > 0 ? r.m : 0) << 16), n0, w0, start);
+                if (nchk > 0) {
+                    const int l_hi = (start + nchk + q - 1) / q;
+                    for (int ll = (start + q - 1) / q; ll < l_hi && ll < 32; ++ll) wm.own[ll] = (uint8_t)lane;
+                }
+                w_sync();
+                int g0 = lane * q;
+                const int g1 = g0 + q < total ? g0 + q : total;
+                int rr = g0 < g1 ? wm.own[lane] : 0;
+                while (g0 < g1) {
+                    const Par4 pr = wm.par[rr];
+                    const int m = (pr.x >> 16) & 0x1FF, nch = (m + 7) >> 3;
+                    const int c_lo = g0 - pr.w;
+                    int c_hi = c_lo + (g1 - g0); if (c_hi > nch) c_hi = nch;
+                    if (c_hi > c_lo) {
+                        count_run_v8<WT>(cnt, wt, wm.qbuf, pr.x & 0xFFFF, wm.sbuf, pr.y, m, pr.z, c_lo, c_hi, minq4);
+                        g0 += c_hi - c_lo;
+                    }
+                    ++rr;
+                }
+            }
         }
+        w_sync();   // every lane is done with the staged rows before the buffers are reused
     }
-    while (nq > 0) {
-        const int nb = nq < AMP7_GN ? nq : AMP7_GN;
-        warp_generic_phase(P, wm, cnt, wbase, nb, nq, lane, TRIM, PILE);
-        nq -= nb;
+    c_sync();
+    if (tid == 0) P.gcount[block] = ctrl[C7_NGEN];
+    if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);
+}
+
+// generic kernel: CTA c works through the list its fast-kernel counterpart wrote
+template <bool TRIM, bool PILE>
+AMP_WD void cta_generic_v8(const KParams& P, unsigned char* smem_base) {
+    const int wt = P.wt;
+    const int tid = c_tid(), nthreads = c_nthreads(), block = c_block();
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n_list = P.gcount[block];
+    if (n_list <= 0) return;                                        // uniform across the CTA
+    int* cnt = (int*)smem_base;
+    int* ctrl = (int*)(smem_base + tile_bytes_v7(wt));
+    const WarpMem7 wm = carve_warp7(smem_base, wt, warp);
+    const uint32_t* glist = P.glist + (size_t)block * P.gcap;
+    const long long g_lo = (long long)block * P.tiles_per_cta;
+    if (PILE) for (int i = tid; i < (AMP7_DEL_ROW + 1) * wt; i += nthreads) cnt[i] = 0;
+    if (tid == 0) ctrl[C7_NEXT] = 0;
+    const int wb = chunk_window_base(P, ctrl, P.b.first + g_lo * P.reads_per_tile, P.b.first + P.b.n, tid, true);
+    const int wbase = PILE ? wb : -1;
+    for (;;) {
+        int at = 0;
+        if (lane == 0) at = atomic_add(&ctrl[C7_NEXT], AMP7_GN);
+        at = w_shfl(at, 0);
+        if (at >= n_list) break;
+        const int nb = n_list - at < AMP7_GN ? n_list - at : AMP7_GN;
+        if (lane < nb) wm.queue[lane] = glist[at + lane];
+        w_sync();
+        warp_generic_phase(P, wm, cnt, wbase, nb, nb, lane, TRIM, PILE);
     }
     c_sync();
     if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);
