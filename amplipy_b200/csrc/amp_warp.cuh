@@ -40,6 +40,7 @@ AMP_WD int w_shfl(int v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
 AMP_WD int w_shfl_xor(int v, int m) { return __shfl_xor_sync(0xFFFFFFFFu, v, m); }
 AMP_WD unsigned w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
 AMP_WD int w_max(int v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
+AMP_WD int w_add(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 AMP_WD void w_sync() { __syncwarp(); }
 AMP_WD void c_sync() { __syncthreads(); }
 AMP_WD unsigned funnel_l(unsigned lo, unsigned hi, unsigned sh) { return __funnelshift_l(lo, hi, sh); }
@@ -81,7 +82,7 @@ AMP_WD void bulk_wait(unsigned long long* bar, uint32_t parity) {
 #define AMP_WD inline
 // implemented by the fiber runtime in tests/emu/amp_emu.cpp
 int c_tid(); int c_nthreads(); int c_block();
-int w_shfl(int v, int src); int w_shfl_xor(int v, int m); unsigned w_ballot(bool p); int w_max(int v);
+int w_shfl(int v, int src); int w_shfl_xor(int v, int m); unsigned w_ballot(bool p); int w_max(int v); int w_add(int v);
 void w_sync(); void c_sync();
 AMP_WD unsigned funnel_l(unsigned lo, unsigned hi, unsigned sh) { return sh ? (hi << sh) | (lo >> (32u - sh)) : hi; }
 AMP_WD unsigned dp4a_acc(unsigned w, unsigned acc) { return acc + (w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24); }
@@ -133,6 +134,8 @@ AMP_HD size_t tile_bytes_v7(int wt) { return ((size_t)AMP7_ROWS * wt + 32 * AMP7
 AMP_HD size_t smem_bytes_v7(int wt, int warps) { return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_WARP_BYTES; }
 
 // launch shape: reads per batch so that a batch's rows fit the staging buffers; one CTA per SM with a contiguous chunk
+struct Par4 { int x, y, z, w; };   // x = qbuf offset | aligned bases << 16, y = first nibble in sbuf, z = tile position, w = first chunk
+AMP_HD Par4 make_par(int x, int y, int z, int w) { Par4 p; p.x = x; p.y = y; p.z = z; p.w = w; return p; }
 struct V7Cfg { int wt, batch_reads; };
 inline V7Cfg pick_v7_cfg(long long n, long long sum_qual, int sm_count) {
     (void)sm_count;
@@ -145,8 +148,6 @@ inline V7Cfg pick_v7_cfg(long long n, long long sum_qual, int sm_count) {
 }
 
 // fast kernel: per-warp staging buffers, the per-read parameters of the count pass, and the bulk-copy barrier
-struct Par4 { int x, y, z, w; };   // x = qbuf offset | aligned bases << 16, y = first nibble in sbuf, z = tile position, w = first chunk
-AMP_HD Par4 make_par(int x, int y, int z, int w) { Par4 p; p.x = x; p.y = y; p.z = z; p.w = w; return p; }
 #define AMP7_FAST_BYTES (AMP7_QBUF + AMP7_SBUF + 32 * 16 + 32 + 16)
 struct FastMem { uint8_t* qbuf; uint8_t* sbuf; Par4* par; uint8_t* own; unsigned long long* bar; };
 AMP_HD size_t smem_bytes_fast(int wt, int warps) { return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_FAST_BYTES; }
@@ -259,21 +260,30 @@ AMP_WD int window_del_blocks(const uint8_t* buf, int a0, int m, bool rev, int mi
 // -> SIMD byte compare q >= minq; one sequence word split into pre-scaled high / low nibbles so that one byte permute per
 // base yields the tile row offset; a masked base increments the sink row instead (no branch).  Lanes of a warp that work
 // on reads with the same start hit the same address and are merged by the hardware (ATOMS.POPC.INC).
+//
+// The chunks of all runs of a batch are dealt out evenly: this lane walks chunks [g0, g1) of their concatenation,
+// starting inside run rr0 (par[r].w = first chunk of run r, par[r].x >> 16 = its aligned bases, 0 = nothing to count) and
+// moving on to the next run inside the loop, so every lane of the warp executes the same number of iterations.
 template <int WT>
-AMP_WD void count_run_v8(int* cnt, int wt, const uint8_t* qbuf, int a0, const uint8_t* sbuf, int n0, int m, int tp0, int c_lo, int c_hi,
-                          unsigned minq4) {
-    const uint32_t* A = (const uint32_t*)(qbuf + (a0 & ~3));
-    const unsigned sh = (unsigned)(a0 & 3) << 3;
-    const int sb = n0 >> 1;
-    const bool par = n0 & 1;
-    const uint32_t* S = (const uint32_t*)(sbuf + (sb & ~3));
-    const unsigned ssh = (unsigned)(sb & 3) << 3;
-    const int nch = (m + 7) >> 3;
-    unsigned qa = A[2 * c_lo];
-    unsigned sa = S[c_lo + 1];
-    unsigned x = funnel_r(S[c_lo], sa, ssh);
-    int* tl = cnt + tp0 + 8 * c_lo;
-    for (int c = c_lo; c < c_hi; ++c, tl += 8) {
+AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t* sbuf, const Par4* par, int rr0, int g0, int g1,
+                            unsigned minq4) {
+    int rr = rr0 - 1, c = 0, nch = 0, m = 0;
+    const uint32_t* A = nullptr; const uint32_t* S = nullptr;
+    unsigned sh = 0, ssh = 0, qa = 0, sa = 0, x = 0;
+    bool odd = false;
+    int* tl = cnt;
+    for (int g = g0; g < g1; ++g, ++c, tl += 8) {
+        if (c >= nch) {                                      // next run with chunks (first iteration: run rr0 at chunk g0)
+            Par4 pr;
+            do { ++rr; pr = par[rr]; m = (pr.x >> 16) & 0x1FF; nch = (m + 7) >> 3; } while (nch == 0);
+            c = g == g0 ? g - pr.w : 0;
+            const int a0 = pr.x & 0xFFFF, sb = pr.y >> 1;
+            A = (const uint32_t*)(qbuf + (a0 & ~3)); sh = (unsigned)(a0 & 3) << 3;
+            S = (const uint32_t*)(sbuf + (sb & ~3)); ssh = (unsigned)(sb & 3) << 3;
+            odd = pr.y & 1;
+            qa = A[2 * c]; sa = S[c + 1]; x = funnel_r(S[c], sa, ssh);
+            tl = cnt + pr.z + 8 * c;
+        }
         const unsigned q1 = A[2 * c + 1], q2 = A[2 * c + 2];
         const unsigned v0 = funnel_r(qa, q1, sh), v1 = funnel_r(q1, q2, sh);
         qa = q2;
@@ -281,17 +291,17 @@ AMP_WD void count_run_v8(int* cnt, int wt, const uint8_t* qbuf, int a0, const ui
         const unsigned xn = funnel_r(sa, s2, ssh);          // sequence word of the next chunk
         sa = s2;
         // q >= minq per byte (exact for every byte value, minq <= 127): bit 7 of each byte
-        unsigned g0 = (((v0 | 0x80808080u) - minq4) | v0) & 0x80808080u;
-        unsigned g1 = (((v1 | 0x80808080u) - minq4) | v1) & 0x80808080u;
+        unsigned k0 = (((v0 | 0x80808080u) - minq4) | v0) & 0x80808080u;
+        unsigned k1 = (((v1 | 0x80808080u) - minq4) | v1) & 0x80808080u;
         if (c == nch - 1) {                                  // bases past the run
             const int left = m - 8 * c;                      // 1 .. 8
             const unsigned long long keep = left >= 8 ? ~0ULL : ((1ULL << (8 * left)) - 1ULL);
-            g0 &= (unsigned)keep; g1 &= (unsigned)(keep >> 32);
+            k0 &= (unsigned)keep; k1 &= (unsigned)(keep >> 32);
         }
         // nibbles scaled by 8, one per byte: E = bases at even nibble positions of x, O = odd ones
         const unsigned E = (x >> 1) & 0x78787878u, O = (x << 3) & 0x78787878u, En = (xn >> 1) & 0x78787878u;
-        const unsigned a = par ? O : E;                      // bases 0, 2, 4, 6 of the chunk
-        const unsigned b = par ? funnel_r(E, En, 8) : O;     // bases 1, 3, 5, 7
+        const unsigned a = odd ? O : E;                      // bases 0, 2, 4, 6 of the chunk
+        const unsigned b = odd ? funnel_r(E, En, 8) : O;     // bases 1, 3, 5, 7
         x = xn;
 #define AMP7_BASE(ii, src, kb, g)                                                                                      \
         {                                                                                                              \
@@ -305,8 +315,8 @@ AMP_WD void count_run_v8(int* cnt, int wt, const uint8_t* qbuf, int a0, const ui
                 atomic_add(tl + o2 + (ii), 1);                                                                         \
             }                                                                                                          \
         }
-        AMP7_BASE(0, a, 0, g0) AMP7_BASE(1, b, 0, g0) AMP7_BASE(2, a, 1, g0) AMP7_BASE(3, b, 1, g0)
-        AMP7_BASE(4, a, 2, g1) AMP7_BASE(5, b, 2, g1) AMP7_BASE(6, a, 3, g1) AMP7_BASE(7, b, 3, g1)
+        AMP7_BASE(0, a, 0, k0) AMP7_BASE(1, b, 0, k0) AMP7_BASE(2, a, 1, k0) AMP7_BASE(3, b, 1, k0)
+        AMP7_BASE(4, a, 2, k1) AMP7_BASE(5, b, 2, k1) AMP7_BASE(6, a, 3, k1) AMP7_BASE(7, b, 3, k1)
 #undef AMP7_BASE
     }
 }
@@ -434,33 +444,40 @@ AMP_HD void warp_read_generic7(const KParams& P, const WarpMem7& wm, long long i
 
 // G phase: the first nb (<= AMP7_GN) queued reads of the warp
 AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, int wbase, int nb, int nq, int lane, bool do_trim,
-                               bool do_pile) {
-    // stage the (scattered) rows into fixed slots, keeping each row's alignment mod 16
-    for (int r = 0; r < nb; ++r) {
-        const long long i = P.b.first + wm.queue[r];
-        const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
-        if ((qo0 & 15u) + (qo1 - qo0) + 16u <= AMP7_GSLOT_Q) {
-            const uint4* gq = (const uint4*)(P.b.qual + (qo0 & ~15u));
-            uint4* sq = (uint4*)(wm.qbuf + AMP7_PAD + (size_t)r * AMP7_GSLOT_Q);
-            const uint32_t hi = (qo0 & 15u) + (qo1 - qo0);
-            const uint32_t full = hi >> 4;
-            for (uint32_t v = lane; v < full; v += 32) sq[v] = gq[v];
-            for (uint32_t k = (full << 4) + lane; k < hi; k += 32) ((uint8_t*)sq)[k] = ((const uint8_t*)gq)[k];
-        }
-        if (do_pile) {
-            const uint32_t so0 = P.b.seq_off[i], so1 = P.b.seq_off[i + 1];
-            if ((so0 & 15u) + (so1 - so0) <= AMP7_GSLOT_S) {
-                const uint4* gs = (const uint4*)(P.b.seq + (so0 & ~15u));
-                uint4* ss = (uint4*)(wm.sbuf + AMP7_PAD + (size_t)r * AMP7_GSLOT_S);
-                const uint32_t hi = (so0 & 15u) + (so1 - so0);
-                const uint32_t full = hi >> 4;
-                for (uint32_t v = lane; v < full; v += 32) ss[v] = gs[v];
-                for (uint32_t k = (full << 4) + lane; k < hi; k += 32) ((uint8_t*)ss)[k] = ((const uint8_t*)gs)[k];
+                               bool do_pile, uint32_t& parity) {
+    // stage the (scattered) rows into fixed slots, keeping each row's alignment mod 16: every lane starts the bulk copies
+    // of its own read (whole 16-byte pieces) and moves the < 16 trailing bytes itself
+    {
+        uint32_t qb = 0, sb = 0, qt = 0, stl = 0;
+        const uint8_t *qsrc = nullptr, *ssrc = nullptr;
+        uint8_t *qdst = nullptr, *sdst = nullptr;
+        if (lane < nb) {
+            const long long i = P.b.first + wm.queue[lane];
+            const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
+            if ((qo0 & 15u) + (qo1 - qo0) + 16u <= AMP7_GSLOT_Q) {
+                const uint32_t hi = (qo0 & 15u) + (qo1 - qo0);
+                qsrc = P.b.qual + (qo0 & ~15u); qdst = wm.qbuf + AMP7_PAD + (size_t)lane * AMP7_GSLOT_Q;
+                qb = hi & ~15u; qt = hi & 15u;
+            }
+            if (do_pile) {
+                const uint32_t so0 = P.b.seq_off[i], so1 = P.b.seq_off[i + 1];
+                if ((so0 & 15u) + (so1 - so0) <= AMP7_GSLOT_S) {
+                    const uint32_t hi = (so0 & 15u) + (so1 - so0);
+                    ssrc = P.b.seq + (so0 & ~15u); sdst = wm.sbuf + AMP7_PAD + (size_t)lane * AMP7_GSLOT_S;
+                    sb = hi & ~15u; stl = hi & 15u;
+                }
             }
         }
+        const uint32_t total = (uint32_t)w_add((int)(qb + sb));
+        if (lane == 0) { wm.ctr[0] = 0; if (total) bulk_expect(wm.bar, total); }
+        w_sync();
+        if (qb) bulk_copy(qdst, qsrc, qb, wm.bar);
+        if (sb) bulk_copy(sdst, ssrc, sb, wm.bar);
+        for (uint32_t k = 0; k < qt; ++k) qdst[qb + k] = qsrc[qb + k];
+        for (uint32_t k = 0; k < stl; ++k) sdst[sb + k] = ssrc[sb + k];
+        w_sync();
+        if (total) { bulk_wait(wm.bar, parity); parity ^= 1u; }
     }
-    if (lane == 0) wm.ctr[0] = 0;
-    w_sync();
     if (lane < nb) warp_read_generic7(P, wm, P.b.first + wm.queue[lane], lane, do_trim, do_pile);
     w_sync();
     if (do_pile) {
@@ -645,20 +662,8 @@ AMP_WD void cta_fast_v8(const KParams& P, unsigned char* smem_base) {
                     for (int ll = (start + q - 1) / q; ll < l_hi && ll < 32; ++ll) wm.own[ll] = (uint8_t)lane;
                 }
                 w_sync();
-                int g0 = lane * q;
-                const int g1 = g0 + q < total ? g0 + q : total;
-                int rr = g0 < g1 ? wm.own[lane] : 0;
-                while (g0 < g1) {
-                    const Par4 pr = wm.par[rr];
-                    const int m = (pr.x >> 16) & 0x1FF, nch = (m + 7) >> 3;
-                    const int c_lo = g0 - pr.w;
-                    int c_hi = c_lo + (g1 - g0); if (c_hi > nch) c_hi = nch;
-                    if (c_hi > c_lo) {
-                        count_run_v8<WT>(cnt, wt, wm.qbuf, pr.x & 0xFFFF, wm.sbuf, pr.y, m, pr.z, c_lo, c_hi, minq4);
-                        g0 += c_hi - c_lo;
-                    }
-                    ++rr;
-                }
+                const int g0 = lane * q, g1 = g0 + q < total ? g0 + q : total;
+                if (g0 < g1) count_chunks_v8<WT>(cnt, wt, wm.qbuf, wm.sbuf, wm.par, wm.own[lane], g0, g1, minq4);
             }
         }
         w_sync();   // every lane is done with the staged rows before the buffers are reused
@@ -683,17 +688,22 @@ AMP_WD void cta_generic_v8(const KParams& P, unsigned char* smem_base) {
     const long long g_lo = (long long)block * P.tiles_per_cta;
     if (PILE) for (int i = tid; i < (AMP7_DEL_ROW + 1) * wt; i += nthreads) cnt[i] = 0;
     if (tid == 0) ctrl[C7_NEXT] = 0;
+    if (lane == 0) mbar_init(wm.bar);
     const int wb = chunk_window_base(P, ctrl, P.b.first + g_lo * P.reads_per_tile, P.b.first + P.b.n, tid, true);
     const int wbase = PILE ? wb : -1;
+    // reads per claim: an even share of the list, so that every warp of the CTA gets work
+    const int nw = nthreads >> 5;
+    int per = (n_list + nw - 1) / nw; if (per > AMP7_GN) per = AMP7_GN;
+    uint32_t parity = 0;
     for (;;) {
         int at = 0;
-        if (lane == 0) at = atomic_add(&ctrl[C7_NEXT], AMP7_GN);
+        if (lane == 0) at = atomic_add(&ctrl[C7_NEXT], per);
         at = w_shfl(at, 0);
         if (at >= n_list) break;
-        const int nb = n_list - at < AMP7_GN ? n_list - at : AMP7_GN;
+        const int nb = n_list - at < per ? n_list - at : per;
         if (lane < nb) wm.queue[lane] = glist[at + lane];
         w_sync();
-        warp_generic_phase(P, wm, cnt, wbase, nb, nb, lane, TRIM, PILE);
+        warp_generic_phase(P, wm, cnt, wbase, nb, nb, lane, TRIM, PILE, parity);
     }
     c_sync();
     if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);

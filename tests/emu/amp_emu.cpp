@@ -115,6 +115,14 @@ unsigned w_ballot(bool p) {
     w_sync();
     return r;
 }
+int w_add(int v) {
+    g_rt.xch[g_rt.cur] = v;
+    w_sync();
+    int r = 0;
+    for (int k = 0; k < 32; ++k) if ((g_rt.cur & ~31) + k < g_rt.nthreads) r += g_rt.xch[(g_rt.cur & ~31) + k];
+    w_sync();
+    return r;
+}
 int w_max(int v) {
     g_rt.xch[g_rt.cur] = v;
     w_sync();
