@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(AMP7_WARPS * 32, 1) amp_trim_pileup_fast_kerne
 template <bool TRIM, bool PILE>
 __global__ void __launch_bounds__(AMP7_GWARPS * 32, 1) amp_trim_pileup_generic_kernel(const __grid_constant__ amp::KParams P) {
     extern __shared__ __align__(128) unsigned char smem7[];
-    amp::cta_generic_v8<TRIM, PILE>(P, smem7);
+    amp::cta_generic_v8<TRIM, PILE, AMP7_WT>(P, smem7);
 }
 
 __device__ const unsigned char kFixedSyms[8] = {'A', 'C', 'G', 'T', 'N', '-', 0, 0};

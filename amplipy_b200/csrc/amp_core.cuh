@@ -277,10 +277,100 @@ AMP_HD int sum4(unsigned w) {                                       // sum of th
     return (int)((w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24));
 #endif
 }
+AMP_HD unsigned funnel_l(unsigned lo, unsigned hi, unsigned sh) {   // high 32 bits of (hi:lo) << sh, sh in [0, 31]
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(lo, hi, sh);
+#else
+    return sh ? (hi << sh) | (lo >> (32u - sh)) : hi;
+#endif
+}
+AMP_HD unsigned dp4a_acc(unsigned w, unsigned acc) {                // acc + sum of the four bytes of w
+#ifdef __CUDA_ARCH__
+    return __dp4a(w, 0x01010101u, acc);
+#else
+    return acc + (w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24);
+#endif
+}
+AMP_HD int ctz32(unsigned x) {
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+AMP_HD int msb32(unsigned x) {
+#ifdef __CUDA_ARCH__
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
+
+// ---- block-wise window search for the default width 4 ---------------------------------------------------------------
+// (sum - 4*minq) of the 8 windows starting in read-relative words u0, u1 (u2 = look-ahead): sign bit set = window fails
+#define AMP7_WIN8(D, u0, u1, u2, nthr)                                                                              \
+    const unsigned D##0 = dp4a_acc(u0, nthr), D##1 = dp4a_acc(funnel_r(u0, u1, 8), nthr),                           \
+                   D##2 = dp4a_acc(funnel_r(u0, u1, 16), nthr), D##3 = dp4a_acc(funnel_r(u0, u1, 24), nthr),        \
+                   D##4 = dp4a_acc(u1, nthr), D##5 = dp4a_acc(funnel_r(u1, u2, 8), nthr),                           \
+                   D##6 = dp4a_acc(funnel_r(u1, u2, 16), nthr), D##7 = dp4a_acc(funnel_r(u1, u2, 24), nthr)
+AMP_HD unsigned win8_bits(unsigned u0, unsigned u1, unsigned u2, unsigned nthr) {   // bit w = window w of the block fails
+    AMP7_WIN8(D, u0, u1, u2, nthr);
+    unsigned F = funnel_l(D7, 0u, 1);
+    F = funnel_l(D6, F, 1); F = funnel_l(D5, F, 1); F = funnel_l(D4, F, 1);
+    F = funnel_l(D3, F, 1); F = funnel_l(D2, F, 1); F = funnel_l(D1, F, 1); F = funnel_l(D0, F, 1);
+    return F;
+}
+// Sliding-window search (closed form of AmpliPy.py:566-587 / 628-649, same result as window_del_len_fwd / _rev with W = 4)
+// for m >= 8, m + (a0 & 3) <= 256: one pass over blocks of 8 windows keeps one "some window fails" bit per block; the
+// first (forward strand) / last (reverse strand) failing block is then resolved exactly; the three shrinking windows at
+// the open end are checked from three bytes.
+AMP_HD int window_del_blocks(const uint8_t* buf, int a0, int m, bool rev, int minq) {
+    const uint32_t* A = (const uint32_t*)(buf + (a0 & ~3));
+    const unsigned sh = (unsigned)(a0 & 3) << 3;
+    const unsigned nthr = (unsigned)(-4 * minq);
+    const int nwin = m - 3;                       // full windows start at 0 .. nwin - 1
+    const int nb = (nwin + 7) >> 3;               // blocks of 8 windows (<= 32)
+    const unsigned last_mask = (1u << (nwin - 8 * (nb - 1))) - 1u;   // valid windows of the last block (1 .. 8 of them)
+    unsigned Fw = 0;
+    unsigned prev = A[1];
+    unsigned u0 = funnel_r(A[0], prev, sh);
+    for (int i = 0; i < nb - 1; ++i) {
+        const unsigned x1 = A[2 * i + 2], x2 = A[2 * i + 3];
+        const unsigned u1 = funnel_r(prev, x1, sh), u2 = funnel_r(x1, x2, sh);
+        AMP7_WIN8(D, u0, u1, u2, nthr);
+        Fw = funnel_l(D0 | D1 | D2 | D3 | D4 | D5 | D6 | D7, Fw, 1);
+        u0 = u2; prev = x2;
+    }
+    {
+        const unsigned x1 = A[2 * nb], x2 = A[2 * nb + 1];
+        const unsigned bits = win8_bits(u0, funnel_r(prev, x1, sh), funnel_r(x1, x2, sh), nthr) & last_mask;
+        Fw = (Fw << 1) | (bits ? 1u : 0u);
+    }
+    if (Fw) {   // block i sits at bit nb - 1 - i
+        const int i = nb - 1 - (rev ? ctz32(Fw) : msb32(Fw));
+        const unsigned x0 = A[2 * i], x1 = A[2 * i + 1], x2 = A[2 * i + 2], x3 = A[2 * i + 3];
+        unsigned bits = win8_bits(funnel_r(x0, x1, sh), funnel_r(x1, x2, sh), funnel_r(x2, x3, sh), nthr);
+        if (i == nb - 1) bits &= last_mask;
+        const int t = 8 * i + (rev ? msb32(bits) : ctz32(bits));
+        return rev ? t + 4 : m - t;
+    }
+    const uint8_t* e3 = buf + a0 + (rev ? 0 : m - 3);   // shrinking windows w = 3, 2, 1 at the open end
+    const int x0 = e3[0], x1 = e3[1], x2 = e3[2];
+    const int e = rev ? x0 : x2;
+    if (x0 + x1 + x2 < 3 * minq) return 3;
+    if (e + x1 < 2 * minq) return 2;
+    if (e < minq) return 1;
+    return 0;
+}
+
 // Same result as window_del_len_fwd / _rev for W == 4, scanning the logical sequence s[t] = rev ? q[len-1-t] : q[t]
 // four positions per step (one aligned word + funnel shifts + dp4a), identical instruction stream for both
-// strands.  Requires 8 readable bytes on either side of q[0, len) (true inside the staging buffers).
+// strands.  Requires 8 readable bytes before and 16 after q[0, len) (true inside the staging buffers).
 AMP_HD int window_del_len_w4(const uint8_t* q, int len, int minq, bool rev) {
+    {   // common case: the block-wise search (16 readable bytes after the run)
+        const int mis = (int)((uintptr_t)q & 3u);
+        if (len >= 8 && mis + len <= 256) return window_del_blocks(q - mis, mis, len, rev, minq);
+    }
     const int thr = 4 * minq;
     int t = 0;
     if (len >= 7) {

@@ -43,10 +43,6 @@ AMP_WD int w_max(int v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
 AMP_WD int w_add(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 AMP_WD void w_sync() { __syncwarp(); }
 AMP_WD void c_sync() { __syncthreads(); }
-AMP_WD unsigned funnel_l(unsigned lo, unsigned hi, unsigned sh) { return __funnelshift_l(lo, hi, sh); }
-AMP_WD unsigned dp4a_acc(unsigned w, unsigned acc) { return __dp4a(w, 0x01010101u, acc); }
-AMP_WD int ctz32(unsigned x) { return __ffs((int)x) - 1; }
-AMP_WD int msb32(unsigned x) { return 31 - __clz((int)x); }
 AMP_WD int popc32(unsigned x) { return __popc(x); }
 AMP_WD unsigned byte_perm2(unsigned x, unsigned sel) { return __byte_perm(x, 0u, sel); }
 AMP_WD uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,10 +80,6 @@ AMP_WD void bulk_wait(unsigned long long* bar, uint32_t parity) {
 int c_tid(); int c_nthreads(); int c_block();
 int w_shfl(int v, int src); int w_shfl_xor(int v, int m); unsigned w_ballot(bool p); int w_max(int v); int w_add(int v);
 void w_sync(); void c_sync();
-AMP_WD unsigned funnel_l(unsigned lo, unsigned hi, unsigned sh) { return sh ? (hi << sh) | (lo >> (32u - sh)) : hi; }
-AMP_WD unsigned dp4a_acc(unsigned w, unsigned acc) { return acc + (w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24); }
-AMP_WD int ctz32(unsigned x) { return __builtin_ctz(x); }
-AMP_WD int msb32(unsigned x) { return 31 - __builtin_clz(x); }
 AMP_WD int popc32(unsigned x) { return __builtin_popcount(x); }
 AMP_WD unsigned byte_perm2(unsigned x, unsigned sel) {
     unsigned r = 0;
@@ -107,7 +99,7 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_WARPS 16            // warps per CTA of the fast kernel
 #endif
 #ifndef AMP7_GWARPS
-#define AMP7_GWARPS 16           // warps per CTA of the generic kernel
+#define AMP7_GWARPS 14           // warps per CTA of the generic kernel
 #endif
 #define AMP7_WT 512              // count tile width on the device (positions)
 #define AMP7_ROWS 18             // count tile rows: BAM nibble 0..15, row 16 = deleted base, row 17 = sink of masked bases
@@ -126,7 +118,8 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_GSLOT_Q 192         // G phase: bytes per staged quality row slot
 #define AMP7_GSLOT_S 96
 #define AMP7_GN 26               // reads per G phase (GN * GSLOT <= DATA)
-#define AMP7_WARP_BYTES (AMP7_QBUF + AMP7_SBUF + AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + 16)
+#define AMP7_CROW 13             // generic path: CIGAR ops (+3) per shared-memory row; two rows per read (odd stride: no bank conflicts)
+#define AMP7_WARP_BYTES (AMP7_QBUF + AMP7_SBUF + AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + 16 + AMP7_GN * 2 * AMP7_CROW * 4 + 32 * 16 + 32)
 enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_WORDS = 16 };
 
 // the sink row is the last one and 32 * KW entries longer: idle slots of a group increment it past the window's end
@@ -163,7 +156,8 @@ AMP_HD FastMem carve_fast(unsigned char* base, int wt, int w) {
 }
 
 struct WarpMem7 {
-    uint8_t* qbuf; uint8_t* sbuf; Seg* runs; uint32_t* queue; int* ctr; unsigned long long* bar;
+    uint8_t* qbuf; uint8_t* sbuf; Seg* runs; uint32_t* queue; int* ctr; unsigned long long* bar; uint32_t* cig;
+    Par4* par; uint8_t* own;
 };
 AMP_HD WarpMem7 carve_warp7(unsigned char* base, int wt, int w) {
     unsigned char* b = base + tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)w * AMP7_WARP_BYTES;
@@ -173,7 +167,10 @@ AMP_HD WarpMem7 carve_warp7(unsigned char* base, int wt, int w) {
     m.runs = (Seg*)b; b += AMP7_RUNCAP * 16;
     m.queue = (uint32_t*)b; b += AMP7_QCAP * 4;
     m.ctr = (int*)b; b += 32;
-    m.bar = (unsigned long long*)b;
+    m.bar = (unsigned long long*)b; b += 16;
+    m.cig = (uint32_t*)b; b += AMP7_GN * 2 * AMP7_CROW * 4;
+    m.par = (Par4*)b; b += 32 * 16;
+    m.own = b;
     return m;
 }
 
@@ -198,62 +195,6 @@ AMP_HD void flush_tile7(const KParams& P, const int* cnt, int wbase, int tid, in
 // `buf + a0` = first aligned quality byte (any alignment), m aligned bases, window width 4.  Both passes walk aligned
 // 4-byte words of the staging buffer and funnel-shift them to read-relative words; they read at most 16 bytes past the run.
 
-// (sum - 4*minq) of the 8 windows starting in read-relative words u0, u1 (u2 = look-ahead): sign bit set = window fails
-#define AMP7_WIN8(D, u0, u1, u2, nthr)                                                                              \
-    const unsigned D##0 = dp4a_acc(u0, nthr), D##1 = dp4a_acc(funnel_r(u0, u1, 8), nthr),                           \
-                   D##2 = dp4a_acc(funnel_r(u0, u1, 16), nthr), D##3 = dp4a_acc(funnel_r(u0, u1, 24), nthr),        \
-                   D##4 = dp4a_acc(u1, nthr), D##5 = dp4a_acc(funnel_r(u1, u2, 8), nthr),                           \
-                   D##6 = dp4a_acc(funnel_r(u1, u2, 16), nthr), D##7 = dp4a_acc(funnel_r(u1, u2, 24), nthr)
-AMP_WD unsigned win8_bits(unsigned u0, unsigned u1, unsigned u2, unsigned nthr) {   // bit w = window w of the block fails
-    AMP7_WIN8(D, u0, u1, u2, nthr);
-    unsigned F = funnel_l(D7, 0u, 1);
-    F = funnel_l(D6, F, 1); F = funnel_l(D5, F, 1); F = funnel_l(D4, F, 1);
-    F = funnel_l(D3, F, 1); F = funnel_l(D2, F, 1); F = funnel_l(D1, F, 1); F = funnel_l(D0, F, 1);
-    return F;
-}
-// Sliding-window search (closed form of AmpliPy.py:566-587 / 628-649, same result as window_del_len_fwd / _rev with W = 4)
-// for m >= 8, m + (a0 & 3) <= 256: one pass over blocks of 8 windows keeps one "some window fails" bit per block; the
-// first (forward strand) / last (reverse strand) failing block is then resolved exactly; the three shrinking windows at
-// the open end are checked from three bytes.
-AMP_WD int window_del_blocks(const uint8_t* buf, int a0, int m, bool rev, int minq) {
-    const uint32_t* A = (const uint32_t*)(buf + (a0 & ~3));
-    const unsigned sh = (unsigned)(a0 & 3) << 3;
-    const unsigned nthr = (unsigned)(-4 * minq);
-    const int nwin = m - 3;                       // full windows start at 0 .. nwin - 1
-    const int nb = (nwin + 7) >> 3;               // blocks of 8 windows (<= 32)
-    const unsigned last_mask = (1u << (nwin - 8 * (nb - 1))) - 1u;   // valid windows of the last block (1 .. 8 of them)
-    unsigned Fw = 0;
-    unsigned prev = A[1];
-    unsigned u0 = funnel_r(A[0], prev, sh);
-    for (int i = 0; i < nb - 1; ++i) {
-        const unsigned x1 = A[2 * i + 2], x2 = A[2 * i + 3];
-        const unsigned u1 = funnel_r(prev, x1, sh), u2 = funnel_r(x1, x2, sh);
-        AMP7_WIN8(D, u0, u1, u2, nthr);
-        Fw = funnel_l(D0 | D1 | D2 | D3 | D4 | D5 | D6 | D7, Fw, 1);
-        u0 = u2; prev = x2;
-    }
-    {
-        const unsigned x1 = A[2 * nb], x2 = A[2 * nb + 1];
-        const unsigned bits = win8_bits(u0, funnel_r(prev, x1, sh), funnel_r(x1, x2, sh), nthr) & last_mask;
-        Fw = (Fw << 1) | (bits ? 1u : 0u);
-    }
-    if (Fw) {   // block i sits at bit nb - 1 - i
-        const int i = nb - 1 - (rev ? ctz32(Fw) : msb32(Fw));
-        const unsigned x0 = A[2 * i], x1 = A[2 * i + 1], x2 = A[2 * i + 2], x3 = A[2 * i + 3];
-        unsigned bits = win8_bits(funnel_r(x0, x1, sh), funnel_r(x1, x2, sh), funnel_r(x2, x3, sh), nthr);
-        if (i == nb - 1) bits &= last_mask;
-        const int t = 8 * i + (rev ? msb32(bits) : ctz32(bits));
-        return rev ? t + 4 : m - t;
-    }
-    const uint8_t* e3 = buf + a0 + (rev ? 0 : m - 3);   // shrinking windows w = 3, 2, 1 at the open end
-    const int x0 = e3[0], x1 = e3[1], x2 = e3[2];
-    const int e = rev ? x0 : x2;
-    if (x0 + x1 + x2 < 3 * minq) return 3;
-    if (e + x1 < 2 * minq) return 2;
-    if (e < minq) return 1;
-    return 0;
-}
-
 // Pileup of one aligned run (update_base_counts, AmpliPy.py:718 + 752-753) inside the count tile: quality byte t at
 // qbuf[a0 + t], base t = nibble n0 + t of sbuf, tile position tp0 + t, t in [0, m); this call covers the 8-base chunks
 // [c_lo, c_hi).  Per chunk: two quality words
@@ -262,20 +203,21 @@ AMP_WD int window_del_blocks(const uint8_t* buf, int a0, int m, bool rev, int mi
 // on reads with the same start hit the same address and are merged by the hardware (ATOMS.POPC.INC).
 //
 // The chunks of all runs of a batch are dealt out evenly: this lane walks chunks [g0, g1) of their concatenation,
-// starting inside run rr0 (par[r].w = first chunk of run r, par[r].x >> 16 = its aligned bases, 0 = nothing to count) and
+// starting inside run rr0 (par[] lists the runs that have chunks: .w = first chunk, .x >> 16 = aligned bases) and
 // moving on to the next run inside the loop, so every lane of the warp executes the same number of iterations.
 template <int WT>
 AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t* sbuf, const Par4* par, int rr0, int g0, int g1,
                             unsigned minq4) {
-    int rr = rr0 - 1, c = 0, nch = 0, m = 0;
+    int rr = rr0 - 1, c = 0, nch = 0;
     const uint32_t* A = nullptr; const uint32_t* S = nullptr;
-    unsigned sh = 0, ssh = 0, qa = 0, sa = 0, x = 0;
+    unsigned sh = 0, ssh = 0, qa = 0, sa = 0, x = 0, mk0 = 0, mk1 = 0;
     bool odd = false;
     int* tl = cnt;
     for (int g = g0; g < g1; ++g, ++c, tl += 8) {
-        if (c >= nch) {                                      // next run with chunks (first iteration: run rr0 at chunk g0)
-            Par4 pr;
-            do { ++rr; pr = par[rr]; m = (pr.x >> 16) & 0x1FF; nch = (m + 7) >> 3; } while (nch == 0);
+        if (c >= nch) {                                      // next run (first iteration: run rr0 at chunk g0)
+            const Par4 pr = par[++rr];
+            const int m = (pr.x >> 16) & 0x1FF;
+            nch = (m + 7) >> 3;
             c = g == g0 ? g - pr.w : 0;
             const int a0 = pr.x & 0xFFFF, sb = pr.y >> 1;
             A = (const uint32_t*)(qbuf + (a0 & ~3)); sh = (unsigned)(a0 & 3) << 3;
@@ -283,6 +225,9 @@ AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t
             odd = pr.y & 1;
             qa = A[2 * c]; sa = S[c + 1]; x = funnel_r(S[c], sa, ssh);
             tl = cnt + pr.z + 8 * c;
+            const int left = m - 8 * (nch - 1);              // bases of the last chunk, 1 .. 8: byte masks for its two words
+            mk0 = left >= 4 ? 0xFFFFFFFFu : (1u << (8 * left)) - 1u;
+            mk1 = left >= 8 ? 0xFFFFFFFFu : (left > 4 ? (1u << (8 * (left - 4))) - 1u : 0u);
         }
         const unsigned q1 = A[2 * c + 1], q2 = A[2 * c + 2];
         const unsigned v0 = funnel_r(qa, q1, sh), v1 = funnel_r(q1, q2, sh);
@@ -293,11 +238,8 @@ AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t
         // q >= minq per byte (exact for every byte value, minq <= 127): bit 7 of each byte
         unsigned k0 = (((v0 | 0x80808080u) - minq4) | v0) & 0x80808080u;
         unsigned k1 = (((v1 | 0x80808080u) - minq4) | v1) & 0x80808080u;
-        if (c == nch - 1) {                                  // bases past the run
-            const int left = m - 8 * c;                      // 1 .. 8
-            const unsigned long long keep = left >= 8 ? ~0ULL : ((1ULL << (8 * left)) - 1ULL);
-            k0 &= (unsigned)keep; k1 &= (unsigned)(keep >> 32);
-        }
+        k0 &= c == nch - 1 ? mk0 : 0xFFFFFFFFu;               // bases past the run
+        k1 &= c == nch - 1 ? mk1 : 0xFFFFFFFFu;
         // nibbles scaled by 8, one per byte: E = bases at even nibble positions of x, O = odd ones
         const unsigned E = (x >> 1) & 0x78787878u, O = (x << 3) & 0x78787878u, En = (xn >> 1) & 0x78787878u;
         const unsigned a = odd ? O : E;                      // bases 0, 2, 4, 6 of the chunk
@@ -319,6 +261,29 @@ AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t
         AMP7_BASE(4, a, 2, k1) AMP7_BASE(5, b, 2, k1) AMP7_BASE(6, a, 3, k1) AMP7_BASE(7, b, 3, k1)
 #undef AMP7_BASE
     }
+}
+
+// Deal the chunks of up to 32 runs (one per lane; nchk = 0: this lane has none) out evenly over the warp and count them.
+// Quality clipping leaves aligned runs of very different lengths; lane l takes chunks [l*q, (l+1)*q) of the concatenation.
+template <int WT>
+AMP_WD void count_runs_balanced(int* cnt, int wt, const uint8_t* qbuf, const uint8_t* sbuf, Par4* par, uint8_t* own, int lane, int nchk,
+                                int a0, int n0, int m, int w0, unsigned minq4) {
+    int incl = nchk;
+    for (int d = 1; d < 32; d <<= 1) { const int t = w_shfl(incl, lane - d); if (lane >= d) incl += t; }
+    const int start = incl - nchk, total = w_shfl(incl, 31);
+    if (total <= 0) return;                                                    // uniform
+    const int q = (total + 31) >> 5;
+    const unsigned hmask = w_ballot(nchk > 0);                                 // the runs that have chunks, in lane order
+    if (nchk > 0) {
+        const int rank = popc32(hmask & ((1u << lane) - 1u));
+        par[rank] = make_par(a0 | (m << 16), n0, w0, start);
+        const int l_hi = (start + nchk + q - 1) / q;
+        for (int ll = (start + q - 1) / q; ll < l_hi && ll < 32; ++ll) own[ll] = (uint8_t)rank;   // lanes that start in this run
+    }
+    w_sync();
+    const int g0 = lane * q, g1 = g0 + q < total ? g0 + q : total;
+    if (g0 < g1) count_chunks_v8<WT>(cnt, wt, qbuf, sbuf, par, own[lane], g0, g1, minq4);
+    w_sync();                                                                  // par / own may be rewritten
 }
 
 // ---- generic path inside a warp (same logic as TileSink / read_generic, warp-private run list) --------------------
@@ -364,37 +329,36 @@ AMP_HD void count_global7(const KParams& P, int* cnt, int wbase, int row, int p,
     atomic_add(&P.counts[(size_t)ch * P.Lpad + p], 1);
 }
 
-// count the warp's run list [0, n_runs): groups of 8 lanes per run, consecutive lanes on consecutive bases
-AMP_HD void count_warp_runs7(const KParams& P, int* cnt, const WarpMem7& wm, int n_runs, int wbase, int lane) {
-    const int l = lane & 7, sub = lane >> 3;
+// count the warp's run list [0, n_runs), 32 runs at a time (one per lane): staged aligned runs inside the tile go through
+// the balanced chunk loop of the fast kernel; deletion runs and everything else are counted base by base by their lane
+template <int WT>
+AMP_WD void count_warp_runs7(const KParams& P, int* cnt, int wt, const WarpMem7& wm, int n_runs, int wbase, int lane, unsigned minq4) {
     const int minq = P.tp.min_quality;
     unsigned errs = 0;
-    for (int s = sub; s < n_runs; s += 4) {
-        const Seg sg = wm.runs[s];
-        const int n = sg.len & 0x3FFFFFFF;
-        const int w0 = sg.rpos - wbase;
-        const bool in_win = wbase >= 0 && w0 >= 0 && w0 + n <= P.wt;
-        if (sg.len < 0) {                                                          // D / N run: unconditional (714-715)
-            if (in_win) { for (int j = l; j < n; j += 8) atomic_add(&cnt[AMP7_DEL_ROW * P.wt + w0 + j], 1); }
-            else for (int j = l; j < n; j += 8) count_global7(P, cnt, wbase, AMP7_DEL_ROW, sg.rpos + j, errs);
-            continue;
-        }
-        const bool staged = (sg.len & 0x40000000) != 0;
-        const uint8_t* qp = staged ? wm.qbuf + sg.qabs : P.b.qual + sg.qabs;
-        const uint8_t* sp = staged ? wm.sbuf : P.b.seq;
-        if (in_win) {
-            for (int j = l; j < n; j += 8) {
-                if (qp[j] < minq) continue;                                        // 718
-                const uint32_t nb = sg.nibabs + (uint32_t)j;
-                atomic_add(&cnt[(int)((sp[nb >> 1] >> ((~nb & 1u) << 2)) & 15u) * P.wt + w0 + j], 1);   // 752-753
-            }
-        } else {
-            for (int j = l; j < n; j += 8) {
-                if (qp[j] < minq) continue;
-                const uint32_t nb = sg.nibabs + (uint32_t)j;
-                count_global7(P, cnt, wbase, (int)((sp[nb >> 1] >> ((~nb & 1u) << 2)) & 15u), sg.rpos + j, errs);
+    for (int base = 0; base < n_runs; base += 32) {
+        int nchk = 0, a0 = 0, n0 = 0, m = 0, w0 = 0;
+        if (base + lane < n_runs) {
+            const Seg sg = wm.runs[base + lane];
+            const int n = sg.len & 0x3FFFFFFF;
+            w0 = sg.rpos - wbase;
+            const bool in_win = wbase >= 0 && w0 >= 0 && w0 + n <= wt;
+            if (sg.len < 0) {                                                      // D / N run: unconditional (714-715)
+                if (in_win) { for (int j = 0; j < n; ++j) atomic_add(&cnt[AMP7_DEL_ROW * wt + w0 + j], 1); }
+                else for (int j = 0; j < n; ++j) count_global7(P, cnt, wbase, AMP7_DEL_ROW, sg.rpos + j, errs);
+            } else if ((sg.len & 0x40000000) && in_win && n > 0 && n < 512 && minq >= 0 && minq <= 127) {
+                a0 = (int)sg.qabs; n0 = (int)sg.nibabs; m = n; nchk = (n + 7) >> 3;
+            } else {
+                const bool staged = (sg.len & 0x40000000) != 0;
+                const uint8_t* qp = staged ? wm.qbuf + sg.qabs : P.b.qual + sg.qabs;
+                const uint8_t* sp = staged ? wm.sbuf : P.b.seq;
+                for (int j = 0; j < n; ++j) {
+                    if (qp[j] < minq) continue;                                    // 718
+                    const uint32_t nb = sg.nibabs + (uint32_t)j;
+                    count_global7(P, cnt, wbase, (int)((sp[nb >> 1] >> ((~nb & 1u) << 2)) & 15u), sg.rpos + j, errs);   // 752-753
+                }
             }
         }
+        count_runs_balanced<WT>(cnt, wt, wm.qbuf, wm.sbuf, wm.par, wm.own, lane, nchk, a0, n0, m, w0, minq4);
     }
     if (errs) atomic_or(P.err, errs);
 }
@@ -415,12 +379,13 @@ AMP_HD void warp_read_generic7(const KParams& P, const WarpMem7& wm, long long i
     const uint8_t* qual = q_st ? wm.qbuf + qdst : P.b.qual + qo0;
     const uint8_t* seq = do_pile ? (s_st ? wm.sbuf + sdst : P.b.seq + so0) : nullptr;
     const uint32_t* cig = P.b.cigar + c0;
-    uint32_t la[AMP_CMAX], lb[AMP_CMAX];
     int f = 0;
     if (do_trim) {
         uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
+        // the two CIGAR work rows of trim_read live in shared memory (local-memory arrays would miss the small L1 left
+        // next to the staging buffers); long CIGARs use the global scratch rows
         uint32_t *A, *B;
-        if (nc + 3 <= AMP_CMAX) { A = la; B = lb; }
+        if (nc + 3 <= AMP7_CROW) { A = wm.cig + (size_t)slot * 2 * AMP7_CROW; B = A + AMP7_CROW; }
         else { A = P.scratch + (size_t)c0 + 3 * (size_t)i; B = A + P.scratch_half; }
         for (int k = 0; k < nc; ++k) A[k] = cig[k];
         uint32_t* res;
@@ -443,7 +408,8 @@ AMP_HD void warp_read_generic7(const KParams& P, const WarpMem7& wm, long long i
 }
 
 // G phase: the first nb (<= AMP7_GN) queued reads of the warp
-AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, int wbase, int nb, int nq, int lane, bool do_trim,
+template <int WT>
+AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, int wt, int wbase, int nb, int nq, int lane, bool do_trim,
                                bool do_pile, uint32_t& parity) {
     // stage the (scattered) rows into fixed slots, keeping each row's alignment mod 16: every lane starts the bulk copies
     // of its own read (whole 16-byte pieces) and moves the < 16 trailing bytes itself
@@ -482,7 +448,7 @@ AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, i
     w_sync();
     if (do_pile) {
         int nr = wm.ctr[0]; if (nr > AMP7_RUNCAP) nr = AMP7_RUNCAP;
-        count_warp_runs7(P, cnt, wm, nr, wbase, lane);
+        count_warp_runs7<WT>(P, cnt, wt, wm, nr, wbase, lane, (unsigned)P.tp.min_quality * 0x01010101u);
     }
     // drop the processed entries (the queue holds < 64 entries: at most one move per lane and round)
     for (int base = 0; base + nb < nq; base += 32) {
@@ -648,24 +614,8 @@ AMP_WD void cta_fast_v8(const KParams& P, unsigned char* smem_base) {
                 }
             }
         }
-        // ---- B2: pileup.  Quality clipping leaves aligned runs of very different lengths, so the chunks of the whole
-        // batch are dealt out evenly: lane l takes chunks [l*q, (l+1)*q) of the concatenation of all runs.
-        if (PILE) {
-            int incl = nchk;
-            for (int d = 1; d < 32; d <<= 1) { const int t = w_shfl(incl, lane - d); if (lane >= d) incl += t; }
-            const int start = incl - nchk, total = w_shfl(incl, 31);
-            if (total > 0) {
-                const int q = (total + 31) >> 5;
-                wm.par[lane] = make_par(qa0 | ((nchk > 0 ? r.m : 0) << 16), n0, w0, start);
-                if (nchk > 0) {
-                    const int l_hi = (start + nchk + q - 1) / q;
-                    for (int ll = (start + q - 1) / q; ll < l_hi && ll < 32; ++ll) wm.own[ll] = (uint8_t)lane;
-                }
-                w_sync();
-                const int g0 = lane * q, g1 = g0 + q < total ? g0 + q : total;
-                if (g0 < g1) count_chunks_v8<WT>(cnt, wt, wm.qbuf, wm.sbuf, wm.par, wm.own[lane], g0, g1, minq4);
-            }
-        }
+        // ---- B2: pileup of the batch's aligned runs, chunks dealt out evenly over the lanes ----------------------------------
+        if (PILE) count_runs_balanced<WT>(cnt, wt, wm.qbuf, wm.sbuf, wm.par, wm.own, lane, nchk, qa0, n0, r.m, w0, minq4);
         w_sync();   // every lane is done with the staged rows before the buffers are reused
     }
     c_sync();
@@ -674,9 +624,9 @@ AMP_WD void cta_fast_v8(const KParams& P, unsigned char* smem_base) {
 }
 
 // generic kernel: CTA c works through the list its fast-kernel counterpart wrote
-template <bool TRIM, bool PILE>
+template <bool TRIM, bool PILE, int WT>
 AMP_WD void cta_generic_v8(const KParams& P, unsigned char* smem_base) {
-    const int wt = P.wt;
+    const int wt = WT ? WT : P.wt;
     const int tid = c_tid(), nthreads = c_nthreads(), block = c_block();
     const int lane = tid & 31, warp = tid >> 5;
     const int n_list = P.gcount[block];
@@ -703,7 +653,7 @@ AMP_WD void cta_generic_v8(const KParams& P, unsigned char* smem_base) {
         const int nb = n_list - at < per ? n_list - at : per;
         if (lane < nb) wm.queue[lane] = glist[at + lane];
         w_sync();
-        warp_generic_phase(P, wm, cnt, wbase, nb, nb, lane, TRIM, PILE, parity);
+        warp_generic_phase<WT>(P, wm, cnt, wt, wbase, nb, nb, lane, TRIM, PILE, parity);
     }
     c_sync();
     if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);

@@ -220,9 +220,9 @@ static void v8_fast_body(void* a) {
 }
 static void v8_generic_body(void* a) {
     V7Launch* v = (V7Launch*)a;
-    if (v->mode == 3) amp::cta_generic_v8<true, true>(*v->P, v->smem);
-    else if (v->mode == 1) amp::cta_generic_v8<true, false>(*v->P, v->smem);
-    else amp::cta_generic_v8<false, true>(*v->P, v->smem);
+    if (v->mode == 3) amp::cta_generic_v8<true, true, 0>(*v->P, v->smem);
+    else if (v->mode == 1) amp::cta_generic_v8<true, false, 0>(*v->P, v->smem);
+    else amp::cta_generic_v8<false, true, 0>(*v->P, v->smem);
 }
 int emu_process_v7(void* h, long long first, long long n, const int32_t* pos, const uint16_t* flag, const int32_t* tlen,
                    const uint32_t* cig_off, const uint32_t* cigar, const uint32_t* seq_off, const uint8_t* seq,
@@ -296,7 +296,7 @@ void emu_ins_merge(void* h, long long n, const int32_t* sample, const int32_t* p
     }
 }
 
-// unit hooks for the sliding-window closed forms (q must have 8 readable bytes on both sides for mode 2)
+// unit hooks for the sliding-window closed forms (q must have 8 readable bytes before and 16 after it for mode 2)
 int emu_window(const uint8_t* q, int len, int W, int minq, int rev, int mode) {
     if (mode == 2) return amp::window_del_len_w4(q, len, minq, rev != 0);
     return rev ? amp::window_del_len_rev(q, len, W, minq) : amp::window_del_len_fwd(q, len, W, minq);
