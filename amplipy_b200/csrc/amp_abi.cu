@@ -197,6 +197,12 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
         // per-CTA lists of the reads that need the generic kernel
         P.gcap = (long long)P.tiles_per_cta * P.reads_per_tile;
         P.glist = glist; P.gcount = (int*)(glist + (size_t)grid * (size_t)P.gcap);
+#ifdef AMP7_TIMING
+        static long long* d_phase7 = nullptr;
+        if (!d_phase7) CK(cudaMalloc((void**)&d_phase7, 16 * 8));
+        CK(cudaMemsetAsync(d_phase7, 0, 16 * 8, st));
+        P.phase_cycles = d_phase7;
+#endif
         const bool tr = mode & AMP_MODE_TRIM, pl = mode & AMP_MODE_PILEUP;
         if (tr && pl) amp_trim_pileup_fast_kernel<true, true><<<grid, AMP7_WARPS * 32, smem_f, st>>>(P);
         else if (tr) amp_trim_pileup_fast_kernel<true, false><<<grid, AMP7_WARPS * 32, smem_f, st>>>(P);
@@ -206,6 +212,16 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
         else if (tr) amp_trim_pileup_generic_kernel<true, false><<<grid, AMP7_GWARPS * 32, smem_g, st>>>(P);
         else amp_trim_pileup_generic_kernel<false, true><<<grid, AMP7_GWARPS * 32, smem_g, st>>>(P);
         CK(cudaGetLastError());
+#ifdef AMP7_TIMING
+        {
+            CK(cudaStreamSynchronize(st));
+            long long h[16];
+            CK(cudaMemcpy(h, d_phase7, sizeof h, cudaMemcpyDeviceToHost));
+            const double wf = (double)grid * AMP7_WARPS, wg = (double)grid * AMP7_GWARPS;
+            fprintf(stderr, "[cycles per warp] fast: prologue %.0f  A %.0f  bulk-wait %.0f  window+trim %.0f  count %.0f  tail-sync %.0f | generic: prologue %.0f  stage %.0f  trim+plan %.0f  count %.0f  idle %.0f  sync %.0f  flush %.0f\n",
+                    h[0] / wf, h[1] / wf, h[2] / wf, h[3] / wf, h[4] / wf, h[5] / wf, h[8] / wg, h[9] / wg, h[10] / wg, h[11] / wg, h[12] / wg, h[13] / wg, h[14] / wg);
+        }
+#endif
         c->last_launches += 2;
         return AMP_OK;
     }

@@ -481,6 +481,19 @@ AMP_HD bool classify_simple(const uint32_t* cig, int nc, int l_seq, SimpleRead& 
     if (k < nc) { if (c_op(cig[k]) != OP_S) return false; r.s2 = c_len(cig[k]); if (r.s2 < 1) return false; ++k; }
     return k == nc && r.m >= 1 && r.s1 + r.m + r.s2 == l_seq;
 }
+// the same classification from the first three CIGAR words held in registers (w_k is ignored for k >= nc)
+AMP_HD bool classify_simple3(int nc, uint32_t w0, uint32_t w1, uint32_t w2, int l_seq, SimpleRead& r) {
+    if (nc < 1 || nc > 3) return false;
+    int k = 0;
+    r.s1 = 0; r.s2 = 0;
+    if (c_op(w0) == OP_S) { r.s1 = c_len(w0); if (r.s1 < 1) return false; k = 1; }
+    if (k >= nc) return false;
+    const uint32_t mw = k ? w1 : w0;
+    if (!cons_qr(c_op(mw))) return false;
+    r.mop = c_op(mw); r.m = c_len(mw); ++k;
+    if (k < nc) { const uint32_t sw = k == 1 ? w1 : w2; if (c_op(sw) != OP_S) return false; r.s2 = c_len(sw); if (r.s2 < 1) return false; ++k; }
+    return k == nc && r.m >= 1 && r.s1 + r.m + r.s2 == l_seq;
+}
 // Steps 1-2 (primer start / end) of the closed form.  On success r / pos hold the shape after primer clipping.
 AMP_HD bool trim_simple_primers(SimpleRead& r, int& pos, int flag, int tlen, int l_seq, const TrimParams& P, int* flags_out) {
     const int p = pos, ref_end = p + r.m;

@@ -65,6 +65,10 @@ AMP_WD void tile_inc_if(int* cnt, int idx, unsigned cond) {
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.add.u32 [%0], 1; }" ::"r"(smem_addr(cnt) + 4u * (uint32_t)idx), "r"(cond)
                  : "memory");
 }
+// pull [src, src + bytes) towards L2 (bytes a multiple of 16); purely a hint
+AMP_WD void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 AMP_WD void bulk_wait(unsigned long long* bar, uint32_t parity) {
     uint32_t ok;
     do {
@@ -90,8 +94,21 @@ AMP_WD void mbar_init(unsigned long long*) {}
 AMP_WD void bulk_expect(unsigned long long*, uint32_t) {}
 AMP_WD void bulk_copy(void* dst, const void* src, uint32_t bytes, unsigned long long*) { memcpy(dst, src, bytes); }
 AMP_WD void bulk_wait(unsigned long long*, uint32_t) {}
+AMP_WD void bulk_prefetch_l2(const void*, uint32_t) {}
 AMP_WD void tile_inc_if(int* cnt, int idx, unsigned cond) { if (cond) cnt[idx] += 1; }
 static long long g_v7_stats[2];   // emulation only: reads finished on the cooperative path / reads sent to the generic path
+#endif
+
+// debug builds (-DAMP7_TIMING): per-warp cycle counters of the kernels' phases, summed over all warps into
+// P.phase_cycles[base + k]; slot 7 of the local array holds the last time stamp
+#if defined(__CUDA_ARCH__) && defined(AMP7_TIMING)
+#define AMP7_T0(t) long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; t[7] = clock64()
+#define AMP7_TICK(t, k) do { const long long n_ = clock64(); (t)[k] += n_ - (t)[7]; (t)[7] = n_; } while (0)
+#define AMP7_TDUMP(t, base) do { if ((threadIdx.x & 31) == 0 && P.phase_cycles) for (int k_ = 0; k_ < 7; ++k_) atomicAdd((unsigned long long*)&P.phase_cycles[(base) + k_], (unsigned long long)(t)[k_]); } while (0)
+#else
+#define AMP7_T0(t) long long* t = nullptr; (void)t
+#define AMP7_TICK(t, k) ((void)0)
+#define AMP7_TDUMP(t, base) ((void)0)
 #endif
 
 // ---- shared-memory layout ------------------------------------------------------------------------------------------
@@ -203,20 +220,20 @@ AMP_HD void flush_tile7(const KParams& P, const int* cnt, int wbase, int tid, in
 // on reads with the same start hit the same address and are merged by the hardware (ATOMS.POPC.INC).
 //
 // The chunks of all runs of a batch are dealt out evenly: this lane walks chunks [g0, g1) of their concatenation,
-// starting inside run rr0 (par[] lists the runs that have chunks: .w = first chunk, .x >> 16 = aligned bases) and
+// starting inside run rr0 (par[] lists the runs: .w = first chunk, .x = qbuf offset | bases << 16 | phi << 26) and
 // moving on to the next run inside the loop, so every lane of the warp executes the same number of iterations.
 template <int WT>
 AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t* sbuf, const Par4* par, int rr0, int g0, int g1,
                             unsigned minq4) {
     int rr = rr0 - 1, c = 0, nch = 0;
     const uint32_t* A = nullptr; const uint32_t* S = nullptr;
-    unsigned sh = 0, ssh = 0, qa = 0, sa = 0, x = 0, mk0 = 0, mk1 = 0;
+    unsigned sh = 0, ssh = 0, qa = 0, sa = 0, x = 0, mk0 = 0, mk1 = 0, mf0 = 0, mf1 = 0;
     bool odd = false;
     int* tl = cnt;
     for (int g = g0; g < g1; ++g, ++c, tl += 8) {
         if (c >= nch) {                                      // next run (first iteration: run rr0 at chunk g0)
             const Par4 pr = par[++rr];
-            const int m = (pr.x >> 16) & 0x1FF;
+            const int m = (pr.x >> 16) & 0x3FF, phi = (pr.x >> 26) & 7;   // bases incl. the phi masked ones in front
             nch = (m + 7) >> 3;
             c = g == g0 ? g - pr.w : 0;
             const int a0 = pr.x & 0xFFFF, sb = pr.y >> 1;
@@ -228,6 +245,8 @@ AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t
             const int left = m - 8 * (nch - 1);              // bases of the last chunk, 1 .. 8: byte masks for its two words
             mk0 = left >= 4 ? 0xFFFFFFFFu : (1u << (8 * left)) - 1u;
             mk1 = left >= 8 ? 0xFFFFFFFFu : (left > 4 ? (1u << (8 * (left - 4))) - 1u : 0u);
+            mf0 = phi >= 4 ? 0u : 0xFFFFFFFFu << (8 * phi);  // first chunk: the phi bases in front of the run
+            mf1 = phi > 4 ? 0xFFFFFFFFu << (8 * (phi - 4)) : 0xFFFFFFFFu;
         }
         const unsigned q1 = A[2 * c + 1], q2 = A[2 * c + 2];
         const unsigned v0 = funnel_r(qa, q1, sh), v1 = funnel_r(q1, q2, sh);
@@ -238,8 +257,8 @@ AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t
         // q >= minq per byte (exact for every byte value, minq <= 127): bit 7 of each byte
         unsigned k0 = (((v0 | 0x80808080u) - minq4) | v0) & 0x80808080u;
         unsigned k1 = (((v1 | 0x80808080u) - minq4) | v1) & 0x80808080u;
-        k0 &= c == nch - 1 ? mk0 : 0xFFFFFFFFu;               // bases past the run
-        k1 &= c == nch - 1 ? mk1 : 0xFFFFFFFFu;
+        k0 &= (c == nch - 1 ? mk0 : 0xFFFFFFFFu) & (c == 0 ? mf0 : 0xFFFFFFFFu);   // bases past / in front of the run
+        k1 &= (c == nch - 1 ? mk1 : 0xFFFFFFFFu) & (c == 0 ? mf1 : 0xFFFFFFFFu);
         // nibbles scaled by 8, one per byte: E = bases at even nibble positions of x, O = odd ones
         const unsigned E = (x >> 1) & 0x78787878u, O = (x << 3) & 0x78787878u, En = (xn >> 1) & 0x78787878u;
         const unsigned a = odd ? O : E;                      // bases 0, 2, 4, 6 of the chunk
@@ -265,18 +284,22 @@ AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t
 
 // Deal the chunks of up to 32 runs (one per lane; nchk = 0: this lane has none) out evenly over the warp and count them.
 // Quality clipping leaves aligned runs of very different lengths; lane l takes chunks [l*q, (l+1)*q) of the concatenation.
+// The chunk grid of run k starts phi = k & 7 bases in front of the run (those bases are masked): in coordinate-sorted
+// amplicon data most runs of a batch start at the same position, and lanes that are at different chunks of such runs would
+// otherwise all fall into the same four banks of the tile (phi <= w0: never in front of the tile).
 template <int WT>
-AMP_WD void count_runs_balanced(int* cnt, int wt, const uint8_t* qbuf, const uint8_t* sbuf, Par4* par, uint8_t* own, int lane, int nchk,
+AMP_WD void count_runs_balanced(int* cnt, int wt, const uint8_t* qbuf, const uint8_t* sbuf, Par4* par, uint8_t* own, int lane, bool has,
                                 int a0, int n0, int m, int w0, unsigned minq4) {
+    const unsigned hmask = w_ballot(has);                                      // the runs, in lane order
+    if (!hmask) return;                                                        // uniform
+    const int rank = popc32(hmask & ((1u << lane) - 1u)), phi = (rank & 7) < w0 ? (rank & 7) : (w0 > 0 ? w0 : 0);
+    const int nchk = has ? (m + phi + 7) >> 3 : 0;
     int incl = nchk;
     for (int d = 1; d < 32; d <<= 1) { const int t = w_shfl(incl, lane - d); if (lane >= d) incl += t; }
     const int start = incl - nchk, total = w_shfl(incl, 31);
-    if (total <= 0) return;                                                    // uniform
     const int q = (total + 31) >> 5;
-    const unsigned hmask = w_ballot(nchk > 0);                                 // the runs that have chunks, in lane order
-    if (nchk > 0) {
-        const int rank = popc32(hmask & ((1u << lane) - 1u));
-        par[rank] = make_par(a0 | (m << 16), n0, w0, start);
+    if (has) {
+        par[rank] = make_par((a0 - phi) | ((m + phi) << 16) | (phi << 26), n0 - phi, w0 - phi, start);
         const int l_hi = (start + nchk + q - 1) / q;
         for (int ll = (start + q - 1) / q; ll < l_hi && ll < 32; ++ll) own[ll] = (uint8_t)rank;   // lanes that start in this run
     }
@@ -336,7 +359,8 @@ AMP_WD void count_warp_runs7(const KParams& P, int* cnt, int wt, const WarpMem7&
     const int minq = P.tp.min_quality;
     unsigned errs = 0;
     for (int base = 0; base < n_runs; base += 32) {
-        int nchk = 0, a0 = 0, n0 = 0, m = 0, w0 = 0;
+        int a0 = 0, n0 = 0, m = 0, w0 = 0;
+        bool has = false;
         if (base + lane < n_runs) {
             const Seg sg = wm.runs[base + lane];
             const int n = sg.len & 0x3FFFFFFF;
@@ -346,7 +370,7 @@ AMP_WD void count_warp_runs7(const KParams& P, int* cnt, int wt, const WarpMem7&
                 if (in_win) { for (int j = 0; j < n; ++j) atomic_add(&cnt[AMP7_DEL_ROW * wt + w0 + j], 1); }
                 else for (int j = 0; j < n; ++j) count_global7(P, cnt, wbase, AMP7_DEL_ROW, sg.rpos + j, errs);
             } else if ((sg.len & 0x40000000) && in_win && n > 0 && n < 512 && minq >= 0 && minq <= 127) {
-                a0 = (int)sg.qabs; n0 = (int)sg.nibabs; m = n; nchk = (n + 7) >> 3;
+                a0 = (int)sg.qabs; n0 = (int)sg.nibabs; m = n; has = true;
             } else {
                 const bool staged = (sg.len & 0x40000000) != 0;
                 const uint8_t* qp = staged ? wm.qbuf + sg.qabs : P.b.qual + sg.qabs;
@@ -358,7 +382,7 @@ AMP_WD void count_warp_runs7(const KParams& P, int* cnt, int wt, const WarpMem7&
                 }
             }
         }
-        count_runs_balanced<WT>(cnt, wt, wm.qbuf, wm.sbuf, wm.par, wm.own, lane, nchk, a0, n0, m, w0, minq4);
+        count_runs_balanced<WT>(cnt, wt, wm.qbuf, wm.sbuf, wm.par, wm.own, lane, has, a0, n0, m, w0, minq4);
     }
     if (errs) atomic_or(P.err, errs);
 }
@@ -410,7 +434,7 @@ AMP_HD void warp_read_generic7(const KParams& P, const WarpMem7& wm, long long i
 // G phase: the first nb (<= AMP7_GN) queued reads of the warp
 template <int WT>
 AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, int wt, int wbase, int nb, int nq, int lane, bool do_trim,
-                               bool do_pile, uint32_t& parity) {
+                               bool do_pile, uint32_t& parity, long long* tk) {
     // stage the (scattered) rows into fixed slots, keeping each row's alignment mod 16: every lane starts the bulk copies
     // of its own read (whole 16-byte pieces) and moves the < 16 trailing bytes itself
     {
@@ -444,8 +468,10 @@ AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, i
         w_sync();
         if (total) { bulk_wait(wm.bar, parity); parity ^= 1u; }
     }
+    AMP7_TICK(tk, 1);
     if (lane < nb) warp_read_generic7(P, wm, P.b.first + wm.queue[lane], lane, do_trim, do_pile);
     w_sync();
+    AMP7_TICK(tk, 2);
     if (do_pile) {
         int nr = wm.ctr[0]; if (nr > AMP7_RUNCAP) nr = AMP7_RUNCAP;
         count_warp_runs7<WT>(P, cnt, wt, wm, nr, wbase, lane, (unsigned)P.tp.min_quality * 0x01010101u);
@@ -459,6 +485,7 @@ AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, i
         w_sync();
     }
     w_sync();
+    AMP7_TICK(tk, 3);
 }
 
 // ---- the kernels -----------------------------------------------------------------------------------------------------
@@ -513,26 +540,53 @@ AMP_WD void cta_fast_v8(const KParams& P, unsigned char* smem_base) {
     const bool fast_ok = minq >= 0 && minq <= 127 && (!TRIM || P.tp.window == 4);
     const unsigned minq4 = (unsigned)minq * 0x01010101u;
     uint32_t parity = 0;
+    AMP7_T0(tk);
+    AMP7_TICK(tk, 0);
 
-    for (;;) {
-        int bi = 0;
-        if (lane == 0) bi = atomic_add(&ctrl[C7_NEXT], 1);
-        bi = w_shfl(bi, 0);
-        if (bi >= n_batches) break;
+    // Software pipeline over the warp's batches: the per-read metadata of the next batch is loaded while the current one is
+    // in its window pass, its first CIGAR words (and an L2 prefetch of its rows) while the current one is being counted.
+    struct Meta { uint32_t c0, c1, qo0, qo1, so0, so1; int flag, pos, tlen; uint32_t g0, g1, g2; };
+    auto claim = [&]() -> int {
+        int b = 0;
+        if (lane == 0) b = atomic_add(&ctrl[C7_NEXT], 1);
+        return w_shfl(b, 0);
+    };
+    auto read_index = [&](int b) -> long long {              // this lane's read of batch b (clamped to the batch's first read)
+        const long long t0 = P.b.first + (g_lo + b) * BR;
+        long long t1 = t0 + BR; if (t1 > n_end) t1 = n_end;
+        return lane < (int)(t1 - t0) ? t0 + lane : t0;
+    };
+    auto load_meta = [&](int b, Meta& M) {
+        const long long i = read_index(b);
+        M.c0 = P.b.cig_off[i]; M.c1 = P.b.cig_off[i + 1];
+        M.qo0 = P.b.qual_off[i]; M.qo1 = P.b.qual_off[i + 1];
+        M.so0 = 0; M.so1 = 0;
+        if (PILE) { M.so0 = P.b.seq_off[i]; M.so1 = P.b.seq_off[i + 1]; }
+        M.flag = P.b.flag[i]; M.pos = P.b.pos[i];
+        M.tlen = TRIM ? P.b.tlen[i] : 0;
+    };
+    auto load_cigar3 = [&](Meta& M) {
+        const int nc = (int)(M.c1 - M.c0);
+        M.g0 = nc > 0 ? P.b.cigar[M.c0] : 0u;
+        M.g1 = nc > 1 ? P.b.cigar[M.c0 + 1] : 0u;
+        M.g2 = nc > 2 ? P.b.cigar[M.c0 + 2] : 0u;
+    };
+    Meta M, Mn;
+    M.c0 = M.c1 = M.qo0 = M.qo1 = M.so0 = M.so1 = M.g0 = M.g1 = M.g2 = 0; M.flag = M.pos = M.tlen = 0;
+    Mn = M;
+    int bi = claim();
+    if (bi < n_batches) { load_meta(bi, M); load_cigar3(M); }
+    while (bi < n_batches) {
         const long long t0 = P.b.first + (g_lo + bi) * BR;
         long long t1 = t0 + BR; if (t1 > n_end) t1 = n_end;
         const int nreads = (int)(t1 - t0);
         const bool have = lane < nreads;
         const long long i = have ? t0 + lane : t0;
 
-        // ---- A: metadata -----------------------------------------------------------------------------------------
-        const uint32_t c0 = P.b.cig_off[i], c1 = P.b.cig_off[i + 1];
-        const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
-        uint32_t so0 = 0, so1 = 0;
-        if (PILE) { so0 = P.b.seq_off[i]; so1 = P.b.seq_off[i + 1]; }
-        const int flag = P.b.flag[i];
-        int pos = P.b.pos[i];
-        const int tlen = TRIM ? P.b.tlen[i] : 0;
+        // ---- A: staging + classification (metadata already in registers) -------------------------------------------------
+        const uint32_t c0 = M.c0, c1 = M.c1, qo0 = M.qo0, qo1 = M.qo1, so0 = M.so0, so1 = M.so1;
+        const int flag = M.flag, tlen = M.tlen;
+        int pos = M.pos;
         // staged byte ranges [lo, hi) of the batch: rows of consecutive reads are contiguous
         const uint32_t q_lo = (uint32_t)w_shfl((int)qo0, 0) & ~15u, q_end = (uint32_t)w_shfl((int)qo1, nreads - 1);
         const uint32_t q_hi = (q_end - q_lo <= (uint32_t)AMP7_QDATA) ? q_end : q_lo + (uint32_t)AMP7_QDATA;
@@ -557,7 +611,7 @@ AMP_WD void cta_fast_v8(const KParams& P, unsigned char* smem_base) {
         const bool skipped = have && ((flag & 4) || nc == 0);                          // AmpliPy.py:902
         SimpleRead r; r.s1 = 0; r.m = 0; r.s2 = 0; r.mop = 0;
         int f = 0;
-        bool fast = have && !skipped && fast_ok && qo1 <= q_hi && (!PILE || so1 <= s_hi) && classify_simple(cig, nc, l_seq, r);
+        bool fast = have && !skipped && fast_ok && qo1 <= q_hi && (!PILE || so1 <= s_hi) && classify_simple3(nc, M.g0, M.g1, M.g2, l_seq, r);
         if (fast && TRIM) fast = trim_simple_primers(r, pos, flag, tlen, l_seq, P.tp, &f);
         if (fast && !TRIM && (pos < 0 || pos + r.m > P.tp.L)) fast = false;
         const uint32_t a0 = AMP7_PAD + (qo0 - q_lo) + (uint32_t)r.s1;                  // first aligned quality byte in qbuf
@@ -583,10 +637,14 @@ AMP_WD void cta_fast_v8(const KParams& P, unsigned char* smem_base) {
         if (fast) ++g_v7_stats[0]; else if (have && !skipped) ++g_v7_stats[1];
 #endif
         w_sync();
+        AMP7_TICK(tk, 1);
         if (q_bulk + s_bulk > 0) { bulk_wait(wm.bar, parity); parity ^= 1u; }
+        AMP7_TICK(tk, 2);
+        const int bn = claim();                                        // next batch: its metadata loads fly during B1
+        if (bn < n_batches) load_meta(bn, Mn);
 
         // ---- B1: lane per read: window search, quality clip + write gate + outputs ---------------------------------------
-        int nchk = 0;                                                  // 8-base chunks of this lane's read to count in the tile
+        bool in_tile = false;                                          // this lane's read is counted in the tile (pass B2)
         int qa0 = 0, n0 = 0, w0 = 0;
         if (fast) {
             if (TRIM) {
@@ -602,7 +660,7 @@ AMP_WD void cta_fast_v8(const KParams& P, unsigned char* smem_base) {
                 n0 = (int)(2u * (AMP7_PAD + so0 - s_lo)) + r.s1;
                 w0 = pos - wbase;
                 if (wbase >= 0 && w0 >= 0 && w0 + r.m <= wt) {
-                    nchk = (r.m + 7) >> 3;
+                    in_tile = true;
                 } else {   // outside the tile: base by base into the global matrix (exact, rare on sorted input)
                     unsigned errs = 0;
                     for (int t = 0; t < r.m; ++t) {
@@ -614,11 +672,29 @@ AMP_WD void cta_fast_v8(const KParams& P, unsigned char* smem_base) {
                 }
             }
         }
+        AMP7_TICK(tk, 3);
+        if (bn < n_batches) {                                          // stage 2 of the next batch: CIGAR words, rows towards L2
+            load_cigar3(Mn);
+            const long long tn0 = P.b.first + (g_lo + bn) * BR;
+            long long tn1 = tn0 + BR; if (tn1 > n_end) tn1 = n_end;
+            const uint32_t pq_lo = (uint32_t)w_shfl((int)Mn.qo0, 0) & ~15u, pq_hi = (uint32_t)w_shfl((int)Mn.qo1, (int)(tn1 - tn0) - 1);
+            const uint32_t ps_lo = (uint32_t)w_shfl((int)Mn.so0, 0) & ~15u, ps_hi = (uint32_t)w_shfl((int)Mn.so1, (int)(tn1 - tn0) - 1);
+            if (lane == 0) {
+                uint32_t nq = (pq_hi - pq_lo) & ~15u; if (nq > (uint32_t)AMP7_QDATA) nq = AMP7_QDATA;
+                if (nq) bulk_prefetch_l2(P.b.qual + pq_lo, nq);
+                uint32_t ns = (ps_hi - ps_lo) & ~15u; if (ns > (uint32_t)AMP7_SDATA) ns = AMP7_SDATA;
+                if (PILE && ns) bulk_prefetch_l2(P.b.seq + ps_lo, ns);
+            }
+        }
         // ---- B2: pileup of the batch's aligned runs, chunks dealt out evenly over the lanes ----------------------------------
-        if (PILE) count_runs_balanced<WT>(cnt, wt, wm.qbuf, wm.sbuf, wm.par, wm.own, lane, nchk, qa0, n0, r.m, w0, minq4);
+        if (PILE) count_runs_balanced<WT>(cnt, wt, wm.qbuf, wm.sbuf, wm.par, wm.own, lane, in_tile, qa0, n0, r.m, w0, minq4);
         w_sync();   // every lane is done with the staged rows before the buffers are reused
+        AMP7_TICK(tk, 4);
+        M = Mn; bi = bn;
     }
     c_sync();
+    AMP7_TICK(tk, 5);
+    AMP7_TDUMP(tk, 0);
     if (tid == 0) P.gcount[block] = ctrl[C7_NGEN];
     if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);
 }
@@ -631,6 +707,7 @@ AMP_WD void cta_generic_v8(const KParams& P, unsigned char* smem_base) {
     const int lane = tid & 31, warp = tid >> 5;
     const int n_list = P.gcount[block];
     if (n_list <= 0) return;                                        // uniform across the CTA
+    AMP7_T0(tk);
     int* cnt = (int*)smem_base;
     int* ctrl = (int*)(smem_base + tile_bytes_v7(wt));
     const WarpMem7 wm = carve_warp7(smem_base, wt, warp);
@@ -645,6 +722,7 @@ AMP_WD void cta_generic_v8(const KParams& P, unsigned char* smem_base) {
     const int nw = nthreads >> 5;
     int per = (n_list + nw - 1) / nw; if (per > AMP7_GN) per = AMP7_GN;
     uint32_t parity = 0;
+    AMP7_TICK(tk, 0);
     for (;;) {
         int at = 0;
         if (lane == 0) at = atomic_add(&ctrl[C7_NEXT], per);
@@ -653,10 +731,14 @@ AMP_WD void cta_generic_v8(const KParams& P, unsigned char* smem_base) {
         const int nb = n_list - at < per ? n_list - at : per;
         if (lane < nb) wm.queue[lane] = glist[at + lane];
         w_sync();
-        warp_generic_phase<WT>(P, wm, cnt, wt, wbase, nb, nb, lane, TRIM, PILE, parity);
+        warp_generic_phase<WT>(P, wm, cnt, wt, wbase, nb, nb, lane, TRIM, PILE, parity, tk);
     }
+    AMP7_TICK(tk, 4);
     c_sync();
+    AMP7_TICK(tk, 5);
     if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);
+    AMP7_TICK(tk, 6);
+    AMP7_TDUMP(tk, 8);
 }
 
 }  // namespace amp
