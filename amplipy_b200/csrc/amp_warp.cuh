@@ -136,7 +136,7 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_GSLOT_S 96
 #define AMP7_GN 26               // reads per G phase (GN * GSLOT <= DATA)
 #define AMP7_CROW 13             // generic path: CIGAR ops (+3) per shared-memory row; two rows per read (odd stride: no bank conflicts)
-#define AMP7_WARP_BYTES (AMP7_QBUF + AMP7_SBUF + AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + 16 + AMP7_GN * 2 * AMP7_CROW * 4 + 32 * 16 + 32)
+#define AMP7_WARP_BYTES (AMP7_QBUF + AMP7_SBUF + AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + 16 + AMP7_GN * 2 * AMP7_CROW * 4 + 32 * 32 + 32)
 enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_WORDS = 16 };
 
 // the sink row is the last one and 32 * KW entries longer: idle slots of a group increment it past the window's end
@@ -144,8 +144,23 @@ AMP_HD size_t tile_bytes_v7(int wt) { return ((size_t)AMP7_ROWS * wt + 32 * AMP7
 AMP_HD size_t smem_bytes_v7(int wt, int warps) { return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_WARP_BYTES; }
 
 // launch shape: reads per batch so that a batch's rows fit the staging buffers; one CTA per SM with a contiguous chunk
-struct Par4 { int x, y, z, w; };   // x = qbuf offset | aligned bases << 16, y = first nibble in sbuf, z = tile position, w = first chunk
-AMP_HD Par4 make_par(int x, int y, int z, int w) { Par4 p; p.x = x; p.y = y; p.z = z; p.w = w; return p; }
+// One aligned run of the count pass, fully decoded by its owner lane so that switching runs inside the chunk loop is cheap:
+//   x = aligned qbuf offset | quality funnel shift << 13 | sequence funnel shift << 18 | odd first nibble << 23 | chunks << 24
+//   y = aligned sbuf offset, z = tile position of chunk 0, w = first chunk in the batch's concatenation
+//   mk0/mk1 = byte masks of the last chunk's two quality words, mf0/mf1 = of the first chunk's (phi bases in front)
+struct Par4 { int x, y, z, w; unsigned mk0, mk1, mf0, mf1; };
+AMP_HD Par4 make_par(int a0, int n0, int m, int phi, int z, int w) {   // a0 / n0 / z: of the first of the m bases (incl. phi in front)
+    Par4 p;
+    const int sb = n0 >> 1, nch = (m + 7) >> 3;
+    p.x = (a0 & ~3) | (((a0 & 3) << 3) << 13) | (((sb & 3) << 3) << 18) | ((n0 & 1) << 23) | (nch << 24);
+    p.y = sb & ~3; p.z = z; p.w = w;
+    const int left = m - 8 * (nch - 1);              // bases of the last chunk, 1 .. 8
+    p.mk0 = left >= 4 ? 0xFFFFFFFFu : (1u << (8 * left)) - 1u;
+    p.mk1 = left >= 8 ? 0xFFFFFFFFu : (left > 4 ? (1u << (8 * (left - 4))) - 1u : 0u);
+    p.mf0 = phi >= 4 ? 0u : 0xFFFFFFFFu << (8 * phi);
+    p.mf1 = phi > 4 ? 0xFFFFFFFFu << (8 * (phi - 4)) : 0xFFFFFFFFu;
+    return p;
+}
 struct V7Cfg { int wt, batch_reads; };
 inline V7Cfg pick_v7_cfg(long long n, long long sum_qual, int sm_count) {
     (void)sm_count;
@@ -158,7 +173,7 @@ inline V7Cfg pick_v7_cfg(long long n, long long sum_qual, int sm_count) {
 }
 
 // fast kernel: per-warp staging buffers, the per-read parameters of the count pass, and the bulk-copy barrier
-#define AMP7_FAST_BYTES (AMP7_QBUF + AMP7_SBUF + 32 * 16 + 32 + 16)
+#define AMP7_FAST_BYTES (AMP7_QBUF + AMP7_SBUF + 32 * 32 + 32 + 16)
 struct FastMem { uint8_t* qbuf; uint8_t* sbuf; Par4* par; uint8_t* own; unsigned long long* bar; };
 AMP_HD size_t smem_bytes_fast(int wt, int warps) { return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_FAST_BYTES; }
 AMP_HD FastMem carve_fast(unsigned char* base, int wt, int w) {
@@ -166,7 +181,7 @@ AMP_HD FastMem carve_fast(unsigned char* base, int wt, int w) {
     FastMem m;
     m.qbuf = b; b += AMP7_QBUF;
     m.sbuf = b; b += AMP7_SBUF;
-    m.par = (Par4*)b; b += 32 * 16;
+    m.par = (Par4*)b; b += 32 * 32;
     m.own = b; b += 32;
     m.bar = (unsigned long long*)b;
     return m;
@@ -186,7 +201,7 @@ AMP_HD WarpMem7 carve_warp7(unsigned char* base, int wt, int w) {
     m.ctr = (int*)b; b += 32;
     m.bar = (unsigned long long*)b; b += 16;
     m.cig = (uint32_t*)b; b += AMP7_GN * 2 * AMP7_CROW * 4;
-    m.par = (Par4*)b; b += 32 * 16;
+    m.par = (Par4*)b; b += 32 * 32;
     m.own = b;
     return m;
 }
@@ -220,7 +235,7 @@ AMP_HD void flush_tile7(const KParams& P, const int* cnt, int wbase, int tid, in
 // on reads with the same start hit the same address and are merged by the hardware (ATOMS.POPC.INC).
 //
 // The chunks of all runs of a batch are dealt out evenly: this lane walks chunks [g0, g1) of their concatenation,
-// starting inside run rr0 (par[] lists the runs: .w = first chunk, .x = qbuf offset | bases << 16 | phi << 26) and
+// starting inside run rr0 (par[] lists the decoded runs, .w = first chunk) and
 // moving on to the next run inside the loop, so every lane of the warp executes the same number of iterations.
 template <int WT>
 AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t* sbuf, const Par4* par, int rr0, int g0, int g1,
@@ -233,20 +248,14 @@ AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t
     for (int g = g0; g < g1; ++g, ++c, tl += 8) {
         if (c >= nch) {                                      // next run (first iteration: run rr0 at chunk g0)
             const Par4 pr = par[++rr];
-            const int m = (pr.x >> 16) & 0x3FF, phi = (pr.x >> 26) & 7;   // bases incl. the phi masked ones in front
-            nch = (m + 7) >> 3;
+            nch = pr.x >> 24;
             c = g == g0 ? g - pr.w : 0;
-            const int a0 = pr.x & 0xFFFF, sb = pr.y >> 1;
-            A = (const uint32_t*)(qbuf + (a0 & ~3)); sh = (unsigned)(a0 & 3) << 3;
-            S = (const uint32_t*)(sbuf + (sb & ~3)); ssh = (unsigned)(sb & 3) << 3;
-            odd = pr.y & 1;
+            A = (const uint32_t*)(qbuf + (pr.x & 0x1FFC)); sh = (unsigned)(pr.x >> 13) & 31u;
+            S = (const uint32_t*)(sbuf + pr.y); ssh = (unsigned)(pr.x >> 18) & 31u;
+            odd = (pr.x >> 23) & 1;
             qa = A[2 * c]; sa = S[c + 1]; x = funnel_r(S[c], sa, ssh);
             tl = cnt + pr.z + 8 * c;
-            const int left = m - 8 * (nch - 1);              // bases of the last chunk, 1 .. 8: byte masks for its two words
-            mk0 = left >= 4 ? 0xFFFFFFFFu : (1u << (8 * left)) - 1u;
-            mk1 = left >= 8 ? 0xFFFFFFFFu : (left > 4 ? (1u << (8 * (left - 4))) - 1u : 0u);
-            mf0 = phi >= 4 ? 0u : 0xFFFFFFFFu << (8 * phi);  // first chunk: the phi bases in front of the run
-            mf1 = phi > 4 ? 0xFFFFFFFFu << (8 * (phi - 4)) : 0xFFFFFFFFu;
+            mk0 = pr.mk0; mk1 = pr.mk1; mf0 = pr.mf0; mf1 = pr.mf1;
         }
         const unsigned q1 = A[2 * c + 1], q2 = A[2 * c + 2];
         const unsigned v0 = funnel_r(qa, q1, sh), v1 = funnel_r(q1, q2, sh);
@@ -299,7 +308,7 @@ AMP_WD void count_runs_balanced(int* cnt, int wt, const uint8_t* qbuf, const uin
     const int start = incl - nchk, total = w_shfl(incl, 31);
     const int q = (total + 31) >> 5;
     if (has) {
-        par[rank] = make_par((a0 - phi) | ((m + phi) << 16) | (phi << 26), n0 - phi, w0 - phi, start);
+        par[rank] = make_par(a0 - phi, n0 - phi, m + phi, phi, w0 - phi, start);
         const int l_hi = (start + nchk + q - 1) / q;
         for (int ll = (start + q - 1) / q; ll < l_hi && ll < 32; ++ll) own[ll] = (uint8_t)rank;   // lanes that start in this run
     }
