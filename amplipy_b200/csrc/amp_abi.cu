@@ -57,17 +57,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) amp_trim_pileup_indel_ke
     amp::cta_trim_pileup<true>(P, smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
-// warp-autonomous kernels for short-read batches (amp_warp.cuh): one CTA per SM, independent warps.
-// fast: [S]M[S] reads, lane per read; generic: every other mapped read, from the per-CTA lists the fast kernel wrote.
+// warp-autonomous kernel for short-read batches (amp_warp.cuh): one CTA per SM, AMP7_WARPS independent warps
 template <bool TRIM, bool PILE>
-__global__ void __launch_bounds__(AMP7_WARPS * 32, 1) amp_trim_pileup_fast_kernel(const __grid_constant__ amp::KParams P) {
+__global__ void __launch_bounds__(AMP7_WARPS * 32, 1) amp_trim_pileup_warp_kernel(const __grid_constant__ amp::KParams P) {
     extern __shared__ __align__(128) unsigned char smem7[];
-    amp::cta_fast_v8<TRIM, PILE, AMP7_WT>(P, smem7);
-}
-template <bool TRIM, bool PILE>
-__global__ void __launch_bounds__(AMP7_GWARPS * 32, 1) amp_trim_pileup_generic_kernel(const __grid_constant__ amp::KParams P) {
-    extern __shared__ __align__(128) unsigned char smem7[];
-    amp::cta_generic_v8<TRIM, PILE, AMP7_WT>(P, smem7);
+    amp::cta_trim_pileup_v9<TRIM, PILE, AMP7_WT>(P, smem7, AMP7_GWARPS);
 }
 
 __device__ const unsigned char kFixedSyms[8] = {'A', 'C', 'G', 'T', 'N', '-', 0, 0};
@@ -184,19 +178,16 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
         int grid = std::max(1, std::min(P.ntiles, c->sm_count));
         P.tiles_per_cta = (P.ntiles + grid - 1) / grid;
         grid = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
-        const size_t smem_f = amp::smem_bytes_fast(P.wt, AMP7_WARPS), smem_g = amp::smem_bytes_v7(P.wt, AMP7_GWARPS);
+        const size_t smem = amp::smem_bytes_v9(P.wt, AMP7_WARPS, AMP7_GWARPS);
         if (!c->v7_attr) {
-            CK(cudaFuncSetAttribute(amp_trim_pileup_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-            CK(cudaFuncSetAttribute(amp_trim_pileup_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-            CK(cudaFuncSetAttribute(amp_trim_pileup_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-            CK(cudaFuncSetAttribute(amp_trim_pileup_generic_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-            CK(cudaFuncSetAttribute(amp_trim_pileup_generic_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-            CK(cudaFuncSetAttribute(amp_trim_pileup_generic_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_warp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             c->v7_attr = true;
         }
-        // per-CTA lists of the reads that need the generic kernel
+        // per-CTA lists of the reads that need the generic phase
         P.gcap = (long long)P.tiles_per_cta * P.reads_per_tile;
-        P.glist = glist; P.gcount = (int*)(glist + (size_t)grid * (size_t)P.gcap);
+        P.glist = glist;
 #ifdef AMP7_TIMING
         static long long* d_phase7 = nullptr;
         if (!d_phase7) CK(cudaMalloc((void**)&d_phase7, 16 * 8));
@@ -204,25 +195,21 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
         P.phase_cycles = d_phase7;
 #endif
         const bool tr = mode & AMP_MODE_TRIM, pl = mode & AMP_MODE_PILEUP;
-        if (tr && pl) amp_trim_pileup_fast_kernel<true, true><<<grid, AMP7_WARPS * 32, smem_f, st>>>(P);
-        else if (tr) amp_trim_pileup_fast_kernel<true, false><<<grid, AMP7_WARPS * 32, smem_f, st>>>(P);
-        else amp_trim_pileup_fast_kernel<false, true><<<grid, AMP7_WARPS * 32, smem_f, st>>>(P);
-        CK(cudaGetLastError());
-        if (tr && pl) amp_trim_pileup_generic_kernel<true, true><<<grid, AMP7_GWARPS * 32, smem_g, st>>>(P);
-        else if (tr) amp_trim_pileup_generic_kernel<true, false><<<grid, AMP7_GWARPS * 32, smem_g, st>>>(P);
-        else amp_trim_pileup_generic_kernel<false, true><<<grid, AMP7_GWARPS * 32, smem_g, st>>>(P);
+        if (tr && pl) amp_trim_pileup_warp_kernel<true, true><<<grid, AMP7_WARPS * 32, smem, st>>>(P);
+        else if (tr) amp_trim_pileup_warp_kernel<true, false><<<grid, AMP7_WARPS * 32, smem, st>>>(P);
+        else amp_trim_pileup_warp_kernel<false, true><<<grid, AMP7_WARPS * 32, smem, st>>>(P);
         CK(cudaGetLastError());
 #ifdef AMP7_TIMING
         {
             CK(cudaStreamSynchronize(st));
             long long h[16];
             CK(cudaMemcpy(h, d_phase7, sizeof h, cudaMemcpyDeviceToHost));
-            const double wf = (double)grid * AMP7_WARPS, wg = (double)grid * AMP7_GWARPS;
-            fprintf(stderr, "[cycles per warp] fast: prologue %.0f  A %.0f  bulk-wait %.0f  window+trim %.0f  count %.0f  tail-sync %.0f | generic: prologue %.0f  stage %.0f  trim+plan %.0f  count %.0f  idle %.0f  sync %.0f  flush %.0f\n",
-                    h[0] / wf, h[1] / wf, h[2] / wf, h[3] / wf, h[4] / wf, h[5] / wf, h[8] / wg, h[9] / wg, h[10] / wg, h[11] / wg, h[12] / wg, h[13] / wg, h[14] / wg);
+            const double wf = (double)grid * AMP7_WARPS;
+            fprintf(stderr, "[cycles per warp] prologue %.0f  A %.0f  bulk-wait %.0f  window+trim %.0f  count %.0f  (barrier issue %.0f)  wait+generic %.0f\n",
+                    h[0] / wf, h[1] / wf, h[2] / wf, h[3] / wf, h[4] / wf, h[5] / wf, h[6] / wf);
         }
 #endif
-        c->last_launches += 2;
+        c->last_launches += 1;
         return AMP_OK;
     }
     P.wt = t.wt; P.maxseg = t.maxseg; P.qbytes = t.qbytes; P.sbytes = t.sbytes; P.reads_per_tile = t.reads_per_tile;

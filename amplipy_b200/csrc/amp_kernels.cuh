@@ -67,7 +67,7 @@ struct KParams {
     int reads_per_tile, ntiles, tiles_per_cta;
     int wt, maxseg, qbytes, sbytes;   // shared-memory carve-up
     int direct;                       // 1: launch the indel-rich kernel variant
-    uint32_t* glist; int* gcount;     // warp-autonomous kernels: per-CTA lists of reads for the generic kernel,
+    uint32_t* glist;                  // warp-autonomous kernel: per-CTA lists of the reads for its generic phase,
     long long gcap;                   //   gcap entries per CTA
     long long* phase_cycles;          // debug builds (-DAMP_PHASE_TIMING): per-CTA cycles in S, T, W, C
 };

@@ -116,7 +116,7 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_WARPS 16            // warps per CTA of the fast kernel
 #endif
 #ifndef AMP7_GWARPS
-#define AMP7_GWARPS 14           // warps per CTA of the generic kernel
+#define AMP7_GWARPS 11           // warps that take part in the generic phase (their extra shared memory must fit)
 #endif
 #define AMP7_WT 512              // count tile width on the device (positions)
 #define AMP7_ROWS 18             // count tile rows: BAM nibble 0..15, row 16 = deleted base, row 17 = sink of masked bases
@@ -130,18 +130,18 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_SSLACK 144
 #define AMP7_QBUF (AMP7_PAD + AMP7_QDATA + AMP7_QSLACK)
 #define AMP7_SBUF (AMP7_PAD + AMP7_SDATA + AMP7_SSLACK)
-#define AMP7_RUNCAP 96           // run descriptors per warp (generic path)
-#define AMP7_QCAP 64             // queued generic-path reads per warp
+#define AMP7_RUNCAP 72           // run descriptors per warp (generic path)
+#define AMP7_QCAP 32             // generic-path reads per warp and round
 #define AMP7_GSLOT_Q 192         // G phase: bytes per staged quality row slot
 #define AMP7_GSLOT_S 96
-#define AMP7_GN 26               // reads per G phase (GN * GSLOT <= DATA)
+#define AMP7_GN 28               // reads per G phase (GN * GSLOT <= DATA)
 #define AMP7_CROW 13             // generic path: CIGAR ops (+3) per shared-memory row; two rows per read (odd stride: no bank conflicts)
-#define AMP7_WARP_BYTES (AMP7_QBUF + AMP7_SBUF + AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + 16 + AMP7_GN * 2 * AMP7_CROW * 4 + 32 * 32 + 32)
-enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_WORDS = 16 };
+#define AMP7_GEXTRA_BYTES (AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + AMP7_GN * 2 * AMP7_CROW * 4)   // generic phase: runs, queue, counters, CIGAR rows
+enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_GNEXT = 3, C7_WORDS = 16 };
 
 // the sink row is the last one and 32 * KW entries longer: idle slots of a group increment it past the window's end
 AMP_HD size_t tile_bytes_v7(int wt) { return ((size_t)AMP7_ROWS * wt + 32 * AMP7_KW) * 4; }
-AMP_HD size_t smem_bytes_v7(int wt, int warps) { return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_WARP_BYTES; }
+AMP_HD size_t smem_bytes_v9(int wt, int warps, int gwarps);   // below
 
 // launch shape: reads per batch so that a batch's rows fit the staging buffers; one CTA per SM with a contiguous chunk
 // One aligned run of the count pass, fully decoded by its owner lane so that switching runs inside the chunk loop is cheap:
@@ -191,18 +191,19 @@ struct WarpMem7 {
     uint8_t* qbuf; uint8_t* sbuf; Seg* runs; uint32_t* queue; int* ctr; unsigned long long* bar; uint32_t* cig;
     Par4* par; uint8_t* own;
 };
-AMP_HD WarpMem7 carve_warp7(unsigned char* base, int wt, int w) {
-    unsigned char* b = base + tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)w * AMP7_WARP_BYTES;
+AMP_HD size_t smem_bytes_v9(int wt, int warps, int gwarps) {
+    return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_FAST_BYTES + (size_t)gwarps * AMP7_GEXTRA_BYTES;
+}
+// generic phase of warp w (< gwarps): the warp's fast-part buffers + its extra block behind all fast-part blocks
+AMP_HD WarpMem7 carve_warp7(unsigned char* base, int wt, int warps, int w) {
+    const FastMem f = carve_fast(base, wt, w);
+    unsigned char* b = base + tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_FAST_BYTES + (size_t)w * AMP7_GEXTRA_BYTES;
     WarpMem7 m;
-    m.qbuf = b; b += AMP7_QBUF;
-    m.sbuf = b; b += AMP7_SBUF;
+    m.qbuf = f.qbuf; m.sbuf = f.sbuf; m.par = f.par; m.own = f.own; m.bar = f.bar;
     m.runs = (Seg*)b; b += AMP7_RUNCAP * 16;
     m.queue = (uint32_t*)b; b += AMP7_QCAP * 4;
     m.ctr = (int*)b; b += 32;
-    m.bar = (unsigned long long*)b; b += 16;
-    m.cig = (uint32_t*)b; b += AMP7_GN * 2 * AMP7_CROW * 4;
-    m.par = (Par4*)b; b += 32 * 32;
-    m.own = b;
+    m.cig = (uint32_t*)b;
     return m;
 }
 
@@ -472,15 +473,23 @@ AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, i
         w_sync();
         if (qb) bulk_copy(qdst, qsrc, qb, wm.bar);
         if (sb) bulk_copy(sdst, ssrc, sb, wm.bar);
-        for (uint32_t k = 0; k < qt; ++k) qdst[qb + k] = qsrc[qb + k];
-        for (uint32_t k = 0; k < stl; ++k) sdst[sb + k] = ssrc[sb + k];
+        // trailing bytes: all loads first (one round trip), then the stores
+        {
+            uint8_t tq[15], ts[15];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (uint32_t k = 0; k < 15; ++k) { tq[k] = k < qt ? qsrc[qb + k] : (uint8_t)0; ts[k] = k < stl ? ssrc[sb + k] : (uint8_t)0; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (uint32_t k = 0; k < 15; ++k) { if (k < qt) qdst[qb + k] = tq[k]; if (k < stl) sdst[sb + k] = ts[k]; }
+        }
         w_sync();
         if (total) { bulk_wait(wm.bar, parity); parity ^= 1u; }
     }
-    AMP7_TICK(tk, 1);
     if (lane < nb) warp_read_generic7(P, wm, P.b.first + wm.queue[lane], lane, do_trim, do_pile);
     w_sync();
-    AMP7_TICK(tk, 2);
     if (do_pile) {
         int nr = wm.ctr[0]; if (nr > AMP7_RUNCAP) nr = AMP7_RUNCAP;
         count_warp_runs7<WT>(P, cnt, wt, wm, nr, wbase, lane, (unsigned)P.tp.min_quality * 0x01010101u);
@@ -494,18 +503,15 @@ AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, i
         w_sync();
     }
     w_sync();
-    AMP7_TICK(tk, 3);
 }
 
-// ---- the kernels -----------------------------------------------------------------------------------------------------
+// ---- the kernel ------------------------------------------------------------------------------------------------------
 // P.reads_per_tile = reads per batch (<= 32), P.ntiles = batches, P.tiles_per_cta = batches per CTA (contiguous chunk).
 // WT = width of the count tile as a compile-time constant (0: P.wt, used by the emulation tests).
-//
-// Two launches per batch of reads, same grid, CTA c owns the same chunk of reads in both:
-//   fast kernel    : [S]M[S] reads, lane per read (phases A and B above); every other mapped read is appended to the
-//                    CTA's segment of P.glist
-//   generic kernel : the reads of that list, AMP7_GN at a time per warp (phase G)
-// Keeping the loop-for-loop generic code out of the fast kernel keeps the latter's instruction footprint small.
+// One CTA per SM.  Fast part: the warps work through the chunk's batches ([S]M[S] reads, phases A and B); every other
+// mapped read is appended to the CTA's segment of P.glist.  After one block barrier the first `gwarps` warps run the
+// generic phase G over that list.  The loop-for-loop generic code therefore never runs on an SM while its warps are in
+// the fast loops (instruction-cache footprint), and CTAs that finish their fast part early start on their list at once.
 
 // window base of a CTA's chunk: smallest start among its first reads (coordinate-sorted input => of the whole chunk)
 AMP_WD int chunk_window_base(const KParams& P, int* ctrl, long long first_read, long long n_end, int tid, bool any) {
@@ -524,7 +530,7 @@ AMP_WD int chunk_window_base(const KParams& P, int* ctrl, long long first_read, 
 }
 
 template <bool TRIM, bool PILE, int WT>
-AMP_WD void cta_fast_v8(const KParams& P, unsigned char* smem_base) {
+AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int gwarps) {
     const int wt = WT ? WT : P.wt;
     const int tid = c_tid(), nthreads = c_nthreads(), block = c_block();
     const int lane = tid & 31, warp = tid >> 5;
@@ -539,7 +545,7 @@ AMP_WD void cta_fast_v8(const KParams& P, unsigned char* smem_base) {
     uint32_t* glist = P.glist + (size_t)block * P.gcap;
 
     if (PILE) for (int i = tid; i < (AMP7_DEL_ROW + 1) * wt; i += nthreads) cnt[i] = 0;   // the sink row is never read
-    if (tid == 0) { ctrl[C7_NEXT] = 0; ctrl[C7_NGEN] = 0; }
+    if (tid == 0) { ctrl[C7_NEXT] = 0; ctrl[C7_NGEN] = 0; ctrl[C7_GNEXT] = 0; }
     if (lane == 0) mbar_init(wm.bar);
     const int wb = chunk_window_base(P, ctrl, P.b.first + g_lo * BR, n_end, tid, n_batches > 0);
     const int wbase = PILE ? wb : -1;
@@ -701,53 +707,28 @@ AMP_WD void cta_fast_v8(const KParams& P, unsigned char* smem_base) {
         AMP7_TICK(tk, 4);
         M = Mn; bi = bn;
     }
-    c_sync();
     AMP7_TICK(tk, 5);
-    AMP7_TDUMP(tk, 0);
-    if (tid == 0) P.gcount[block] = ctrl[C7_NGEN];
-    if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);
-}
-
-// generic kernel: CTA c works through the list its fast-kernel counterpart wrote
-template <bool TRIM, bool PILE, int WT>
-AMP_WD void cta_generic_v8(const KParams& P, unsigned char* smem_base) {
-    const int wt = WT ? WT : P.wt;
-    const int tid = c_tid(), nthreads = c_nthreads(), block = c_block();
-    const int lane = tid & 31, warp = tid >> 5;
-    const int n_list = P.gcount[block];
-    if (n_list <= 0) return;                                        // uniform across the CTA
-    AMP7_T0(tk);
-    int* cnt = (int*)smem_base;
-    int* ctrl = (int*)(smem_base + tile_bytes_v7(wt));
-    const WarpMem7 wm = carve_warp7(smem_base, wt, warp);
-    const uint32_t* glist = P.glist + (size_t)block * P.gcap;
-    const long long g_lo = (long long)block * P.tiles_per_cta;
-    if (PILE) for (int i = tid; i < (AMP7_DEL_ROW + 1) * wt; i += nthreads) cnt[i] = 0;
-    if (tid == 0) ctrl[C7_NEXT] = 0;
-    if (lane == 0) mbar_init(wm.bar);
-    const int wb = chunk_window_base(P, ctrl, P.b.first + g_lo * P.reads_per_tile, P.b.first + P.b.n, tid, true);
-    const int wbase = PILE ? wb : -1;
-    // reads per claim: an even share of the list, so that every warp of the CTA gets work
-    const int nw = nthreads >> 5;
-    int per = (n_list + nw - 1) / nw; if (per > AMP7_GN) per = AMP7_GN;
-    uint32_t parity = 0;
-    AMP7_TICK(tk, 0);
-    for (;;) {
-        int at = 0;
-        if (lane == 0) at = atomic_add(&ctrl[C7_NEXT], per);
-        at = w_shfl(at, 0);
-        if (at >= n_list) break;
-        const int nb = n_list - at < per ? n_list - at : per;
-        if (lane < nb) wm.queue[lane] = glist[at + lane];
-        w_sync();
-        warp_generic_phase<WT>(P, wm, cnt, wt, wbase, nb, nb, lane, TRIM, PILE, parity, tk);
+    c_sync();                                                       // the CTA's list is complete (and visible)
+    // ---- G: the reads of the list, an even share per warp and round --------------------------------------------------
+    const int n_list = ctrl[C7_NGEN];
+    if (n_list > 0 && warp < gwarps) {                              // n_list is uniform across the CTA
+        const WarpMem7 gm = carve_warp7(smem_base, wt, nthreads >> 5, warp);
+        int per = (n_list + gwarps - 1) / gwarps; if (per > AMP7_GN) per = AMP7_GN;
+        for (;;) {
+            int at = 0;
+            if (lane == 0) at = atomic_add(&ctrl[C7_GNEXT], per);
+            at = w_shfl(at, 0);
+            if (at >= n_list) break;
+            const int nb = n_list - at < per ? n_list - at : per;
+            if (lane < nb) gm.queue[lane] = glist[at + lane];
+            w_sync();
+            warp_generic_phase<WT>(P, gm, cnt, wt, wbase, nb, nb, lane, TRIM, PILE, parity, tk);
+        }
     }
-    AMP7_TICK(tk, 4);
-    c_sync();
-    AMP7_TICK(tk, 5);
-    if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);
     AMP7_TICK(tk, 6);
-    AMP7_TDUMP(tk, 8);
+    AMP7_TDUMP(tk, 0);
+    c_sync();
+    if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);
 }
 
 }  // namespace amp

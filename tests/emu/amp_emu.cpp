@@ -210,19 +210,13 @@ int emu_process(void* h, long long first, long long n, const int32_t* pos, const
     return 0;
 }
 
-// the warp-autonomous kernels (amp_warp.cuh): one CTA at a time, every thread a fiber
-struct V7Launch { const amp::KParams* P; unsigned char* smem; int mode; };
-static void v8_fast_body(void* a) {
+// the warp-autonomous kernel (amp_warp.cuh): one CTA at a time, every thread a fiber
+struct V7Launch { const amp::KParams* P; unsigned char* smem; int mode, gwarps; };
+static void v9_body(void* a) {
     V7Launch* v = (V7Launch*)a;
-    if (v->mode == 3) amp::cta_fast_v8<true, true, 0>(*v->P, v->smem);
-    else if (v->mode == 1) amp::cta_fast_v8<true, false, 0>(*v->P, v->smem);
-    else amp::cta_fast_v8<false, true, 0>(*v->P, v->smem);
-}
-static void v8_generic_body(void* a) {
-    V7Launch* v = (V7Launch*)a;
-    if (v->mode == 3) amp::cta_generic_v8<true, true, 0>(*v->P, v->smem);
-    else if (v->mode == 1) amp::cta_generic_v8<true, false, 0>(*v->P, v->smem);
-    else amp::cta_generic_v8<false, true, 0>(*v->P, v->smem);
+    if (v->mode == 3) amp::cta_trim_pileup_v9<true, true, 0>(*v->P, v->smem, v->gwarps);
+    else if (v->mode == 1) amp::cta_trim_pileup_v9<true, false, 0>(*v->P, v->smem, v->gwarps);
+    else amp::cta_trim_pileup_v9<false, true, 0>(*v->P, v->smem, v->gwarps);
 }
 int emu_process_v7(void* h, long long first, long long n, const int32_t* pos, const uint16_t* flag, const int32_t* tlen,
                    const uint32_t* cig_off, const uint32_t* cigar, const uint32_t* seq_off, const uint8_t* seq,
@@ -248,16 +242,15 @@ int emu_process_v7(void* h, long long first, long long n, const int32_t* pos, co
     P.tiles_per_cta = (P.ntiles + grid - 1) / grid;
     grid = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
     if (!warps) warps = AMP7_WARPS;
-    std::vector<unsigned char> smem(std::max(amp::smem_bytes_v7(P.wt, warps), amp::smem_bytes_fast(P.wt, warps)) + 64);
+    const int gwarps = std::max(1, std::min(warps, AMP7_GWARPS));
+    std::vector<unsigned char> smem(amp::smem_bytes_v9(P.wt, warps, gwarps) + 64);
     unsigned char* sbase = smem.data();
     sbase += (16 - ((uintptr_t)sbase & 15)) & 15;
     P.gcap = (long long)P.tiles_per_cta * P.reads_per_tile;
     std::vector<uint32_t> glist((size_t)grid * P.gcap + 1);
-    std::vector<int> gcount(grid + 1, 0);
-    P.glist = glist.data(); P.gcount = gcount.data();
-    V7Launch v{&P, sbase, mode};
-    for (int b = 0; b < grid; ++b) run_cta(b, warps * 32, v8_fast_body, &v);
-    for (int b = 0; b < grid; ++b) run_cta(b, warps * 32, v8_generic_body, &v);
+    P.glist = glist.data();
+    V7Launch v{&P, sbase, mode, gwarps};
+    for (int b = 0; b < grid; ++b) run_cta(b, warps * 32, v9_body, &v);
     return 0;
 }
 
