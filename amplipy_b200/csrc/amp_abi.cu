@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) amp_trim_pileup_indel_ke
 template <bool TRIM, bool PILE>
 __global__ void __launch_bounds__(AMP7_WARPS * 32, 1) amp_trim_pileup_warp_kernel(const __grid_constant__ amp::KParams P) {
     extern __shared__ __align__(128) unsigned char smem7[];
-    amp::cta_trim_pileup_v9<TRIM, PILE, AMP7_WT>(P, smem7, AMP7_GWARPS);
+    amp::cta_trim_pileup_v9<TRIM, PILE, AMP7_WT>(P, smem7, AMP7_GWARPS, AMP7_DWARPS);
 }
 
 __device__ const unsigned char kFixedSyms[8] = {'A', 'C', 'G', 'T', 'N', '-', 0, 0};

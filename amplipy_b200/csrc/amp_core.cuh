@@ -72,6 +72,13 @@ AMP_HD unsigned long long atomic_cas64(unsigned long long* p, unsigned long long
     unsigned long long o = *p; if (o == cmp) *p = val; return o;
 #endif
 }
+AMP_HD int atomic_cas(int* p, int cmp, int val) {
+#ifdef __CUDA_ARCH__
+    return atomicCAS(p, cmp, val);
+#else
+    int o = *p; if (o == cmp) *p = val; return o;
+#endif
+}
 AMP_HD void atomic_min(int* p, int v) {
 #ifdef __CUDA_ARCH__
     atomicMin(p, v);

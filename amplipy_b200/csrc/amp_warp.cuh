@@ -43,6 +43,11 @@ AMP_WD int w_max(int v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
 AMP_WD int w_add(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 AMP_WD void w_sync() { __syncwarp(); }
 AMP_WD void c_sync() { __syncthreads(); }
+AMP_WD void c_yield() { __nanosleep(200); }                        // polite spin-wait
+AMP_WD int ld_vol(const int* p) { return *(const volatile int*)p; }
+AMP_WD uint32_t ld_cg_u32(const uint32_t* p) { return __ldcg(p); }  // L2: entries written by another warp of the CTA
+AMP_WD void st_cg_u32(uint32_t* p, uint32_t v) { __stcg(p, v); }
+AMP_WD void fence_block() { __threadfence_block(); }
 AMP_WD int popc32(unsigned x) { return __popc(x); }
 AMP_WD unsigned byte_perm2(unsigned x, unsigned sel) { return __byte_perm(x, 0u, sel); }
 AMP_WD uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,7 +88,11 @@ AMP_WD void bulk_wait(unsigned long long* bar, uint32_t parity) {
 // implemented by the fiber runtime in tests/emu/amp_emu.cpp
 int c_tid(); int c_nthreads(); int c_block();
 int w_shfl(int v, int src); int w_shfl_xor(int v, int m); unsigned w_ballot(bool p); int w_max(int v); int w_add(int v);
-void w_sync(); void c_sync();
+void w_sync(); void c_sync(); void c_yield();
+AMP_WD int ld_vol(const int* p) { return *p; }
+AMP_WD uint32_t ld_cg_u32(const uint32_t* p) { return *p; }
+AMP_WD void st_cg_u32(uint32_t* p, uint32_t v) { *p = v; }
+AMP_WD void fence_block() {}
 AMP_WD int popc32(unsigned x) { return __builtin_popcount(x); }
 AMP_WD unsigned byte_perm2(unsigned x, unsigned sel) {
     unsigned r = 0;
@@ -116,7 +125,10 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_WARPS 16            // warps per CTA of the fast kernel
 #endif
 #ifndef AMP7_GWARPS
-#define AMP7_GWARPS 11           // warps that take part in the generic phase (their extra shared memory must fit)
+#define AMP7_GWARPS 11           // warps that can run the generic phase (their extra shared memory must fit): the last ones
+#endif
+#ifndef AMP7_DWARPS
+#define AMP7_DWARPS 1            // of those, warps that do nothing else (they work on the list while it is being filled)
 #endif
 #define AMP7_WT 512              // count tile width on the device (positions)
 #define AMP7_ROWS 18             // count tile rows: BAM nibble 0..15, row 16 = deleted base, row 17 = sink of masked bases
@@ -137,7 +149,7 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_GN 28               // reads per G phase (GN * GSLOT <= DATA)
 #define AMP7_CROW 13             // generic path: CIGAR ops (+3) per shared-memory row; two rows per read (odd stride: no bank conflicts)
 #define AMP7_GEXTRA_BYTES (AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + AMP7_GN * 2 * AMP7_CROW * 4)   // generic phase: runs, queue, counters, CIGAR rows
-enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_GNEXT = 3, C7_WORDS = 16 };
+enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_GNEXT = 3, C7_FASTDONE = 4, C7_WORDS = 16 };
 
 // the sink row is the last one and 32 * KW entries longer: idle slots of a group increment it past the window's end
 AMP_HD size_t tile_bytes_v7(int wt) { return ((size_t)AMP7_ROWS * wt + 32 * AMP7_KW) * 4; }
@@ -194,10 +206,10 @@ struct WarpMem7 {
 AMP_HD size_t smem_bytes_v9(int wt, int warps, int gwarps) {
     return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_FAST_BYTES + (size_t)gwarps * AMP7_GEXTRA_BYTES;
 }
-// generic phase of warp w (< gwarps): the warp's fast-part buffers + its extra block behind all fast-part blocks
-AMP_HD WarpMem7 carve_warp7(unsigned char* base, int wt, int warps, int w) {
-    const FastMem f = carve_fast(base, wt, w);
-    unsigned char* b = base + tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_FAST_BYTES + (size_t)w * AMP7_GEXTRA_BYTES;
+// generic phase: the warp's fast-part buffers + its extra block behind all fast-part blocks
+AMP_HD WarpMem7 carve_warp7(unsigned char* base, int wt, int warps, int gwarps, int g) {   // g-th generic-capable warp = warp warps - gwarps + g
+    const FastMem f = carve_fast(base, wt, warps - gwarps + g);
+    unsigned char* b = base + tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_FAST_BYTES + (size_t)g * AMP7_GEXTRA_BYTES;
     WarpMem7 m;
     m.qbuf = f.qbuf; m.sbuf = f.sbuf; m.par = f.par; m.own = f.own; m.bar = f.bar;
     m.runs = (Seg*)b; b += AMP7_RUNCAP * 16;
@@ -508,10 +520,10 @@ AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, i
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 // P.reads_per_tile = reads per batch (<= 32), P.ntiles = batches, P.tiles_per_cta = batches per CTA (contiguous chunk).
 // WT = width of the count tile as a compile-time constant (0: P.wt, used by the emulation tests).
-// One CTA per SM.  Fast part: the warps work through the chunk's batches ([S]M[S] reads, phases A and B); every other
-// mapped read is appended to the CTA's segment of P.glist.  After one block barrier the first `gwarps` warps run the
-// generic phase G over that list.  The loop-for-loop generic code therefore never runs on an SM while its warps are in
-// the fast loops (instruction-cache footprint), and CTAs that finish their fast part early start on their list at once.
+// One CTA per SM.  Warps [0, nwarps - dwarps) work through the chunk's batches ([S]M[S] reads, phases A and B); every other
+// mapped read is appended to the CTA's segment of P.glist.  The last dwarps warps do nothing but the generic phase G over
+// that list while it is being filled (latency-bound, divergent code that hides behind the batch warps); the other
+// generic-capable warps help with what is left when their batches are done.  All of them count into the same tile.
 
 // window base of a CTA's chunk: smallest start among its first reads (coordinate-sorted input => of the whole chunk)
 AMP_WD int chunk_window_base(const KParams& P, int* ctrl, long long first_read, long long n_end, int tid, bool any) {
@@ -530,7 +542,7 @@ AMP_WD int chunk_window_base(const KParams& P, int* ctrl, long long first_read, 
 }
 
 template <bool TRIM, bool PILE, int WT>
-AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int gwarps) {
+AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int gwarps, int dwarps) {
     const int wt = WT ? WT : P.wt;
     const int tid = c_tid(), nthreads = c_nthreads(), block = c_block();
     const int lane = tid & 31, warp = tid >> 5;
@@ -545,7 +557,9 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
     uint32_t* glist = P.glist + (size_t)block * P.gcap;
 
     if (PILE) for (int i = tid; i < (AMP7_DEL_ROW + 1) * wt; i += nthreads) cnt[i] = 0;   // the sink row is never read
-    if (tid == 0) { ctrl[C7_NEXT] = 0; ctrl[C7_NGEN] = 0; ctrl[C7_GNEXT] = 0; }
+    if (tid == 0) { ctrl[C7_NEXT] = 0; ctrl[C7_NGEN] = 0; ctrl[C7_GNEXT] = 0; ctrl[C7_FASTDONE] = 0; }
+    for (long long k = tid; k < (long long)n_batches * BR; k += nthreads) st_cg_u32(&glist[k], 0u);   // list entries: 0 = not written yet
+    const int nwarps = nthreads >> 5, n_fast = nwarps - dwarps;     // warps [0, n_fast) take batches, the rest only the list
     if (lane == 0) mbar_init(wm.bar);
     const int wb = chunk_window_base(P, ctrl, P.b.first + g_lo * BR, n_end, tid, n_batches > 0);
     const int wbase = PILE ? wb : -1;
@@ -589,7 +603,7 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
     Meta M, Mn;
     M.c0 = M.c1 = M.qo0 = M.qo1 = M.so0 = M.so1 = M.g0 = M.g1 = M.g2 = 0; M.flag = M.pos = M.tlen = 0;
     Mn = M;
-    int bi = claim();
+    int bi = warp < n_fast ? claim() : n_batches;
     if (bi < n_batches) { load_meta(bi, M); load_cigar3(M); }
     while (bi < n_batches) {
         const long long t0 = P.b.first + (g_lo + bi) * BR;
@@ -632,7 +646,7 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
         const uint32_t a0 = AMP7_PAD + (qo0 - q_lo) + (uint32_t)r.s1;                  // first aligned quality byte in qbuf
         if (fast && (r.m < 8 || (int)(a0 & 3u) + r.m > 256)) fast = false;
         const bool rev = (flag & 16) != 0;
-        // everything else goes to the CTA's list for the generic kernel
+        // everything else goes to the CTA's list for the generic phase
         {
             const bool gen = have && !skipped && !fast;
             const unsigned gmask = w_ballot(gen);
@@ -640,7 +654,7 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
                 int base = 0;
                 if (lane == 0) base = atomic_add(&ctrl[C7_NGEN], popc32(gmask));
                 base = w_shfl(base, 0);
-                if (gen) glist[base + popc32(gmask & ((1u << lane) - 1u))] = (uint32_t)(i - P.b.first);
+                if (gen) st_cg_u32(&glist[base + popc32(gmask & ((1u << lane) - 1u))], (uint32_t)(i - P.b.first) + 1u);   // 0 = not written yet
             }
         }
         if (skipped && TRIM) {
@@ -708,21 +722,37 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
         M = Mn; bi = bn;
     }
     AMP7_TICK(tk, 5);
-    c_sync();                                                       // the CTA's list is complete (and visible)
-    // ---- G: the reads of the list, an even share per warp and round --------------------------------------------------
-    const int n_list = ctrl[C7_NGEN];
-    if (n_list > 0 && warp < gwarps) {                              // n_list is uniform across the CTA
-        const WarpMem7 gm = carve_warp7(smem_base, wt, nthreads >> 5, warp);
-        int per = (n_list + gwarps - 1) / gwarps; if (per > AMP7_GN) per = AMP7_GN;
+    if (warp < n_fast) { fence_block(); if (lane == 0) atomic_add(&ctrl[C7_FASTDONE], 1); }   // this warp appends no more
+    // ---- G: the reads of the list.  The dedicated warps have been here from the start and take AMP7_GN reads whenever that
+    // many are waiting; the other generic-capable warps join when their batches are done; once every batch warp is done the
+    // rest of the list is taken in whatever pieces are left.
+    if (warp >= nwarps - gwarps) {
+        const WarpMem7 gm = carve_warp7(smem_base, wt, nwarps, gwarps, warp - (nwarps - gwarps));
         for (;;) {
-            int at = 0;
-            if (lane == 0) at = atomic_add(&ctrl[C7_GNEXT], per);
-            at = w_shfl(at, 0);
-            if (at >= n_list) break;
-            const int nb = n_list - at < per ? n_list - at : per;
-            if (lane < nb) gm.queue[lane] = glist[at + lane];
+            int at = -1, n = 0;
+            if (lane == 0) {
+                for (;;) {
+                    const bool done = ld_vol(&ctrl[C7_FASTDONE]) >= n_fast;     // read before the counters: then they are final
+                    const int reserved = ld_vol(&ctrl[C7_NGEN]), claimed = ld_vol(&ctrl[C7_GNEXT]);
+                    const int avail = reserved - claimed;
+                    if (avail >= AMP7_GN || (done && avail > 0)) {
+                        n = avail < AMP7_GN ? avail : AMP7_GN;
+                        if (atomic_cas(&ctrl[C7_GNEXT], claimed, claimed + n) == claimed) { at = claimed; break; }
+                        continue;
+                    }
+                    if (done) break;
+                    c_yield();
+                }
+            }
+            at = w_shfl(at, 0); n = w_shfl(n, 0);
+            if (at < 0) break;
+            if (lane < n) {
+                uint32_t v;
+                while ((v = ld_cg_u32(&glist[at + lane])) == 0u) c_yield();     // reserved but not yet written
+                gm.queue[lane] = v - 1u;
+            }
             w_sync();
-            warp_generic_phase<WT>(P, gm, cnt, wt, wbase, nb, nb, lane, TRIM, PILE, parity, tk);
+            warp_generic_phase<WT>(P, gm, cnt, wt, wbase, n, n, lane, TRIM, PILE, parity, tk);
         }
     }
     AMP7_TICK(tk, 6);

@@ -99,6 +99,7 @@ int c_nthreads() { return g_rt.nthreads; }
 int c_block() { return g_rt.block; }
 void w_sync() { fiber_wait(FB_WAIT_WARP); }
 void c_sync() { fiber_wait(FB_WAIT_CTA); }
+void c_yield() { fiber_wait(FB_READY); }             // spin-wait: let the other fibers run
 int w_shfl(int v, int src) {
     g_rt.xch[g_rt.cur] = v;
     w_sync();
@@ -211,12 +212,12 @@ int emu_process(void* h, long long first, long long n, const int32_t* pos, const
 }
 
 // the warp-autonomous kernel (amp_warp.cuh): one CTA at a time, every thread a fiber
-struct V7Launch { const amp::KParams* P; unsigned char* smem; int mode, gwarps; };
+struct V7Launch { const amp::KParams* P; unsigned char* smem; int mode, gwarps, dwarps; };
 static void v9_body(void* a) {
     V7Launch* v = (V7Launch*)a;
-    if (v->mode == 3) amp::cta_trim_pileup_v9<true, true, 0>(*v->P, v->smem, v->gwarps);
-    else if (v->mode == 1) amp::cta_trim_pileup_v9<true, false, 0>(*v->P, v->smem, v->gwarps);
-    else amp::cta_trim_pileup_v9<false, true, 0>(*v->P, v->smem, v->gwarps);
+    if (v->mode == 3) amp::cta_trim_pileup_v9<true, true, 0>(*v->P, v->smem, v->gwarps, v->dwarps);
+    else if (v->mode == 1) amp::cta_trim_pileup_v9<true, false, 0>(*v->P, v->smem, v->gwarps, v->dwarps);
+    else amp::cta_trim_pileup_v9<false, true, 0>(*v->P, v->smem, v->gwarps, v->dwarps);
 }
 int emu_process_v7(void* h, long long first, long long n, const int32_t* pos, const uint16_t* flag, const int32_t* tlen,
                    const uint32_t* cig_off, const uint32_t* cigar, const uint32_t* seq_off, const uint8_t* seq,
@@ -249,7 +250,8 @@ int emu_process_v7(void* h, long long first, long long n, const int32_t* pos, co
     P.gcap = (long long)P.tiles_per_cta * P.reads_per_tile;
     std::vector<uint32_t> glist((size_t)grid * P.gcap + 1);
     P.glist = glist.data();
-    V7Launch v{&P, sbase, mode, gwarps};
+    const int dwarps = warps >= 3 ? 1 : 0;              // one dedicated list warp when there are warps to spare
+    V7Launch v{&P, sbase, mode, gwarps, dwarps};
     for (int b = 0; b < grid; ++b) run_cta(b, warps * 32, v9_body, &v);
     return 0;
 }
