@@ -190,8 +190,9 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
         P.glist = glist;
 #ifdef AMP7_TIMING
         static long long* d_phase7 = nullptr;
-        if (!d_phase7) CK(cudaMalloc((void**)&d_phase7, 16 * 8));
+        if (!d_phase7) CK(cudaMalloc((void**)&d_phase7, 336 * 8));
         CK(cudaMemsetAsync(d_phase7, 0, 16 * 8, st));
+        { const long long big = 1LL << 60; CK(cudaMemcpyAsync(d_phase7 + 9, &big, 8, cudaMemcpyHostToDevice, st)); }
         P.phase_cycles = d_phase7;
 #endif
         const bool tr = mode & AMP_MODE_TRIM, pl = mode & AMP_MODE_PILEUP;
@@ -202,11 +203,13 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
 #ifdef AMP7_TIMING
         {
             CK(cudaStreamSynchronize(st));
-            long long h[16];
+            long long h[336];
             CK(cudaMemcpy(h, d_phase7, sizeof h, cudaMemcpyDeviceToHost));
+            if (getenv("AMP7_DUMP_CTAS")) { for (int b = 0; b < grid && b < 160; ++b) fprintf(stderr, "%lld:%lld ", h[16 + b] / 1000, h[176 + b]); fprintf(stderr, "\n"); }
             const double wf = (double)grid * AMP7_WARPS;
             fprintf(stderr, "[cycles per warp] prologue %.0f  A %.0f  bulk-wait %.0f  window+trim %.0f  count %.0f  (barrier issue %.0f)  wait+generic %.0f\n",
                     h[0] / wf, h[1] / wf, h[2] / wf, h[3] / wf, h[4] / wf, h[5] / wf, h[6] / wf);
+            fprintf(stderr, "[cycles per CTA] mean %.0f  min %lld  max %lld\n", (double)h[8] / grid, h[9], h[10]);
         }
 #endif
         c->last_launches += 1;

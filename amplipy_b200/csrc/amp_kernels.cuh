@@ -603,13 +603,31 @@ AMP_HD Sym slot_sym(const CallParams& P, int slot) {
     Sym s; s.p = rec + 8; s.len = (int)((const unsigned int*)rec)[1]; return s;
 }
 
-AMP_HD void call_position(const CallParams& P, const unsigned char* fixed_syms, long long gp) {
-    const int sample = (int)(gp / P.L), p = (int)(gp - (long long)sample * P.L);
-    const int* cnt = P.counts + (size_t)sample * AMP_NCH * P.Lpad;
-    int c[AMP_NCH]; long long total = 0;
-    for (int ch = 0; ch < AMP_NCH; ++ch) { c[ch] = cnt[(size_t)ch * P.Lpad + p]; total += c[ch]; }
-    const int head = P.heads[(size_t)sample * P.Lpad + p];
-    for (int s = head; s >= 0; s = P.slots[s].next) total += P.slots[s].count;
+// The insertion alleles of one position, either walked through the linked list on every use or (the normal case)
+// copied once into per-thread arrays: the O(k^2) allele ordering then costs k dependent global loads instead of k^2.
+struct ChainLinked {
+    const CallParams* P; int head;
+    AMP_HD int first() const { return head; }
+    AMP_HD int next(int it) const { return P->slots[it].next; }
+    AMP_HD bool valid(int it) const { return it >= 0; }
+    AMP_HD int count(int it) const { return P->slots[it].count; }
+    AMP_HD Sym sym(int it) const { return slot_sym(*P, it); }
+    AMP_HD int slot(int it) const { return it; }
+};
+#define AMP_CHAIN_MAX 24
+struct ChainCached {
+    int n; int slot_[AMP_CHAIN_MAX], cnt_[AMP_CHAIN_MAX]; Sym sym_[AMP_CHAIN_MAX];
+    AMP_HD int first() const { return 0; }
+    AMP_HD int next(int it) const { return it + 1; }
+    AMP_HD bool valid(int it) const { return it < n; }
+    AMP_HD int count(int it) const { return cnt_[it]; }
+    AMP_HD Sym sym(int it) const { return sym_[it]; }
+    AMP_HD int slot(int it) const { return slot_[it]; }
+};
+
+template <class Chain>
+AMP_HD void call_position_impl(const CallParams& P, const unsigned char* fixed_syms, long long gp, int p, const int* c, long long total,
+                               const Chain& ch_) {
     P.depth[gp] = (int)total;
     int best_id = -1, best_c = 0; Sym best_s; best_s.p = fixed_syms; best_s.len = 0;
     int refc = 0; double reff = 0.0; unsigned alt = 0; int n_alt = 0;
@@ -622,22 +640,22 @@ AMP_HD void call_position(const CallParams& P, const unsigned char* fixed_syms, 
             Sym me; me.p = fixed_syms + ch; me.len = 1;
             rank = 0;
             for (int o = 0; o < AMP_NCH; ++o) if (o != ch && c[o]) { Sym os; os.p = fixed_syms + o; os.len = 1; if (allele_greater(c[o], os, c[ch], me)) ++rank; }
-            for (int s = head; s >= 0; s = P.slots[s].next) if (P.slots[s].count && allele_greater(P.slots[s].count, slot_sym(P, s), c[ch], me)) ++rank;
+            for (int t = ch_.first(); ch_.valid(t); t = ch_.next(t)) if (ch_.count(t) && allele_greater(ch_.count(t), ch_.sym(t), c[ch], me)) ++rank;
             if (best_id < 0 || allele_greater(c[ch], me, best_c, best_s)) { best_id = ch; best_c = c[ch]; best_s = me; }
             if (fixed_syms[ch] == refsym) { refc = c[ch]; reff = f; }                  // 936-937
             else if (f >= P.min_freq_variants) { alt |= 1u << ch; ++n_alt; }           // 938-939
         }
         P.fixed_rank[gp * AMP_NCH + ch] = rank;
     }
-    for (int s = head; s >= 0; s = P.slots[s].next) {
-        const int cs = P.slots[s].count;
+    for (int s = ch_.first(); ch_.valid(s); s = ch_.next(s)) {
+        const int cs = ch_.count(s);
         if (!cs) continue;
-        const Sym me = slot_sym(P, s);
+        const Sym me = ch_.sym(s);
         const double f = (double)cs / (double)total;
         int rank = 0;
         for (int o = 0; o < AMP_NCH; ++o) if (c[o]) { Sym os; os.p = fixed_syms + o; os.len = 1; if (allele_greater(c[o], os, cs, me)) ++rank; }
-        for (int t = head; t >= 0; t = P.slots[t].next) if (t != s && P.slots[t].count && allele_greater(P.slots[t].count, slot_sym(P, t), cs, me)) ++rank;
-        const int kk = P.slot_entry[s];
+        for (int t = ch_.first(); ch_.valid(t); t = ch_.next(t)) if (t != s && ch_.count(t) && allele_greater(ch_.count(t), ch_.sym(t), cs, me)) ++rank;
+        const int kk = P.slot_entry[ch_.slot(s)];
         P.ins_freq[kk] = f; P.ins_rank[kk] = rank;
         if (best_id < 0 || allele_greater(cs, me, best_c, best_s)) { best_id = 6 + kk; best_c = cs; best_s = me; }
         // an insertion key can never equal the 1-character reference symbol except a 1-char key, which
@@ -658,6 +676,29 @@ AMP_HD void call_position(const CallParams& P, const unsigned char* fixed_syms, 
         if (refc >= P.min_depth_variants && reff >= P.min_freq_variants) fl |= 4;      // 948
     }
     P.pos_flags[gp] = fl; P.ref_count[gp] = refc; P.alt_mask[gp] = (unsigned char)alt;
+}
+
+AMP_HD void call_position(const CallParams& P, const unsigned char* fixed_syms, long long gp) {
+    const int sample = (int)(gp / P.L), p = (int)(gp - (long long)sample * P.L);
+    const int* cnt = P.counts + (size_t)sample * AMP_NCH * P.Lpad;
+    int c[AMP_NCH]; long long total = 0;
+    for (int ch = 0; ch < AMP_NCH; ++ch) { c[ch] = cnt[(size_t)ch * P.Lpad + p]; total += c[ch]; }
+    const int head = P.heads[(size_t)sample * P.Lpad + p];
+    ChainCached cc; cc.n = 0;
+    int k = 0;
+    for (int s = head; s >= 0; s = P.slots[s].next, ++k) {
+        const int cs = P.slots[s].count;
+        total += cs;
+        if (k < AMP_CHAIN_MAX) { cc.slot_[k] = s; cc.cnt_[k] = cs; }
+    }
+    if (k <= AMP_CHAIN_MAX) {
+        cc.n = k;
+        for (int j = 0; j < k; ++j) cc.sym_[j] = slot_sym(P, cc.slot_[j]);
+        call_position_impl(P, fixed_syms, gp, p, c, total, cc);
+    } else {
+        ChainLinked cl; cl.P = &P; cl.head = head;
+        call_position_impl(P, fixed_syms, gp, p, c, total, cl);
+    }
 }
 
 }  // namespace amp

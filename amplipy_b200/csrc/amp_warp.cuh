@@ -543,6 +543,9 @@ AMP_WD int chunk_window_base(const KParams& P, int* ctrl, long long first_read, 
 
 template <bool TRIM, bool PILE, int WT>
 AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int gwarps, int dwarps) {
+#if defined(__CUDA_ARCH__) && defined(AMP7_TIMING)
+    const long long t_cta0 = clock64();
+#endif
     const int wt = WT ? WT : P.wt;
     const int tid = c_tid(), nthreads = c_nthreads(), block = c_block();
     const int lane = tid & 31, warp = tid >> 5;
@@ -759,6 +762,15 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
     AMP7_TDUMP(tk, 0);
     c_sync();
     if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);
+#if defined(__CUDA_ARCH__) && defined(AMP7_TIMING)
+    if (tid == 0 && P.phase_cycles) {   // whole-CTA cycles: sum / min / max over CTAs
+        const long long tot = clock64() - t_cta0;
+        atomicAdd((unsigned long long*)&P.phase_cycles[8], (unsigned long long)tot);
+        atomicMin((long long*)&P.phase_cycles[9], tot);
+        atomicMax((long long*)&P.phase_cycles[10], tot);
+        if (block < 160) { P.phase_cycles[16 + block] = tot; P.phase_cycles[176 + block] = ctrl[C7_NGEN]; }
+    }
+#endif
 }
 
 }  // namespace amp

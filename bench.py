@@ -311,7 +311,7 @@ def main():
                     "note": "amp_process_host (pinned host SoA -> chunked H2D -> fused kernel -> D2H trim outputs) + amp_call (D2H call outputs)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(b.n) if args.workload == "illumina" else None, "kernel": "amp_trim_pileup_kernel", "kernel_ms": kern_ms,
+                         "traffic": ncu_traffic(b.n) if args.workload == "illumina" else None, "kernel": "amp_trim_pileup_warp_kernel" if args.workload == "illumina" else "amp_trim_pileup_indel_kernel", "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": in_bytes + out_bytes, "bytes_per_read": (in_bytes + out_bytes) / b.n,
                          "peak_source": peak_src, "kernel_share_of_step": kern_ms / ms_per_step},
             "clocks": sampler.summary(), "device_error_flags": flags_dev,
