@@ -125,7 +125,7 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_WARPS 16            // warps per CTA of the fast kernel
 #endif
 #ifndef AMP7_GWARPS
-#define AMP7_GWARPS 11           // warps that can run the generic phase (their extra shared memory must fit): the last ones
+#define AMP7_GWARPS 12           // warps that can run the generic phase (their extra shared memory must fit): the last ones
 #endif
 #ifndef AMP7_DWARPS
 #define AMP7_DWARPS 1            // of those, warps that do nothing else (they work on the list while it is being filled)
@@ -138,18 +138,19 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_PAD 16              // bytes in front of the staged data (phase B may address up to 3 nibbles before it)
 #define AMP7_QDATA 5120          // staged quality bytes per batch (32 x 150 + alignment)
 #define AMP7_SDATA 2560
-#define AMP7_QSLACK 272          // idle lanes of phase B read up to KW * 32 + 8 bytes past a row start
-#define AMP7_SSLACK 144
+#define AMP7_QSLACK 32           // the word-wise passes read up to 16 bytes past a run
+#define AMP7_SSLACK 32
 #define AMP7_QBUF (AMP7_PAD + AMP7_QDATA + AMP7_QSLACK)
 #define AMP7_SBUF (AMP7_PAD + AMP7_SDATA + AMP7_SSLACK)
-#define AMP7_RUNCAP 72           // run descriptors per warp (generic path)
+#define AMP7_RUNCAP 64           // run descriptors per warp (generic path)
 #define AMP7_QCAP 32             // generic-path reads per warp and round
 #define AMP7_GSLOT_Q 192         // G phase: bytes per staged quality row slot
 #define AMP7_GSLOT_S 96
-#define AMP7_GN 28               // reads per G phase (GN * GSLOT <= DATA)
+#define AMP7_GN 26               // reads per G phase (GN * GSLOT <= DATA)
 #define AMP7_CROW 13             // generic path: CIGAR ops (+3) per shared-memory row; two rows per read (odd stride: no bank conflicts)
 #define AMP7_GEXTRA_BYTES (AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + AMP7_GN * 2 * AMP7_CROW * 4)   // generic phase: runs, queue, counters, CIGAR rows
-enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_GNEXT = 3, C7_FASTDONE = 4, C7_WORDS = 16 };
+#define AMP7_PSLICE 640          // positions of the two primer tables kept in shared memory, from the window base
+enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_GNEXT = 3, C7_FASTDONE = 4, C7_PTAB = 16, C7_WORDS = 16 + 2 * AMP7_PSLICE };
 
 // the sink row is the last one and 32 * KW entries longer: idle slots of a group increment it past the window's end
 AMP_HD size_t tile_bytes_v7(int wt) { return ((size_t)AMP7_ROWS * wt + 32 * AMP7_KW) * 4; }
@@ -458,25 +459,23 @@ template <int WT>
 AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, int wt, int wbase, int nb, int nq, int lane, bool do_trim,
                                bool do_pile, uint32_t& parity, long long* tk) {
     // stage the (scattered) rows into fixed slots, keeping each row's alignment mod 16: every lane starts the bulk copies
-    // of its own read (whole 16-byte pieces) and moves the < 16 trailing bytes itself
+    // of its own read (whole 16-byte pieces, rounded up)
     {
-        uint32_t qb = 0, sb = 0, qt = 0, stl = 0;
+        uint32_t qb = 0, sb = 0;
         const uint8_t *qsrc = nullptr, *ssrc = nullptr;
         uint8_t *qdst = nullptr, *sdst = nullptr;
         if (lane < nb) {
             const long long i = P.b.first + wm.queue[lane];
             const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
             if ((qo0 & 15u) + (qo1 - qo0) + 16u <= AMP7_GSLOT_Q) {
-                const uint32_t hi = (qo0 & 15u) + (qo1 - qo0);
                 qsrc = P.b.qual + (qo0 & ~15u); qdst = wm.qbuf + AMP7_PAD + (size_t)lane * AMP7_GSLOT_Q;
-                qb = hi & ~15u; qt = hi & 15u;
+                qb = ((qo0 & 15u) + (qo1 - qo0) + 15u) & ~15u;
             }
             if (do_pile) {
                 const uint32_t so0 = P.b.seq_off[i], so1 = P.b.seq_off[i + 1];
                 if ((so0 & 15u) + (so1 - so0) <= AMP7_GSLOT_S) {
-                    const uint32_t hi = (so0 & 15u) + (so1 - so0);
                     ssrc = P.b.seq + (so0 & ~15u); sdst = wm.sbuf + AMP7_PAD + (size_t)lane * AMP7_GSLOT_S;
-                    sb = hi & ~15u; stl = hi & 15u;
+                    sb = ((so0 & 15u) + (so1 - so0) + 15u) & ~15u;
                 }
             }
         }
@@ -485,18 +484,6 @@ AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, i
         w_sync();
         if (qb) bulk_copy(qdst, qsrc, qb, wm.bar);
         if (sb) bulk_copy(sdst, ssrc, sb, wm.bar);
-        // trailing bytes: all loads first (one round trip), then the stores
-        {
-            uint8_t tq[15], ts[15];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (uint32_t k = 0; k < 15; ++k) { tq[k] = k < qt ? qsrc[qb + k] : (uint8_t)0; ts[k] = k < stl ? ssrc[sb + k] : (uint8_t)0; }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (uint32_t k = 0; k < 15; ++k) { if (k < qt) qdst[qb + k] = tq[k]; if (k < stl) sdst[sb + k] = ts[k]; }
-        }
         w_sync();
         if (total) { bulk_wait(wm.bar, parity); parity ^= 1u; }
     }
@@ -566,6 +553,18 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
     if (lane == 0) mbar_init(wm.bar);
     const int wb = chunk_window_base(P, ctrl, P.b.first + g_lo * BR, n_end, tid, n_batches > 0);
     const int wbase = PILE ? wb : -1;
+    // the stretch of the two primer tables this chunk looks at (from its window base), for phase A
+    TrimParams tps = P.tp;
+    const int pbase = wb >= 0 ? wb : 0;
+    if (TRIM) {
+        int* ptab = ctrl + C7_PTAB;
+        for (int k = tid; k < 2 * AMP7_PSLICE; k += nthreads) {
+            const int p = pbase + (k < AMP7_PSLICE ? k : k - AMP7_PSLICE);
+            ptab[k] = p < P.tp.L ? (k < AMP7_PSLICE ? P.tp.min_primer_start[p] : P.tp.max_primer_end[p]) : -1;
+        }
+        tps.min_primer_start = ptab - pbase; tps.max_primer_end = ptab + AMP7_PSLICE - pbase;
+        c_sync();
+    }
 
     const int minq = P.tp.min_quality;
     // the word-wise passes need the default window and a quality threshold that fits the SIMD byte compare
@@ -628,15 +627,13 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
             const uint32_t s_end = (uint32_t)w_shfl((int)so1, nreads - 1);
             s_hi = (s_end - s_lo <= (uint32_t)AMP7_SDATA) ? s_end : s_lo + (uint32_t)AMP7_SDATA;
         }
-        const uint32_t q_bulk = (q_hi - q_lo) & ~15u, s_bulk = (s_hi - s_lo) & ~15u;
+        // whole 16-byte pieces, rounded up: the arrays are readable up to the next 16-byte boundary (include/amplipy_b200.h)
+        const uint32_t q_bulk = (q_hi - q_lo + 15u) & ~15u, s_bulk = (s_hi - s_lo + 15u) & ~15u;
         if (lane == 0 && q_bulk + s_bulk > 0) {
             bulk_expect(wm.bar, q_bulk + s_bulk);
             if (q_bulk) bulk_copy(wm.qbuf + AMP7_PAD, P.b.qual + q_lo, q_bulk, wm.bar);
             if (s_bulk) bulk_copy(wm.sbuf + AMP7_PAD, P.b.seq + s_lo, s_bulk, wm.bar);
         }
-        // the < 16 trailing bytes of each range with ordinary loads
-        if (lane < (int)((q_hi - q_lo) & 15u)) wm.qbuf[AMP7_PAD + q_bulk + lane] = P.b.qual[q_lo + q_bulk + lane];
-        if (PILE && lane < (int)((s_hi - s_lo) & 15u)) wm.sbuf[AMP7_PAD + s_bulk + lane] = P.b.seq[s_lo + s_bulk + lane];
 
         const int nc = (int)(c1 - c0), l_seq = (int)(qo1 - qo0);
         const uint32_t* cig = P.b.cigar + c0;
@@ -644,7 +641,10 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
         SimpleRead r; r.s1 = 0; r.m = 0; r.s2 = 0; r.mop = 0;
         int f = 0;
         bool fast = have && !skipped && fast_ok && qo1 <= q_hi && (!PILE || so1 <= s_hi) && classify_simple3(nc, M.g0, M.g1, M.g2, l_seq, r);
-        if (fast && TRIM) fast = trim_simple_primers(r, pos, flag, tlen, l_seq, P.tp, &f);
+        if (fast && TRIM) {   // both lookups (pos and reference_end - 1) inside the cached stretch?
+            const bool in_slice = pos >= pbase && pos + r.m <= pbase + AMP7_PSLICE;
+            fast = trim_simple_primers(r, pos, flag, tlen, l_seq, in_slice ? tps : P.tp, &f);
+        }
         if (fast && !TRIM && (pos < 0 || pos + r.m > P.tp.L)) fast = false;
         const uint32_t a0 = AMP7_PAD + (qo0 - q_lo) + (uint32_t)r.s1;                  // first aligned quality byte in qbuf
         if (fast && (r.m < 8 || (int)(a0 & 3u) + r.m > 256)) fast = false;

@@ -234,6 +234,12 @@ class Engine:
 
         def up(a):
             return torch.from_numpy(a).to(dev, non_blocking=False)
+
+        def up_rows(a):   # seq / qual: readable up to the next 16-byte boundary past the end (include/amplipy_b200.h)
+            t = torch.zeros(a.size + 16, dtype=torch.uint8, device=dev)
+            if a.size:
+                t[:a.size].copy_(torch.from_numpy(a))
+            return t
         d = {"n": batch.n, "sum_cig": int(batch.cig_off[-1]), "sum_qual": int(batch.qual_off[-1])}
         # views of narrower dtypes that torch lacks are uploaded as raw bytes
         d["pos"] = up(batch.pos)
@@ -242,9 +248,9 @@ class Engine:
         d["cig_off"] = up(batch.cig_off.view(np.int32))
         d["cigar"] = up(batch.cigar.view(np.int32)) if batch.cigar.size else torch.zeros(1, dtype=torch.int32, device=dev)
         d["seq_off"] = up(batch.seq_off.view(np.int32))
-        d["seq"] = up(batch.seq) if batch.seq.size else torch.zeros(16, dtype=torch.uint8, device=dev)
+        d["seq"] = up_rows(batch.seq)
         d["qual_off"] = up(batch.qual_off.view(np.int32))
-        d["qual"] = up(batch.qual) if batch.qual.size else torch.zeros(16, dtype=torch.uint8, device=dev)
+        d["qual"] = up_rows(batch.qual)
         if trim_out:
             d["o_pos"] = torch.empty(batch.n, dtype=torch.int32, device=dev)
             d["o_ncig"] = torch.empty(batch.n, dtype=torch.int16, device=dev)

@@ -14,7 +14,8 @@
  *   pos i32, flag u16, tlen i32, cig_off u32[N+1], cigar u32[sumC] (BAM: len<<4|op),
  *   seq_off u32[N+1] (bytes), seq u8 (BAM 4-bit, (l_seq+1)/2 bytes per read),
  *   qual_off u32[N+1] (bytes; l_seq = diff), qual u8 (phred).
- *   `seq` and `qual` base addresses must be 16-byte aligned.
+ *   `seq` and `qual` base addresses must be 16-byte aligned, and device copies of them must be readable up to the
+ *   next 16-byte boundary past their last byte (the kernels move them in whole 16-byte pieces).
  * Trim output layout: row i of out_cigar starts at cig_off[i] + 3*i (capacity n_cigar[i] + 3).
  */
 #ifndef AMPLIPY_B200_H

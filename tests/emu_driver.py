@@ -145,9 +145,8 @@ class EmuEngine:
 
 
 def _aligned(a, align=16):
-    if a.ctypes.data % align == 0:
-        return a
-    buf = np.empty(a.size + align, a.dtype)
+    """16-byte aligned copy that is readable up to the next 16-byte boundary past its end (the staging contract)."""
+    buf = np.zeros(a.size + 2 * align, a.dtype)
     o = (-buf.ctypes.data) % align
     v = buf[o:o + a.size]
     v[:] = a
