@@ -78,9 +78,83 @@ __global__ void amp_link_kernel(amp::InsSlot* slots, const unsigned int* entries
     }
 }
 
-__global__ void amp_call_kernel(const amp::CallParams P) {
-    const long long gp = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (gp < (long long)P.n_samples * P.L) amp::call_position(P, kFixedSyms, gp);
+// Calling: sixteen lanes per (sample, position), one allele per lane: lanes 0..5 the fixed symbols A C G T N '-', lanes
+// 6..15 the position's insertion alleles when there are at most ten (with more, the first lane of the group runs the serial
+// form amp::call_position -- the same function the CPU emulation runs for every position).  One float64 division per
+// allele, the allele order (count, then python string order, descending: AmpliPy.py:771) from fifteen shuffles, the
+// position-level facts from ballots.
+#define AMP_CALL_LANES 16
+__global__ void __launch_bounds__(256) amp_call_kernel(const amp::CallParams P) {
+    constexpr int G = AMP_CALL_LANES, NINS = G - AMP_NCH;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long gp = t / G;
+    const int ch = (int)(t % G);
+    if (gp >= (long long)P.n_samples * P.L) return;             // whole groups: blockDim is a multiple of G
+    const int sample = (int)(gp / P.L), p = (int)(gp - (long long)sample * P.L);
+    const int g0 = threadIdx.x & (32 - G) & 31;               // first lane of this group
+    const unsigned gmask = (G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u) << g0);
+    // insertion alleles of the position: lane 6 + j takes the j-th entry of the list
+    int slot = -1, s = P.heads[(size_t)sample * P.Lpad + p];
+    for (int j = 0; j < NINS && s >= 0; ++j) {
+        if (ch == AMP_NCH + j) slot = s;
+        s = P.slots[s].next;
+    }
+    if (s >= 0) {                                             // longer list (uniform within the group)
+        if (ch == 0) amp::call_position(P, kFixedSyms, gp);
+        return;
+    }
+    const int* cnt = P.counts + (size_t)sample * AMP_NCH * P.Lpad;
+    int c = 0;
+    amp::Sym me; me.p = kFixedSyms + (ch < AMP_NCH ? ch : 7); me.len = 1;
+    if (ch < AMP_NCH) c = cnt[(size_t)ch * P.Lpad + p];
+    else if (slot >= 0) { c = P.slots[slot].count; me = amp::slot_sym(P, slot); }
+    int total = c;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) total += __shfl_xor_sync(gmask, total, d);
+    const unsigned char refsym = P.ref_seq[p];
+    const double f = c ? (double)c / (double)total : 0.0;
+    // index in the sorted allele list = number of alleles that are greater
+    int rank = 0;
+#pragma unroll
+    for (int o = 0; o < G; ++o) {
+        const int co = __shfl_sync(gmask, c, g0 + o);
+        amp::Sym so;
+        so.p = (const unsigned char*)__shfl_sync(gmask, (unsigned long long)me.p, g0 + o);
+        so.len = __shfl_sync(gmask, me.len, g0 + o);
+        if (o != ch && co && c && amp::allele_greater(co, so, c, me)) ++rank;
+    }
+    if (!c) rank = -1;
+    const bool is_ref = c && me.len == 1 && me.p[0] == refsym;                     // 936-937
+    const bool is_alt = c && !is_ref && f >= P.min_freq_variants;                  // 938-939
+    const unsigned lanes = G == 32 ? 0xFFFFFFFFu : (1u << G) - 1u;
+    const unsigned top_m = (__ballot_sync(gmask, rank == 0) >> g0) & lanes;
+    const unsigned ref_m = (__ballot_sync(gmask, is_ref) >> g0) & lanes;
+    const unsigned alt_m = (__ballot_sync(gmask, is_alt) >> g0) & lanes;
+    const int best_l = top_m ? __ffs((int)top_m) - 1 : 0;
+    const int best_c = __shfl_sync(gmask, c, g0 + best_l);
+    const double best_f = __shfl_sync(gmask, f, g0 + best_l);
+    const int kk = slot >= 0 ? P.slot_entry[slot] : -1;       // dense index of the insertion allele (amp_ins_export order)
+    const int best_kk = __shfl_sync(gmask, kk, g0 + best_l);
+    // the reference's loop visits the fixed symbols first, then the insertion alleles: the last match wins (936-937)
+    const int ref_l = ref_m ? 31 - __clz((int)ref_m) : 0;
+    const int refc0 = __shfl_sync(gmask, c, g0 + ref_l);
+    const double reff0 = __shfl_sync(gmask, f, g0 + ref_l);
+    if (ch < AMP_NCH) { P.fixed_freq[gp * AMP_NCH + ch] = f; P.fixed_rank[gp * AMP_NCH + ch] = rank; }
+    else if (slot >= 0 && c) { P.ins_freq[kk] = f; P.ins_rank[kk] = rank; P.ins_alt[kk] = is_alt ? 1 : 0; }
+    if (ch == 0) {
+        const int refc = ref_m ? refc0 : 0;
+        const double reff = ref_m ? reff0 : 0.0;
+        P.depth[gp] = total;
+        P.top_id[gp] = top_m ? (best_l < AMP_NCH ? best_l : 6 + best_kk) : -1;
+        P.top_count[gp] = top_m ? best_c : 0;
+        unsigned char fl = 0;
+        if (top_m && best_c >= P.min_depth_consensus && best_f >= P.min_freq_consensus) fl |= 1;     // 928
+        if (total > 0 && total >= P.min_depth_variants && alt_m != 0) {                             // 940
+            fl |= 2;
+            if (refc >= P.min_depth_variants && reff >= P.min_freq_variants) fl |= 4;               // 948
+        }
+        P.pos_flags[gp] = fl; P.ref_count[gp] = refc; P.alt_mask[gp] = (unsigned char)(alt_m & 0x3Fu);
+    }
 }
 
 __global__ void amp_gather_entries_kernel(const amp::InsSlot* slots, const unsigned int* entries, unsigned long long n,
@@ -599,7 +673,7 @@ int amp_call_device(amp_ctx* c, const amp_call_params* p, void* stream) {
     P.pos_flags = blk + c->o_fl; P.ref_count = (int*)(blk + c->o_refc); P.fixed_freq = (double*)(blk + c->o_ff);
     P.fixed_rank = (int*)(blk + c->o_fr); P.alt_mask = blk + c->o_alt; P.ins_freq = (double*)(blk + c->o_if);
     P.ins_rank = (int*)(blk + c->o_ir); P.ins_alt = blk + c->o_ia;
-    amp_call_kernel<<<(unsigned)((SL + 127) / 128), 128, 0, st>>>(P);
+    amp_call_kernel<<<(unsigned)((SL * AMP_CALL_LANES + 255) / 256), 256, 0, st>>>(P);
     CK(cudaGetLastError());
     c->last_launches = 2;
     return AMP_OK;
