@@ -125,7 +125,7 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_WARPS 16            // warps per CTA of the fast kernel
 #endif
 #ifndef AMP7_GWARPS
-#define AMP7_GWARPS 12           // warps that can run the generic phase (their extra shared memory must fit): the last ones
+#define AMP7_GWARPS 14           // warps that can run the generic phase (their extra shared memory must fit): the last ones
 #endif
 #ifndef AMP7_DWARPS
 #define AMP7_DWARPS 1            // of those, warps that do nothing else (they work on the list while it is being filled)
@@ -142,12 +142,12 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_SSLACK 32
 #define AMP7_QBUF (AMP7_PAD + AMP7_QDATA + AMP7_QSLACK)
 #define AMP7_SBUF (AMP7_PAD + AMP7_SDATA + AMP7_SSLACK)
-#define AMP7_RUNCAP 64           // run descriptors per warp (generic path)
+#define AMP7_RUNCAP 80           // run descriptors per warp (generic path)
 #define AMP7_QCAP 32             // generic-path reads per warp and round
 #define AMP7_GSLOT_Q 192         // G phase: bytes per staged quality row slot
 #define AMP7_GSLOT_S 96
 #define AMP7_GN 26               // reads per G phase (GN * GSLOT <= DATA)
-#define AMP7_CROW 13             // generic path: CIGAR ops (+3) per shared-memory row; two rows per read (odd stride: no bank conflicts)
+#define AMP7_CROW 9              // generic path: CIGAR ops (+3) per shared-memory row; two rows per read (odd stride: no bank conflicts)
 #define AMP7_GEXTRA_BYTES (AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + AMP7_GN * 2 * AMP7_CROW * 4)   // generic phase: runs, queue, counters, CIGAR rows
 #define AMP7_PSLICE 640          // positions of the two primer tables kept in shared memory, from the window base
 enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_GNEXT = 3, C7_FASTDONE = 4, C7_PTAB = 16, C7_WORDS = 16 + 2 * AMP7_PSLICE };
