@@ -297,6 +297,16 @@ int emu_window(const uint8_t* q, int len, int W, int minq, int rev, int mode) {
     return rev ? amp::window_del_len_rev(q, len, W, minq) : amp::window_del_len_fwd(q, len, W, minq);
 }
 
+// unit hook: the register form of the [S]M[S] classification against the array form (returns 1 when they agree)
+int emu_classify_agree(const uint32_t* cig, int nc, int l_seq) {
+    amp::SimpleRead a, b;
+    a.s1 = a.m = a.s2 = 0; a.mop = 0; b = a;
+    const bool ra = amp::classify_simple(cig, nc, l_seq, a);
+    const bool rb = amp::classify_simple3(nc, nc > 0 ? cig[0] : 0u, nc > 1 ? cig[1] : 0u, nc > 2 ? cig[2] : 0u, l_seq, b);
+    if (ra != rb) return 0;
+    return !ra || (a.s1 == b.s1 && a.m == b.m && a.s2 == b.s2 && a.mop == b.mop);
+}
+
 void emu_call(void* h, const char* ref_seq, int mdc, double mfc, int mdv, double mfv, int32_t* depth, int32_t* top_id,
               int32_t* top_count, uint8_t* pos_flags, int32_t* ref_count, double* fixed_freq, int32_t* fixed_rank,
               uint8_t* alt_mask, double* ins_freq, int32_t* ins_rank, uint8_t* ins_alt) {

@@ -103,3 +103,22 @@ def test_window_edges_vs_oracle(oracle_lib):
     parity.check_against_oracle(v7(grid=3, warps=4), oracle_lib, b, g, prim)
     fast, generic = emu_driver.v7_stats()
     assert fast > 0.85 * b.n, (fast, generic)
+
+
+def test_register_classification_matches_array_form():
+    """classify_simple3 (CIGAR words in registers, used by the pipelined phase A) == classify_simple on random CIGARs."""
+    import ctypes
+    lib = emu_driver.lib()
+    rng = np.random.default_rng(11)
+    n_simple = 0
+    for _ in range(20000):
+        nc = int(rng.integers(0, 6))
+        ops = rng.choice([0, 0, 0, 4, 4, 1, 2, 5, 7, 8], size=nc)
+        lens = rng.integers(0, 60, size=nc)
+        cig = (lens.astype(np.uint32) << 4 | ops.astype(np.uint32)).astype(np.uint32)
+        buf = np.zeros(8, np.uint32); buf[:nc] = cig
+        q_len = int(sum(l for l, o in zip(lens, ops) if o in (0, 1, 4, 7, 8)))
+        for l_seq in (q_len, q_len + 1):
+            assert lib.emu_classify_agree(ctypes.c_void_p(buf.ctypes.data), nc, l_seq) == 1, (ops, lens, l_seq)
+        n_simple += nc >= 1 and all(o in (0, 4, 7, 8) for o in ops)
+    assert n_simple > 1000
