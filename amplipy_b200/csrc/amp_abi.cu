@@ -157,6 +157,16 @@ __global__ void __launch_bounds__(256) amp_call_kernel(const amp::CallParams P) 
     }
 }
 
+// reset of the insertion table between samples: only the slots that are in use (listed in entries[]) are cleared
+__global__ void amp_clear_slots_kernel(amp::InsSlot* slots, const unsigned int* entries, unsigned long long* cursor) {
+    const unsigned long long n = cursor[1];
+    for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        amp::InsSlot z; z.key = 0; z.count = 0; z.next = 0;
+        slots[entries[k]] = z;
+    }
+}
+
 __global__ void amp_gather_entries_kernel(const amp::InsSlot* slots, const unsigned int* entries, unsigned long long n,
                                           int* count, unsigned long long* off) {
     for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n;
@@ -405,7 +415,10 @@ int amp_reset_async(amp_ctx* c, void* stream) {
     CK(cudaSetDevice(c->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemsetAsync(c->d_counts, 0, (size_t)c->cfg.n_samples * AMP_NCH * c->Lpad * 4, st));
-    CK(cudaMemsetAsync(c->tab.slots, 0, c->nslots * sizeof(amp::InsSlot), st));
+    // the table was zero after amp_create / amp_reset and every slot taken since then is listed in entries[]:
+    // clearing those is enough (the full table is tens of MB)
+    amp_clear_slots_kernel<<<c->sm_count, 256, 0, st>>>(c->tab.slots, c->tab.entries, c->tab.cursor);
+    CK(cudaGetLastError());
     CK(cudaMemsetAsync(c->tab.cursor, 0, 16, st));
     CK(cudaMemsetAsync(c->d_err, 0, 4, st));
     return AMP_OK;
