@@ -1,28 +1,28 @@
 // amp_warp.cuh -- warp-autonomous fused trim + pileup kernel for short-read batches (sm_100a).
 //
-// One CTA per SM; every warp loops on its own over batches of up to 32 consecutive reads and never waits for another
-// warp (one block barrier after set-up, one before the final flush).  Per batch:
+// One CTA per SM owns a contiguous chunk of the (coordinate-sorted) reads and one privatised count tile over the
+// reference window of that chunk, indexed directly by the BAM base nibble (18 rows x WT: rows 1,2,4,8,15 = A,C,G,T,N;
+// row 16 = '-'; row 17 = sink for masked bases; any other row only raises the KeyError flag at the flush).  The warps are
+// autonomous: no block barrier between set-up and the final flush.
 //
-//   A  lane per read : metadata loads, [S]M[S] classification, closed form of the two primer clips
-//                      (trim_read, AmpliPy.py:450-558).  Lane 0 starts ONE bulk async copy (cp.async.bulk, completion on
-//                      an mbarrier) of the batch's contiguous quality / sequence byte ranges into the warp's buffers;
-//                      it lands while the lanes chase cig_off -> cigar -> primer tables.
-//   B  8 lanes per read, four reads per step: lane l owns the aligned 4-byte words l, l+8, l+16, ... of the read's
-//                      aligned quality bytes.
-//        window search (AmpliPy.py:566-587 / 628-649): per word four dp4a window sums against -4*minq; the sign bits are
-//                      funnel-shifted into one 32-bit fail mask per lane; first (forward strand) or last (reverse
-//                      strand) failing window by ffs/clz + three shuffles.  The three shrinking windows at the open end
-//                      are checked from three bytes.
-//        counting (update_base_counts, 690-753): per word a SIMD byte compare q >= minq packed to 4 bits per word,
-//                      AND-ed with the lane's mask of the final aligned range; per base one test + one shared-memory atomic
-//                      on a count tile indexed directly by the BAM nibble (17 rows x WT: rows 1,2,4,8,15 = A,C,G,T,N;
-//                      row 16 = '-'; any other row only raises the KeyError flag).  Lanes of a group hit banks 4 apart.
-//   C  lane per read : quality clip + write gate (589-686, 910), trim outputs.
-//   G  reads that are not [S]M[S] (indels, hard clips, corner cases the closed form declines) are queued per warp and
-//      run 26 at a time through the loop-for-loop generic path (trim_read + plan_read of amp_core.cuh), their runs
-//      counted by 8-lane groups from the warp's run list.
+// Batch warps loop over batches of up to 32 consecutive reads, software-pipelined over the batches:
+//   A  lane per read : [S]M[S] classification and the closed form of the two primer clips (trim_read,
+//                      AmpliPy.py:450-558) from metadata / CIGAR words loaded one batch ahead; lane 0 starts one bulk async
+//                      copy (cp.async.bulk, completion on an mbarrier) per array that drops the batch's contiguous quality /
+//                      sequence byte ranges into the warp's staging buffers.
+//   B1 lane per read : sliding-window search (566-587 / 628-649) over aligned words of the row: eight windows per step
+//                      (dp4a against -4*minq), one "some window fails" bit per block, the first (forward) / last (reverse)
+//                      failing block resolved exactly; quality clip + write gate (589-686, 910); trim outputs.
+//   B2 pileup        : (update_base_counts, 718 + 752-753) the 8-base chunks of the batch's aligned runs are dealt out
+//                      evenly over the 32 lanes; per chunk a SIMD byte compare q >= minq, per base one byte permute (row
+//                      offset), one select (sink row for masked bases), one add, one shared-memory atomic.
+//   G  every read that is not [S]M[S] (indels, hard clips, corner cases the closed form declines) goes to the CTA's list.
+//      A dedicated warp works on that list while it is being filled, the other generic-capable warps drain what is left
+//      when the batches are done: rows staged with one bulk copy per lane, the loop-for-loop generic path lane per read
+//      (trim_read + plan_read of amp_core.cuh on CIGAR rows in shared memory), runs counted with the balanced chunk loop.
 //
-// tests/emu runs this very source on the CPU with every lane as a fiber (warp collectives = fiber rendezvous).
+// tests/emu runs this very source on the CPU with every CUDA thread as a fiber (warp collectives, barriers and spin-waits
+// are rendezvous / yield points of a deterministic scheduler).
 #pragma once
 #include <string.h>
 
@@ -37,9 +37,7 @@ AMP_WD int c_tid() { return (int)threadIdx.x; }
 AMP_WD int c_nthreads() { return (int)blockDim.x; }
 AMP_WD int c_block() { return (int)blockIdx.x; }
 AMP_WD int w_shfl(int v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
-AMP_WD int w_shfl_xor(int v, int m) { return __shfl_xor_sync(0xFFFFFFFFu, v, m); }
 AMP_WD unsigned w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
-AMP_WD int w_max(int v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
 AMP_WD int w_add(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 AMP_WD void w_sync() { __syncwarp(); }
 AMP_WD void c_sync() { __syncthreads(); }
@@ -65,11 +63,6 @@ AMP_WD void bulk_copy(void* dst, const void* src, uint32_t bytes, unsigned long 
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
-// predicated shared-memory increment (no branch): cnt[idx] += 1 when cond != 0
-AMP_WD void tile_inc_if(int* cnt, int idx, unsigned cond) {
-    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.add.u32 [%0], 1; }" ::"r"(smem_addr(cnt) + 4u * (uint32_t)idx), "r"(cond)
-                 : "memory");
-}
 // pull [src, src + bytes) towards L2 (bytes a multiple of 16); purely a hint
 AMP_WD void bulk_prefetch_l2(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
@@ -87,7 +80,7 @@ AMP_WD void bulk_wait(unsigned long long* bar, uint32_t parity) {
 #define AMP_WD inline
 // implemented by the fiber runtime in tests/emu/amp_emu.cpp
 int c_tid(); int c_nthreads(); int c_block();
-int w_shfl(int v, int src); int w_shfl_xor(int v, int m); unsigned w_ballot(bool p); int w_max(int v); int w_add(int v);
+int w_shfl(int v, int src); unsigned w_ballot(bool p); int w_add(int v);
 void w_sync(); void c_sync(); void c_yield();
 AMP_WD int ld_vol(const int* p) { return *p; }
 AMP_WD uint32_t ld_cg_u32(const uint32_t* p) { return *p; }
@@ -104,7 +97,6 @@ AMP_WD void bulk_expect(unsigned long long*, uint32_t) {}
 AMP_WD void bulk_copy(void* dst, const void* src, uint32_t bytes, unsigned long long*) { memcpy(dst, src, bytes); }
 AMP_WD void bulk_wait(unsigned long long*, uint32_t) {}
 AMP_WD void bulk_prefetch_l2(const void*, uint32_t) {}
-AMP_WD void tile_inc_if(int* cnt, int idx, unsigned cond) { if (cond) cnt[idx] += 1; }
 static long long g_v7_stats[2];   // emulation only: reads finished on the cooperative path / reads sent to the generic path
 #endif
 
@@ -134,7 +126,6 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_ROWS 18             // count tile rows: BAM nibble 0..15, row 16 = deleted base, row 17 = sink of masked bases
 #define AMP7_DEL_ROW 16
 #define AMP7_SINK_ROW 17
-#define AMP7_KW 8                // 4-byte words per lane in phase B: aligned runs up to 8 * 32 bytes
 #define AMP7_PAD 16              // bytes in front of the staged data (phase B may address up to 3 nibbles before it)
 #define AMP7_QDATA 5120          // staged quality bytes per batch (32 x 150 + alignment)
 #define AMP7_SDATA 2560
@@ -152,8 +143,8 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_PSLICE 640          // positions of the two primer tables kept in shared memory, from the window base
 enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_GNEXT = 3, C7_FASTDONE = 4, C7_PTAB = 16, C7_WORDS = 16 + 2 * AMP7_PSLICE };
 
-// the sink row is the last one and 32 * KW entries longer: idle slots of a group increment it past the window's end
-AMP_HD size_t tile_bytes_v7(int wt) { return ((size_t)AMP7_ROWS * wt + 32 * AMP7_KW) * 4; }
+// the sink row is the last one and 256 entries longer: masked bases of a run's last chunk increment it past the window's end
+AMP_HD size_t tile_bytes_v7(int wt) { return ((size_t)AMP7_ROWS * wt + 256) * 4; }
 AMP_HD size_t smem_bytes_v9(int wt, int warps, int gwarps);   // below
 
 // launch shape: reads per batch so that a batch's rows fit the staging buffers; one CTA per SM with a contiguous chunk

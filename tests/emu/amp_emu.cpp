@@ -107,7 +107,6 @@ int w_shfl(int v, int src) {
     w_sync();
     return r;
 }
-int w_shfl_xor(int v, int m) { return w_shfl(v, (g_rt.cur & 31) ^ m); }
 unsigned w_ballot(bool p) {
     g_rt.xch[g_rt.cur] = p ? 1 : 0;
     w_sync();
@@ -121,14 +120,6 @@ int w_add(int v) {
     w_sync();
     int r = 0;
     for (int k = 0; k < 32; ++k) if ((g_rt.cur & ~31) + k < g_rt.nthreads) r += g_rt.xch[(g_rt.cur & ~31) + k];
-    w_sync();
-    return r;
-}
-int w_max(int v) {
-    g_rt.xch[g_rt.cur] = v;
-    w_sync();
-    int r = v;
-    for (int k = 0; k < 32; ++k) if ((g_rt.cur & ~31) + k < g_rt.nthreads) r = std::max(r, g_rt.xch[(g_rt.cur & ~31) + k]);
     w_sync();
     return r;
 }
