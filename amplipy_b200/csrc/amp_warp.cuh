@@ -112,6 +112,9 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_TDUMP(t, base) ((void)0)
 #endif
 
+#define AMP7_PRAGMA_(x) _Pragma(#x)
+#define AMP7_UNROLL(n) AMP7_PRAGMA_(unroll n)
+
 // ---- shared-memory layout ------------------------------------------------------------------------------------------
 #ifndef AMP7_WARPS
 #define AMP7_WARPS 16            // warps per CTA of the fast kernel
@@ -250,6 +253,9 @@ AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t
     unsigned sh = 0, ssh = 0, qa = 0, sa = 0, x = 0, mk0 = 0, mk1 = 0, mf0 = 0, mf1 = 0;
     bool odd = false;
     int* tl = cnt;
+#if defined(__CUDA_ARCH__) && defined(AMP7_COUNT_UNROLL)
+    AMP7_UNROLL(AMP7_COUNT_UNROLL)
+#endif
     for (int g = g0; g < g1; ++g, ++c, tl += 8) {
         if (c >= nch) {                                      // next run (first iteration: run rr0 at chunk g0)
             const Par4 pr = par[++rr];
