@@ -274,8 +274,8 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
         P.glist = glist;
 #ifdef AMP7_TIMING
         static long long* d_phase7 = nullptr;
-        if (!d_phase7) CK(cudaMalloc((void**)&d_phase7, 336 * 8));
-        CK(cudaMemsetAsync(d_phase7, 0, 16 * 8, st));
+        if (!d_phase7) CK(cudaMalloc((void**)&d_phase7, 400 * 8));
+        CK(cudaMemsetAsync(d_phase7, 0, 400 * 8, st));
         { const long long big = 1LL << 60; CK(cudaMemcpyAsync(d_phase7 + 9, &big, 8, cudaMemcpyHostToDevice, st)); }
         P.phase_cycles = d_phase7;
 #endif
@@ -287,12 +287,13 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
 #ifdef AMP7_TIMING
         {
             CK(cudaStreamSynchronize(st));
-            long long h[336];
+            long long h[400];
             CK(cudaMemcpy(h, d_phase7, sizeof h, cudaMemcpyDeviceToHost));
             if (getenv("AMP7_DUMP_CTAS")) { for (int b = 0; b < grid && b < 160; ++b) fprintf(stderr, "%lld:%lld ", h[16 + b] / 1000, h[176 + b]); fprintf(stderr, "\n"); }
             const double wf = (double)grid * AMP7_WARPS;
             fprintf(stderr, "[cycles per warp] prologue %.0f  A %.0f  bulk-wait %.0f  window+trim %.0f  count %.0f  (barrier issue %.0f)  wait+generic %.0f\n",
                     h[0] / wf, h[1] / wf, h[2] / wf, h[3] / wf, h[4] / wf, h[5] / wf, h[6] / wf);
+            fprintf(stderr, "[generic phase, cycles summed over its warp-rounds / 1000] load+copy %lld  trim_read %lld  outputs %lld  plan_read %lld\n", h[360] / 1000, h[361] / 1000, h[362] / 1000, h[363] / 1000);
             fprintf(stderr, "[cycles per CTA] mean %.0f  min %lld  max %lld\n", (double)h[8] / grid, h[9], h[10]);
         }
 #endif

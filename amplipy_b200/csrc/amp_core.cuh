@@ -65,6 +65,27 @@ AMP_HD unsigned long long atomic_add64(unsigned long long* p, unsigned long long
     unsigned long long o = *p; *p += v; return o;
 #endif
 }
+// The two cursors of the insertion table (arena words, entry index) are single addresses that every SM hits while the
+// generic phases run: lanes of a warp that arrive together combine their requests into one atomic.
+AMP_HD unsigned long long atomic_add64_warp(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    const unsigned m = __activemask();
+    const int lane = (int)(threadIdx.x & 31u), leader = __ffs((int)m) - 1;
+    unsigned long long pre = 0, tot = 0;
+    for (unsigned r = m; r; r &= r - 1u) {
+        const int l = __ffs((int)r) - 1;
+        const unsigned long long x = __shfl_sync(m, v, l);
+        if (l < lane) pre += x;
+        tot += x;
+    }
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(p, tot);
+    base = __shfl_sync(m, base, leader);
+    return base + pre;
+#else
+    unsigned long long o = *p; *p += v; return o;
+#endif
+}
 AMP_HD unsigned long long atomic_cas64(unsigned long long* p, unsigned long long cmp, unsigned long long val) {
 #ifdef __CUDA_ARCH__
     return atomicCAS(p, cmp, val);
@@ -601,7 +622,7 @@ AMP_HD void ins_table_add(const InsTable& T, int gpos, int len, const Text& text
         if (k == 0) {
             if (my_off < 0) {
                 unsigned long long words = 1 + ((unsigned long long)len + 7) / 8;
-                unsigned long long off = atomic_add64(&T.cursor[0], words);
+                unsigned long long off = atomic_add64_warp(&T.cursor[0], words);
                 if (off + words > T.arena_words) { atomic_or(T.err, AMP_E_ARENA_FULL); return; }
                 unsigned char* rec = T.arena + off * 8;
                 ((int*)rec)[0] = gpos; ((unsigned int*)rec)[1] = (unsigned int)len;
@@ -612,7 +633,7 @@ AMP_HD void ins_table_add(const InsTable& T, int gpos, int len, const Text& text
             unsigned long long old = atomic_cas64(&T.slots[slot].key, 0ULL, (tag << 40) | (unsigned long long)my_off);
             if (old == 0) {
                 atomic_add(&T.slots[slot].count, n);
-                const unsigned long long k_new = atomic_add64(&T.cursor[1], 1ULL);
+                const unsigned long long k_new = atomic_add64_warp(&T.cursor[1], 1ULL);
                 T.entries[k_new] = (unsigned int)slot; T.slot_entry[slot] = (int)k_new;
                 return;
             }

@@ -112,6 +112,13 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_TDUMP(t, base) ((void)0)
 #endif
 
+#if defined(__CUDA_ARCH__) && defined(AMP7_TIMING)
+#define AMP7_GT0() long long gt_ = clock64()
+#define AMP7_GTICK(k) do { __syncwarp(__activemask()); const long long n_ = clock64(); if (P.phase_cycles && (__ffs(__activemask()) - 1) == (int)(threadIdx.x & 31)) atomicAdd((unsigned long long*)&P.phase_cycles[360 + (k)], (unsigned long long)(n_ - gt_)); gt_ = n_; } while (0)
+#else
+#define AMP7_GT0() ((void)0)
+#define AMP7_GTICK(k) ((void)0)
+#endif
 #define AMP7_PRAGMA_(x) _Pragma(#x)
 #define AMP7_UNROLL(n) AMP7_PRAGMA_(unroll n)
 
@@ -409,6 +416,7 @@ AMP_WD void count_warp_runs7(const KParams& P, int* cnt, int wt, const WarpMem7&
 
 // generic path for one queued read (rows staged in slot `slot` of the warp's buffers, or read from global memory)
 AMP_HD void warp_read_generic7(const KParams& P, const WarpMem7& wm, long long i, int slot, bool do_trim, bool do_pile) {
+    AMP7_GT0();
     const uint32_t c0 = P.b.cig_off[i], c1 = P.b.cig_off[i + 1];
     const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
     int nc = (int)(c1 - c0);
@@ -432,12 +440,15 @@ AMP_HD void warp_read_generic7(const KParams& P, const WarpMem7& wm, long long i
         if (nc + 3 <= AMP7_CROW) { A = wm.cig + (size_t)slot * 2 * AMP7_CROW; B = A + AMP7_CROW; }
         else { A = P.scratch + (size_t)c0 + 3 * (size_t)i; B = A + P.scratch_half; }
         for (int k = 0; k < nc; ++k) A[k] = cig[k];
+        AMP7_GTICK(0);
         uint32_t* res;
         f = trim_read(A, B, nc, pos, flag, P.b.tlen[i], l_seq, qual, q_st, P.tp, &res);   // qdst >= AMP7_PAD >= 8
+        AMP7_GTICK(1);
         if (f & AMP_F_ERROR) { nc = 0; f = AMP_F_ERROR; atomic_or(P.err, AMP_E_COORD); }
         for (int k = 0; k < nc; ++k) orow[k] = res[k];
         cig = res;
         P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)f;
+        AMP7_GTICK(2);
     }
     if (do_pile && !(f & AMP_F_ERROR)) {
         WarpSink7 sink; sink.P = &P; sink.wm = wm;
@@ -448,6 +459,7 @@ AMP_HD void warp_read_generic7(const KParams& P, const WarpMem7& wm, long long i
         int e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
         e |= (int)sink.errs;
         if (e) atomic_or(P.err, (unsigned)e);
+        AMP7_GTICK(3);
     }
 }
 
