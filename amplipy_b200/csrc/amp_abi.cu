@@ -197,6 +197,7 @@ struct DevChunk {   // device staging for one in-flight chunk of amp_process_hos
     int32_t* o_pos = nullptr; uint16_t* o_ncig = nullptr; uint8_t* o_flags = nullptr; uint32_t* o_cigar = nullptr;
     uint32_t* scratch = nullptr;
     uint32_t* glist = nullptr; size_t cap_glist = 0;
+    size_t cap_ocigar = 0;
     size_t cap_reads = 0, cap_cig = 0, cap_seq = 0, cap_qual = 0, cap_scratch = 0;
 };
 
@@ -490,7 +491,7 @@ int amp_process_host(amp_ctx* c, const amp_batch* b, int mode, int sample, const
     c->last_launches = 0;
     const bool trim = mode & AMP_MODE_TRIM, pile = mode & AMP_MODE_PILEUP;
     const long long first = b->first, last = b->first + b->n_reads;
-    const long long kChunk = 1 << 18;
+    const long long kChunk = 1 << 18;   // reads per in-flight chunk: three of them keep both copy engines and the SMs busy
     int slot = 0;
     for (long long a = first; a < last; a += kChunk, slot = (slot + 1) % 3) {
         const long long e = std::min(last, a + kChunk), n = e - a;
@@ -518,16 +519,11 @@ int amp_process_host(amp_ctx* c, const amp_batch* b, int mode, int sample, const
             if (pile && (rc = dev_grow(&d.seq, &d.cap_seq, (s1 - s0) + 32))) return rc;
             if (trim) {
                 const size_t orows = (c1 - c0) + 3 * (size_t)n;
-                size_t ocap = d.cap_scratch / 2;   // o_cigar and scratch grow together
-                if (orows + 4 > ocap) {
-                    if (d.o_cigar) CK(cudaFree(d.o_cigar));
-                    if (d.scratch) CK(cudaFree(d.scratch));
-                    d.o_cigar = nullptr; d.scratch = nullptr; d.cap_scratch = 0;
-                    const size_t want = orows + orows / 4 + 64;
-                    CK(cudaMalloc((void**)&d.o_cigar, want * 4));
-                    CK(cudaMalloc((void**)&d.scratch, 2 * want * 4));
-                    d.cap_scratch = 2 * want;
-                }
+                if ((rc = dev_grow(&d.o_cigar, &d.cap_ocigar, orows + 4))) return rc;
+                // the two global scratch rows per read are only touched by CIGARs too long for the kernels' on-chip rows
+                int max_nc = 0;
+                for (long long i = a; i < e; ++i) max_nc = std::max(max_nc, (int)(b->cig_off[i + 1] - b->cig_off[i]));
+                if (max_nc + 3 > AMP7_CROW && (rc = dev_grow(&d.scratch, &d.cap_scratch, 2 * (orows + 4)))) return rc;
             }
         }
         cudaStream_t st = d.stream;
@@ -547,7 +543,7 @@ int amp_process_host(amp_ctx* c, const amp_batch* b, int mode, int sample, const
         const size_t orow0 = c0 + 3 * (size_t)a;
         if (trim) { to.pos = d.o_pos - a; to.ncig = d.o_ncig - a; to.flags = d.o_flags - a; to.cigar = d.o_cigar - orow0; }
         int rc = launch_process(c, bp, (long long)(c1 - c0), 0, (long long)(b->qual_off[e] - b->qual_off[a]), mode, sample, to,
-                                trim ? d.scratch - orow0 : nullptr, d.glist, st);
+                                (trim && d.scratch) ? d.scratch - orow0 : nullptr, d.glist, st);
         if (rc) return rc;
         if (trim) {
             CK(cudaMemcpyAsync(o->pos + a, d.o_pos, n * 4, cudaMemcpyDeviceToHost, st));

@@ -152,6 +152,34 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def file_to_file(args, g, prim, b):
+    """`aio` through the command line on files: BAM decode (host, multi-threaded BGZF) -> GPU path -> BAM encode + VCF +
+    FASTA.  Reported next to the kernel numbers because this is where a real run is bounded (host I/O)."""
+    import shutil
+    import tempfile
+    from amplipy_b200 import alnio, cli, synth
+    d = tempfile.mkdtemp(prefix="amplipy_b200_bench_")
+    try:
+        j = lambda n: os.path.join(d, n)
+        hdr = "@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:ref\tLN:%d\n@PG\tID:synth\tPN:synth\n" % len(g)
+        alnio.write_bam(j("in.bam"), hdr, [("ref", len(g))], b)
+        synth.write_bed(j("primers.bed"), [(s, e, "p%d" % k) for k, (s, e) in enumerate(prim)])
+        synth.write_fasta(j("ref.fas"), "ref", g)
+        t0 = time.perf_counter()
+        a = alnio.read_alignments(j("in.bam"))
+        t_decode = time.perf_counter() - t0
+        assert a.batch.n == b.n
+        t0 = time.perf_counter()
+        cli.main(["aio", "-i", j("in.bam"), "-p", j("primers.bed"), "-r", j("ref.fas"), "-ot", j("trimmed.bam"),
+                  "-ov", j("variants.vcf"), "-oc", j("consensus.fas")])
+        t_all = time.perf_counter() - t0
+        return {"value": b.n / t_all, "unit": "reads/s", "seconds": t_all, "bam_decode_only_reads_per_s": b.n / t_decode,
+                "bam_bytes": os.path.getsize(j("in.bam")), "trimmed_bam_bytes": os.path.getsize(j("trimmed.bam")),
+                "note": "python -m amplipy_b200 aio on files in a temp directory; one run, includes process-level set-up of the engine"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def workload_config(args, n_reads):
     return {"workload": "configs[1]: synthetic SARS-CoV-2-length genome (29,903 bp, seeded random stand-in), ARTIC-v3-like "
                         "98-amplicon scheme (generated), %d %s reads per GPU, coordinate-sorted" %
@@ -172,6 +200,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 10)")
+    ap.add_argument("--file-e2e", action="store_true",
+                    help="also time the command line file to file (BAM in -> trimmed BAM + VCF + FASTA out) and add a file_e2e object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -338,6 +368,8 @@ def main():
                                 "sample": "first %d reads of the workload; oracle/amplipy_oracle.c (C+OpenMP restatement of "
                                           "AmpliPy.py trim+pileup+call), %d threads" % (sample, cores),
                                 "parity_on_sample": same}
+    if rank == 0 and world == 1 and args.file_e2e:
+        line["file_e2e"] = file_to_file(args, g, prim, b)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
