@@ -609,7 +609,7 @@ AMP_HD unsigned long long mix64(unsigned long long h) {
 }
 // text getter: ch(i) -> i-th character of the key
 template <class Text>
-AMP_HD void ins_table_add(const InsTable& T, int gpos, int len, const Text& text, int n) {
+AMP_HD_NOINLINE void ins_table_add(const InsTable& T, int gpos, int len, const Text& text, int n) {
     unsigned long long h = 0xCBF29CE484222325ULL ^ (unsigned long long)(unsigned int)gpos;
     h *= 0x100000001B3ULL;
     for (int i = 0; i < len; ++i) { h ^= (unsigned char)text(i); h *= 0x100000001B3ULL; }
