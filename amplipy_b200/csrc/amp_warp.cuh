@@ -17,9 +17,10 @@
 //                      evenly over the 32 lanes; per chunk a SIMD byte compare q >= minq, per base one byte permute (row
 //                      offset), one select (sink row for masked bases), one add, one shared-memory atomic.
 //   G  every read that is not [S]M[S] (indels, hard clips, corner cases the closed form declines) goes to the CTA's list.
-//      A dedicated warp works on that list while it is being filled, the other generic-capable warps drain what is left
-//      when the batches are done: rows staged with one bulk copy per lane, the loop-for-loop generic path lane per read
-//      (trim_read + plan_read of amp_core.cuh on CIGAR rows in shared memory), runs counted with the balanced chunk loop.
+//      When the batches are done the generic-capable warps work through it (AMP7_DWARPS > 0: that many warps do nothing
+//      else from the start; measured no better): rows staged with one bulk copy per lane, the loop-for-loop generic path
+//      lane per read (trim_read + plan_read of amp_core.cuh on CIGAR rows in shared memory), runs counted with the
+//      balanced chunk loop.
 //
 // tests/emu runs this very source on the CPU with every CUDA thread as a fiber (warp collectives, barriers and spin-waits
 // are rendezvous / yield points of a deterministic scheduler).
@@ -130,7 +131,7 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_GWARPS 14           // warps that can run the generic phase (their extra shared memory must fit): the last ones
 #endif
 #ifndef AMP7_DWARPS
-#define AMP7_DWARPS 1            // of those, warps that do nothing else (they work on the list while it is being filled)
+#define AMP7_DWARPS 0            // of those, warps that do nothing else (they work on the list while it is being filled)
 #endif
 #define AMP7_WT 512              // count tile width on the device (positions)
 #define AMP7_ROWS 18             // count tile rows: BAM nibble 0..15, row 16 = deleted base, row 17 = sink of masked bases
@@ -517,9 +518,9 @@ AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, i
 // P.reads_per_tile = reads per batch (<= 32), P.ntiles = batches, P.tiles_per_cta = batches per CTA (contiguous chunk).
 // WT = width of the count tile as a compile-time constant (0: P.wt, used by the emulation tests).
 // One CTA per SM.  Warps [0, nwarps - dwarps) work through the chunk's batches ([S]M[S] reads, phases A and B); every other
-// mapped read is appended to the CTA's segment of P.glist.  The last dwarps warps do nothing but the generic phase G over
-// that list while it is being filled (latency-bound, divergent code that hides behind the batch warps); the other
-// generic-capable warps help with what is left when their batches are done.  All of them count into the same tile.
+// mapped read is appended to the CTA's segment of P.glist.  The last dwarps warps (default: none) do nothing but the generic
+// phase G over that list while it is being filled; the generic-capable warps work through what is left when their batches
+// are done.  All of them count into the same tile.
 
 // window base of a CTA's chunk: smallest start among its first reads (coordinate-sorted input => of the whole chunk)
 AMP_WD int chunk_window_base(const KParams& P, int* ctrl, long long first_read, long long n_end, int tid, bool any) {
