@@ -217,8 +217,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]           # keep NCCL's version banner off stdout: rank 0 prints one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from amplipy_b200.batch import ReadBatch
     from amplipy_b200.engine import Engine
