@@ -138,17 +138,25 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_DEL_ROW 16
 #define AMP7_SINK_ROW 17
 #define AMP7_PAD 16              // bytes in front of the staged data (phase B may address up to 3 nibbles before it)
+#ifndef AMP7_QDATA
 #define AMP7_QDATA 5120          // staged quality bytes per batch (32 x 150 + alignment)
+#endif
+#ifndef AMP7_SDATA
 #define AMP7_SDATA 2560
+#endif
 #define AMP7_QSLACK 32           // the word-wise passes read up to 16 bytes past a run
 #define AMP7_SSLACK 32
 #define AMP7_QBUF (AMP7_PAD + AMP7_QDATA + AMP7_QSLACK)
 #define AMP7_SBUF (AMP7_PAD + AMP7_SDATA + AMP7_SSLACK)
+#ifndef AMP7_RUNCAP
 #define AMP7_RUNCAP 80           // run descriptors per warp (generic path)
+#endif
 #define AMP7_QCAP 32             // generic-path reads per warp and round
 #define AMP7_GSLOT_Q 192         // G phase: bytes per staged quality row slot
 #define AMP7_GSLOT_S 96
+#ifndef AMP7_GN
 #define AMP7_GN 26               // reads per G phase (GN * GSLOT <= DATA)
+#endif
 #define AMP7_CROW 9              // generic path: CIGAR ops (+3) per shared-memory row; two rows per read (odd stride: no bank conflicts)
 #define AMP7_GEXTRA_BYTES (AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + AMP7_GN * 2 * AMP7_CROW * 4)   // generic phase: runs, queue, counters, CIGAR rows
 #define AMP7_PSLICE 640          // positions of the two primer tables kept in shared memory, from the window base
