@@ -242,3 +242,12 @@ def test_long_reads_vs_oracle(oracle_lib):
     prim = [(s, e) for s, e, _ in primers]
     assert int(b.n_cigar.max()) > 100 and int(b.l_seq.max()) > 5000
     _against_oracle(oracle_lib, b, g, prim, mq=15, ins_slots=1 << 20, arena=64 << 20)
+
+
+def test_longer_short_reads_vs_oracle(oracle_lib):
+    """250- and 301-bp reads through the warp-autonomous kernel: fewer reads per batch, aligned runs that need all
+    thirty-two 8-window blocks, and runs beyond them that take the generic phase."""
+    g, prim, amps = _scheme(seed=5)
+    for n, seed, rl in ((60_000, 51, 250), (30_000, 52, 301)):
+        b = synth.illumina_batch(g, amps, n, seed=seed, read_len=rl)
+        _against_oracle(oracle_lib, b, g, prim)
