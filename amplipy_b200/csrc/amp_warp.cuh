@@ -744,9 +744,9 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
     }
     AMP7_TICK(tk, 5);
     if (warp < n_fast) { fence_block(); if (lane == 0) atomic_add(&ctrl[C7_FASTDONE], 1); }   // this warp appends no more
-    // ---- G: the reads of the list.  The dedicated warps have been here from the start and take AMP7_GN reads whenever that
-    // many are waiting; the other generic-capable warps join when their batches are done; once every batch warp is done the
-    // rest of the list is taken in whatever pieces are left.
+    // ---- G: the reads of the list.  A generic-capable warp comes here when its batches are done (a dedicated one, if there
+    // are any, at once) and takes AMP7_GN reads whenever that many are waiting; once every batch warp is done the rest of
+    // the list is taken in whatever pieces are left.
     if (warp >= nwarps - gwarps) {
         const WarpMem7 gm = carve_warp7(smem_base, wt, nwarps, gwarps, warp - (nwarps - gwarps));
         for (;;) {
