@@ -84,6 +84,96 @@ __global__ void amp_link_kernel(amp::InsSlot* slots, const unsigned int* entries
 // allele, the allele order (count, then python string order, descending: AmpliPy.py:771) from fifteen shuffles, the
 // position-level facts from ballots.
 #define AMP_CALL_LANES 16
+// Positions with more than ten insertion alleles (indel-rich data: every position of an ONT-like sample): the same
+// results as amp::call_position, with the sixteen lanes of the group sharing the allele list -- lane l owns entries
+// l, l + 16, ... and, for each, walks the whole list once to find its place in the reference's order; the fixed
+// symbols are owned by lanes 0..5.  All lanes walk the same addresses in the same order, so the loads are broadcasts.
+__device__ __forceinline__ bool ins_slot_greater(const amp::CallParams& P, int t, int ct, int c, const amp::Sym& me) {
+    return ct > c || (ct == c && amp::sym_cmp(amp::slot_sym(P, t), me) > 0);
+}
+__device__ __noinline__ void call_long_list(const amp::CallParams& P, long long gp, int sample, int p, int ch, int g0, unsigned gmask) {
+    constexpr int G = AMP_CALL_LANES;
+    const int* cnt = P.counts + (size_t)sample * AMP_NCH * P.Lpad;
+    const int head = P.heads[(size_t)sample * P.Lpad + p];
+    int cfix[AMP_NCH]; long long total = 0;
+#pragma unroll
+    for (int o = 0; o < AMP_NCH; ++o) { cfix[o] = cnt[(size_t)o * P.Lpad + p]; total += cfix[o]; }
+    for (int t = head; t >= 0;) { const amp::InsSlot sl = P.slots[t]; total += sl.count; t = sl.next; }
+    const unsigned char refsym = P.ref_seq[p];
+    int n_alt = 0, alt_fixed = 0;
+    int top_id = -1, top_c = 0;                 // set by the lane that owns the first allele of the order
+    int ref_key = -1, refc = 0; double reff = 0.0;   // 936-937: the last match in visiting order wins
+    if (ch < AMP_NCH) {
+        const int c = cfix[ch];
+        const double f = total ? (double)c / (double)total : 0.0;
+        int rank = -1;
+        if (c) {
+            amp::Sym me; me.p = kFixedSyms + ch; me.len = 1;
+            rank = 0;
+#pragma unroll
+            for (int o = 0; o < AMP_NCH; ++o)
+                if (o != ch && cfix[o]) { amp::Sym os; os.p = kFixedSyms + o; os.len = 1; if (amp::allele_greater(cfix[o], os, c, me)) ++rank; }
+            for (int t = head; t >= 0;) { const amp::InsSlot sl = P.slots[t]; if (sl.count && ins_slot_greater(P, t, sl.count, c, me)) ++rank; t = sl.next; }
+            if (rank == 0) { top_id = ch; top_c = c; }
+            if (kFixedSyms[ch] == refsym) { ref_key = ch; refc = c; reff = f; }
+            else if (f >= P.min_freq_variants) { alt_fixed = 1; ++n_alt; }                        // 938-939
+        }
+        P.fixed_freq[gp * AMP_NCH + ch] = f; P.fixed_rank[gp * AMP_NCH + ch] = rank;
+    }
+    int s = head;
+    for (int k = 0; k < ch && s >= 0; ++k) s = P.slots[s].next;
+    for (int j = ch; s >= 0; j += G) {
+        const int cs = P.slots[s].count;
+        if (cs) {
+            const amp::Sym me = amp::slot_sym(P, s);
+            const double f = (double)cs / (double)total;
+            int rank = 0;
+#pragma unroll
+            for (int o = 0; o < AMP_NCH; ++o)
+                if (cfix[o]) { amp::Sym os; os.p = kFixedSyms + o; os.len = 1; if (amp::allele_greater(cfix[o], os, cs, me)) ++rank; }
+            for (int t = head; t >= 0;) { const amp::InsSlot sl = P.slots[t]; if (t != s && sl.count && ins_slot_greater(P, t, sl.count, cs, me)) ++rank; t = sl.next; }
+            const int kk = P.slot_entry[s];
+            P.ins_freq[kk] = f; P.ins_rank[kk] = rank;
+            if (rank == 0) { top_id = 6 + kk; top_c = cs; }
+            unsigned char is_alt = 0;
+            if (me.len == 1 && me.p[0] == refsym) { if (AMP_NCH + j > ref_key) { ref_key = AMP_NCH + j; refc = cs; reff = f; } }
+            else if (f >= P.min_freq_variants) is_alt = 1;
+            P.ins_alt[kk] = is_alt; n_alt += is_alt;
+        }
+        for (int k = 0; k < G && s >= 0; ++k) s = P.slots[s].next;
+    }
+    // position-level facts
+    const unsigned lanes = (1u << G) - 1u;
+    const unsigned top_m = (__ballot_sync(gmask, top_id >= 0) >> g0) & lanes;
+    const unsigned alt_m = (__ballot_sync(gmask, alt_fixed != 0) >> g0) & lanes;
+    const int top_l = top_m ? __ffs((int)top_m) - 1 : 0;
+    top_id = __shfl_sync(gmask, top_id, g0 + top_l);
+    top_c = __shfl_sync(gmask, top_c, g0 + top_l);
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        n_alt += __shfl_xor_sync(gmask, n_alt, d);
+        const int k2 = __shfl_xor_sync(gmask, ref_key, d);
+        const int c2 = __shfl_xor_sync(gmask, refc, d);
+        const double f2 = __shfl_xor_sync(gmask, reff, d);
+        if (k2 > ref_key) { ref_key = k2; refc = c2; reff = f2; }
+    }
+    if (ch == 0) {
+        P.depth[gp] = (int)total;
+        P.top_id[gp] = top_m ? top_id : -1;
+        P.top_count[gp] = top_m ? top_c : 0;
+        unsigned char fl = 0;
+        if (top_m) {
+            const double bf = (double)top_c / (double)total;
+            if (top_c >= P.min_depth_consensus && bf >= P.min_freq_consensus) fl |= 1;            // 928
+        }
+        if (total > 0 && total >= P.min_depth_variants && n_alt != 0) {                           // 940
+            fl |= 2;
+            if (refc >= P.min_depth_variants && reff >= P.min_freq_variants) fl |= 4;             // 948
+        }
+        P.pos_flags[gp] = fl; P.ref_count[gp] = refc; P.alt_mask[gp] = (unsigned char)(alt_m & 0x3Fu);
+    }
+}
+
 __global__ void __launch_bounds__(256) amp_call_kernel(const amp::CallParams P) {
     constexpr int G = AMP_CALL_LANES, NINS = G - AMP_NCH;
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -100,7 +190,7 @@ __global__ void __launch_bounds__(256) amp_call_kernel(const amp::CallParams P) 
         s = P.slots[s].next;
     }
     if (s >= 0) {                                             // longer list (uniform within the group)
-        if (ch == 0) amp::call_position(P, kFixedSyms, gp);
+        call_long_list(P, gp, sample, p, ch, g0, gmask);
         return;
     }
     const int* cnt = P.counts + (size_t)sample * AMP_NCH * P.Lpad;
@@ -180,6 +270,11 @@ __global__ void amp_gather_entries_kernel(const amp::InsSlot* slots, const unsig
 struct RawText {
     const char* p;
     __device__ char operator()(int i) const { return p[i]; }
+    __device__ uint32_t word(int i, int len) const {
+        uint32_t w = 0;
+        for (int j = 0; j < 4 && i + j < len; ++j) w |= (uint32_t)(unsigned char)p[i + j] << (8 * j);
+        return w;
+    }
 };
 __global__ void amp_merge_kernel(amp::InsTable tab, long long n, const int* gpos, const int* count, const long long* str_off,
                                  const char* chars) {
@@ -256,7 +351,8 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
     const amp::TileCfg t = amp::pick_tile_cfg(b.n, sum_cig, sum_qual, mode);
     // short-read batches: warp-autonomous kernel.  AMP_KERNEL=tile forces the older CTA-phased kernel (A/B experiments).
     static const bool force_tile = [] { const char* e = getenv("AMP_KERNEL"); return e && !strcmp(e, "tile"); }();
-    if (!t.direct && !force_tile && sum_qual <= 1000 * b.n) {
+    static const bool force_warp = [] { const char* e = getenv("AMP_KERNEL"); return e && !strcmp(e, "warp"); }();
+    if (force_warp || (!t.direct && !force_tile && sum_qual <= 1000 * b.n)) {
         const amp::V7Cfg v = amp::pick_v7_cfg(b.n, sum_qual, c->sm_count);
         P.wt = v.wt; P.reads_per_tile = v.batch_reads;
         P.ntiles = (int)((b.n + v.batch_reads - 1) / v.batch_reads);

@@ -422,19 +422,46 @@ AMP_HD int window_del_len_w4(const uint8_t* q, int len, int minq, bool rev) {
     return rev ? window_del_len_rev(q, len - t, 4, minq) : window_del_len_fwd(q + t, len - t, 4, minq);
 }
 
+// Both strands of the sliding-window search in one loop: with s[t] = rev ? q[len-1-t] : q[t], window_del_len_fwd and
+// window_del_len_rev are the same scan over t and both return len - t at the first failing window.  Lanes of a warp
+// working on reads of either strand stay together in it.
+AMP_HD int window_del_len_any(const uint8_t* q, int len, int W, int minq, bool rev) {
+    if (len <= 0) return 0;
+    const int step = rev ? -1 : 1;
+    const uint8_t* s = rev ? q + len - 1 : q;
+    int w = W < len ? W : len;
+    int total = 0;
+    for (int j = 0; j < w; ++j) total += s[j * step];
+    for (int t = 0; t < len; ++t) {
+        if (total < minq * w) return len - t;
+        total -= s[t * step];
+        if (t + w < len) total += s[(t + w) * step]; else --w;
+    }
+    return 0;
+}
+
 // trim_read (426-687).  A holds the input CIGAR (capacity nc+3), B is scratch of the same capacity.
 // On return *res points at the buffer holding the final CIGAR.  Returns AMP_F_* bits.
 // qual_padded: the qualities sit in a staging buffer with readable slack around them (enables the word-wise search).
+// lanes != 0 (device, lane-per-read callers): the mask of lanes that entered together; they are brought together again
+// after each of the three steps, whose loops otherwise drift apart for the rest of the read (every lane named in the
+// mask passes every one of these points: the coordinate check only marks the read as bad instead of returning early).
 AMP_HD int trim_read(uint32_t* A, uint32_t* B, int& nc, int& pos, int flag, int tlen, int l_seq, const uint8_t* qual,
-                     bool qual_padded, const TrimParams& P, uint32_t** res) {
+                     bool qual_padded, const TrimParams& P, uint32_t** res, unsigned lanes = 0) {
+#ifdef __CUDA_ARCH__
+#define AMP_TR_SYNC() do { if (lanes) __syncwarp(lanes); } while (0)
+#else
+#define AMP_TR_SYNC() ((void)lanes)
+#endif
     uint32_t* src = A; uint32_t* dst = B;
     int ref_start = pos;
     const bool is_paired = flag & 1, is_reverse = (flag & 16) != 0;
     int ref_end = ref_start + ref_len_of(src, nc);
     *res = src;
-    if (ref_start < 0 || ref_start >= P.L || ref_end - 1 >= P.L) return AMP_F_ERROR;
-    const int left_max_primer_end = P.max_primer_end[ref_start];        // 450
-    const int right_min_primer_start = P.min_primer_start[ref_end - 1];  // 451
+    const bool bad = ref_start < 0 || ref_start >= P.L || ref_end - 1 >= P.L;
+    if (bad && !lanes) return AMP_F_ERROR;
+    const int left_max_primer_end = bad ? -1 : P.max_primer_end[ref_start];        // 450
+    const int right_min_primer_start = bad ? -1 : P.min_primer_start[ref_end - 1];  // 451
     const int abs_tlen = tlen < 0 ? -tlen : tlen;
     const bool isize_flag = (abs_tlen - P.max_primer_len) > l_seq;       // 452
     int out = 0;
@@ -447,6 +474,7 @@ AMP_HD int trim_read(uint32_t* A, uint32_t* B, int& nc, int& pos, int flag, int 
         nc = nd; { uint32_t* t = src; src = dst; dst = t; }
         ref_start += start_pos;                                                          // 514
     }
+    AMP_TR_SYNC();
     if (!(is_paired && isize_flag && !is_reverse) && right_min_primer_start >= 0) {      // 517
         out |= AMP_F_TRIM_END;
         int del_len = l_seq - get_pos_on_query(src, nc, right_min_primer_start, ref_start);   // 520
@@ -455,36 +483,33 @@ AMP_HD int trim_read(uint32_t* A, uint32_t* B, int& nc, int& pos, int flag, int 
         reverse_ops(dst, nd);
         nc = nd; { uint32_t* t = src; src = dst; dst = t; }
     }
+    AMP_TR_SYNC();
     const int qas = q_align_start(src, nc);
     int len = q_align_end(src, nc, l_seq) - qas;                                         // 561-563
     if (len < 0) len = 0;
     const bool w4 = qual_padded && P.window == 4;
-    const int win_del = w4 ? window_del_len_w4(qual + qas, len, P.min_quality, is_reverse) : 0;
-    if (is_reverse) {                                                                    // 566-625
-        int del_len = w4 ? win_del : window_del_len_rev(qual + qas, len, P.window, P.min_quality);
-        int sp = get_pos_on_ref(src, nc, del_len + qas - 1, ref_start);                  // 591
-        if (sp > ref_start) {
-            out |= AMP_F_TRIM_QUAL;
-            int nd = 0;
-            for (int k = 0; k < nc; ++k) qual_rewrite_op(src[k], del_len, dst, nd);
-            nc = nd; { uint32_t* t = src; src = dst; dst = t; }
-            // reference_start is NOT advanced (589-625)
-        }
-    } else {                                                                             // 628-686
-        int del_len = w4 ? win_del : window_del_len_fwd(qual + qas, len, P.window, P.min_quality);
-        if (del_len != 0) {
-            out |= AMP_F_TRIM_QUAL;
-            int nd = 0;
-            for (int k = nc - 1; k >= 0; --k) qual_rewrite_op(src[k], del_len, dst, nd);
-            reverse_ops(dst, nd);
-            nc = nd; { uint32_t* t = src; src = dst; dst = t; }
-        }
+    // 566-587 (reverse strand) / 628-649 (forward strand)
+    const int del_len0 = w4 ? window_del_len_w4(qual + qas, len, P.min_quality, is_reverse)
+                            : window_del_len_any(qual + qas, len, P.window, P.min_quality, is_reverse);
+    AMP_TR_SYNC();
+    // reverse strand: clip from the start iff it moves the first aligned position (591-594); reference_start is NOT
+    // advanced (589-625).  Forward strand: clip from the end iff del_len != 0 (656).
+    const bool clip = !bad && (is_reverse ? get_pos_on_ref(src, nc, del_len0 + qas - 1, ref_start) > ref_start : del_len0 != 0);
+    if (clip) {
+        out |= AMP_F_TRIM_QUAL;
+        int del_len = del_len0, nd = 0;
+        for (int k = 0; k < nc; ++k) qual_rewrite_op(src[is_reverse ? k : nc - 1 - k], del_len, dst, nd);   // 597-622 / 658-683
+        if (!is_reverse) reverse_ops(dst, nd);
+        nc = nd; { uint32_t* t = src; src = dst; dst = t; }
     }
+    AMP_TR_SYNC();
+    if (bad) return AMP_F_ERROR;
     if (ref_len_of(src, nc) >= P.min_length && ((out & (AMP_F_TRIM_START | AMP_F_TRIM_END)) || P.include_no_primer))
         out |= AMP_F_KEEP;                                                               // 910
     pos = ref_start;
     *res = src;
     return out;
+#undef AMP_TR_SYNC
 }
 
 // ---- register-only fast path for the dominant CIGAR shape [S] M [S] --------------------------------------
@@ -582,9 +607,15 @@ AMP_HD int emit_simple(const SimpleRead& r, uint32_t* out) {
 AMP_HD uint32_t nib_at(const uint8_t* seq, uint32_t idx) { return (seq[idx >> 1] >> ((~idx & 1u) << 2)) & 15u; }
 AMP_HD char nib_char(uint32_t nib) {
     // "=ACMGRSVTWYHKDBN"
+#ifdef __CUDA_ARCH__
+    const unsigned lo = __byte_perm(0x4D43413Du, 0x56535247u, nib & 7u);   // byte (nib & 7) of "=ACMGRSV"
+    const unsigned hi = __byte_perm(0x48595754u, 0x4E42444Bu, nib & 7u);   // ... of "TWYHKDBN"
+    return (char)((nib & 8u ? hi : lo) & 0xFFu);
+#else
     const unsigned long long lo = 0x565352474D43413DULL;  // "=ACMGRSV" little-endian bytes
     const unsigned long long hi = 0x4E42444B48595754ULL;  // "TWYHKDBN"
     return (char)(((nib < 8 ? lo : hi) >> ((nib & 7u) * 8u)) & 0xFFu);
+#endif
 }
 // channel of an aligned base: A C G T N -> 0..4, anything else -> -1
 AMP_HD int nib_channel(uint32_t nib) {
@@ -607,12 +638,18 @@ struct InsTable {
 AMP_HD unsigned long long mix64(unsigned long long h) {
     h ^= h >> 30; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 27; h *= 0x94D049BB133111EBULL; h ^= h >> 31; return h;
 }
-// text getter: ch(i) -> i-th character of the key
+// text getter: text(i) -> i-th character of the key; text.word(i, len) -> characters i .. i+3 packed little-endian
+// (i a multiple of 4, zero beyond len).  Keys are hashed, stored and compared a word at a time: insertion alleles that
+// run to the end of the read (exit (B) of the state machine) are hundreds of characters long.
 template <class Text>
 AMP_HD_NOINLINE void ins_table_add(const InsTable& T, int gpos, int len, const Text& text, int n) {
     unsigned long long h = 0xCBF29CE484222325ULL ^ (unsigned long long)(unsigned int)gpos;
     h *= 0x100000001B3ULL;
+#ifdef AMP_KEY_BYTEWISE
     for (int i = 0; i < len; ++i) { h ^= (unsigned char)text(i); h *= 0x100000001B3ULL; }
+#else
+    for (int i = 0; i < len; i += 4) { h ^= text.word(i, len); h *= 0x100000001B3ULL; }
+#endif
     h = mix64(h ^ ((unsigned long long)len << 32));
     const unsigned long long tag = (h >> 40) | 0x800000ULL;            // never zero
     unsigned long long slot = h & T.mask;
@@ -626,7 +663,11 @@ AMP_HD_NOINLINE void ins_table_add(const InsTable& T, int gpos, int len, const T
                 if (off + words > T.arena_words) { atomic_or(T.err, AMP_E_ARENA_FULL); return; }
                 unsigned char* rec = T.arena + off * 8;
                 ((int*)rec)[0] = gpos; ((unsigned int*)rec)[1] = (unsigned int)len;
+#ifdef AMP_KEY_BYTEWISE
                 for (int i = 0; i < len; ++i) rec[8 + i] = (unsigned char)text(i);
+#else
+                for (int i = 0; i < len; i += 4) ((unsigned int*)(rec + 8))[i >> 2] = text.word(i, len);   // records are padded to 8 bytes
+#endif
                 fence();
                 my_off = (long long)off;
             }
@@ -647,8 +688,13 @@ AMP_HD_NOINLINE void ins_table_add(const InsTable& T, int gpos, int len, const T
                 bool same = true;
                 for (int i = 0; i < len && same; i += 4) {
                     unsigned int w = ld_cg32((const unsigned int*)(rec + 8 + i));
+#ifdef AMP_KEY_BYTEWISE
                     for (int j = 0; j < 4 && i + j < len; ++j)
                         if ((unsigned char)(w >> (8 * j)) != (unsigned char)text(i + j)) { same = false; break; }
+#else
+                    if (len - i < 4) w &= (1u << (8 * (len - i))) - 1u;
+                    same = w == text.word(i, len);
+#endif
                 }
                 if (same) { atomic_add(&T.slots[slot].count, n); return; }
             }

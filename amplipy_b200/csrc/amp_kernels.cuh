@@ -48,9 +48,8 @@ struct TrimOut { int32_t* pos; uint16_t* ncig; uint8_t* flags; uint32_t* cigar; 
 #define AMP_MODE_TRIM 1
 #define AMP_MODE_PILEUP 2
 #ifndef AMP_CMAX
-#define AMP_CMAX 24
+#define AMP_CMAX 96      // CIGAR rows of up to 93 ops are rewritten in local memory (ONT-like reads: ~47 ops); longer ones in the global scratch
 #endif
-//         // CIGAR ops (+3) handled in per-thread local arrays; longer ones use global scratch
 
 struct KParams {
     BatchPtrs b;
@@ -182,6 +181,19 @@ struct TileSink {
     struct Text {
         const uint8_t* seq; int b;
         AMP_HD char operator()(int i) const { return nib_char(nib_at(seq, (uint32_t)(b + i))); }
+        AMP_HD uint32_t word(int i, int len) const {
+            // three independent byte loads cover the four nibbles wherever they start; none beyond the key's last byte
+            const uint32_t idx = (uint32_t)(b + i);
+            const uint8_t* a = seq + (idx >> 1);
+            const uint32_t m = len - i < 4 ? (uint32_t)(len - i) : 4u;
+            const uint32_t nb = ((idx + m - 1u) >> 1) - (idx >> 1);        // bytes after a[0] that hold key nibbles (0..2)
+            const uint32_t x = ((uint32_t)a[0] << 16) | ((nb >= 1u ? (uint32_t)a[1] : 0u) << 8) | (nb >= 2u ? (uint32_t)a[2] : 0u);
+            const uint32_t y = x >> ((idx & 1u) ? 4 : 8);              // nibbles idx .. idx+3 in bits 15..0, first one on top
+            uint32_t w = (uint32_t)(unsigned char)nib_char((y >> 12) & 15u) | ((uint32_t)(unsigned char)nib_char((y >> 8) & 15u) << 8) |
+                         ((uint32_t)(unsigned char)nib_char((y >> 4) & 15u) << 16) | ((uint32_t)(unsigned char)nib_char(y & 15u) << 24);
+            if (len - i < 4) w &= (1u << (8 * (len - i))) - 1u;
+            return w;
+        }
     };
     AMP_HD void ins(int pos, int b, int n) {
         if (n == 1) {   // one-character key == that base's own dict entry (AmpliPy.py:745-746)
@@ -254,6 +266,64 @@ struct DirectSink {
     }
 };
 
+// DirectSink in two steps.  Lanes of a warp reach the runs and insertions of their reads at different points of
+// plan_read's CIGAR walk, so counting inside the walk runs a lane or two at a time (ncu on ONT-like batches: 1.9
+// active lanes in the count loop, 1.1 in the insertion-table code).  Here the walk only records what it finds in
+// per-thread lists; replay() then counts every base of the read in one flat loop and adds the insertion alleles in
+// another, with the lanes of the warp together again.  Whatever does not fit a list takes DirectSink's immediate path.
+#ifndef AMP_REC_RUNS
+#define AMP_REC_RUNS 64
+#endif
+#ifndef AMP_REC_INS
+#define AMP_REC_INS 24
+#endif
+struct RecordSink {
+    DirectSink d;
+    int rp[AMP_REC_RUNS]; uint32_t ql[AMP_REC_RUNS];   // run: first reference position; (query index << 16) | deletion << 15 | length
+    int ip[AMP_REC_INS]; uint32_t ib[AMP_REC_INS];     // insertion allele: position; (first base << 16) | length
+    int nrun, nins, steps;
+    AMP_HD void match(int rpos, int q, int n) {
+        if (nrun < AMP_REC_RUNS && q < 65536 && n < 32768) { rp[nrun] = rpos; ql[nrun] = ((uint32_t)q << 16) | (uint32_t)n; ++nrun; steps += n; }
+        else d.match(rpos, q, n);
+    }
+    AMP_HD void del(int rpos, int n) {
+        if (nrun < AMP_REC_RUNS && n < 32768) { rp[nrun] = rpos; ql[nrun] = 0x8000u | (uint32_t)n; ++nrun; steps += n; }
+        else d.del(rpos, n);
+    }
+    AMP_HD void ins(int pos, int b, int n) {
+        if (nins < AMP_REC_INS && b < 65536 && n < 65536) { ip[nins] = pos; ib[nins] = ((uint32_t)b << 16) | (uint32_t)n; ++nins; }
+        else d.ins(pos, b, n);
+    }
+    AMP_HD void replay() {
+        const KParams& P = *d.P;
+        const int* lut = d.sm.ctrl + C_LUT;
+        int* cnt = d.sm.cnt;
+        const int minq = P.tp.min_quality, wbase = d.wbase, wt = P.wt;
+        int k = -1, j = 0, n = 0, rpos = 0, q = 0;
+        bool is_del = false, in_win = false;
+        for (int t = 0; t < steps; ++t, ++j) {
+            if (j == n) {                                                                 // next run (lengths are > 0)
+                ++k;
+                const uint32_t w = ql[k];
+                rpos = rp[k]; n = (int)(w & 0x7FFFu); q = (int)(w >> 16); is_del = (w & 0x8000u) != 0; j = 0;
+                in_win = wbase >= 0 && rpos >= wbase && rpos + n <= wbase + wt;
+            }
+            const int p = rpos + j;
+            if (is_del) {                                                                 // 714-715
+                if (in_win) atomic_add(cnt + 5 * wt + (p - wbase), 1); else atomic_add(&P.counts[(size_t)5 * P.Lpad + p], 1);
+                continue;
+            }
+            if (d.qual_read[q + j] < minq) continue;                                      // 718
+            const uint32_t nib = nib_at(d.seq_read, (uint32_t)(q + j));
+            if (in_win) { atomic_add(cnt + (p - wbase) + lut[nib], 1); continue; }        // 752-753 (row 6 = KeyError flag)
+            const int ch = nib_channel(nib);
+            if (ch < 0) { d.errs |= AMP_E_BASE; continue; }
+            atomic_add(&P.counts[(size_t)ch * P.Lpad + p], 1);
+        }
+        for (int e = 0; e < nins; ++e) d.ins(ip[e], (int)(ib[e] >> 16), (int)(ib[e] & 0xFFFFu));
+    }
+};
+
 // Everything a thread needs to know about the tile it is working on.
 struct TileCtx {
     long long t0; int nreads;
@@ -266,6 +336,13 @@ struct TileCtx {
 template <bool DIRECT>
 AMP_HD void read_generic(const KParams& P, const Smem& sm, const TileCtx& T, int rr, bool direct, int wbase) {
     const long long i = T.t0 + rr;
+#ifdef __CUDA_ARCH__
+    const unsigned lanes = __activemask();     // the lanes that entered together
+#define AMP_RECONVERGE(m) __syncwarp(m)
+#else
+    const unsigned lanes = 0;
+#define AMP_RECONVERGE(m) ((void)0)
+#endif
     const uint32_t c0 = P.b.cig_off[i], c1 = P.b.cig_off[i + 1];
     const uint32_t qo0 = P.b.qual_off[i], qo1 = P.b.qual_off[i + 1];
     const uint32_t so0 = P.b.seq_off[i], so1 = P.b.seq_off[i + 1];
@@ -286,16 +363,22 @@ AMP_HD void read_generic(const KParams& P, const Smem& sm, const TileCtx& T, int
         else { A = P.scratch + (size_t)c0 + 3 * (size_t)i; B = A + P.scratch_half; }
         for (int k = 0; k < nc; ++k) A[k] = cig[k];
         uint32_t* res;
-        f = trim_read(A, B, nc, pos, flag, P.b.tlen[i], l_seq, qual, q_st, P.tp, &res);
+        f = trim_read(A, B, nc, pos, flag, P.b.tlen[i], l_seq, qual, q_st, P.tp, &res, lanes);
         if (f & AMP_F_ERROR) { nc = 0; f = AMP_F_ERROR; atomic_or(P.err, AMP_E_COORD); }
         for (int k = 0; k < nc; ++k) orow[k] = res[k];
         cig = res;
         P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)nc; P.o.flags[i] = (uint8_t)f;
     }
-    if (DIRECT && T.do_pile && !(f & AMP_F_ERROR) && direct) {
-        DirectSink sink; sink.P = &P; sink.sm = sm; sink.wbase = wbase; sink.seq_read = seq; sink.qual_read = qual; sink.errs = 0;
-        int e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
-        e |= (int)sink.errs;
+    AMP_RECONVERGE(lanes);
+    if (DIRECT && T.do_pile && direct) {                  // uniform over the tile
+        RecordSink sink;
+        sink.d.P = &P; sink.d.sm = sm; sink.d.wbase = wbase; sink.d.seq_read = seq; sink.d.qual_read = qual; sink.d.errs = 0;
+        sink.nrun = sink.nins = sink.steps = 0;
+        int e = 0;
+        if (!(f & AMP_F_ERROR)) e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
+        AMP_RECONVERGE(lanes);
+        sink.replay();
+        e |= (int)sink.d.errs;
         if (e) atomic_or(P.err, (unsigned)e);
     } else if (T.do_pile && !(f & AMP_F_ERROR)) {
         TileSink sink; sink.P = &P; sink.sm = sm;

@@ -272,7 +272,15 @@ void emu_ins_export(void* h, int32_t* sample, int32_t* pos, int32_t* count, int6
         memcpy(chars + o, rec + 8, len); o += len; str_off[k + 1] = o;
     }
 }
-struct RawText { const char* p; char operator()(int i) const { return p[i]; } };
+struct RawText {
+    const char* p;
+    char operator()(int i) const { return p[i]; }
+    uint32_t word(int i, int len) const {
+        uint32_t w = 0;
+        for (int j = 0; j < 4 && i + j < len; ++j) w |= (uint32_t)(unsigned char)p[i + j] << (8 * j);
+        return w;
+    }
+};
 void emu_ins_merge(void* h, long long n, const int32_t* sample, const int32_t* pos, const int32_t* count, const int64_t* str_off,
                    const char* chars) {
     EmuCtx* c = (EmuCtx*)h;
