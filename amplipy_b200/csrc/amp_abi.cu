@@ -39,7 +39,7 @@ int fail(int code, const char* what, const char* detail = "") {
 #endif
 constexpr int kThreads = AMP_THREADS;
 #ifndef AMP_CTAS
-#define AMP_CTAS 3
+#define AMP_CTAS 4
 #endif
 constexpr int kCtasPerSm = AMP_CTAS;
 

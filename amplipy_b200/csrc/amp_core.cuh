@@ -617,6 +617,35 @@ AMP_HD char nib_char(uint32_t nib) {
     return (char)(((nib < 8 ? lo : hi) >> ((nib & 7u) * 8u)) & 0xFFu);
 #endif
 }
+// one packed byte -> the characters of its two bases (first base in the low byte): 256 x u16, constant memory on the device
+#define AMP_NIBPAIR_INIT \
+    0x3D3D, 0x413D, 0x433D, 0x4D3D, 0x473D, 0x523D, 0x533D, 0x563D, 0x543D, 0x573D, 0x593D, 0x483D, 0x4B3D, 0x443D, 0x423D, 0x4E3D, \
+    0x3D41, 0x4141, 0x4341, 0x4D41, 0x4741, 0x5241, 0x5341, 0x5641, 0x5441, 0x5741, 0x5941, 0x4841, 0x4B41, 0x4441, 0x4241, 0x4E41, \
+    0x3D43, 0x4143, 0x4343, 0x4D43, 0x4743, 0x5243, 0x5343, 0x5643, 0x5443, 0x5743, 0x5943, 0x4843, 0x4B43, 0x4443, 0x4243, 0x4E43, \
+    0x3D4D, 0x414D, 0x434D, 0x4D4D, 0x474D, 0x524D, 0x534D, 0x564D, 0x544D, 0x574D, 0x594D, 0x484D, 0x4B4D, 0x444D, 0x424D, 0x4E4D, \
+    0x3D47, 0x4147, 0x4347, 0x4D47, 0x4747, 0x5247, 0x5347, 0x5647, 0x5447, 0x5747, 0x5947, 0x4847, 0x4B47, 0x4447, 0x4247, 0x4E47, \
+    0x3D52, 0x4152, 0x4352, 0x4D52, 0x4752, 0x5252, 0x5352, 0x5652, 0x5452, 0x5752, 0x5952, 0x4852, 0x4B52, 0x4452, 0x4252, 0x4E52, \
+    0x3D53, 0x4153, 0x4353, 0x4D53, 0x4753, 0x5253, 0x5353, 0x5653, 0x5453, 0x5753, 0x5953, 0x4853, 0x4B53, 0x4453, 0x4253, 0x4E53, \
+    0x3D56, 0x4156, 0x4356, 0x4D56, 0x4756, 0x5256, 0x5356, 0x5656, 0x5456, 0x5756, 0x5956, 0x4856, 0x4B56, 0x4456, 0x4256, 0x4E56, \
+    0x3D54, 0x4154, 0x4354, 0x4D54, 0x4754, 0x5254, 0x5354, 0x5654, 0x5454, 0x5754, 0x5954, 0x4854, 0x4B54, 0x4454, 0x4254, 0x4E54, \
+    0x3D57, 0x4157, 0x4357, 0x4D57, 0x4757, 0x5257, 0x5357, 0x5657, 0x5457, 0x5757, 0x5957, 0x4857, 0x4B57, 0x4457, 0x4257, 0x4E57, \
+    0x3D59, 0x4159, 0x4359, 0x4D59, 0x4759, 0x5259, 0x5359, 0x5659, 0x5459, 0x5759, 0x5959, 0x4859, 0x4B59, 0x4459, 0x4259, 0x4E59, \
+    0x3D48, 0x4148, 0x4348, 0x4D48, 0x4748, 0x5248, 0x5348, 0x5648, 0x5448, 0x5748, 0x5948, 0x4848, 0x4B48, 0x4448, 0x4248, 0x4E48, \
+    0x3D4B, 0x414B, 0x434B, 0x4D4B, 0x474B, 0x524B, 0x534B, 0x564B, 0x544B, 0x574B, 0x594B, 0x484B, 0x4B4B, 0x444B, 0x424B, 0x4E4B, \
+    0x3D44, 0x4144, 0x4344, 0x4D44, 0x4744, 0x5244, 0x5344, 0x5644, 0x5444, 0x5744, 0x5944, 0x4844, 0x4B44, 0x4444, 0x4244, 0x4E44, \
+    0x3D42, 0x4142, 0x4342, 0x4D42, 0x4742, 0x5242, 0x5342, 0x5642, 0x5442, 0x5742, 0x5942, 0x4842, 0x4B42, 0x4442, 0x4242, 0x4E42, \
+    0x3D4E, 0x414E, 0x434E, 0x4D4E, 0x474E, 0x524E, 0x534E, 0x564E, 0x544E, 0x574E, 0x594E, 0x484E, 0x4B4E, 0x444E, 0x424E, 0x4E4E
+#ifdef __CUDACC__
+__device__ __constant__ uint16_t kNibPairDev[256] = {AMP_NIBPAIR_INIT};
+#endif
+static const uint16_t kNibPairHost[256] = {AMP_NIBPAIR_INIT};
+AMP_HD uint32_t nib_pair_chars(uint32_t byte) {
+#ifdef __CUDA_ARCH__
+    return kNibPairDev[byte & 255u];
+#else
+    return kNibPairHost[byte & 255u];
+#endif
+}
 // channel of an aligned base: A C G T N -> 0..4, anything else -> -1
 AMP_HD int nib_channel(uint32_t nib) {
     switch (nib) { case 1: return 0; case 2: return 1; case 4: return 2; case 8: return 3; case 15: return 4; default: return -1; }
@@ -645,15 +674,32 @@ template <class Text>
 AMP_HD_NOINLINE void ins_table_add(const InsTable& T, int gpos, int len, const Text& text, int n) {
     unsigned long long h = 0xCBF29CE484222325ULL ^ (unsigned long long)(unsigned int)gpos;
     h *= 0x100000001B3ULL;
-#ifdef AMP_KEY_BYTEWISE
-    for (int i = 0; i < len; ++i) { h ^= (unsigned char)text(i); h *= 0x100000001B3ULL; }
-#else
-    for (int i = 0; i < len; i += 4) { h ^= text.word(i, len); h *= 0x100000001B3ULL; }
+    long long my_off = -1;
+#ifndef AMP_KEY_SPEC
+#define AMP_KEY_SPEC 32
 #endif
+    if (len >= AMP_KEY_SPEC) {
+        // a key this long is almost always new (an insertion running into a deletion: the rest of the read): its record
+        // is written while it is hashed, one pass over the text instead of two; if the allele turns out to be known the
+        // record stays behind unused
+        const unsigned long long words = 1 + ((unsigned long long)len + 7) / 8;
+        const unsigned long long off = atomic_add64_warp(&T.cursor[0], words);
+        if (off + words > T.arena_words) { atomic_or(T.err, AMP_E_ARENA_FULL); return; }
+        unsigned char* rec = T.arena + off * 8;
+        ((int*)rec)[0] = gpos; ((unsigned int*)rec)[1] = (unsigned int)len;
+        for (int i = 0; i < len; i += 4) {
+            const unsigned int w = text.word(i, len);
+            ((unsigned int*)(rec + 8))[i >> 2] = w;
+            h ^= w; h *= 0x100000001B3ULL;
+        }
+        fence();
+        my_off = (long long)off;
+    } else {
+        for (int i = 0; i < len; i += 4) { h ^= text.word(i, len); h *= 0x100000001B3ULL; }
+    }
     h = mix64(h ^ ((unsigned long long)len << 32));
     const unsigned long long tag = (h >> 40) | 0x800000ULL;            // never zero
     unsigned long long slot = h & T.mask;
-    long long my_off = -1;
     for (unsigned long long probes = 0; probes <= T.mask; ++probes, slot = (slot + 1) & T.mask) {
         unsigned long long k = ld_cg64(&T.slots[slot].key);
         if (k == 0) {
@@ -663,11 +709,7 @@ AMP_HD_NOINLINE void ins_table_add(const InsTable& T, int gpos, int len, const T
                 if (off + words > T.arena_words) { atomic_or(T.err, AMP_E_ARENA_FULL); return; }
                 unsigned char* rec = T.arena + off * 8;
                 ((int*)rec)[0] = gpos; ((unsigned int*)rec)[1] = (unsigned int)len;
-#ifdef AMP_KEY_BYTEWISE
-                for (int i = 0; i < len; ++i) rec[8 + i] = (unsigned char)text(i);
-#else
                 for (int i = 0; i < len; i += 4) ((unsigned int*)(rec + 8))[i >> 2] = text.word(i, len);   // records are padded to 8 bytes
-#endif
                 fence();
                 my_off = (long long)off;
             }
@@ -688,13 +730,8 @@ AMP_HD_NOINLINE void ins_table_add(const InsTable& T, int gpos, int len, const T
                 bool same = true;
                 for (int i = 0; i < len && same; i += 4) {
                     unsigned int w = ld_cg32((const unsigned int*)(rec + 8 + i));
-#ifdef AMP_KEY_BYTEWISE
-                    for (int j = 0; j < 4 && i + j < len; ++j)
-                        if ((unsigned char)(w >> (8 * j)) != (unsigned char)text(i + j)) { same = false; break; }
-#else
                     if (len - i < 4) w &= (1u << (8 * (len - i))) - 1u;
                     same = w == text.word(i, len);
-#endif
                 }
                 if (same) { atomic_add(&T.slots[slot].count, n); return; }
             }

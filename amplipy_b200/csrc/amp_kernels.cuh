@@ -189,8 +189,7 @@ struct TileSink {
             const uint32_t nb = ((idx + m - 1u) >> 1) - (idx >> 1);        // bytes after a[0] that hold key nibbles (0..2)
             const uint32_t x = ((uint32_t)a[0] << 16) | ((nb >= 1u ? (uint32_t)a[1] : 0u) << 8) | (nb >= 2u ? (uint32_t)a[2] : 0u);
             const uint32_t y = x >> ((idx & 1u) ? 4 : 8);              // nibbles idx .. idx+3 in bits 15..0, first one on top
-            uint32_t w = (uint32_t)(unsigned char)nib_char((y >> 12) & 15u) | ((uint32_t)(unsigned char)nib_char((y >> 8) & 15u) << 8) |
-                         ((uint32_t)(unsigned char)nib_char((y >> 4) & 15u) << 16) | ((uint32_t)(unsigned char)nib_char(y & 15u) << 24);
+            uint32_t w = nib_pair_chars(y >> 8) | (nib_pair_chars(y) << 16);
             if (len - i < 4) w &= (1u << (8 * (len - i))) - 1u;
             return w;
         }
@@ -294,11 +293,10 @@ struct RecordSink {
         if (nins < AMP_REC_INS && b < 65536 && n < 65536) { ip[nins] = pos; ib[nins] = ((uint32_t)b << 16) | (uint32_t)n; ++nins; }
         else d.ins(pos, b, n);
     }
-    AMP_HD void replay() {
-        const KParams& P = *d.P;
-        const int* lut = d.sm.ctrl + C_LUT;
-        int* cnt = d.sm.cnt;
-        const int minq = P.tp.min_quality, wbase = d.wbase, wt = P.wt;
+    // cnt / lut: the CTA's tile and nibble -> row table, passed by the caller so that they stay shared-memory pointers
+    // (this struct lives in local memory: pointers read back from it would be generic, and so would the atomics)
+    AMP_HD void replay(const KParams& P, int* cnt, const int* lut, int wbase, const uint8_t* seq_read, const uint8_t* qual_read) {
+        const int minq = P.tp.min_quality, wt = P.wt;
         int k = -1, j = 0, n = 0, rpos = 0, q = 0;
         bool is_del = false, in_win = false;
         for (int t = 0; t < steps; ++t, ++j) {
@@ -313,8 +311,8 @@ struct RecordSink {
                 if (in_win) atomic_add(cnt + 5 * wt + (p - wbase), 1); else atomic_add(&P.counts[(size_t)5 * P.Lpad + p], 1);
                 continue;
             }
-            if (d.qual_read[q + j] < minq) continue;                                      // 718
-            const uint32_t nib = nib_at(d.seq_read, (uint32_t)(q + j));
+            if (qual_read[q + j] < minq) continue;                                        // 718
+            const uint32_t nib = nib_at(seq_read, (uint32_t)(q + j));
             if (in_win) { atomic_add(cnt + (p - wbase) + lut[nib], 1); continue; }        // 752-753 (row 6 = KeyError flag)
             const int ch = nib_channel(nib);
             if (ch < 0) { d.errs |= AMP_E_BASE; continue; }
@@ -377,7 +375,7 @@ AMP_HD void read_generic(const KParams& P, const Smem& sm, const TileCtx& T, int
         int e = 0;
         if (!(f & AMP_F_ERROR)) e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
         AMP_RECONVERGE(lanes);
-        sink.replay();
+        sink.replay(P, sm.cnt, sm.ctrl + C_LUT, wbase, seq, qual);
         e |= (int)sink.d.errs;
         if (e) atomic_or(P.err, (unsigned)e);
     } else if (T.do_pile && !(f & AMP_F_ERROR)) {
