@@ -251,3 +251,114 @@ def test_longer_short_reads_vs_oracle(oracle_lib):
     for n, seed, rl in ((60_000, 51, 250), (30_000, 52, 301)):
         b = synth.illumina_batch(g, amps, n, seed=seed, read_len=rl)
         _against_oracle(oracle_lib, b, g, prim)
+
+
+def _ins_table_arrays(ins, sample=None):
+    """Canonical array form of an insertion table: rows (sample, pos, len, count, FNV of the text), sorted."""
+    off = np.asarray(ins.str_off, np.int64)
+    ln = np.diff(off)
+    h = np.full(len(ln), 0xCBF29CE484222325, np.uint64)
+    ch = np.asarray(ins.chars, np.uint8)
+    with np.errstate(over="ignore"):
+        for j in range(int(ln.max()) if len(ln) else 0):      # column-wise over the strings (vectorised over alleles)
+            m = ln > j
+            h[m] = (h[m] ^ ch[off[:-1][m] + j].astype(np.uint64)) * np.uint64(0x100000001B3)
+    rows = np.stack([ins.sample.astype(np.int64), ins.pos.astype(np.int64), ln, ins.count.astype(np.int64), h.view(np.int64)], 1)
+    if sample is not None:
+        rows = rows[rows[:, 0] == sample]
+    return rows[np.lexsort(rows.T[::-1])]
+
+
+def test_full_depth_properties_cfg3():
+    """Config 3's shape (v4.1-like scheme with alt primers, 20 M reads, ~100,000x): one million seeded reads accumulated twenty
+    times into one context.  Counts and insertion counts scale by exactly 20 (no saturation / lost updates at that
+    depth), and calling is scale-invariant: count/total is the same rational, so the float64 frequencies, the allele
+    order and the consensus are bit-identical to the 1x sample."""
+    g, prim, amps = _scheme(seed=3, n_alt=10)
+    L = len(g)
+    b = synth.illumina_batch(g, amps, 1_000_000, seed=3)
+    tables = find_overlapping_primers(L, prim, 0)
+    mk = lambda: make_engine(ref_len=L, primer_tables=tables, max_primer_len=max_primer_len(prim))
+    e1 = mk()
+    e1.process(b)
+    c1 = e1.counts().astype(np.int64); i1 = _ins_table_arrays(e1.insertions())
+    r1 = e1.call(g, min_depth_consensus=10, min_depth_variants=1)
+    e20 = mk()
+    d = e20.upload(b)
+    for _ in range(20):
+        e20.process_device(d)
+    import torch
+    torch.cuda.synchronize()
+    c20 = e20.counts().astype(np.int64); i20 = _ins_table_arrays(e20.insertions())
+    assert int(c20.max()) > 50_000                                   # the depth the config is about
+    assert np.array_equal(c20, 20 * c1)
+    assert np.array_equal(i20[:, [0, 1, 2, 4]], i1[:, [0, 1, 2, 4]]) and np.array_equal(i20[:, 3], 20 * i1[:, 3])
+    r20 = e20.call(g, min_depth_consensus=10, min_depth_variants=1)
+    assert np.array_equal(r20.depth.astype(np.int64), 20 * r1.depth.astype(np.int64))
+    assert np.array_equal(r20.fixed_freq, r1.fixed_freq) and np.array_equal(r20.fixed_rank, r1.fixed_rank)
+    deep = r1.top_count >= 10                                        # consensus gate passes in both
+    assert np.array_equal(r20.top_id[deep], r1.top_id[deep]) and np.array_equal(r20.alt_mask, r1.alt_mask)
+    assert e20.error_flags() == 0
+
+
+def test_ont_properties_cfg4():
+    """Config 4's shape (ONT-like, indel-rich) at 500 k reads: host path == device path, accumulation in halves in reverse
+    order == one pass (counts and the whole insertion table), and the depth identity."""
+    import torch
+    g, prim, amps = _scheme()
+    L = len(g)
+    b = synth.ont_batch(g, amps, 500_000, seed=4)
+    tables = find_overlapping_primers(L, prim, 0)
+    mk = lambda: make_engine(ref_len=L, primer_tables=tables, max_primer_len=max_primer_len(prim), ins_slots=1 << 25,
+                             ins_arena_bytes=2 << 30)
+    e1 = mk()
+    t1 = e1.process(b)
+    c1 = e1.counts(); i1 = _ins_table_arrays(e1.insertions())
+    assert len(i1) > 100_000 and e1.error_flags() == 0
+    res = e1.call(g)
+    assert int(res.depth.astype(np.int64).sum()) == int(c1.astype(np.int64).sum()) + int(i1[:, 3].sum())
+    del e1
+    e2 = mk()
+    d = e2.upload(b)
+    h = b.n // 2
+    e2.process_device(d, first=h, n=b.n - h)
+    e2.process_device(d, first=0, n=h)
+    torch.cuda.synchronize()
+    t2 = e2.download_trim(b, d)
+    assert np.array_equal(e2.counts(), c1) and np.array_equal(_ins_table_arrays(e2.insertions()), i1)
+    assert np.array_equal(t1.pos, t2.pos) and np.array_equal(t1.flags, t2.flags) and np.array_equal(t1.ncig, t2.ncig)
+    for i in range(0, b.n, 257):
+        assert t1.cigartuples(i) == t2.cigartuples(i)
+    assert e2.error_flags() == 0
+
+
+def test_plate_384_samples_cfg5():
+    """Config 5's shape: 384 samples in one context (reduced to 3,000 reads per sample).  Every sample's count matrix and
+    insertion alleles equal a solo run of that sample (spot-checked), and one calling launch over the plate equals the
+    solo calls."""
+    g, prim, amps = _scheme()
+    L = len(g)
+    tables = find_overlapping_primers(L, prim, 0)
+    S = 384
+    plate = make_engine(ref_len=L, primer_tables=tables, max_primer_len=max_primer_len(prim), n_samples=S)
+    batches = {}
+    for i in range(S):
+        bi = synth.illumina_batch(g, amps, 3_000, seed=1000 + i, snvs=[(500 + 70 * i, "T", 0.6)])
+        plate.process(bi, sample=i)
+        if i in (0, 1, 191, 383):
+            batches[i] = bi
+    pins = plate.insertions()
+    pres = plate.call(g)
+    assert pres.depth.shape == (S * L,)
+    for i, bi in batches.items():
+        solo = make_engine(ref_len=L, primer_tables=tables, max_primer_len=max_primer_len(prim))
+        solo.process(bi)
+        assert np.array_equal(solo.counts(), plate.counts(i))
+        assert solo.insertions().as_dict() == pins.as_dict(i)
+        sres = solo.call(g)
+        sl = slice(i * L, (i + 1) * L)
+        for f in ("depth", "top_count", "pos_flags", "ref_count", "fixed_freq", "fixed_rank", "alt_mask"):
+            assert np.array_equal(getattr(pres, f)[sl], getattr(sres, f)), f
+        fixed = sres.top_id < 6                                       # insertion ids are table-order dependent
+        assert np.array_equal(pres.top_id[sl][fixed], sres.top_id[fixed])
+    assert plate.error_flags() == 0
