@@ -616,10 +616,9 @@ int amp_process_host(amp_ctx* c, const amp_batch* b, int mode, int sample, const
             if (trim) {
                 const size_t orows = (c1 - c0) + 3 * (size_t)n;
                 if ((rc = dev_grow(&d.o_cigar, &d.cap_ocigar, orows + 4))) return rc;
-                // the two global scratch rows per read are only touched by CIGARs too long for the kernels' on-chip rows
-                int max_nc = 0;
-                for (long long i = a; i < e; ++i) max_nc = std::max(max_nc, (int)(b->cig_off[i + 1] - b->cig_off[i]));
-                if (max_nc + 3 > AMP7_CROW && (rc = dev_grow(&d.scratch, &d.cap_scratch, 2 * (orows + 4)))) return rc;
+                // the two global scratch rows per read are only touched by CIGARs too long for the kernels' on-chip rows;
+                // they are allocated regardless (a scan of the chunk for its longest CIGAR would sit in front of the copies)
+                if ((rc = dev_grow(&d.scratch, &d.cap_scratch, 2 * (orows + 4)))) return rc;
             }
         }
         cudaStream_t st = d.stream;
@@ -791,24 +790,27 @@ int amp_call(amp_ctx* c, const char* ref_seq, const amp_call_params* p, const am
     int rc;
     if (ref_seq && (rc = amp_set_reference(c, ref_seq))) return rc;
     CK(cudaDeviceSynchronize());
-    if ((rc = amp_call_device(c, p, nullptr))) return rc;
-    CK(cudaDeviceSynchronize());
+    cudaStream_t st = c->chunk[0].stream;   // idle after the synchronize; copies queue behind the kernels on it
+    if ((rc = amp_call_device(c, p, st))) return rc;
     const size_t L = (size_t)c->cfg.ref_len, S = (size_t)c->cfg.n_samples, SL = S * L;
     unsigned long long cur[2];
-    CK(cudaMemcpy(cur, c->tab.cursor, 16, cudaMemcpyDeviceToHost));
-    const size_t K = (size_t)cur[1];
+    CK(cudaMemcpyAsync(cur, c->tab.cursor, 16, cudaMemcpyDeviceToHost, st));
     unsigned char* blk = c->d_call;
-    if (ho->depth) CK(cudaMemcpy(ho->depth, blk + c->o_depth, SL * 4, cudaMemcpyDeviceToHost));
-    if (ho->top_id) CK(cudaMemcpy(ho->top_id, blk + c->o_top, SL * 4, cudaMemcpyDeviceToHost));
-    if (ho->top_count) CK(cudaMemcpy(ho->top_count, blk + c->o_topc, SL * 4, cudaMemcpyDeviceToHost));
-    if (ho->pos_flags) CK(cudaMemcpy(ho->pos_flags, blk + c->o_fl, SL, cudaMemcpyDeviceToHost));
-    if (ho->ref_count) CK(cudaMemcpy(ho->ref_count, blk + c->o_refc, SL * 4, cudaMemcpyDeviceToHost));
-    if (ho->fixed_freq) CK(cudaMemcpy(ho->fixed_freq, blk + c->o_ff, SL * 6 * 8, cudaMemcpyDeviceToHost));
-    if (ho->fixed_rank) CK(cudaMemcpy(ho->fixed_rank, blk + c->o_fr, SL * 6 * 4, cudaMemcpyDeviceToHost));
-    if (ho->alt_mask) CK(cudaMemcpy(ho->alt_mask, blk + c->o_alt, SL, cudaMemcpyDeviceToHost));
-    if (K && ins_freq) CK(cudaMemcpy(ins_freq, blk + c->o_if, K * 8, cudaMemcpyDeviceToHost));
-    if (K && ins_rank) CK(cudaMemcpy(ins_rank, blk + c->o_ir, K * 4, cudaMemcpyDeviceToHost));
-    if (K && ins_alt) CK(cudaMemcpy(ins_alt, blk + c->o_ia, K, cudaMemcpyDeviceToHost));
+    // one queue of asynchronous copies and one wait: with page-locked destinations (amp_host_alloc) they run back to back
+    if (ho->depth) CK(cudaMemcpyAsync(ho->depth, blk + c->o_depth, SL * 4, cudaMemcpyDeviceToHost, st));
+    if (ho->top_id) CK(cudaMemcpyAsync(ho->top_id, blk + c->o_top, SL * 4, cudaMemcpyDeviceToHost, st));
+    if (ho->top_count) CK(cudaMemcpyAsync(ho->top_count, blk + c->o_topc, SL * 4, cudaMemcpyDeviceToHost, st));
+    if (ho->pos_flags) CK(cudaMemcpyAsync(ho->pos_flags, blk + c->o_fl, SL, cudaMemcpyDeviceToHost, st));
+    if (ho->ref_count) CK(cudaMemcpyAsync(ho->ref_count, blk + c->o_refc, SL * 4, cudaMemcpyDeviceToHost, st));
+    if (ho->fixed_freq) CK(cudaMemcpyAsync(ho->fixed_freq, blk + c->o_ff, SL * 6 * 8, cudaMemcpyDeviceToHost, st));
+    if (ho->fixed_rank) CK(cudaMemcpyAsync(ho->fixed_rank, blk + c->o_fr, SL * 6 * 4, cudaMemcpyDeviceToHost, st));
+    if (ho->alt_mask) CK(cudaMemcpyAsync(ho->alt_mask, blk + c->o_alt, SL, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const size_t K = (size_t)cur[1];
+    if (K && ins_freq) CK(cudaMemcpyAsync(ins_freq, blk + c->o_if, K * 8, cudaMemcpyDeviceToHost, st));
+    if (K && ins_rank) CK(cudaMemcpyAsync(ins_rank, blk + c->o_ir, K * 4, cudaMemcpyDeviceToHost, st));
+    if (K && ins_alt) CK(cudaMemcpyAsync(ins_alt, blk + c->o_ia, K, cudaMemcpyDeviceToHost, st));
+    if (K) CK(cudaStreamSynchronize(st));
     return AMP_OK;
 }
 

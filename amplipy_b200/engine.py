@@ -339,18 +339,37 @@ class Engine:
         _check(self.lib.amp_ins_merge(self._ctx, ctypes.c_int64(len(pos)), _ptr(sample), _ptr(pos), _ptr(count),
                                       _ptr(str_off), _ptr(chars)), "amp_ins_merge")
 
-    def call(self, ref_seq, min_depth_consensus=10, min_freq_consensus=0.0, min_depth_variants=1,
-             min_freq_variants=0.03, n_ins=None):
+    def _call_buffers(self, n_ins, pinned):
+        """Result arrays of ``call``: fresh numpy arrays, or (``pinned``) page-locked arrays owned by the engine and reused."""
         SL = self.n_samples * self.L
+        K = max(n_ins, 1)
+        spec = [((SL,), np.int32), ((SL,), np.int32), ((SL,), np.int32), ((SL,), np.uint8), ((SL,), np.int32),
+                ((SL, 6), np.float64), ((SL, 6), np.int32), ((SL,), np.uint8), ((K,), np.float64), ((K,), np.int32),
+                ((K,), np.uint8)]
+        if not pinned:
+            return [np.empty(sh, dt) if i < 8 else np.zeros(sh, dt) for i, (sh, dt) in enumerate(spec)]
+        import torch
+        cache = getattr(self, "_pinned_call", None)
+        if cache is None or cache[0] < K:
+            cap = max(K, 1024) * 2 if cache is not None else max(K, 1024)
+            tens = [torch.zeros(sh if i < 8 else (cap,), dtype=getattr(torch, np.dtype(dt).name), pin_memory=True)
+                    for i, (sh, dt) in enumerate(spec)]
+            cache = self._pinned_call = (cap, tens)
+        arrs = [t.numpy() for t in cache[1]]
+        for a in arrs[8:]:
+            a[:K] = 0
+        return arrs[:8] + [a[:K] for a in arrs[8:]]
+
+    def call(self, ref_seq, min_depth_consensus=10, min_freq_consensus=0.0, min_depth_variants=1,
+             min_freq_variants=0.03, n_ins=None, pinned=False):
+        """``pinned=True``: the result arrays are page-locked buffers owned by the engine (the device-to-host copies run
+        at full PCIe speed) and stay valid until the next ``call`` on this engine."""
         if n_ins is None:
             n = ctypes.c_int64(0)
             nch = ctypes.c_int64(0)
             _check(self.lib.amp_ins_count(self._ctx, ctypes.byref(n), ctypes.byref(nch)), "amp_ins_count")
             n_ins = int(n.value)
-        r = CallResult(self.L, self.n_samples, np.empty(SL, np.int32), np.empty(SL, np.int32), np.empty(SL, np.int32),
-                       np.empty(SL, np.uint8), np.empty(SL, np.int32), np.empty((SL, 6), np.float64),
-                       np.empty((SL, 6), np.int32), np.empty(SL, np.uint8), np.zeros(max(n_ins, 1), np.float64),
-                       np.zeros(max(n_ins, 1), np.int32), np.zeros(max(n_ins, 1), np.uint8))
+        r = CallResult(self.L, self.n_samples, *self._call_buffers(n_ins, pinned))
         co = AmpCallOut(_ptr(r.depth), _ptr(r.top_id), _ptr(r.top_count), _ptr(r.pos_flags), _ptr(r.ref_count),
                         _ptr(r.fixed_freq), _ptr(r.fixed_rank), _ptr(r.alt_mask))
         cp = AmpCallParams(int(min_depth_consensus), float(min_freq_consensus), int(min_depth_variants),

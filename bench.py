@@ -315,7 +315,7 @@ def main():
     def step_e2e():
         eng.reset()
         eng.process(pb, trim=True, pileup=True, out=pouts)
-        return eng.call(None)
+        return eng.call(None, pinned=True)
 
     for _ in range(2):
         res = step_e2e()
