@@ -174,7 +174,7 @@ __device__ __noinline__ void call_long_list(const amp::CallParams& P, long long 
     }
 }
 
-__global__ void __launch_bounds__(256) amp_call_kernel(const amp::CallParams P) {
+__global__ void __launch_bounds__(256) amp_call_kernel(const __grid_constant__ amp::CallParams P) {
     constexpr int G = AMP_CALL_LANES, NINS = G - AMP_NCH;
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long gp = t / G;
