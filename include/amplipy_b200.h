@@ -142,7 +142,9 @@ int amp_ins_merge(amp_ctx* ctx, int64_t n, const int32_t* sample, const int32_t*
                   const int64_t* str_off, const char* chars);
 
 /* Replaces alleles_from_counts + the calling loop (AmpliPy.py:756-771, 921-951) for every sample.
- * ref_seq: L raw FASTA characters.  Per-insertion-allele outputs are indexed like amp_ins_export. */
+ * ref_seq: L raw FASTA characters.  Per-insertion-allele outputs are indexed like amp_ins_export.
+ * The outputs are copied back as one queue of asynchronous copies followed by a single wait: destinations from
+ * amp_host_alloc (page-locked) receive them at full PCIe speed, pageable ones work but are staged by the driver. */
 int amp_call(amp_ctx* ctx, const char* ref_seq, const amp_call_params* p, const amp_call_out* host_out,
              double* ins_freq, int32_t* ins_rank, uint8_t* ins_alt);
 /* the same kernels without the device->host copies: reference characters are uploaded once, results stay
