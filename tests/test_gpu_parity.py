@@ -1,6 +1,7 @@
 """GPU (B200): parity of the CUDA path, called through the C ABI, against (1) the golden fixtures
 produced by the unmodified reference and (2) the oracle on larger seeded inputs; plus
-size-independent properties at the full config-2 size."""
+size-independent properties at the sizes of configs 2-5 (1 M reads; 20 M-read depth; 500 k ONT-like
+reads; a 384-sample plate)."""
 import numpy as np
 import pytest
 
