@@ -38,6 +38,9 @@
 struct uint4 { unsigned int x, y, z, w; };   // host emulation build only
 #endif
 
+#define AMP_PRAGMA_X(x) _Pragma(#x)
+#define AMP_UNROLL_N(n) AMP_PRAGMA_X(unroll n)
+
 namespace amp {
 
 enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };
@@ -282,10 +285,11 @@ AMP_HD int window_del_len_rev(const uint8_t* q, int len, int W, int minq) {
 }
 
 // ---- word-at-a-time window search for the default width 4 ----------------------------------------
-AMP_HD unsigned funnel_r(unsigned lo, unsigned hi, unsigned sh) {   // low 32 bits of (hi:lo) >> sh, sh in [0, 31]
+AMP_HD unsigned funnel_r(unsigned lo, unsigned hi, unsigned sh) {   // low 32 bits of (hi:lo) >> (sh & 31)
 #ifdef __CUDA_ARCH__
     return __funnelshift_r(lo, hi, sh);
 #else
+    sh &= 31u;
     return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
 #endif
 }
@@ -362,6 +366,9 @@ AMP_HD int window_del_blocks(const uint8_t* buf, int a0, int m, bool rev, int mi
     unsigned Fw = 0;
     unsigned prev = A[1];
     unsigned u0 = funnel_r(A[0], prev, sh);
+#if defined(__CUDA_ARCH__) && defined(AMP_WINDOW_UNROLL)
+    AMP_UNROLL_N(AMP_WINDOW_UNROLL)
+#endif
     for (int i = 0; i < nb - 1; ++i) {
         const unsigned x1 = A[2 * i + 2], x2 = A[2 * i + 3];
         const unsigned u1 = funnel_r(prev, x1, sh), u2 = funnel_r(x1, x2, sh);
@@ -603,6 +610,154 @@ AMP_HD int emit_simple(const SimpleRead& r, uint32_t* out) {
     return n;
 }
 
+// ---- register-only closed form for  [H] [S] M [ (I|D) M ] [S] [H]  ------------------------------------------------------
+// The shapes short-read aligners produce for all but a fraction of a percent of the reads: one aligned run or two runs
+// around a single insertion / deletion, with optional soft and hard clips.  trim_read (426-687) and update_base_counts
+// (690-753) are evaluated symbolically on the seven lengths:
+//   primer clips : as for [S]M[S]; they must end strictly inside the outer aligned run on their side, otherwise the closed
+//                  form declines and the caller runs the generic trim_read (a hard clip on a clipped side is dropped, 481/505)
+//   quality clip : T query bases leave the aligned part from the end (forward) or the start (reverse, pos stays: F6),
+//                  whatever they cross: an insertion shrinks base by base (597-622: I -> S), a deletion survives only when the
+//                  clip stops exactly at it and is dropped as soon as it is crossed
+//   pileup       : up to two aligned runs, one deletion run, and the insertion state machine (730-748) over the k inserted
+//                  bases with its exits (A) next pair is a match, (C) next pair is the trailing clip, (D) low-quality base
+struct Shape5 {
+    int h1, s1, m, k, m2, s2, h2;   // lengths; k = 0: no indel left; m / m2 may reach 0 by clipping
+    uint32_t ops;                   // op code of the first run | of the second run << 4 | OP_I or OP_D << 8
+};
+AMP_HD uint32_t shape_xop(const Shape5& r) { return (r.ops >> 8) & 15u; }
+AMP_HD bool shape_is_ins(const Shape5& r) { return r.k > 0 && shape_xop(r) == OP_I; }
+AMP_HD bool shape_is_del(const Shape5& r) { return r.k > 0 && shape_xop(r) == OP_D; }
+AMP_HD int shape_qlen(const Shape5& r) { return r.m + r.m2 + (shape_is_ins(r) ? r.k : 0); }      // aligned query bases
+AMP_HD int shape_rlen(const Shape5& r) { return r.m + r.m2 + (shape_is_del(r) ? r.k : 0); }      // reference bases
+// classification from the first five CIGAR words held in registers (w_k is ignored for k >= nc)
+AMP_HD bool classify_shape5(int nc, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, int l_seq, Shape5& r) {
+    r.h1 = r.s1 = r.m = r.k = r.m2 = r.s2 = r.h2 = 0; r.ops = 0;
+    if (nc < 1 || nc > 5) return false;
+    if (nc < 5) w4 = 15u;            // op 15 matches nothing
+    if (nc < 4) w3 = 15u;
+    if (nc < 3) w2 = 15u;
+    if (nc < 2) w1 = 15u;
+    int used = 0;
+#define AMP_POP() do { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = 15u; ++used; } while (0)
+    if (c_op(w0) == OP_H) { r.h1 = c_len(w0); if (r.h1 < 1) return false; AMP_POP(); }
+    if (c_op(w0) == OP_S) { r.s1 = c_len(w0); if (r.s1 < 1) return false; AMP_POP(); }
+    if (!cons_qr(c_op(w0))) return false;
+    r.ops = c_op(w0); r.m = c_len(w0); if (r.m < 1) return false; AMP_POP();
+    if (c_op(w0) == OP_I || c_op(w0) == OP_D) {
+        r.ops |= c_op(w0) << 8; r.k = c_len(w0); if (r.k < 1) return false; AMP_POP();
+        if (!cons_qr(c_op(w0))) return false;
+        r.ops |= c_op(w0) << 4; r.m2 = c_len(w0); if (r.m2 < 1) return false; AMP_POP();
+    }
+    if (c_op(w0) == OP_S) { r.s2 = c_len(w0); if (r.s2 < 1) return false; AMP_POP(); }
+    if (c_op(w0) == OP_H) { r.h2 = c_len(w0); if (r.h2 < 1) return false; AMP_POP(); }
+#undef AMP_POP
+    return used == nc && r.s1 + shape_qlen(r) + r.s2 == l_seq;
+}
+// Steps 1-2 (primer start / end).  On success r / pos hold the shape after primer clipping.
+AMP_HD bool trim_shape_primers(Shape5& r, int& pos, int flag, int tlen, int l_seq, const TrimParams& P, int* flags_out) {
+    const int gap = shape_is_del(r) ? r.k : 0;
+    const int p = pos, ref_end = p + r.m + gap + r.m2;
+    if (p < 0 || ref_end > P.L) return false;
+    const bool paired = flag & 1, rev = (flag & 16) != 0;
+    const int L1 = P.max_primer_end[p];                                   // 450
+    const int R1 = P.min_primer_start[ref_end - 1];                       // 451
+    const int abs_tlen = tlen < 0 ? -tlen : tlen;
+    const bool isize = (abs_tlen - P.max_primer_len) > l_seq;             // 452
+    int pp = p, f = 0;
+    if (!(paired && isize && rev) && L1 >= 0) {                           // 460
+        const int d1 = L1 + 1 - p;                                        // one base past the primer (463)
+        if (d1 < 1 || d1 >= r.m) return false;
+        f |= AMP_F_TRIM_START; r.s1 += d1; r.m -= d1; pp += d1; r.h1 = 0;
+    }
+    if (!(paired && isize && !rev) && R1 >= 0) {                          // 517
+        if (r.k == 0) {
+            const int e = R1 - pp;                                        // aligned bases that stay
+            if (e < 1 || e >= r.m) return false;
+            r.s2 += r.m - e; r.m = e;
+        } else {
+            const int e = R1 - (pp + r.m + gap);                          // bases of the second run that stay
+            if (e < 1 || e >= r.m2) return false;
+            r.s2 += r.m2 - e; r.m2 = e;
+        }
+        f |= AMP_F_TRIM_END; r.h2 = 0;
+    }
+    pos = pp; *flags_out = f;
+    return true;
+}
+// Step 3 (quality clip, given the window search result `del` over the aligned query bases) + the write gate (910).
+AMP_HD void trim_shape_finish(Shape5& r, int del, bool rev, const TrimParams& P, int* flags_io) {
+    int f = *flags_io;
+    if (rev ? del >= 2 : del != 0) {                                      // 591-594 / 656
+        f |= AMP_F_TRIM_QUAL;
+        const bool is_ins = shape_is_ins(r);
+        int T = del;
+        if (rev) {                                                        // from the start; pos stays (F6)
+            r.s1 += T;
+            if (T < r.m) r.m -= T;
+            else {
+                T -= r.m; r.m = 0;
+                if (r.k > 0) {
+                    if (is_ins) { if (T < r.k) { r.k -= T; T = 0; } else { T -= r.k; r.k = 0; } }
+                    else if (T > 0) r.k = 0;                              // a crossed deletion is dropped
+                }
+                r.m2 -= T;
+            }
+        } else {                                                          // from the end
+            r.s2 += T;
+            if (T < r.m2) r.m2 -= T;
+            else {
+                T -= r.m2; r.m2 = 0;
+                if (r.k > 0) {
+                    if (is_ins) { if (T < r.k) { r.k -= T; T = 0; } else { T -= r.k; r.k = 0; } }
+                    else if (T > 0) r.k = 0;
+                }
+                r.m -= T;
+            }
+        }
+        if (r.m <= 0 && r.k == 0 && r.m2 > 0) { r.m = r.m2; r.m2 = 0; r.ops = (r.ops & ~15u) | ((r.ops >> 4) & 15u); }
+    }
+    const int rl = shape_rlen(r);
+    const int ref_len = rl > 0 ? rl : 1;
+    if (ref_len >= P.min_length && ((f & (AMP_F_TRIM_START | AMP_F_TRIM_END)) || P.include_no_primer)) f |= AMP_F_KEEP;   // 910
+    *flags_io = f;
+}
+// final CIGAR; an emptied aligned part leaves one merged soft clip (fix_cigar)
+AMP_HD int emit_shape5(const Shape5& r, uint32_t* out) {
+    int n = 0;
+    if (r.h1 > 0) out[n++] = c_pack(OP_H, r.h1);
+    if (r.m <= 0 && r.k <= 0 && r.m2 <= 0) out[n++] = c_pack(OP_S, r.s1 + r.s2);
+    else {
+        if (r.s1 > 0) out[n++] = c_pack(OP_S, r.s1);
+        if (r.m > 0) out[n++] = c_pack(r.ops & 15u, r.m);
+        if (r.k > 0) out[n++] = c_pack(shape_xop(r), r.k);
+        if (r.m2 > 0) out[n++] = c_pack((r.ops >> 4) & 15u, r.m2);
+        if (r.s2 > 0) out[n++] = c_pack(OP_S, r.s2);
+    }
+    if (r.h2 > 0) out[n++] = c_pack(OP_H, r.h2);
+    return n;
+}
+// the insertion alleles of the final shape (730-748); emit(pos, first base, length) as plan_read's sink.ins.
+// qual = the read's qualities (query index 0 at qual[0]).
+template <class Emit>
+AMP_HD void shape_ins_events(const Shape5& r, int pos, int l_seq, const uint8_t* qual, int minq, Emit& emit) {
+    if (!shape_is_ins(r)) return;
+    const int qI = r.s1 + r.m, rI = pos + r.m, qend = qI + r.k;
+    const int rl = r.m + r.m2;
+    int anchor = pos + (rl > 0 ? rl : 1) - 1; if (anchor < 0) anchor = 0;        // max(reference_end - 1, 0)
+    int q0 = -1;
+    for (int j = qI; j < qend; ++j) {
+        const bool pass = qual[j] >= minq;
+        if (q0 < 0) { if (pass) q0 = j; }                                        // 718 / 732
+        else if (!pass) { emit(anchor, q0 - 1, j - (q0 - 1)); q0 = -1; }         // exit (D)
+    }
+    if (q0 < 0) return;
+    if (r.m2 > 0) {                                                              // exit (A) / (A')
+        if (rI == 0) { const int e = qend + 1 < l_seq ? qend + 1 : l_seq; emit(0, q0, e - q0); }
+        else emit(rI - 1, q0 - 1, qend - (q0 - 1));
+    } else emit(anchor, q0 - 1, qend - (q0 - 1));                                // exit (C): the trailing clip follows
+}
+
 // ---- sequence access: BAM 4-bit nibbles, high nibble first ---------------------------------------
 AMP_HD uint32_t nib_at(const uint8_t* seq, uint32_t idx) { return (seq[idx >> 1] >> ((~idx & 1u) << 2)) & 15u; }
 AMP_HD char nib_char(uint32_t nib) {
@@ -750,21 +905,22 @@ AMP_HD int plan_read(const uint32_t* c, int nc, int pos, int l_seq, const uint8_
     const int qs = q_align_start(c, nc);                      // 700
     const int qe = q_align_end(c, nc, l_seq);                 // 701
     const int ref_end = pos + ref_len_of(c, nc);              // 705
-    if (pos < 0 || ref_end > L) return AMP_E_COORD;
-    {   // pysam pair list consistency: query-advancing ops (incl. P, as pysam 0.17 does) within l_seq
-        int qt = 0;
-        for (int k = 0; k < nc; ++k) { uint32_t op = c_op(c[k]); if (op > OP_X) return AMP_E_CIGAR; if (cons_q(op) || op == OP_P) qt += c_len(c[k]); }
-        if (qt > l_seq) return AMP_E_CIGAR;
-    }
+    // Errors are raised where the reference would raise them: a reference position outside the genome when it is indexed
+    // (a fully clipped read at pos == L indexes nothing), a query index past l_seq when its quality is looked up (a CIGAR
+    // whose P ops overrun the read still finishes through the break at 726 when the trailing clip comes first).
+    if (pos < 0) return AMP_E_COORD;
+    for (int k = 0; k < nc; ++k) if (c_op(c[k]) > OP_X) return AMP_E_CIGAR;
     int q = 0, r = pos, q0 = -1;   // q0 >= 0: an insertion event is open (730-734)
     // key slice [q0-1 : end) with python's negative-index wrap for q0 == 0
 #define AMP_KEY(end_, at_) do { int b_ = q0 - 1; if (b_ < 0) { b_ += l_seq; if (b_ < 0) b_ = 0; } \
         int e_ = (end_) < l_seq ? (end_) : l_seq; int n_ = e_ - b_; if (n_ < 0) n_ = 0; \
-        int p_ = (at_) - 1; if (p_ < 0) p_ = 0; sink.ins(p_, b_, n_); q0 = -1; } while (0)
+        int p_ = (at_) - 1; if (p_ < 0) p_ = 0; if (p_ >= L) return AMP_E_COORD; sink.ins(p_, b_, n_); q0 = -1; } while (0)
     for (int k = 0; k < nc; ++k) {
         const uint32_t op = c_op(c[k]); const int n = c_len(c[k]);
         if (op == OP_H || n == 0) continue;
         if (cons_qr(op)) {
+            if (r + n > L) return AMP_E_COORD;
+            if (q + n > l_seq) return AMP_E_CIGAR;
             if (q0 >= 0) {                                    // exit (A)/(A'): next pair is a match
                 if (r == 0) { int e_ = q + 1 < l_seq ? q + 1 : l_seq; sink.ins(0, q0, e_ - q0); q0 = -1; }   // 735-736
                 else AMP_KEY(q, r);
@@ -772,6 +928,7 @@ AMP_HD int plan_read(const uint32_t* c, int nc, int pos, int l_seq, const uint8_
             sink.match(r, q, n);
             q += n; r += n;
         } else if (op == OP_D || op == OP_N) {
+            if (r + n > L) return AMP_E_COORD;
             if (q0 >= 0) {                                    // exit (B): key runs to the end of the read
                 if (r == 0) return AMP_E_INS_END;             // None + 1 -> TypeError in the reference
                 AMP_KEY(l_seq, r);
@@ -783,6 +940,7 @@ AMP_HD int plan_read(const uint32_t* c, int nc, int pos, int l_seq, const uint8_
             if (q0 < 0 && j < qs) j = hi < qs ? hi : qs;      // rules 718/722 both skip: leading clip
             for (; j < hi; ++j) {
                 if (q0 < 0 && j >= qe) return 0;   // trailing clip: every later pair is skipped (718) or breaks (726)
+                if (j >= l_seq) return AMP_E_CIGAR;           // quality lookup past the read (IndexError, 718)
                 if (q0 >= 0) {
                     if (j >= qe) { AMP_KEY(j, ref_end); }                  // exit (C), pair consumed
                     else if (qual[j] < minq) { AMP_KEY(j, ref_end); }      // exit (D), pair consumed

@@ -34,6 +34,7 @@ namespace amp {
 // ---- warp / CTA primitives: hardware on the device, fibers in tests/emu -------------------------------------------
 #if defined(__CUDA_ARCH__)
 #define AMP_WD __device__ __forceinline__
+#define AMP_WD_COLD __device__ __noinline__            // rarely executed: kept out of the hot loops' instruction footprint
 AMP_WD int c_tid() { return (int)threadIdx.x; }
 AMP_WD int c_nthreads() { return (int)blockDim.x; }
 AMP_WD int c_block() { return (int)blockIdx.x; }
@@ -44,11 +45,18 @@ AMP_WD void w_sync() { __syncwarp(); }
 AMP_WD void c_sync() { __syncthreads(); }
 AMP_WD void c_yield() { __nanosleep(200); }                        // polite spin-wait
 AMP_WD int ld_vol(const int* p) { return *(const volatile int*)p; }
+AMP_WD void st_vol(int* p, int v) { *(volatile int*)p = v; }
 AMP_WD uint32_t ld_cg_u32(const uint32_t* p) { return __ldcg(p); }  // L2: entries written by another warp of the CTA
 AMP_WD void st_cg_u32(uint32_t* p, uint32_t v) { __stcg(p, v); }
 AMP_WD void fence_block() { __threadfence_block(); }
 AMP_WD int popc32(unsigned x) { return __popc(x); }
 AMP_WD unsigned byte_perm2(unsigned x, unsigned sel) { return __byte_perm(x, 0u, sel); }
+// prmt.b32 with the selector's replicate-sign bit honoured: nibble 8 + k = byte k's top bit over the whole byte
+AMP_WD unsigned prmt_sx(unsigned a, unsigned b, unsigned sel) {
+    unsigned r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
 AMP_WD uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 AMP_WD void mbar_init(unsigned long long* bar) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
@@ -79,11 +87,13 @@ AMP_WD void bulk_wait(unsigned long long* bar, uint32_t parity) {
 }
 #else
 #define AMP_WD inline
+#define AMP_WD_COLD inline
 // implemented by the fiber runtime in tests/emu/amp_emu.cpp
 int c_tid(); int c_nthreads(); int c_block();
 int w_shfl(int v, int src); unsigned w_ballot(bool p); int w_add(int v);
 void w_sync(); void c_sync(); void c_yield();
 AMP_WD int ld_vol(const int* p) { return *p; }
+AMP_WD void st_vol(int* p, int v) { *p = v; }
 AMP_WD uint32_t ld_cg_u32(const uint32_t* p) { return *p; }
 AMP_WD void st_cg_u32(uint32_t* p, uint32_t v) { *p = v; }
 AMP_WD void fence_block() {}
@@ -91,6 +101,16 @@ AMP_WD int popc32(unsigned x) { return __builtin_popcount(x); }
 AMP_WD unsigned byte_perm2(unsigned x, unsigned sel) {
     unsigned r = 0;
     for (int i = 0; i < 4; ++i) { const unsigned k = (sel >> (4 * i)) & 7u; r |= (k < 4 ? (x >> (8 * k)) & 0xFFu : 0u) << (8 * i); }
+    return r;
+}
+AMP_WD unsigned prmt_sx(unsigned a, unsigned b, unsigned sel) {
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned n = (sel >> (4 * i)) & 15u, k = n & 7u;
+        unsigned v = ((k < 4 ? a >> (8 * k) : b >> (8 * (k - 4))) & 0xFFu);
+        if (n & 8u) v = (v & 0x80u) ? 0xFFu : 0u;
+        r |= v << (8 * i);
+    }
     return r;
 }
 AMP_WD void mbar_init(unsigned long long*) {}
@@ -128,15 +148,14 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_WARPS 16            // warps per CTA of the fast kernel
 #endif
 #ifndef AMP7_GWARPS
-#define AMP7_GWARPS 14           // warps that can run the generic phase (their extra shared memory must fit): the last ones
+#define AMP7_GWARPS 8            // warps that can run the generic phase (their extra shared memory must fit): the last ones
 #endif
 #ifndef AMP7_DWARPS
 #define AMP7_DWARPS 0            // of those, warps that do nothing else (they work on the list while it is being filled)
 #endif
 #define AMP7_WT 512              // count tile width on the device (positions)
-#define AMP7_ROWS 18             // count tile rows: BAM nibble 0..15, row 16 = deleted base, row 17 = sink of masked bases
-#define AMP7_DEL_ROW 16
-#define AMP7_SINK_ROW 17
+#define AMP7_SINK_ROW 16         // count tile rows: BAM nibble 0..15, row 16 = sink of masked bases (never read), then the '-' row
+#define AMP7_SINK_SLACK 32       // the sink row is this much longer: masked bases of a run's last chunk land past the window's end
 #define AMP7_PAD 16              // bytes in front of the staged data (phase B may address up to 3 nibbles before it)
 #ifndef AMP7_QDATA
 #define AMP7_QDATA 5120          // staged quality bytes per batch (32 x 150 + alignment)
@@ -160,28 +179,39 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #define AMP7_CROW 9              // generic path: CIGAR ops (+3) per shared-memory row; two rows per read (odd stride: no bank conflicts)
 #define AMP7_GEXTRA_BYTES (AMP7_RUNCAP * 16 + AMP7_QCAP * 4 + 32 + AMP7_GN * 2 * AMP7_CROW * 4)   // generic phase: runs, queue, counters, CIGAR rows
 #define AMP7_PSLICE 640          // positions of the two primer tables kept in shared memory, from the window base
-enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_GNEXT = 3, C7_FASTDONE = 4, C7_PTAB = 16, C7_WORDS = 16 + 2 * AMP7_PSLICE };
+#ifndef AMP7_EVCAP
+#define AMP7_EVCAP 256           // insertion alleles of a CTA's reads wait here (three words each) until its batches are done
+#endif
+#ifndef AMP7_GLCAP
+#define AMP7_GLCAP 512           // reads for the generic phase listed in shared memory (whatever does not fit: P.glist)
+#endif
+enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_GNEXT = 3, C7_FASTDONE = 4, C7_NEV = 5, C7_PTAB = 16, C7_EV = C7_PTAB + 2 * AMP7_PSLICE,
+       C7_GL = C7_EV + 3 * AMP7_EVCAP, C7_WORDS = C7_GL + AMP7_GLCAP };
 
-// the sink row is the last one and 256 entries longer: masked bases of a run's last chunk increment it past the window's end
-AMP_HD size_t tile_bytes_v7(int wt) { return ((size_t)AMP7_ROWS * wt + 256) * 4; }
+AMP_HD int del_row_off(int wt) { return (AMP7_SINK_ROW + 1) * wt + AMP7_SINK_SLACK; }      // first element of the '-' row
+AMP_HD size_t tile_bytes_v7(int wt) { return ((size_t)(AMP7_SINK_ROW + 2) * wt + AMP7_SINK_SLACK) * 4; }
 AMP_HD size_t smem_bytes_v9(int wt, int warps, int gwarps);   // below
 
-// launch shape: reads per batch so that a batch's rows fit the staging buffers; one CTA per SM with a contiguous chunk
 // One aligned run of the count pass, fully decoded by its owner lane so that switching runs inside the chunk loop is cheap:
-//   x = aligned qbuf offset | quality funnel shift << 13 | sequence funnel shift << 18 | odd first nibble << 23 | chunks << 24
-//   y = aligned sbuf offset, z = tile position of chunk 0, w = first chunk in the batch's concatenation
-//   mk0/mk1 = byte masks of the last chunk's two quality words, mf0/mf1 = of the first chunk's (phi bases in front)
-struct Par4 { int x, y, z, w; unsigned mk0, mk1, mf0, mf1; };
-AMP_HD Par4 make_par(int a0, int n0, int m, int phi, int z, int w) {   // a0 / n0 / z: of the first of the m bases (incl. phi in front)
+//   a = aligned qbuf offset of chunk 0 | aligned sbuf offset << 16
+//   b = tile position of chunk 0 | chunks << 16 | odd first nibble << 24
+//   s = quality funnel shift (bits) | sequence funnel shift << 8,  w = first chunk in the batch's concatenation
+//   mka/mkb = byte masks of the last chunk's bases 0,2,4,6 / 1,3,5,7, mfa/mfb = of the first chunk's (phi bases in front)
+struct Par4 { unsigned a, b, s, w, mka, mkb, mfa, mfb; };
+AMP_WD Par4 make_par(int a0, int n0, int m, int phi, int z, int w) {   // a0 / n0 / z: of the first of the m bases (incl. phi in front)
     Par4 p;
     const int sb = n0 >> 1, nch = (m + 7) >> 3;
-    p.x = (a0 & ~3) | (((a0 & 3) << 3) << 13) | (((sb & 3) << 3) << 18) | ((n0 & 1) << 23) | (nch << 24);
-    p.y = sb & ~3; p.z = z; p.w = w;
+    p.a = (unsigned)(a0 & ~3) | ((unsigned)(sb & ~3) << 16);
+    p.b = (unsigned)z | ((unsigned)nch << 16) | ((unsigned)(n0 & 1) << 24);
+    p.s = (unsigned)((a0 & 3) << 3) | ((unsigned)((sb & 3) << 3) << 8);
+    p.w = (unsigned)w;
     const int left = m - 8 * (nch - 1);              // bases of the last chunk, 1 .. 8
-    p.mk0 = left >= 4 ? 0xFFFFFFFFu : (1u << (8 * left)) - 1u;
-    p.mk1 = left >= 8 ? 0xFFFFFFFFu : (left > 4 ? (1u << (8 * (left - 4))) - 1u : 0u);
-    p.mf0 = phi >= 4 ? 0u : 0xFFFFFFFFu << (8 * phi);
-    p.mf1 = phi > 4 ? 0xFFFFFFFFu << (8 * (phi - 4)) : 0xFFFFFFFFu;
+    const unsigned mk0 = left >= 4 ? 0xFFFFFFFFu : (1u << (8 * left)) - 1u;
+    const unsigned mk1 = left >= 8 ? 0xFFFFFFFFu : (left > 4 ? (1u << (8 * (left - 4))) - 1u : 0u);
+    const unsigned mf0 = phi >= 4 ? 0u : 0xFFFFFFFFu << (8 * phi);
+    const unsigned mf1 = phi > 4 ? 0xFFFFFFFFu << (8 * (phi - 4)) : 0xFFFFFFFFu;
+    p.mka = prmt_sx(mk0, mk1, 0x6420u); p.mkb = prmt_sx(mk0, mk1, 0x7531u);
+    p.mfa = prmt_sx(mf0, mf1, 0x6420u); p.mfb = prmt_sx(mf0, mf1, 0x7531u);
     return p;
 }
 struct V7Cfg { int wt, batch_reads; };
@@ -195,7 +225,7 @@ inline V7Cfg pick_v7_cfg(long long n, long long sum_qual, int sm_count) {
     return t;
 }
 
-// fast kernel: per-warp staging buffers, the per-read parameters of the count pass, and the bulk-copy barrier
+// fast kernel: per-warp staging buffers, the per-run parameters of the count pass, and the bulk-copy barrier
 #define AMP7_FAST_BYTES (AMP7_QBUF + AMP7_SBUF + 32 * 32 + 32 + 16)
 struct FastMem { uint8_t* qbuf; uint8_t* sbuf; Par4* par; uint8_t* own; unsigned long long* bar; };
 AMP_HD size_t smem_bytes_fast(int wt, int warps) { return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_FAST_BYTES; }
@@ -212,7 +242,7 @@ AMP_HD FastMem carve_fast(unsigned char* base, int wt, int w) {
 
 struct WarpMem7 {
     uint8_t* qbuf; uint8_t* sbuf; Seg* runs; uint32_t* queue; int* ctr; unsigned long long* bar; uint32_t* cig;
-    Par4* par; uint8_t* own;
+    Par4* par; uint8_t* own; int* ctrl;
 };
 AMP_HD size_t smem_bytes_v9(int wt, int warps, int gwarps) {
     return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_FAST_BYTES + (size_t)gwarps * AMP7_GEXTRA_BYTES;
@@ -227,15 +257,16 @@ AMP_HD WarpMem7 carve_warp7(unsigned char* base, int wt, int warps, int gwarps, 
     m.queue = (uint32_t*)b; b += AMP7_QCAP * 4;
     m.ctr = (int*)b; b += 32;
     m.cig = (uint32_t*)b;
+    m.ctrl = (int*)(base + tile_bytes_v7(wt));
     return m;
 }
 
-// channel of a tile row (nibble-indexed), -1 = not a countable base
-AMP_HD int row_channel(int row) { return row == AMP7_DEL_ROW ? 5 : nib_channel((uint32_t)row); }
+// channel of a nibble row, -1 = not a countable base
+AMP_HD int row_channel(int row) { return nib_channel((uint32_t)row); }
 
 // tile -> global count matrix; rows that are no base only raise the KeyError flag (AmpliPy.py:753)
 AMP_HD void flush_tile7(const KParams& P, const int* cnt, int wbase, int tid, int nthreads) {
-    for (int row = 0; row <= AMP7_DEL_ROW; ++row) {
+    for (int row = 0; row < AMP7_SINK_ROW; ++row) {
         const int ch = row_channel(row);
         for (int w = tid; w < P.wt; w += nthreads) {
             const int v = cnt[row * P.wt + w];
@@ -245,76 +276,111 @@ AMP_HD void flush_tile7(const KParams& P, const int* cnt, int wbase, int tid, in
             }
         }
     }
+    const int* del = cnt + del_row_off(P.wt);
+    for (int w = tid; w < P.wt; w += nthreads) {
+        const int v = del[w];
+        if (v) atomic_add(&P.counts[(size_t)5 * P.Lpad + wbase + w], v);
+    }
 }
 
-// ---- lane-per-read passes over a staged [S]M[S] read ---------------------------------------------------------------------
+// An insertion allele of a read: straight into the table, or (the CTA's list has room) parked until the CTA's batches are
+// done, when all of them are added with one thread each -- inside the per-read code an add would run with one lane active.
+AMP_HD void ins_commit(const KParams& P, const uint8_t* seq_read, int pos, int b, int n) {
+    if (n == 1) {   // one-character key == that base's own dict entry (AmpliPy.py:745-746)
+        const int ch = nib_channel(nib_at(seq_read, (uint32_t)b));
+        if (ch >= 0) { atomic_add(&P.counts[(size_t)ch * P.Lpad + pos], 1); return; }
+    }
+    TileSink::Text t; t.seq = seq_read; t.b = b;
+    ins_table_add(P.tab, P.gpos_base + pos, n, t, 1);
+}
+AMP_HD void ins_defer(const KParams& P, int* ctrl, uint32_t so0, int pos, int b, int n) {   // so0: the read's offset in P.b.seq
+    if (b < 65536 && n < 65536) {
+        const int idx = atomic_add(&ctrl[C7_NEV], 1);
+        if (idx < AMP7_EVCAP) { int* e = ctrl + C7_EV + 3 * idx; e[0] = pos; e[1] = (int)so0; e[2] = (int)((uint32_t)b | ((uint32_t)n << 16)); return; }
+    }
+    ins_commit(P, P.b.seq + so0, pos, b, n);
+}
+AMP_HD void ins_drain(const KParams& P, const int* ctrl, int tid, int nthreads) {
+    int nev = ctrl[C7_NEV]; if (nev > AMP7_EVCAP) nev = AMP7_EVCAP;
+    for (int k = tid; k < nev; k += nthreads) {
+        const int* e = ctrl + C7_EV + 3 * k;
+        ins_commit(P, P.b.seq + (uint32_t)e[1], e[0], (int)((uint32_t)e[2] & 0xFFFFu), (int)((uint32_t)e[2] >> 16));
+    }
+}
+
+// ---- lane-per-read passes over a staged read ---------------------------------------------------------------------------
 // `buf + a0` = first aligned quality byte (any alignment), m aligned bases, window width 4.  Both passes walk aligned
 // 4-byte words of the staging buffer and funnel-shift them to read-relative words; they read at most 16 bytes past the run.
 
 // Pileup of one aligned run (update_base_counts, AmpliPy.py:718 + 752-753) inside the count tile: quality byte t at
 // qbuf[a0 + t], base t = nibble n0 + t of sbuf, tile position tp0 + t, t in [0, m); this call covers the 8-base chunks
-// [c_lo, c_hi).  Per chunk: two quality words
-// -> SIMD byte compare q >= minq; one sequence word split into pre-scaled high / low nibbles so that one byte permute per
-// base yields the tile row offset; a masked base increments the sink row instead (no branch).  Lanes of a warp that work
-// on reads with the same start hit the same address and are merged by the hardware (ATOMS.POPC.INC).
+// [c_lo, c_hi).  Per chunk: two quality words -> SIMD byte compare q >= minq (bit 7 of each byte), spread by two
+// sign-replicating byte permutes into byte masks in the order of the base words; one sequence word split into pre-scaled
+// high / low nibbles (bases 0,2,4,6 / 1,3,5,7), masked bases replaced by the sink row's code with one logic op per word;
+// then per base one byte permute (row offset), one add, one shared-memory atomic.  Lanes of a warp that work on reads
+// with the same start hit the same address and are merged by the hardware (ATOMS.POPC.INC).
 //
 // The chunks of all runs of a batch are dealt out evenly: this lane walks chunks [g0, g1) of their concatenation,
 // starting inside run rr0 (par[] lists the decoded runs, .w = first chunk) and
 // moving on to the next run inside the loop, so every lane of the warp executes the same number of iterations.
 template <int WT>
-AMP_WD void count_chunks_v8(int* cnt, int wt, const uint8_t* qbuf, const uint8_t* sbuf, const Par4* par, int rr0, int g0, int g1,
+AMP_WD void count_chunks_v9(int* cnt, int wt, const uint8_t* qbuf, const uint8_t* sbuf, const Par4* par, int rr0, int g0, int g1,
                             unsigned minq4) {
-    int rr = rr0 - 1, c = 0, nch = 0;
+    int rr = rr0 - 1, rem = 0;                               // rem = chunks of the current run still to do
     const uint32_t* A = nullptr; const uint32_t* S = nullptr;
-    unsigned sh = 0, ssh = 0, qa = 0, sa = 0, x = 0, mk0 = 0, mk1 = 0, mf0 = 0, mf1 = 0;
+    unsigned sh = 0, ssh = 0, qa = 0, sa = 0, x = 0, mka = 0, mkb = 0, ma = 0xFFFFFFFFu, mb = 0xFFFFFFFFu;
     bool odd = false;
     int* tl = cnt;
+    const unsigned nminq4 = 0u - minq4;
 #if defined(__CUDA_ARCH__) && defined(AMP7_COUNT_UNROLL)
     AMP7_UNROLL(AMP7_COUNT_UNROLL)
 #endif
-    for (int g = g0; g < g1; ++g, ++c, tl += 8) {
-        if (c >= nch) {                                      // next run (first iteration: run rr0 at chunk g0)
+    for (int g = g0; g < g1; ++g) {
+        if (rem == 0) {                                      // next run: chunk g is its chunk g - w (0 unless it is the lane's first run)
             const Par4 pr = par[++rr];
-            nch = pr.x >> 24;
-            c = g == g0 ? g - pr.w : 0;
-            A = (const uint32_t*)(qbuf + (pr.x & 0x1FFC)); sh = (unsigned)(pr.x >> 13) & 31u;
-            S = (const uint32_t*)(sbuf + pr.y); ssh = (unsigned)(pr.x >> 18) & 31u;
-            odd = (pr.x >> 23) & 1;
-            qa = A[2 * c]; sa = S[c + 1]; x = funnel_r(S[c], sa, ssh);
-            tl = cnt + pr.z + 8 * c;
-            mk0 = pr.mk0; mk1 = pr.mk1; mf0 = pr.mf0; mf1 = pr.mf1;
+            const int c = g - (int)pr.w;
+            rem = (int)((pr.b >> 16) & 0xFFu) - c;
+            A = (const uint32_t*)(qbuf + (pr.a & 0xFFFFu)) + 2 * c; sh = pr.s;          // (funnel shifts use the low five bits)
+            S = (const uint32_t*)(sbuf + (pr.a >> 16)) + c; ssh = pr.s >> 8;
+            odd = (pr.b >> 24) != 0;
+            qa = A[0]; sa = S[1]; x = funnel_r(S[0], sa, ssh);
+            tl = cnt + (pr.b & 0xFFFFu) + 8 * c;
+            mka = pr.mka; mkb = pr.mkb;
+            ma = c == 0 ? pr.mfa : 0xFFFFFFFFu; mb = c == 0 ? pr.mfb : 0xFFFFFFFFu;
         }
-        const unsigned q1 = A[2 * c + 1], q2 = A[2 * c + 2];
+        const unsigned q1 = A[1], q2 = A[2];
         const unsigned v0 = funnel_r(qa, q1, sh), v1 = funnel_r(q1, q2, sh);
-        qa = q2;
-        const unsigned s2 = S[c + 2];
+        qa = q2; A += 2;
+        const unsigned s2 = S[2];
         const unsigned xn = funnel_r(sa, s2, ssh);          // sequence word of the next chunk
-        sa = s2;
+        sa = s2; S += 1;
         // q >= minq per byte (exact for every byte value, minq <= 127): bit 7 of each byte
-        unsigned k0 = (((v0 | 0x80808080u) - minq4) | v0) & 0x80808080u;
-        unsigned k1 = (((v1 | 0x80808080u) - minq4) | v1) & 0x80808080u;
-        k0 &= (c == nch - 1 ? mk0 : 0xFFFFFFFFu) & (c == 0 ? mf0 : 0xFFFFFFFFu);   // bases past / in front of the run
-        k1 &= (c == nch - 1 ? mk1 : 0xFFFFFFFFu) & (c == 0 ? mf1 : 0xFFFFFFFFu);
+        const unsigned t0 = ((v0 | 0x80808080u) + nminq4) | v0;
+        const unsigned t1 = ((v1 | 0x80808080u) + nminq4) | v1;
+        unsigned ka = prmt_sx(t0, t1, 0xECA8u) & ma, kb = prmt_sx(t0, t1, 0xFDB9u) & mb;   // 0xFF per passing base, in a / b order;
+        ma = 0xFFFFFFFFu; mb = 0xFFFFFFFFu;                                               // bases in front of the run masked
+        if (rem == 1) { ka &= mka; kb &= mkb; }             // bases past the run
         // nibbles scaled by 8, one per byte: E = bases at even nibble positions of x, O = odd ones
         const unsigned E = (x >> 1) & 0x78787878u, O = (x << 3) & 0x78787878u, En = (xn >> 1) & 0x78787878u;
-        const unsigned a = odd ? O : E;                      // bases 0, 2, 4, 6 of the chunk
-        const unsigned b = odd ? funnel_r(E, En, 8) : O;     // bases 1, 3, 5, 7
+        unsigned a = odd ? O : E;                            // bases 0, 2, 4, 6 of the chunk
+        unsigned b = odd ? funnel_r(E, En, 8) : O;           // bases 1, 3, 5, 7
         x = xn;
-#define AMP7_BASE(ii, src, kb, g)                                                                                      \
+        a = (a & ka) | (~ka & 0x80808080u);                  // masked bases: code 16 = the sink row
+        b = (b & kb) | (~kb & 0x80808080u);
+#define AMP7_BASE(ii, src, kbyte)                                                                                      \
         {                                                                                                              \
             if (WT == 512) {                                                                                           \
-                const unsigned off = byte_perm2(src, 0x4404u | ((kb) << 4));          /* nibble * 2048 bytes */         \
-                const unsigned o2 = ((g) & (0x80u << (8 * ((ii) & 3)))) ? off : (unsigned)(AMP7_SINK_ROW * 2048 + 64);  \
-                atomic_add((int*)((char*)tl + o2) + (ii), 1);                                                          \
+                const unsigned off = byte_perm2(src, 0x4404u | ((kbyte) << 4));       /* row * 2048 bytes */            \
+                atomic_add((int*)((char*)tl + off) + (ii), 1);                                                         \
             } else {                                                                                                   \
-                const unsigned row = ((src) >> (8 * (kb) + 3)) & 15u;                                                  \
-                const int o2 = ((g) & (0x80u << (8 * ((ii) & 3)))) ? (int)row * wt : AMP7_SINK_ROW * wt + 16;            \
-                atomic_add(tl + o2 + (ii), 1);                                                                         \
+                const unsigned row = ((src) >> (8 * (kbyte) + 3)) & 31u;                                               \
+                atomic_add(tl + (int)row * wt + (ii), 1);                                                              \
             }                                                                                                          \
         }
-        AMP7_BASE(0, a, 0, k0) AMP7_BASE(1, b, 0, k0) AMP7_BASE(2, a, 1, k0) AMP7_BASE(3, b, 1, k0)
-        AMP7_BASE(4, a, 2, k1) AMP7_BASE(5, b, 2, k1) AMP7_BASE(6, a, 3, k1) AMP7_BASE(7, b, 3, k1)
+        AMP7_BASE(0, a, 0) AMP7_BASE(1, b, 0) AMP7_BASE(2, a, 1) AMP7_BASE(3, b, 1)
+        AMP7_BASE(4, a, 2) AMP7_BASE(5, b, 2) AMP7_BASE(6, a, 3) AMP7_BASE(7, b, 3)
 #undef AMP7_BASE
+        tl += 8; --rem;
     }
 }
 
@@ -341,14 +407,14 @@ AMP_WD void count_runs_balanced(int* cnt, int wt, const uint8_t* qbuf, const uin
     }
     w_sync();
     const int g0 = lane * q, g1 = g0 + q < total ? g0 + q : total;
-    if (g0 < g1) count_chunks_v8<WT>(cnt, wt, qbuf, sbuf, par, own[lane], g0, g1, minq4);
+    if (g0 < g1) count_chunks_v9<WT>(cnt, wt, qbuf, sbuf, par, own[lane], g0, g1, minq4);
     w_sync();                                                                  // par / own may be rewritten
 }
 
 // ---- generic path inside a warp (same logic as TileSink / read_generic, warp-private run list) --------------------
 struct WarpSink7 {
     const KParams* P; WarpMem7 wm;
-    uint32_t qabs0, nibabs0; bool staged;
+    uint32_t qabs0, nibabs0, so0; bool staged;   // so0: the read's offset in P.b.seq
     const uint8_t* seq_read; const uint8_t* qual_read;
     unsigned int errs;
     AMP_HD void push(int rpos, int len_kind, int q) {
@@ -369,21 +435,15 @@ struct WarpSink7 {
     }
     AMP_HD void match(int rpos, int q, int n) { push(rpos, n, q); }
     AMP_HD void del(int rpos, int n) { push(rpos, (int)(0x80000000u | (unsigned)n), 0); }
-    AMP_HD void ins(int pos, int b, int n) {
-        if (n == 1) {   // one-character key == that base's own dict entry (AmpliPy.py:745-746)
-            const int ch = nib_channel(nib_at(seq_read, (uint32_t)b));
-            if (ch >= 0) { atomic_add(&P->counts[(size_t)ch * P->Lpad + pos], 1); return; }
-        }
-        TileSink::Text t; t.seq = seq_read; t.b = b;
-        ins_table_add(P->tab, P->gpos_base + pos, n, t, 1);
-    }
+    AMP_HD void ins(int pos, int b, int n) { ins_defer(*P, wm.ctrl, so0, pos, b, n); }
 };
 
-// one base outside the tile (or of an unstaged run): straight to the global matrix
+// one base outside the tile (or of an unstaged run): straight to the global matrix.  row = BAM nibble, or AMP7_DEL_CODE
+#define AMP7_DEL_CODE 17
 AMP_HD void count_global7(const KParams& P, int* cnt, int wbase, int row, int p, unsigned& errs) {
     const unsigned w = (unsigned)(p - wbase);
-    if (wbase >= 0 && w < (unsigned)P.wt) { atomic_add(&cnt[row * P.wt + (int)w], 1); return; }
-    const int ch = row_channel(row);
+    if (wbase >= 0 && w < (unsigned)P.wt) { atomic_add(&cnt[(row == AMP7_DEL_CODE ? del_row_off(P.wt) : row * P.wt) + (int)w], 1); return; }
+    const int ch = row == AMP7_DEL_CODE ? 5 : row_channel(row);
     if (ch < 0) { errs |= AMP_E_BASE; return; }
     atomic_add(&P.counts[(size_t)ch * P.Lpad + p], 1);
 }
@@ -403,8 +463,8 @@ AMP_WD void count_warp_runs7(const KParams& P, int* cnt, int wt, const WarpMem7&
             w0 = sg.rpos - wbase;
             const bool in_win = wbase >= 0 && w0 >= 0 && w0 + n <= wt;
             if (sg.len < 0) {                                                      // D / N run: unconditional (714-715)
-                if (in_win) { for (int j = 0; j < n; ++j) atomic_add(&cnt[AMP7_DEL_ROW * wt + w0 + j], 1); }
-                else for (int j = 0; j < n; ++j) count_global7(P, cnt, wbase, AMP7_DEL_ROW, sg.rpos + j, errs);
+                if (in_win) { for (int j = 0; j < n; ++j) atomic_add(&cnt[del_row_off(wt) + w0 + j], 1); }
+                else for (int j = 0; j < n; ++j) count_global7(P, cnt, wbase, AMP7_DEL_CODE, sg.rpos + j, errs);
             } else if ((sg.len & 0x40000000) && in_win && n > 0 && n < 512 && minq >= 0 && minq <= 127) {
                 a0 = (int)sg.qabs; n0 = (int)sg.nibabs; m = n; has = true;
             } else {
@@ -464,7 +524,7 @@ AMP_HD void warp_read_generic7(const KParams& P, const WarpMem7& wm, long long i
         sink.staged = q_st && s_st;
         sink.qabs0 = sink.staged ? qdst : qo0;
         sink.nibabs0 = sink.staged ? sdst * 2u : so0 * 2u;
-        sink.seq_read = seq; sink.qual_read = qual; sink.errs = 0;
+        sink.seq_read = seq; sink.qual_read = qual; sink.errs = 0; sink.so0 = so0;
         int e = plan_read(cig, nc, pos, l_seq, qual, P.tp.min_quality, P.tp.L, sink);
         e |= (int)sink.errs;
         if (e) atomic_or(P.err, (unsigned)e);
@@ -474,7 +534,7 @@ AMP_HD void warp_read_generic7(const KParams& P, const WarpMem7& wm, long long i
 
 // G phase: the first nb (<= AMP7_GN) queued reads of the warp
 template <int WT>
-AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, int wt, int wbase, int nb, int nq, int lane, bool do_trim,
+AMP_WD_COLD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, int wt, int wbase, int nb, int nq, int lane, bool do_trim,
                                bool do_pile, uint32_t& parity, long long* tk) {
     // stage the (scattered) rows into fixed slots, keeping each row's alignment mod 16: every lane starts the bulk copies
     // of its own read (whole 16-byte pieces, rounded up)
@@ -522,6 +582,18 @@ AMP_WD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* cnt, i
     w_sync();
 }
 
+// an aligned run of a staged read that does not lie inside the tile: base by base, exact (rare on coordinate-sorted input)
+AMP_WD_COLD void count_run_slow(const KParams& P, int* cnt, int wbase, const uint8_t* qrun, const uint8_t* sbuf, int nb0, int rpos, int m) {
+    const int minq = P.tp.min_quality;
+    unsigned errs = 0;
+    for (int t = 0; t < m; ++t) {
+        if (qrun[t] < minq) continue;                                              // 718
+        const uint32_t nb = (uint32_t)(nb0 + t);
+        count_global7(P, cnt, wbase, (int)((sbuf[nb >> 1] >> ((~nb & 1u) << 2)) & 15u), rpos + t, errs);   // 752-753
+    }
+    if (errs) atomic_or(P.err, errs);
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 // P.reads_per_tile = reads per batch (<= 32), P.ntiles = batches, P.tiles_per_cta = batches per CTA (contiguous chunk).
 // WT = width of the count tile as a compile-time constant (0: P.wt, used by the emulation tests).
@@ -562,11 +634,14 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
     long long g_hi = g_lo + P.tiles_per_cta; if (g_hi > P.ntiles) g_hi = P.ntiles;
     const int n_batches = g_hi > g_lo ? (int)(g_hi - g_lo) : 0;
     const long long n_end = P.b.first + P.b.n;
-    uint32_t* glist = P.glist + (size_t)block * P.gcap;
+    uint32_t* glist = P.glist + (size_t)block * P.gcap;          // overflow of the shared-memory list
 
-    if (PILE) for (int i = tid; i < (AMP7_DEL_ROW + 1) * wt; i += nthreads) cnt[i] = 0;   // the sink row is never read
-    if (tid == 0) { ctrl[C7_NEXT] = 0; ctrl[C7_NGEN] = 0; ctrl[C7_GNEXT] = 0; ctrl[C7_FASTDONE] = 0; }
-    for (long long k = tid; k < (long long)n_batches * BR; k += nthreads) st_cg_u32(&glist[k], 0u);   // list entries: 0 = not written yet
+    if (PILE) {                                                   // the sink row is never read
+        for (int i = tid; i < AMP7_SINK_ROW * wt; i += nthreads) cnt[i] = 0;
+        for (int i = tid; i < wt; i += nthreads) cnt[del_row_off(wt) + i] = 0;
+    }
+    if (tid == 0) { ctrl[C7_NEXT] = 0; ctrl[C7_NGEN] = 0; ctrl[C7_GNEXT] = 0; ctrl[C7_FASTDONE] = 0; ctrl[C7_NEV] = 0; }
+    for (int k = tid; k < AMP7_GLCAP; k += nthreads) ctrl[C7_GL + k] = 0;   // list entries: 0 = not written yet
     const int nwarps = nthreads >> 5, n_fast = nwarps - dwarps;     // warps [0, n_fast) take batches, the rest only the list
     if (lane == 0) mbar_init(wm.bar);
     const int wb = chunk_window_base(P, ctrl, P.b.first + g_lo * BR, n_end, tid, n_batches > 0);
@@ -594,7 +669,7 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
 
     // Software pipeline over the warp's batches: the per-read metadata of the next batch is loaded while the current one is
     // in its window pass, its first CIGAR words (and an L2 prefetch of its rows) while the current one is being counted.
-    struct Meta { uint32_t c0, c1, qo0, qo1, so0, so1; int flag, pos, tlen; uint32_t g0, g1, g2; };
+    struct Meta { uint32_t c0, c1, qo0, qo1, so0, so1; int flag, pos, tlen; uint32_t g0, g1, g2, g3, g4; };
     auto claim = [&]() -> int {
         int b = 0;
         if (lane == 0) b = atomic_add(&ctrl[C7_NEXT], 1);
@@ -614,17 +689,19 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
         M.flag = P.b.flag[i]; M.pos = P.b.pos[i];
         M.tlen = TRIM ? P.b.tlen[i] : 0;
     };
-    auto load_cigar3 = [&](Meta& M) {
+    auto load_cigar5 = [&](Meta& M) {
         const int nc = (int)(M.c1 - M.c0);
         M.g0 = nc > 0 ? P.b.cigar[M.c0] : 0u;
         M.g1 = nc > 1 ? P.b.cigar[M.c0 + 1] : 0u;
         M.g2 = nc > 2 ? P.b.cigar[M.c0 + 2] : 0u;
+        M.g3 = nc > 3 ? P.b.cigar[M.c0 + 3] : 0u;
+        M.g4 = nc > 4 ? P.b.cigar[M.c0 + 4] : 0u;
     };
     Meta M, Mn;
-    M.c0 = M.c1 = M.qo0 = M.qo1 = M.so0 = M.so1 = M.g0 = M.g1 = M.g2 = 0; M.flag = M.pos = M.tlen = 0;
+    M.c0 = M.c1 = M.qo0 = M.qo1 = M.so0 = M.so1 = M.g0 = M.g1 = M.g2 = M.g3 = M.g4 = 0; M.flag = M.pos = M.tlen = 0;
     Mn = M;
     int bi = warp < n_fast ? claim() : n_batches;
-    if (bi < n_batches) { load_meta(bi, M); load_cigar3(M); }
+    if (bi < n_batches) { load_meta(bi, M); load_cigar5(M); }
     while (bi < n_batches) {
         const long long t0 = P.b.first + (g_lo + bi) * BR;
         long long t1 = t0 + BR; if (t1 > n_end) t1 = n_end;
@@ -656,16 +733,19 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
         const int nc = (int)(c1 - c0), l_seq = (int)(qo1 - qo0);
         const uint32_t* cig = P.b.cigar + c0;
         const bool skipped = have && ((flag & 4) || nc == 0);                          // AmpliPy.py:902
-        SimpleRead r; r.s1 = 0; r.m = 0; r.s2 = 0; r.mop = 0;
+        Shape5 r = {0, 0, 0, 0, 0, 0, 0, 0u};
         int f = 0;
-        bool fast = have && !skipped && fast_ok && qo1 <= q_hi && (!PILE || so1 <= s_hi) && classify_simple3(nc, M.g0, M.g1, M.g2, l_seq, r);
+        bool fast = have && !skipped && fast_ok && qo1 <= q_hi && (!PILE || so1 <= s_hi) &&
+                    classify_shape5(nc, M.g0, M.g1, M.g2, M.g3, M.g4, l_seq, r);
         if (fast && TRIM) {   // both lookups (pos and reference_end - 1) inside the cached stretch?
-            const bool in_slice = pos >= pbase && pos + r.m <= pbase + AMP7_PSLICE;
-            fast = trim_simple_primers(r, pos, flag, tlen, l_seq, in_slice ? tps : P.tp, &f);
+            const bool in_slice = pos >= pbase && pos + shape_rlen(r) <= pbase + AMP7_PSLICE;
+            fast = trim_shape_primers(r, pos, flag, tlen, l_seq, in_slice ? tps : P.tp, &f);
         }
-        if (fast && !TRIM && (pos < 0 || pos + r.m > P.tp.L)) fast = false;
-        const uint32_t a0 = AMP7_PAD + (qo0 - q_lo) + (uint32_t)r.s1;                  // first aligned quality byte in qbuf
-        if (fast && (r.m < 8 || (int)(a0 & 3u) + r.m > 256)) fast = false;
+        if (fast && !TRIM && (pos < 0 || pos + shape_rlen(r) > P.tp.L)) fast = false;
+        const int qrow = (int)(AMP7_PAD + (qo0 - q_lo));                               // the read's first quality byte in qbuf
+        const int a0 = qrow + r.s1;                                                    // first aligned quality byte
+        const int qlen = shape_qlen(r);                                                // aligned query bases (561-563)
+        if (fast && (qlen < 8 || (a0 & 3) + qlen > 256)) fast = false;
         const bool rev = (flag & 16) != 0;
         // everything else goes to the CTA's list for the generic phase
         {
@@ -675,7 +755,11 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
                 int base = 0;
                 if (lane == 0) base = atomic_add(&ctrl[C7_NGEN], popc32(gmask));
                 base = w_shfl(base, 0);
-                if (gen) st_cg_u32(&glist[base + popc32(gmask & ((1u << lane) - 1u))], (uint32_t)(i - P.b.first) + 1u);   // 0 = not written yet
+                if (gen) {
+                    const int idx = base + popc32(gmask & ((1u << lane) - 1u));
+                    const uint32_t v = (uint32_t)(i - P.b.first) + 1u;                 // 0 = not written yet
+                    if (idx < AMP7_GLCAP) st_vol(&ctrl[C7_GL + idx], (int)v); else st_cg_u32(&glist[idx - AMP7_GLCAP], v);
+                }
             }
         }
         if (skipped && TRIM) {
@@ -693,38 +777,47 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
         const int bn = claim();                                        // next batch: its metadata loads fly during B1
         if (bn < n_batches) load_meta(bn, Mn);
 
-        // ---- B1: lane per read: window search, quality clip + write gate + outputs ---------------------------------------
-        bool in_tile = false;                                          // this lane's read is counted in the tile (pass B2)
-        int qa0 = 0, n0 = 0, w0 = 0;
+        // ---- B1: lane per read: window search, quality clip + write gate + outputs; the read's runs for pass B2 -------------
+        bool in1 = false, in2 = false;                                 // this lane's first / second aligned run is counted in the tile
+        int qa1 = 0, nb1 = 0, w1 = 0, m1 = 0, qa2 = 0, nb2 = 0, w2 = 0, m2 = 0;
         if (fast) {
             if (TRIM) {
-                const int del = window_del_blocks(wm.qbuf, (int)a0, r.m, rev, minq);
-                trim_simple_finish(r, del, rev, P.tp, &f);                            // 589-686 (pos stays on the reverse strand, F6), 910
+                const int del = window_del_blocks(wm.qbuf, a0, qlen, rev, minq);
+                trim_shape_finish(r, del, rev, P.tp, &f);                             // 589-686 (pos stays on the reverse strand, F6), 910
                 uint32_t* orow = P.o.cigar + (size_t)c0 + 3 * (size_t)i;
-                const int no = emit_simple(r, orow);
+                const int no = emit_shape5(r, orow);
                 P.o.pos[i] = pos; P.o.ncig[i] = (uint16_t)no; P.o.flags[i] = (uint8_t)f;
             }
-            if (PILE && r.m > 0) {
-                // final shape S(s1) M(m) S(s2) at pos: query base s1 + t sits on reference position pos + t
-                qa0 = (int)(AMP7_PAD + (qo0 - q_lo)) + r.s1;
-                n0 = (int)(2u * (AMP7_PAD + so0 - s_lo)) + r.s1;
-                w0 = pos - wbase;
-                if (wbase >= 0 && w0 >= 0 && w0 + r.m <= wt) {
-                    in_tile = true;
-                } else {   // outside the tile: base by base into the global matrix (exact, rare on sorted input)
-                    unsigned errs = 0;
-                    for (int t = 0; t < r.m; ++t) {
-                        if (wm.qbuf[qa0 + t] < minq) continue;
-                        const uint32_t nb = (uint32_t)(n0 + t);
-                        count_global7(P, cnt, wbase, (int)((wm.sbuf[nb >> 1] >> ((~nb & 1u) << 2)) & 15u), pos + t, errs);
+            if (PILE) {
+                // final shape [S] M [I|D] [M] [S] at pos: walk it as update_base_counts walks the aligned pairs
+                const int nrow = (int)(2u * (AMP7_PAD + so0 - s_lo));                 // nibble index of the read's first base in sbuf
+                unsigned errs = 0;
+                int q = r.s1, rp = pos;
+                m1 = r.m; qa1 = qrow + q; nb1 = nrow + q; w1 = rp - wbase;
+                q += r.m; rp += r.m;
+                if (r.k > 0) {
+                    if (shape_xop(r) == OP_D) {                                       // 714-715
+                        for (int j = 0; j < r.k; ++j) count_global7(P, cnt, wbase, AMP7_DEL_CODE, rp + j, errs);
+                        rp += r.k;
+                    } else {
+                        auto emit = [&](int ipos, int b, int n) { ins_defer(P, ctrl, so0, ipos, b, n); };
+                        shape_ins_events(r, pos, l_seq, wm.qbuf + qrow, minq, emit);  // 730-748
+                        q += r.k;
                     }
-                    if (errs) atomic_or(P.err, errs);
                 }
+                m2 = r.m2; qa2 = qrow + q; nb2 = nrow + q; w2 = rp - wbase;
+                if (m1 <= 0) { m1 = m2; qa1 = qa2; nb1 = nb2; w1 = w2; m2 = 0; }
+                in1 = m1 > 0 && wbase >= 0 && w1 >= 0 && w1 + m1 <= wt;
+                in2 = m2 > 0 && wbase >= 0 && w2 >= 0 && w2 + m2 <= wt;
+                // outside the tile: base by base into the global matrix (exact, rare on sorted input)
+                if (m1 > 0 && !in1) count_run_slow(P, cnt, wbase, wm.qbuf + qa1, wm.sbuf, nb1, w1 + wbase, m1);
+                if (m2 > 0 && !in2) count_run_slow(P, cnt, wbase, wm.qbuf + qa2, wm.sbuf, nb2, w2 + wbase, m2);
+                if (errs) atomic_or(P.err, errs);
             }
         }
         AMP7_TICK(tk, 3);
         if (bn < n_batches) {                                          // stage 2 of the next batch: CIGAR words, rows towards L2
-            load_cigar3(Mn);
+            load_cigar5(Mn);
             const long long tn0 = P.b.first + (g_lo + bn) * BR;
             long long tn1 = tn0 + BR; if (tn1 > n_end) tn1 = n_end;
             const uint32_t pq_lo = (uint32_t)w_shfl((int)Mn.qo0, 0) & ~15u, pq_hi = (uint32_t)w_shfl((int)Mn.qo1, (int)(tn1 - tn0) - 1);
@@ -737,16 +830,22 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
             }
         }
         // ---- B2: pileup of the batch's aligned runs, chunks dealt out evenly over the lanes ----------------------------------
-        if (PILE) count_runs_balanced<WT>(cnt, wt, wm.qbuf, wm.sbuf, wm.par, wm.own, lane, in_tile, qa0, n0, r.m, w0, minq4);
+        if (PILE) {   // (one call site: the loop body is the kernel's hottest code and should exist once)
+            const int npass = w_ballot(in2) ? 2 : 1;
+            for (int pass = 0; pass < npass; ++pass) {
+                count_runs_balanced<WT>(cnt, wt, wm.qbuf, wm.sbuf, wm.par, wm.own, lane, pass ? in2 : in1, pass ? qa2 : qa1, pass ? nb2 : nb1,
+                                        pass ? m2 : m1, pass ? w2 : w1, minq4);
+            }
+        }
         w_sync();   // every lane is done with the staged rows before the buffers are reused
         AMP7_TICK(tk, 4);
         M = Mn; bi = bn;
     }
     AMP7_TICK(tk, 5);
     if (warp < n_fast) { fence_block(); if (lane == 0) atomic_add(&ctrl[C7_FASTDONE], 1); }   // this warp appends no more
-    // ---- G: the reads of the list.  A generic-capable warp comes here when its batches are done (a dedicated one, if there
-    // are any, at once) and takes AMP7_GN reads whenever that many are waiting; once every batch warp is done the rest of
-    // the list is taken in whatever pieces are left.
+    // ---- G: the reads of the list.  A generic-capable warp comes here when its batches are done and takes up to AMP7_GN
+    // of the listed reads whenever there are any (it has nothing else to do); entries in shared memory may be taken while
+    // the list is still being filled, the overflow in global memory once every batch warp is done.
     if (warp >= nwarps - gwarps) {
         const WarpMem7 gm = carve_warp7(smem_base, wt, nwarps, gwarps, warp - (nwarps - gwarps));
         for (;;) {
@@ -755,8 +854,10 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
                 for (;;) {
                     const bool done = ld_vol(&ctrl[C7_FASTDONE]) >= n_fast;     // read before the counters: then they are final
                     const int reserved = ld_vol(&ctrl[C7_NGEN]), claimed = ld_vol(&ctrl[C7_GNEXT]);
-                    const int avail = reserved - claimed;
-                    if (avail >= AMP7_GN || (done && avail > 0)) {
+                    int avail = reserved - claimed;
+                    if (claimed < AMP7_GLCAP) { if (avail > AMP7_GLCAP - claimed) avail = AMP7_GLCAP - claimed; }
+                    else if (!done) avail = 0;
+                    if (avail > 0) {
                         n = avail < AMP7_GN ? avail : AMP7_GN;
                         if (atomic_cas(&ctrl[C7_GNEXT], claimed, claimed + n) == claimed) { at = claimed; break; }
                         continue;
@@ -767,9 +868,12 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
             }
             at = w_shfl(at, 0); n = w_shfl(n, 0);
             if (at < 0) break;
+            fence_block();
             if (lane < n) {
+                const int idx = at + lane;
                 uint32_t v;
-                while ((v = ld_cg_u32(&glist[at + lane])) == 0u) c_yield();     // reserved but not yet written
+                if (idx < AMP7_GLCAP) { while ((v = (uint32_t)ld_vol(&ctrl[C7_GL + idx])) == 0u) c_yield(); }   // reserved but not yet written
+                else v = ld_cg_u32(&glist[idx - AMP7_GLCAP]);
                 gm.queue[lane] = v - 1u;
             }
             w_sync();
@@ -779,6 +883,7 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
     AMP7_TICK(tk, 6);
     AMP7_TDUMP(tk, 0);
     c_sync();
+    if (PILE) ins_drain(P, ctrl, tid, nthreads);                   // the parked insertion alleles, one thread each
     if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);
 #if defined(__CUDA_ARCH__) && defined(AMP7_TIMING)
     if (tid == 0 && P.phase_cycles) {   // whole-CTA cycles: sum / min / max over CTAs

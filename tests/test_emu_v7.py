@@ -122,3 +122,50 @@ def test_register_classification_matches_array_form():
             assert lib.emu_classify_agree(ctypes.c_void_p(buf.ctypes.data), nc, l_seq) == 1, (ops, lens, l_seq)
         n_simple += nc >= 1 and all(o in (0, 4, 7, 8) for o in ops)
     assert n_simple > 1000
+
+
+def _weaken_qualities(b, seed):
+    """Weak windows / ends / whole rows at random places: quality clips that stop in front of, inside and beyond an indel."""
+    rng = np.random.default_rng(seed)
+    q = b.qual.copy()
+    for i in range(b.n):
+        lo, hi = int(b.qual_off[i]), int(b.qual_off[i + 1])
+        if hi - lo < 12:
+            continue
+        kind = rng.integers(0, 8)
+        if kind == 0:
+            p = rng.integers(lo, hi - 4); q[p:p + 4] = rng.integers(0, 25, 4)
+        elif kind == 1:
+            k = rng.integers(1, 4); q[hi - k:hi] = rng.integers(0, 20, k)
+        elif kind == 2:
+            k = rng.integers(1, 4); q[lo:lo + k] = rng.integers(0, 20, k)
+        elif kind == 3:
+            p = rng.integers(lo, hi - 4); q[p:p + 4] = [20, 20, 20, rng.integers(19, 22)]
+        elif kind == 4:
+            q[lo:hi] = rng.integers(15, 26, hi - lo)
+        elif kind == 5:    # single weak bases sprinkled over the row (inserted bases below the threshold, split insertions)
+            k = rng.integers(1, 12); q[rng.integers(lo, hi, k)] = rng.integers(0, 20, k)
+        elif kind == 6:    # everything weak
+            q[lo:hi] = rng.integers(0, 19, hi - lo)
+    b.qual[:] = q
+    return b
+
+
+@pytest.mark.parametrize("seed,mq", [(41, 20), (42, 20), (43, 30), (44, 5)])
+def test_single_indel_shapes_vs_oracle(oracle_lib, seed, mq):
+    """[H][S] M (I|D) M [S][H] reads are finished in registers like [S]M[S]: heavy indel / clip rates and quality patterns
+    that move the quality clip across the indel on both strands; they must stay on the cooperative path."""
+    g, prim, amps = _scheme(seed=seed % 3 + 2, n_alt=5 * (seed % 2))
+    b = synth.illumina_batch(g, amps, 12_000, seed=seed, p_ins=0.3, p_del=0.3, p_clip=0.3, p_hard=0.1, p_short=0.2)
+    b = _weaken_qualities(b, seed + 100)
+    emu_driver.v7_stats()
+    parity.check_against_oracle(v7(grid=3, warps=4), oracle_lib, b, g, prim, mq=mq)
+    fast, generic = emu_driver.v7_stats()
+    assert fast > 0.8 * b.n, (fast, generic)
+
+
+def test_many_generic_reads_overflow_the_shared_list(oracle_lib):
+    """Window width 6 sends every read down the generic path: the shared-memory list overflows into P.glist."""
+    g, prim, amps = _scheme(seed=3)
+    b = synth.illumina_batch(g, amps, 5_000, seed=45, p_ins=0.2, p_del=0.2)
+    parity.check_against_oracle(v7(grid=2, warps=3), oracle_lib, b, g, prim, w=6)
