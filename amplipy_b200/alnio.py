@@ -152,15 +152,22 @@ def _read_bam(raw, threads=0):
     buf = bgzf_decompress(raw, threads)
     if buf.size < 12 or bytes(buf[:4]) != b"BAM\x01":
         raise InputError("Invalid BAM file")
-    l_text = int(buf[4:8].view(np.int32)[0])
-    header_text = bytes(buf[8:8 + l_text]).split(b"\0", 1)[0].decode()
-    p = 8 + l_text
-    n_ref = int(buf[p:p + 4].view(np.int32)[0]); p += 4
-    refs = []
-    for _ in range(n_ref):
-        l_name = int(buf[p:p + 4].view(np.int32)[0]); p += 4
-        name = bytes(buf[p:p + l_name - 1]).decode(); p += l_name
-        refs.append((name, int(buf[p:p + 4].view(np.int32)[0]))); p += 4
+    try:
+        l_text = int(buf[4:8].view(np.int32)[0])
+        if l_text < 0 or 8 + l_text + 4 > buf.size:
+            raise ValueError
+        header_text = bytes(buf[8:8 + l_text]).split(b"\0", 1)[0].decode()
+        p = 8 + l_text
+        n_ref = int(buf[p:p + 4].view(np.int32)[0]); p += 4
+        refs = []
+        for _ in range(n_ref):
+            l_name = int(buf[p:p + 4].view(np.int32)[0]); p += 4
+            if l_name < 1 or p + l_name + 4 > buf.size:
+                raise ValueError
+            name = bytes(buf[p:p + l_name - 1]).decode(); p += l_name
+            refs.append((name, int(buf[p:p + 4].view(np.int32)[0]))); p += 4
+    except (ValueError, IndexError, UnicodeDecodeError):
+        raise InputError("Invalid BAM file")
     n = lib.amp_bam_scan(_p(buf), _ll(buf.size), _ll(p), None, None, None, _ll(0))
     if n < 0:
         raise InputError("Corrupt BAM record stream")

@@ -24,6 +24,7 @@ DEFAULT_MIN_QUALITY = 20
 DEFAULT_PRIMER_POS_OFFSET = 0
 DEFAULT_SLIDING_WINDOW_WIDTH = 4
 DEFAULT_UNKNOWN_SYMBOL = 'N'
+PROGRESS_NUM_READS = 50000          # AmpliPy.py:19
 
 # messages (AmpliPy.py:47-78)
 ERROR_TEXT_FILE_NOT_FOUND = "File not found"
@@ -206,7 +207,11 @@ def _run(untrimmed_reads_fn, primer_fn, reference_fn, trimmed_reads_fn, variants
     if variants_fn is not None:
         print_log("Output variants VCF: %s" % variants_fn)
         vcf.check_output_path(variants_fn)
+    import time as _time
+    tm = {}
+    _t = _time.perf_counter()
     aln = alnio.read_alignments(in_fn)
+    tm["decode"] = _time.perf_counter() - _t
     out_header = alnio.header_with_pg(aln.header_text, argv) if run_trim else None
 
     from .engine import Engine
@@ -219,10 +224,28 @@ def _run(untrimmed_reads_fn, primer_fn, reference_fn, trimmed_reads_fn, variants
                  ins_slots=(1 << 24) if indel_rich else 0, ins_arena_bytes=(1 << 30) if indel_rich else 0)
     print_log("Processing reads...")
     pile = run_variants or run_consensus
+    _t = _time.perf_counter()
     trim = eng.process(aln.batch, trim=run_trim, pileup=pile)
     eng.raise_on_device_errors()
+    tm["gpu_process"] = _time.perf_counter() - _t
+    # the reference reports its progress every PROGRESS_NUM_READS reads of its loop (AmpliPy.py:19, 898-899); the reads
+    # are processed as one batch here, so the same lines are written once the batch is through
+    for k in range(PROGRESS_NUM_READS, aln.n, PROGRESS_NUM_READS):
+        print_log("Processed %d reads..." % k)
+    writer = None
     if run_trim:
-        alnio.write_alignments(trimmed_reads_fn, aln, out_header, trim)
+        # the trimmed reads are encoded (record rewrite + BGZF deflate, both outside the GIL) while calling and the text outputs run
+        import threading
+        def _write():
+            t0 = _time.perf_counter()
+            try:
+                alnio.write_alignments(trimmed_reads_fn, aln, out_header, trim)
+            except BaseException as e:      # re-raised on the main thread
+                tm["_write_error"] = e
+            tm["encode_bam"] = _time.perf_counter() - t0
+        writer = threading.Thread(target=_write)
+        writer.start()
+    _t = _time.perf_counter()
     if pile:
         counts = eng.counts()
         ins = eng.insertions()
@@ -243,6 +266,15 @@ def _run(untrimmed_reads_fn, primer_fn, reference_fn, trimmed_reads_fn, variants
             else:
                 with open(consensus_fn, 'w') as f:
                     f.write(text)
+    tm["call_and_text"] = _time.perf_counter() - _t
+    if writer is not None:
+        writer.join()
+        if "_write_error" in tm:
+            raise tm.pop("_write_error")
+    if os.environ.get("AMP_CLI_TIMINGS"):      # bench.py's file-to-file leg: where the wall time went
+        import json
+        with open(os.environ["AMP_CLI_TIMINGS"], "w") as f:
+            json.dump({k: round(v, 4) for k, v in tm.items()}, f)
     print_log("Finished Processing %d reads" % max(aln.n - 1, 0))
     return eng
 

@@ -1,6 +1,7 @@
 // amp_abi.cu -- kernels' __global__ wrappers + the C ABI declared in include/amplipy_b200.h.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -284,6 +285,54 @@ __global__ void amp_merge_kernel(amp::InsTable tab, long long n, const int* gpos
     }
 }
 
+// ---- deep-sample exchange: a rank's insertion table packed into one fixed-size slot, all slots gathered
+// with one collective, everybody else's alleles merged by one kernel -- no host round trip, no size negotiation.
+// slot = { u64 n_alleles, u64 arena_words, {u64 arena word offset, u64 count}[cap_entries], arena bytes [cap_arena] }
+__global__ void amp_ins_pack_kernel(amp::InsTable tab, unsigned long long* slot, unsigned long long cap_entries,
+                                    unsigned long long cap_arena_words) {
+    const unsigned long long words = tab.cursor[0], n = tab.cursor[1];
+    const bool fits = n <= cap_entries && words <= cap_arena_words;
+    const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x, nth = (unsigned long long)gridDim.x * blockDim.x;
+    if (tid == 0) {
+        slot[0] = fits ? n : 0ULL; slot[1] = fits ? words : 0ULL;
+        if (!fits) atomicOr(tab.err, n > cap_entries ? AMP_E_TABLE_FULL : AMP_E_ARENA_FULL);
+    }
+    if (!fits) return;
+    unsigned long long* ent = slot + 2;
+    for (unsigned long long k = tid; k < n; k += nth) {
+        const amp::InsSlot s = tab.slots[tab.entries[k]];
+        ent[2 * k] = s.key & 0xFFFFFFFFFFULL; ent[2 * k + 1] = (unsigned long long)(unsigned int)s.count;
+    }
+    unsigned long long* dst = slot + 2 + 2 * cap_entries;
+    const unsigned long long* src = (const unsigned long long*)tab.arena;
+    for (unsigned long long k = tid; k < words; k += nth) dst[k] = src[k];
+}
+struct ArenaText {   // key characters of a packed record
+    const unsigned char* p;
+    __device__ char operator()(int i) const { return (char)p[i]; }
+    __device__ uint32_t word(int i, int len) const {
+        uint32_t w = *(const uint32_t*)(p + i);                 // records are padded to 8 bytes
+        if (len - i < 4) w &= (1u << (8 * (len - i))) - 1u;
+        return w;
+    }
+};
+__global__ void amp_ins_merge_packed_kernel(amp::InsTable tab, const unsigned long long* slots, unsigned long long slot_words,
+                                            unsigned long long cap_entries, int my_rank) {
+    const int r = (int)blockIdx.y;
+    if (r == my_rank) return;
+    const unsigned long long* slot = slots + (unsigned long long)r * slot_words;
+    const unsigned long long n = slot[0];
+    const unsigned long long* ent = slot + 2;
+    const unsigned char* arena = (const unsigned char*)(slot + 2 + 2 * cap_entries);
+    for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n; k += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned char* rec = arena + ent[2 * k] * 8;
+        const int gpos = ((const int*)rec)[0];
+        const int len = (int)((const unsigned int*)rec)[1];
+        ArenaText t{rec + 8};
+        amp::ins_table_add(tab, gpos, len, t, (int)ent[2 * k + 1]);
+    }
+}
+
 struct DevChunk {   // device staging for one in-flight chunk of amp_process_host
     cudaStream_t stream = nullptr;
     int32_t* pos = nullptr; uint16_t* flag = nullptr; int32_t* tlen = nullptr;
@@ -313,6 +362,7 @@ struct amp_ctx {
     int last_launches = 0;
     size_t max_dyn_smem = 0;
     bool v7_attr = false;
+    unsigned char* d_xbuf = nullptr; size_t xbuf_bytes = 0;   // scratch of amp_ins_export / amp_ins_merge (grown at high-water marks)
     unsigned char* d_ref = nullptr;     // reference characters (amp_set_reference)
     unsigned char* d_call = nullptr;    // calling outputs (one block, offsets below)
     size_t o_depth = 0, o_top = 0, o_topc = 0, o_fl = 0, o_refc = 0, o_ff = 0, o_fr = 0, o_alt = 0, o_if = 0, o_ir = 0, o_ia = 0;
@@ -375,6 +425,7 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
         CK(cudaMemsetAsync(d_phase7, 0, 400 * 8, st));
         { const long long big = 1LL << 60; CK(cudaMemcpyAsync(d_phase7 + 9, &big, 8, cudaMemcpyHostToDevice, st)); }
         P.phase_cycles = d_phase7;
+        P.direct = getenv("AMP7_REVERSE") ? 1 : 0;
 #endif
         const bool tr = mode & AMP_MODE_TRIM, pl = mode & AMP_MODE_PILEUP;
         if (tr && pl) amp_trim_pileup_warp_kernel<true, true><<<grid, AMP7_WARPS * 32, smem, st>>>(P);
@@ -486,7 +537,7 @@ int amp_destroy(amp_ctx* c) {
     cudaFree(c->d_min_start); cudaFree(c->d_max_end);
     if (c->counts_owned) cudaFree(c->d_counts);
     cudaFree(c->tab.slots); cudaFree(c->tab.entries); cudaFree(c->tab.slot_entry); cudaFree(c->tab.arena); cudaFree(c->tab.cursor);
-    cudaFree(c->d_err); cudaFree(c->d_heads); cudaFree(c->d_scratch); cudaFree(c->d_glist); cudaFree(c->d_ref); cudaFree(c->d_call);
+    cudaFree(c->d_err); cudaFree(c->d_heads); cudaFree(c->d_scratch); cudaFree(c->d_glist); cudaFree(c->d_ref); cudaFree(c->d_call); cudaFree(c->d_xbuf);
     for (auto& ch : c->chunk) {
         cudaFree(ch.pos); cudaFree(ch.flag); cudaFree(ch.tlen); cudaFree(ch.cig_off); cudaFree(ch.seq_off); cudaFree(ch.qual_off);
         cudaFree(ch.cigar); cudaFree(ch.seq); cudaFree(ch.qual); cudaFree(ch.o_pos); cudaFree(ch.o_ncig); cudaFree(ch.o_flags);
@@ -696,9 +747,12 @@ int amp_ins_export(amp_ctx* c, int32_t* sample, int32_t* pos, int32_t* count, in
     const unsigned long long n = cur[1];
     str_off[0] = 0;
     if (n == 0) return AMP_OK;
-    int* d_count = nullptr; unsigned long long* d_off = nullptr;
-    CK(cudaMalloc((void**)&d_count, n * 4));
-    CK(cudaMalloc((void**)&d_off, n * 8));
+    {
+        int rc = dev_grow(&c->d_xbuf, &c->xbuf_bytes, (size_t)n * 16 + 64);
+        if (rc) return rc;
+    }
+    unsigned long long* d_off = (unsigned long long*)c->d_xbuf;
+    int* d_count = (int*)(c->d_xbuf + (size_t)n * 8);
     amp_gather_entries_kernel<<<(unsigned)std::min<unsigned long long>((n + 255) / 256, 1184), 256>>>(c->tab.slots, c->tab.entries, n, d_count, d_off);
     CK(cudaGetLastError());
     std::vector<unsigned long long> off(n);
@@ -706,7 +760,6 @@ int amp_ins_export(amp_ctx* c, int32_t* sample, int32_t* pos, int32_t* count, in
     CK(cudaMemcpy(count, d_count, n * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(off.data(), d_off, n * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(arena.data(), c->tab.arena, cur[0] * 8, cudaMemcpyDeviceToHost));
-    CK(cudaFree(d_count)); CK(cudaFree(d_off));
     int64_t o = 0;
     for (unsigned long long k = 0; k < n; ++k) {
         const unsigned char* rec = arena.data() + off[k] * 8;
@@ -726,10 +779,14 @@ int amp_ins_merge(amp_ctx* c, int64_t n, const int32_t* sample, const int32_t* p
     CK(cudaSetDevice(c->cfg.device));
     std::vector<int> gpos(n);
     for (int64_t k = 0; k < n; ++k) gpos[k] = sample[k] * c->Lpad + pos[k];
-    int *d_gpos = nullptr, *d_count = nullptr; long long* d_off = nullptr; char* d_chars = nullptr;
     const size_t nch = (size_t)str_off[n];
-    CK(cudaMalloc((void**)&d_gpos, n * 4)); CK(cudaMalloc((void**)&d_count, n * 4));
-    CK(cudaMalloc((void**)&d_off, (n + 1) * 8)); CK(cudaMalloc((void**)&d_chars, nch + 8));
+    const size_t o_count = (size_t)n * 4, o_off = ((size_t)n * 8 + 7) & ~(size_t)7, o_chars = o_off + ((size_t)n + 1) * 8;
+    {
+        int rc = dev_grow(&c->d_xbuf, &c->xbuf_bytes, o_chars + nch + 64);
+        if (rc) return rc;
+    }
+    int* d_gpos = (int*)c->d_xbuf; int* d_count = (int*)(c->d_xbuf + o_count);
+    long long* d_off = (long long*)(c->d_xbuf + o_off); char* d_chars = (char*)(c->d_xbuf + o_chars);
     CK(cudaMemcpy(d_gpos, gpos.data(), n * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_count, count, n * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_off, str_off, (n + 1) * 8, cudaMemcpyHostToDevice));
@@ -737,7 +794,6 @@ int amp_ins_merge(amp_ctx* c, int64_t n, const int32_t* sample, const int32_t* p
     amp_merge_kernel<<<(unsigned)std::min<int64_t>((n + 127) / 128, 1184), 128>>>(c->tab, n, d_gpos, d_count, d_off, d_chars);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
-    CK(cudaFree(d_gpos)); CK(cudaFree(d_count)); CK(cudaFree(d_off)); CK(cudaFree(d_chars));
     return AMP_OK;
 }
 
@@ -821,6 +877,152 @@ int amp_host_alloc(void** p, int64_t bytes) {
 }
 int amp_host_free(void* p) {
     if (p) CK(cudaFreeHost(p));
+    return AMP_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// deep-sample mode: NCCL sum of the count matrices + packed insertion-table exchange
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+// NCCL is resolved at run time (the library already mapped by the host process, e.g. the one PyTorch ships, else the
+// system's): the C ABI keeps no link-time dependency on it
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.handle ? &api : nullptr;
+    tried = true;
+    const char* names[] = {getenv("AMP_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names) if (nm && !h) h = dlopen(nm, RTLD_NOW | RTLD_NOLOAD);
+    for (const char* nm : names) if (nm && !h) h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return nullptr;
+    api.GetUniqueId = (int (*)(NcclId*))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+    api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+    api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.AllGather) return nullptr;
+    api.handle = h;
+    return &api;
+}
+int nccl_fail(NcclApi* a, int rc, const char* what) {
+    return fail(AMP_ERR_CUDA, what, a && a->GetErrorString ? a->GetErrorString(rc) : "NCCL error");
+}
+#define NCCL_OR_FAIL(a) NcclApi* a = nccl_api(); if (!a) return fail(AMP_ERR_STATE, "NCCL library not found (libnccl.so.2; set AMP_NCCL_LIB)")
+}  // namespace
+
+extern "C" {
+
+int amp_nccl_unique_id(uint8_t* id128) {
+    if (!id128) return fail(AMP_ERR_ARG, "amp_nccl_unique_id: null argument");
+    NCCL_OR_FAIL(a);
+    NcclId id;
+    const int rc = a->GetUniqueId(&id);
+    if (rc) return nccl_fail(a, rc, "ncclGetUniqueId");
+    memcpy(id128, id.internal, 128);
+    return AMP_OK;
+}
+int amp_nccl_comm_init(int device, int n_ranks, int rank, const uint8_t* id128, void** comm) {
+    if (!id128 || !comm || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(AMP_ERR_ARG, "amp_nccl_comm_init: bad argument");
+    NCCL_OR_FAIL(a);
+    CK(cudaSetDevice(device));
+    NcclId id;
+    memcpy(id.internal, id128, 128);
+    const int rc = a->CommInitRank(comm, n_ranks, id, rank);
+    if (rc) return nccl_fail(a, rc, "ncclCommInitRank");
+    return AMP_OK;
+}
+int amp_nccl_comm_destroy(void* comm) {
+    if (!comm) return AMP_OK;
+    NCCL_OR_FAIL(a);
+    const int rc = a->CommDestroy(comm);
+    if (rc) return nccl_fail(a, rc, "ncclCommDestroy");
+    return AMP_OK;
+}
+int amp_nccl_allgather(void* comm, const void* dev_send, void* dev_recv, int64_t bytes_per_rank, void* stream) {
+    if (!comm || !dev_send || !dev_recv || bytes_per_rank < 0) return fail(AMP_ERR_ARG, "amp_nccl_allgather: bad argument");
+    NCCL_OR_FAIL(a);
+    const int rc = a->AllGather(dev_send, dev_recv, (size_t)bytes_per_rank, /*ncclUint8*/ 1, comm, (cudaStream_t)stream);
+    if (rc) return nccl_fail(a, rc, "ncclAllGather");
+    return AMP_OK;
+}
+
+// one ncclAllReduce(sum, int32) over the whole [n_samples][6][lpad] block, in place, asynchronous on `stream`
+int amp_allreduce_counts(amp_ctx* c, void* comm, void* stream) {
+    if (!c || !comm) return fail(AMP_ERR_ARG, "amp_allreduce_counts: null argument");
+    NCCL_OR_FAIL(a);
+    CK(cudaSetDevice(c->cfg.device));
+    const size_t n = (size_t)c->cfg.n_samples * AMP_NCH * (size_t)c->Lpad;
+    const int rc = a->AllReduce(c->d_counts, c->d_counts, n, /*ncclInt32*/ 2, /*ncclSum*/ 0, comm, (cudaStream_t)stream);
+    if (rc) return nccl_fail(a, rc, "ncclAllReduce");
+    return AMP_OK;
+}
+
+int64_t amp_ins_slot_bytes(int64_t cap_entries, int64_t cap_arena_bytes) {
+    if (cap_entries < 0 || cap_arena_bytes < 0) return -1;
+    return 16 + 16 * cap_entries + ((cap_arena_bytes + 7) & ~(int64_t)7);
+}
+int amp_ins_pack_device(amp_ctx* c, void* dev_slot, int64_t cap_entries, int64_t cap_arena_bytes, void* stream) {
+    if (!c || !dev_slot || cap_entries < 0 || cap_arena_bytes < 0) return fail(AMP_ERR_ARG, "amp_ins_pack_device: bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    amp_ins_pack_kernel<<<c->sm_count * 2, 512, 0, (cudaStream_t)stream>>>(c->tab, (unsigned long long*)dev_slot, (unsigned long long)cap_entries,
+                                                                          (unsigned long long)((cap_arena_bytes + 7) / 8));
+    CK(cudaGetLastError());
+    return AMP_OK;
+}
+int amp_ins_merge_packed(amp_ctx* c, const void* dev_slots, int n_ranks, int my_rank, int64_t cap_entries, int64_t cap_arena_bytes,
+                         void* stream) {
+    if (!c || !dev_slots || n_ranks < 1 || cap_entries < 0 || cap_arena_bytes < 0) return fail(AMP_ERR_ARG, "amp_ins_merge_packed: bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    const unsigned long long slot_words = (unsigned long long)amp_ins_slot_bytes(cap_entries, cap_arena_bytes) / 8;
+    dim3 grid((unsigned)c->sm_count, (unsigned)n_ranks);
+    amp_ins_merge_packed_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(c->tab, (const unsigned long long*)dev_slots, slot_words,
+                                                                       (unsigned long long)cap_entries, my_rank);
+    CK(cudaGetLastError());
+    return AMP_OK;
+}
+
+// Allocate what amp_process_device would otherwise allocate lazily (long-CIGAR scratch rows, overflow of the per-CTA lists)
+// for batches of up to max_reads reads / max_cigar_ops CIGAR ops, so that no later call allocates or synchronises.
+int amp_reserve(amp_ctx* c, int64_t max_reads, int64_t max_cigar_ops) {
+    if (!c || max_reads < 0 || max_cigar_ops < 0) return fail(AMP_ERR_ARG, "amp_reserve: bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaDeviceSynchronize());
+    const size_t need_s = 2 * ((size_t)max_cigar_ops + 3 * (size_t)max_reads);
+    if (c->d_min_start && need_s > c->scratch_words) {
+        if (c->d_scratch) CK(cudaFree(c->d_scratch));
+        c->d_scratch = nullptr; c->scratch_words = 0;
+        CK(cudaMalloc((void**)&c->d_scratch, need_s * 4));
+        c->scratch_words = need_s;
+    }
+    const size_t need_g = glist_words_for(c, max_reads);
+    if (need_g > c->glist_words) {
+        if (c->d_glist) CK(cudaFree(c->d_glist));
+        c->d_glist = nullptr; c->glist_words = 0;
+        CK(cudaMalloc((void**)&c->d_glist, need_g * 4));
+        c->glist_words = need_g;
+    }
+    return AMP_OK;
+}
+
+// device-to-device copy of the count matrices into a caller-owned buffer of the same shape (asynchronous on `stream`)
+int amp_counts_copy_device(amp_ctx* c, int32_t* dev_dst, void* stream) {
+    if (!c || !dev_dst) return fail(AMP_ERR_ARG, "amp_counts_copy_device: null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaMemcpyAsync(dev_dst, c->d_counts, (size_t)c->cfg.n_samples * AMP_NCH * c->Lpad * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return AMP_OK;
 }
 

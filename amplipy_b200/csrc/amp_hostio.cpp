@@ -29,13 +29,16 @@ long long amp_bgzf_scan(const uint8_t* in, long long in_len, long long* in_off, 
         if (in[p] != 31 || in[p + 1] != 139 || in[p + 2] != 8 || !(in[p + 3] & 4)) return -1;
         const uint32_t xlen = rd16(in + p + 10);
         long long x = p + 12, xend = x + xlen;
+        if (xend > in_len) return -1;                                   // extra field runs past the buffer
         long long bsize = -1;
         while (x + 4 <= xend) {
             const uint32_t slen = rd16(in + x + 2);
+            if (x + 4 + (long long)slen > xend) return -1;              // subfield runs past the extra field
             if (in[x] == 66 && in[x + 1] == 67 && slen == 2) bsize = (long long)rd16(in + x + 4) + 1;
             x += 4 + slen;
         }
-        if (bsize < 0 || p + bsize > in_len) return -1;
+        // header (12) + extra field + trailer (CRC32, ISIZE) must fit inside the block, the block inside the buffer
+        if (bsize < 0 || 12 + (long long)xlen + 8 > bsize || p + bsize > in_len) return -1;
         if (max_blocks) {
             if (k >= max_blocks) return -1;
             in_off[k] = p; out_len[k] = rd32(in + p + bsize - 4);
@@ -59,6 +62,7 @@ int amp_bgzf_inflate(const uint8_t* in, const long long* in_off, const uint32_t*
         const uint32_t xlen = rd16(b + 10);
         const uint8_t* cdata = b + 12 + xlen;
         const long long clen = bend - in_off[k] - 12 - xlen - 8;
+        if (clen < 0 || clen > 0x7fffffffLL) { bad |= 1; continue; }
         if (out_len[k] == 0) continue;
         z_stream zs; memset(&zs, 0, sizeof zs);
         if (inflateInit2(&zs, -15) != Z_OK) { bad |= 1; continue; }
@@ -122,7 +126,12 @@ long long amp_bam_scan(const uint8_t* buf, long long len, long long start, long 
     long long p = start, k = 0;
     while (p + 4 <= len) {
         const uint32_t bs = rd32(buf + p);
-        if (bs < 32 || p + 4 + bs > len) return -1;
+        if (bs < 32 || p + 4 + (long long)bs > len) return -1;
+        {   // the variable-length fields named by the fixed header must fit inside the record (untrusted input)
+            const uint8_t* r = buf + p + 4;
+            const long long lname = r[8], nc = rd16(r + 12), ls = (int32_t)rd32(r + 16);
+            if (ls < 0 || 32 + lname + 4 * nc + (ls + 1) / 2 + ls > (long long)bs) return -1;
+        }
         if (max_records) {
             if (k >= max_records) return -1;
             rec_off[k] = p; n_cigar[k] = rd16(buf + p + 4 + 12); l_seq[k] = (int32_t)rd32(buf + p + 4 + 16);

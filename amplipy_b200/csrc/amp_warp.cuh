@@ -145,10 +145,10 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 
 // ---- shared-memory layout ------------------------------------------------------------------------------------------
 #ifndef AMP7_WARPS
-#define AMP7_WARPS 16            // warps per CTA of the fast kernel
+#define AMP7_WARPS 18            // warps per CTA of the fast kernel (112 registers per thread)
 #endif
 #ifndef AMP7_GWARPS
-#define AMP7_GWARPS 8            // warps that can run the generic phase (their extra shared memory must fit): the last ones
+#define AMP7_GWARPS 4            // warps that can run the generic phase (their extra shared memory must fit): the last ones
 #endif
 #ifndef AMP7_DWARPS
 #define AMP7_DWARPS 0            // of those, warps that do nothing else (they work on the list while it is being filled)
@@ -624,7 +624,11 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
     const long long t_cta0 = clock64();
 #endif
     const int wt = WT ? WT : P.wt;
+#if defined(__CUDA_ARCH__) && defined(AMP7_TIMING)
+    const int tid = c_tid(), nthreads = c_nthreads(), block = P.direct ? (int)gridDim.x - 1 - c_block() : c_block();   // experiment: chunks in reverse order
+#else
     const int tid = c_tid(), nthreads = c_nthreads(), block = c_block();
+#endif
     const int lane = tid & 31, warp = tid >> 5;
     const int BR = P.reads_per_tile;
     int* cnt = (int*)smem_base;

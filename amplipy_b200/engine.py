@@ -35,7 +35,9 @@ EXPORTED_SYMBOLS = [
     "amp_last_error", "amp_abi_version", "amp_create", "amp_destroy", "amp_reset", "amp_error_flags", "amp_lpad",
     "amp_sm_count", "amp_process_device", "amp_process_host", "amp_last_launches", "amp_counts_device",
     "amp_bind_counts", "amp_counts_host", "amp_ins_count", "amp_ins_export", "amp_ins_merge", "amp_call",
-    "amp_host_alloc", "amp_host_free", "amp_reset_async", "amp_set_reference", "amp_call_device"]
+    "amp_host_alloc", "amp_host_free", "amp_reset_async", "amp_set_reference", "amp_call_device",
+    "amp_nccl_unique_id", "amp_nccl_comm_init", "amp_nccl_comm_destroy", "amp_nccl_allgather", "amp_allreduce_counts",
+    "amp_ins_slot_bytes", "amp_ins_pack_device", "amp_ins_merge_packed", "amp_reserve", "amp_counts_copy_device"]
 
 
 class AmpConfig(ctypes.Structure):
@@ -79,6 +81,7 @@ def load_library():
                                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
         lib = ctypes.CDLL(LIB_PATH)
         lib.amp_last_error.restype = ctypes.c_char_p
+        lib.amp_ins_slot_bytes.restype = ctypes.c_int64
         for name in EXPORTED_SYMBOLS:
             getattr(lib, name)   # AttributeError if the build is stale
         _lib = lib
@@ -207,9 +210,10 @@ class Engine:
     # ---------------------------------------------------------------- host-buffer path (e2e)
     @staticmethod
     def alloc_trim_out(batch):
+        # zero-initialised: process(first, n) fills only [first, first + n); flags == 0 means "not kept" for the other reads
         n = batch.n
-        return (np.empty(n, np.int32), np.empty(n, np.uint16), np.empty(n, np.uint8),
-                np.empty(int(batch.cig_off[-1]) + 3 * n, np.uint32))
+        return (np.zeros(n, np.int32), np.zeros(n, np.uint16), np.zeros(n, np.uint8),
+                np.zeros(int(batch.cig_off[-1]) + 3 * n, np.uint32))
 
     def process(self, batch, trim=True, pileup=True, sample=0, out=None, first=0, n=None):
         """H2D + fused kernel + D2H through amp_process_host.  Returns TrimResult when trim=True."""
@@ -226,6 +230,16 @@ class Engine:
                "amp_process_host")
         self.launches += int(self.lib.amp_last_launches(self._ctx))
         return TrimResult(batch, *out) if trim else None
+
+    def host_copy_bytes(self, batch, trim=True, pileup=True, call=True):
+        """(host->device, device->host) bytes one `process` (+ `call`) of this batch moves over PCIe, counted from the
+        arrays the C ABI copies: inputs = the batch's nine arrays, outputs = the trim rows + the calling arrays."""
+        n, sc = batch.n, int(batch.cig_off[-1])
+        h2d = n * (4 + 2 + 4) + 3 * 4 * (n + 1) + 4 * sc + int(batch.qual.size) + (int(batch.seq.size) if pileup else 0)
+        d2h = (n * (4 + 2 + 1) + 4 * (sc + 3 * n)) if trim else 0
+        if call:
+            d2h += self.n_samples * self.L * (4 + 4 + 4 + 1 + 4 + 48 + 24 + 1)
+        return h2d, d2h
 
     # ---------------------------------------------------------------- device-resident path (kernel-only)
     def upload(self, batch, trim_out=True):
@@ -291,17 +305,15 @@ class Engine:
         return p.value
 
     def counts_tensor(self):
-        """The int32 device tensor [n_samples, 6, lpad] the kernels accumulate into (allocated through torch
-        on first use so that torch.distributed / NCCL can all-reduce it in place)."""
+        """The int32 device tensor [n_samples, 6, lpad] the kernels accumulate into (allocated through torch on first use
+        so that torch.distributed can all-reduce it in place; what has been accumulated so far is carried over with a
+        device-to-device copy).  The NCCL path of dist.py does not need it: amp_allreduce_counts works on the
+        context's own matrix."""
         if getattr(self, "_bound", None) is None:
             import torch
             dev = torch.device("cuda", self.device)
-            t = torch.zeros((self.n_samples, 6, self.lpad), dtype=torch.int32, device=dev)
-            # carry over what has been accumulated so far
-            host = np.zeros((self.n_samples, 6, self.lpad), np.int32)
-            for smp in range(self.n_samples):
-                host[smp, :, :self.L] = self.counts(smp)
-            t.copy_(torch.from_numpy(host))
+            t = torch.empty((self.n_samples, 6, self.lpad), dtype=torch.int32, device=dev)
+            _check(self.lib.amp_counts_copy_device(self._ctx, ctypes.c_void_p(t.data_ptr()), None), "amp_counts_copy_device")
             torch.cuda.synchronize(dev)
             self.bind_counts(t)
         return self._bound
@@ -338,6 +350,32 @@ class Engine:
         chars = np.ascontiguousarray(chars, np.uint8) if len(chars) else np.zeros(1, np.uint8)
         _check(self.lib.amp_ins_merge(self._ctx, ctypes.c_int64(len(pos)), _ptr(sample), _ptr(pos), _ptr(count),
                                       _ptr(str_off), _ptr(chars)), "amp_ins_merge")
+
+    # ---------------------------------------------------------------- deep-sample exchange (dist.py)
+    def reserve(self, max_reads, max_cigar_ops):
+        """Pre-size the buffers process_device would otherwise grow on demand (no allocation on the hot path afterwards)."""
+        _check(self.lib.amp_reserve(self._ctx, ctypes.c_int64(int(max_reads)), ctypes.c_int64(int(max_cigar_ops))), "amp_reserve")
+
+    def allreduce_counts(self, comm, stream=None):
+        """One ncclAllReduce(sum, int32) of the count matrices, in place (``comm``: NcclComm or a raw ncclComm_t value)."""
+        h = comm.handle if hasattr(comm, "handle") else comm
+        _check(self.lib.amp_allreduce_counts(self._ctx, ctypes.c_void_p(h), ctypes.c_void_p(stream) if stream else None),
+               "amp_allreduce_counts")
+
+    def ins_slot_bytes(self, cap_entries, cap_arena_bytes):
+        return int(self.lib.amp_ins_slot_bytes(ctypes.c_int64(cap_entries), ctypes.c_int64(cap_arena_bytes)))
+
+    def ins_pack_device(self, dev_ptr, cap_entries, cap_arena_bytes, stream=None):
+        _check(self.lib.amp_ins_pack_device(self._ctx, ctypes.c_void_p(dev_ptr), ctypes.c_int64(cap_entries),
+                                            ctypes.c_int64(cap_arena_bytes), ctypes.c_void_p(stream) if stream else None),
+               "amp_ins_pack_device")
+        self.launches += 1
+
+    def ins_merge_packed(self, dev_ptr, n_ranks, my_rank, cap_entries, cap_arena_bytes, stream=None):
+        _check(self.lib.amp_ins_merge_packed(self._ctx, ctypes.c_void_p(dev_ptr), int(n_ranks), int(my_rank),
+                                             ctypes.c_int64(cap_entries), ctypes.c_int64(cap_arena_bytes),
+                                             ctypes.c_void_p(stream) if stream else None), "amp_ins_merge_packed")
+        self.launches += 1
 
     def _call_buffers(self, n_ins, pinned):
         """Result arrays of ``call``: fresh numpy arrays, or (``pinned``) page-locked arrays owned by the engine and reused."""
@@ -384,3 +422,45 @@ class Engine:
                                  _ptr(r.ins_rank), _ptr(r.ins_alt)), "amp_call")
         self.launches += int(self.lib.amp_last_launches(self._ctx))
         return r
+
+
+class NcclComm:
+    """An ncclComm_t created through the C ABI (amp_nccl_unique_id / amp_nccl_comm_init).  The 128-byte id of rank 0 has
+    to reach the other ranks somehow; ``from_torch_group`` broadcasts it over an initialised torch.distributed group."""
+
+    def __init__(self, handle, rank, world):
+        self.handle, self.rank, self.world = handle, rank, world
+
+    @staticmethod
+    def unique_id():
+        buf = (ctypes.c_uint8 * 128)()
+        _check(load_library().amp_nccl_unique_id(buf), "amp_nccl_unique_id")
+        return bytes(buf)
+
+    @classmethod
+    def create(cls, device, world, rank, unique_id):
+        assert len(unique_id) == 128
+        h = ctypes.c_void_p()
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(load_library().amp_nccl_comm_init(int(device), int(world), int(rank), buf, ctypes.byref(h)), "amp_nccl_comm_init")
+        return cls(h.value, rank, world)
+
+    @classmethod
+    def from_torch_group(cls, device, group=None):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        uid = cls.unique_id() if rank == 0 else bytes(128)
+        t = torch.tensor(list(uid), dtype=torch.uint8, device=torch.device("cuda", device) if dist.get_backend(group) == "nccl" else "cpu")
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls.create(device, world, rank, bytes(t.cpu().tolist()))
+
+    def allgather(self, send_ptr, recv_ptr, bytes_per_rank, stream=None):
+        _check(load_library().amp_nccl_allgather(ctypes.c_void_p(self.handle), ctypes.c_void_p(send_ptr), ctypes.c_void_p(recv_ptr),
+                                                 ctypes.c_int64(bytes_per_rank), ctypes.c_void_p(stream) if stream else None),
+               "amp_nccl_allgather")
+
+    def close(self):
+        if self.handle:
+            load_library().amp_nccl_comm_destroy(ctypes.c_void_p(self.handle))
+            self.handle = None

@@ -413,8 +413,9 @@ def _ont_chunk(rng, ref, amps, n, sub_rate, ins_rate, del_rate, p_clip):
 # ---------------------------------------------------------------------------------------------
 # adversarial small cases (python loops; parity tests only)
 # ---------------------------------------------------------------------------------------------
-def fuzz_records(L, n, seed=0, max_len=60, ont_like=False):
-    """Random well-formed reads with H/S/M/I/D/N/=/X shapes, I->D adjacency, all flag/tlen combos."""
+def fuzz_records(L, n, seed=0, max_len=60, ont_like=False, edges=0.0):
+    """Random well-formed reads with H/S/M/I/D/N/=/X shapes, I->D adjacency, all flag/tlen combos.
+    ``edges`` = fraction of the reads placed at position 0 or ending exactly on the last reference base."""
     rng = np.random.default_rng(seed)
     recs = []
     while len(recs) < n:
@@ -458,6 +459,8 @@ def fuzz_records(L, n, seed=0, max_len=60, ont_like=False):
         if rlen + 2 >= L:
             continue
         pos = int(rng.integers(1, L - rlen - 1))
+        if edges and rng.random() < edges:
+            pos = 0 if rng.random() < 0.5 else L - rlen
         seq = "".join(rng.choice(list("ACGTN"), p=[0.24, 0.24, 0.24, 0.24, 0.04]) for _ in range(qlen))
         mode = rng.random()
         if mode < 0.5:

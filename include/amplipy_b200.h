@@ -152,6 +152,32 @@ int amp_call(amp_ctx* ctx, const char* ref_seq, const amp_call_params* p, const 
 int amp_set_reference(amp_ctx* ctx, const char* ref_seq);
 int amp_call_device(amp_ctx* ctx, const amp_call_params* p, void* stream);
 
+/* ---- deep-sample mode: one sample's reads sharded over ranks (the reference has no counterpart, its loop
+ * AmpliPy.py:896-915 is sequential).  After every rank has processed its read range:
+ *   amp_allreduce_counts  one ncclAllReduce(sum, int32) of the [n_samples][6][lpad] matrices, in place
+ *   amp_ins_pack_device   this rank's insertion table -> one fixed-size slot in device memory
+ *                         { u64 n_alleles, u64 arena_words, {u64 arena offset, u64 count}[cap_entries], arena[cap_arena_bytes] }
+ *   (all-gather of the slots: amp_nccl_allgather, or any collective the host prefers)
+ *   amp_ins_merge_packed  everybody else's alleles added to this rank's table by one kernel
+ * Everything is asynchronous on `stream`; nothing allocates.  A table that does not fit its slot raises
+ * AMP_DEVERR_TABLE_FULL / AMP_DEVERR_ARENA_FULL (amp_error_flags) and packs as empty.
+ * NCCL is resolved with dlopen at the first call (libnccl.so.2 as already mapped by the process, else the system's;
+ * AMP_NCCL_LIB overrides); `comm` is an ncclComm_t, from amp_nccl_comm_init or the caller's own ncclCommInitRank. */
+int amp_nccl_unique_id(uint8_t* id128 /* [128] */);
+int amp_nccl_comm_init(int device, int n_ranks, int rank, const uint8_t* id128, void** comm);
+int amp_nccl_comm_destroy(void* comm);
+int amp_nccl_allgather(void* comm, const void* dev_send, void* dev_recv, int64_t bytes_per_rank, void* stream);
+int amp_allreduce_counts(amp_ctx* ctx, void* comm, void* stream);
+int64_t amp_ins_slot_bytes(int64_t cap_entries, int64_t cap_arena_bytes);
+int amp_ins_pack_device(amp_ctx* ctx, void* dev_slot, int64_t cap_entries, int64_t cap_arena_bytes, void* stream);
+int amp_ins_merge_packed(amp_ctx* ctx, const void* dev_slots, int n_ranks, int my_rank, int64_t cap_entries,
+                         int64_t cap_arena_bytes, void* stream);
+
+/* pre-size what amp_process_device would otherwise grow on demand (it synchronises `stream` when it has to allocate) */
+int amp_reserve(amp_ctx* ctx, int64_t max_reads, int64_t max_cigar_ops);
+/* device-to-device copy of the count matrices into a caller-owned buffer of the same shape */
+int amp_counts_copy_device(amp_ctx* ctx, int32_t* dev_dst, void* stream);
+
 /* pinned host memory helpers for callers that want full-speed amp_process_host */
 int amp_host_alloc(void** p, int64_t bytes);
 int amp_host_free(void* p);

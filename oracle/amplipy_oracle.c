@@ -57,6 +57,14 @@ int oracle_num_threads(void) {
     return 1;
 #endif
 }
+/* fix the number of OpenMP threads whatever OMP_NUM_THREADS says (bench.py: the same count at every --gpus N) */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 /* ---- AmpliPy.py:174-209 find_overlapping_primers (deque emulated with head/tail indices) ---- */
 int oracle_find_overlapping_primers(int L, int P, const int32_t* starts, const int32_t* ends, int offset,

@@ -24,6 +24,23 @@ def build(force=False):
     return _SO
 
 
+def use_native_build():
+    """bench.py's CPU legs: build the same source with -O3 -march=native ON THE MACHINE THAT RUNS IT (the portable
+    -O2 build is what travels with the repository) and load that one.  Call before the first use of the library."""
+    global _SO, _lib
+    src = os.path.join(_HERE, "amplipy_oracle.c")
+    so = os.path.join(_HERE, "_build", "libamplipy_oracle_native.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    cc = "/usr/bin/gcc" if os.path.isfile("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-O3", "-march=native", "-fPIC", "-fopenmp", "-shared", "-o", so, src])
+    _SO, _lib = so, None
+    return so
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(ctypes.c_int(int(n)))
+
+
 def _p(a, ct=None):
     if a is None:
         return None

@@ -169,3 +169,18 @@ def test_many_generic_reads_overflow_the_shared_list(oracle_lib):
     g, prim, amps = _scheme(seed=3)
     b = synth.illumina_batch(g, amps, 5_000, seed=45, p_ins=0.2, p_del=0.2)
     parity.check_against_oracle(v7(grid=2, warps=3), oracle_lib, b, g, prim, w=6)
+
+
+@pytest.mark.parametrize("kernel", ["v7", "tile"])
+def test_reads_at_the_ends_of_the_reference_vs_oracle(oracle_lib, kernel):
+    """Reads at position 0 / ending on the last base, a primer that reaches the last base: a read swallowed by the start clip
+    ends up at pos == L with an all-S CIGAR; the reference piles it up without touching anything and so must the kernels."""
+    from amplipy_b200.batch import ReadBatch
+    L = 240
+    g = synth.random_genome(L, 3)
+    prim = [(0, 22), (60, 84), (150, 171), (L - 24, L)]
+    recs = synth.fuzz_records(L, 1500, seed=111, max_len=40, edges=0.5)
+    recs += [(L - 2, 0, 0, [(0, 2)], "AC", [30, 30]), (L - 6, 16, 0, [(0, 6)], "ACGTAC", [30] * 6)]
+    b = ReadBatch.from_records(sorted(recs, key=lambda r: r[0]))
+    mk = (lambda **kw: emu_driver.EmuEngine(kernel=kernel, grid=2, **({"warps": 3} if kernel == "v7" else {}), **kw))
+    parity.check_against_oracle(mk, oracle_lib, b, g, prim, offset=1, ml=5)

@@ -112,6 +112,38 @@ def test_fuzz_vs_oracle(oracle_lib):
                         inc=bool(seed & 2))
 
 
+def test_reads_at_the_ends_of_the_reference_vs_oracle(oracle_lib):
+    """Reads at position 0 / ending on the last base, a primer that reaches the last base: a read swallowed by the start clip
+    ends up at pos == L with an all-S CIGAR; the reference piles it up without touching anything and so must the kernels."""
+    L = 240
+    g = synth.random_genome(L, 3)
+    prim = [(0, 22), (60, 84), (150, 171), (L - 24, L)]
+    for seed in (111, 112):
+        recs = synth.fuzz_records(L, 3000, seed=seed, max_len=40, edges=0.5)
+        recs += [(L - 2, 0, 0, [(0, 2)], "AC", [30, 30]), (L - 6, 16, 0, [(0, 6)], "ACGTAC", [30] * 6)]
+        b = ReadBatch.from_records(sorted(recs, key=lambda r: r[0]))
+        _against_oracle(oracle_lib, b, g, prim, offset=seed % 3, ml=5)
+
+
+def test_single_indel_reads_vs_oracle(oracle_lib):
+    """[H][S] M (I|D) M [S][H] reads finished in registers next to [S]M[S]: heavy indel / clip rates and quality patterns that
+    move the quality clip across the indel on both strands."""
+    g, prim, amps = _scheme(seed=3, n_alt=5)
+    rng = np.random.default_rng(9)
+    b = synth.illumina_batch(g, amps, 200_000, seed=41, p_ins=0.3, p_del=0.3, p_clip=0.3, p_hard=0.1, p_short=0.2)
+    q = b.qual
+    for i in range(0, b.n, 3):                       # weak windows / sprinkled weak bases on every third read
+        lo, hi = int(b.qual_off[i]), int(b.qual_off[i + 1])
+        if hi - lo < 12:
+            continue
+        if i % 2:
+            p0 = int(rng.integers(lo, hi - 4)); q[p0:p0 + 4] = rng.integers(0, 25, 4)
+        else:
+            k = int(rng.integers(1, 12)); q[rng.integers(lo, hi, k)] = rng.integers(0, 20, k)
+    _against_oracle(oracle_lib, b, g, prim)
+    _against_oracle(oracle_lib, b, g, prim, mq=30, offset=2)
+
+
 def test_empty_and_tiny_batches():
     g, prim, amps = _scheme(L=3000, n_amp=9)
     tables = find_overlapping_primers(3000, prim, 0)
