@@ -667,18 +667,34 @@ AMP_HD bool trim_shape_primers(Shape5& r, int& pos, int flag, int tlen, int l_se
     int pp = p, f = 0;
     if (!(paired && isize && rev) && L1 >= 0) {                           // 460
         const int d1 = L1 + 1 - p;                                        // one base past the primer (463)
-        if (d1 < 1 || d1 >= r.m) return false;
-        f |= AMP_F_TRIM_START; r.s1 += d1; r.m -= d1; pp += d1; r.h1 = 0;
+        if (d1 < 1) return false;
+        if (d1 < r.m) { r.s1 += d1; r.m -= d1; pp += d1; }
+        else {
+            // the clip crosses the indel (467-510): an insertion inside the clipped span becomes soft clip (487-488 when the
+            // clip ends exactly in front of it), a deletion is dropped and the start advances over it (quirk table);
+            // d more bases leave the second run, which is all that remains
+            if (r.k == 0) return false;
+            const int d = gap ? (d1 - r.m - gap > 0 ? d1 - r.m - gap : 0) : d1 - r.m;
+            if (d >= r.m2) return false;
+            r.s1 += r.m + (gap ? 0 : r.k) + d; pp += r.m + gap + d;
+            r.m = r.m2 - d; r.ops = (r.ops >> 4) & 15u; r.k = 0; r.m2 = 0;
+        }
+        f |= AMP_F_TRIM_START; r.h1 = 0;
     }
     if (!(paired && isize && !rev) && R1 >= 0) {                          // 517
-        if (r.k == 0) {
-            const int e = R1 - pp;                                        // aligned bases that stay
-            if (e < 1 || e >= r.m) return false;
-            r.s2 += r.m - e; r.m = e;
-        } else {
-            const int e = R1 - (pp + r.m + gap);                          // bases of the second run that stay
-            if (e < 1 || e >= r.m2) return false;
+        const int gap2 = shape_is_del(r) ? r.k : 0;
+        if (r.k > 0 && R1 > pp + r.m + gap2) {
+            const int e = R1 - (pp + r.m + gap2);                         // bases of the second run that stay
+            if (e >= r.m2) return false;
             r.s2 += r.m2 - e; r.m2 = e;
+        } else {
+            // inside the only run -- or, across the indel, inside the first run (524-555 over the reversed ops: the inserted
+            // bases turn into soft clip, a deletion is dropped; a target inside the deletion keeps the whole first run)
+            int e = R1 - pp;                                              // aligned bases that stay
+            if (e < 1) return false;
+            if (r.k > 0) { if (e > r.m) e = r.m; r.k = 0; r.m2 = 0; r.ops &= 15u; }
+            else if (e >= r.m) return false;
+            r.m = e; r.s2 = l_seq - r.s1 - e;
         }
         f |= AMP_F_TRIM_END; r.h2 = 0;
     }

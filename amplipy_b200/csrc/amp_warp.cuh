@@ -185,7 +185,7 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #ifndef AMP7_GLCAP
 #define AMP7_GLCAP 512           // reads for the generic phase listed in shared memory (whatever does not fit: P.glist)
 #endif
-enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_GNEXT = 3, C7_FASTDONE = 4, C7_NEV = 5, C7_PTAB = 16, C7_EV = C7_PTAB + 2 * AMP7_PSLICE,
+enum { C7_TMIN = 0, C7_NEXT = 1, C7_NGEN = 2, C7_GNEXT = 3, C7_FASTDONE = 4, C7_NEV = 5, C7_EVDONE = 6, C7_PTAB = 16, C7_EV = C7_PTAB + 2 * AMP7_PSLICE,
        C7_GL = C7_EV + 3 * AMP7_EVCAP, C7_WORDS = C7_GL + AMP7_GLCAP };
 
 AMP_HD int del_row_off(int wt) { return (AMP7_SINK_ROW + 1) * wt + AMP7_SINK_SLACK; }      // first element of the '-' row
@@ -293,18 +293,43 @@ AMP_HD void ins_commit(const KParams& P, const uint8_t* seq_read, int pos, int b
     TileSink::Text t; t.seq = seq_read; t.b = b;
     ins_table_add(P.tab, P.gpos_base + pos, n, t, 1);
 }
-AMP_HD void ins_defer(const KParams& P, int* ctrl, uint32_t so0, int pos, int b, int n) {   // so0: the read's offset in P.b.seq
-    if (b < 65536 && n < 65536) {
+AMP_WD void ins_defer(const KParams& P, int* ctrl, uint32_t so0, int pos, int b, int n) {   // so0: the read's offset in P.b.seq
+    if (b < 65536 && n > 0 && n < 65536) {
         const int idx = atomic_add(&ctrl[C7_NEV], 1);
-        if (idx < AMP7_EVCAP) { int* e = ctrl + C7_EV + 3 * idx; e[0] = pos; e[1] = (int)so0; e[2] = (int)((uint32_t)b | ((uint32_t)n << 16)); return; }
+        if (idx < AMP7_EVCAP) {      // the third word (never 0) is written last: it tells a draining warp that the entry is complete
+            int* e = ctrl + C7_EV + 3 * idx;
+            e[0] = pos; e[1] = (int)so0;
+            fence_block();
+            st_vol(&e[2], (int)((uint32_t)b | ((uint32_t)n << 16)));
+            return;
+        }
     }
     ins_commit(P, P.b.seq + so0, pos, b, n);
 }
-AMP_HD void ins_drain(const KParams& P, const int* ctrl, int tid, int nthreads) {
-    int nev = ctrl[C7_NEV]; if (nev > AMP7_EVCAP) nev = AMP7_EVCAP;
-    for (int k = tid; k < nev; k += nthreads) {
-        const int* e = ctrl + C7_EV + 3 * k;
-        ins_commit(P, P.b.seq + (uint32_t)e[1], e[0], (int)((uint32_t)e[2] & 0xFFFFu), (int)((uint32_t)e[2] >> 16));
+// Add parked alleles to the table, up to 32 at a time (a lane each), until none is left: called by warps that have run out
+// of batches while the others still append, and by every warp once all of them are done.
+AMP_WD void ins_drain(const KParams& P, int* ctrl, int lane) {
+    for (;;) {
+        int at = -1, n = 0;
+        if (lane == 0) {
+            for (;;) {
+                const int done = ld_vol(&ctrl[C7_EVDONE]);
+                int have = ld_vol(&ctrl[C7_NEV]); if (have > AMP7_EVCAP) have = AMP7_EVCAP;
+                if (have <= done) break;
+                n = have - done < 32 ? have - done : 32;
+                if (atomic_cas(&ctrl[C7_EVDONE], done, done + n) == done) { at = done; break; }
+            }
+        }
+        at = w_shfl(at, 0); n = w_shfl(n, 0);
+        if (at < 0) return;
+        if (lane < n) {
+            int* e = ctrl + C7_EV + 3 * (at + lane);
+            int w;
+            while ((w = ld_vol(&e[2])) == 0) c_yield();            // reserved but not yet written
+            fence_block();
+            ins_commit(P, P.b.seq + (uint32_t)ld_vol(&e[1]), ld_vol(&e[0]), (int)((uint32_t)w & 0xFFFFu), (int)((uint32_t)w >> 16));
+        }
+        w_sync();
     }
 }
 
@@ -435,7 +460,7 @@ struct WarpSink7 {
     }
     AMP_HD void match(int rpos, int q, int n) { push(rpos, n, q); }
     AMP_HD void del(int rpos, int n) { push(rpos, (int)(0x80000000u | (unsigned)n), 0); }
-    AMP_HD void ins(int pos, int b, int n) { ins_defer(*P, wm.ctrl, so0, pos, b, n); }
+    AMP_WD void ins(int pos, int b, int n) { ins_defer(*P, wm.ctrl, so0, pos, b, n); }
 };
 
 // one base outside the tile (or of an unstaged run): straight to the global matrix.  row = BAM nibble, or AMP7_DEL_CODE
@@ -644,8 +669,9 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
         for (int i = tid; i < AMP7_SINK_ROW * wt; i += nthreads) cnt[i] = 0;
         for (int i = tid; i < wt; i += nthreads) cnt[del_row_off(wt) + i] = 0;
     }
-    if (tid == 0) { ctrl[C7_NEXT] = 0; ctrl[C7_NGEN] = 0; ctrl[C7_GNEXT] = 0; ctrl[C7_FASTDONE] = 0; ctrl[C7_NEV] = 0; }
+    if (tid == 0) { ctrl[C7_NEXT] = 0; ctrl[C7_NGEN] = 0; ctrl[C7_GNEXT] = 0; ctrl[C7_FASTDONE] = 0; ctrl[C7_NEV] = 0; ctrl[C7_EVDONE] = 0; }
     for (int k = tid; k < AMP7_GLCAP; k += nthreads) ctrl[C7_GL + k] = 0;   // list entries: 0 = not written yet
+    for (int k = tid; k < AMP7_EVCAP; k += nthreads) ctrl[C7_EV + 3 * k + 2] = 0;
     const int nwarps = nthreads >> 5, n_fast = nwarps - dwarps;     // warps [0, n_fast) take batches, the rest only the list
     if (lane == 0) mbar_init(wm.bar);
     const int wb = chunk_window_base(P, ctrl, P.b.first + g_lo * BR, n_end, tid, n_batches > 0);
@@ -700,6 +726,42 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
         M.g2 = nc > 2 ? P.b.cigar[M.c0 + 2] : 0u;
         M.g3 = nc > 3 ? P.b.cigar[M.c0 + 3] : 0u;
         M.g4 = nc > 4 ? P.b.cigar[M.c0 + 4] : 0u;
+    };
+    // One round of the generic phase: up to AMP7_GN listed reads, taken by a generic-capable warp between two of its batches
+    // (wait = false: only what is there) or when its batches are done (wait = true: until the list is complete and empty).
+    const bool is_gwarp = warp >= nwarps - gwarps;
+    const WarpMem7 gm = carve_warp7(smem_base, wt, nwarps, gwarps, is_gwarp ? warp - (nwarps - gwarps) : 0);
+    auto generic_round = [&](bool wait) -> bool {
+        int at = -1, n = 0;
+        if (lane == 0) {
+            for (;;) {
+                const bool done = ld_vol(&ctrl[C7_FASTDONE]) >= n_fast;     // read before the counters: then they are final
+                const int reserved = ld_vol(&ctrl[C7_NGEN]), claimed = ld_vol(&ctrl[C7_GNEXT]);
+                int avail = reserved - claimed;
+                if (claimed < AMP7_GLCAP) { if (avail > AMP7_GLCAP - claimed) avail = AMP7_GLCAP - claimed; }
+                else if (!done) avail = 0;
+                if (avail > 0) {
+                    n = avail < AMP7_GN ? avail : AMP7_GN;
+                    if (atomic_cas(&ctrl[C7_GNEXT], claimed, claimed + n) == claimed) { at = claimed; break; }
+                    continue;
+                }
+                if (done || !wait) break;
+                c_yield();
+            }
+        }
+        at = w_shfl(at, 0); n = w_shfl(n, 0);
+        if (at < 0) return false;
+        fence_block();
+        if (lane < n) {
+            const int idx = at + lane;
+            uint32_t v;
+            if (idx < AMP7_GLCAP) { while ((v = (uint32_t)ld_vol(&ctrl[C7_GL + idx])) == 0u) c_yield(); }   // reserved but not yet written
+            else v = ld_cg_u32(&glist[idx - AMP7_GLCAP]);
+            gm.queue[lane] = v - 1u;
+        }
+        w_sync();
+        warp_generic_phase<WT>(P, gm, cnt, wt, wbase, n, n, lane, TRIM, PILE, parity, tk);
+        return true;
     };
     Meta M, Mn;
     M.c0 = M.c1 = M.qo0 = M.qo1 = M.so0 = M.so1 = M.g0 = M.g1 = M.g2 = M.g3 = M.g4 = 0; M.flag = M.pos = M.tlen = 0;
@@ -847,47 +909,14 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
     }
     AMP7_TICK(tk, 5);
     if (warp < n_fast) { fence_block(); if (lane == 0) atomic_add(&ctrl[C7_FASTDONE], 1); }   // this warp appends no more
-    // ---- G: the reads of the list.  A generic-capable warp comes here when its batches are done and takes up to AMP7_GN
-    // of the listed reads whenever there are any (it has nothing else to do); entries in shared memory may be taken while
-    // the list is still being filled, the overflow in global memory once every batch warp is done.
-    if (warp >= nwarps - gwarps) {
-        const WarpMem7 gm = carve_warp7(smem_base, wt, nwarps, gwarps, warp - (nwarps - gwarps));
-        for (;;) {
-            int at = -1, n = 0;
-            if (lane == 0) {
-                for (;;) {
-                    const bool done = ld_vol(&ctrl[C7_FASTDONE]) >= n_fast;     // read before the counters: then they are final
-                    const int reserved = ld_vol(&ctrl[C7_NGEN]), claimed = ld_vol(&ctrl[C7_GNEXT]);
-                    int avail = reserved - claimed;
-                    if (claimed < AMP7_GLCAP) { if (avail > AMP7_GLCAP - claimed) avail = AMP7_GLCAP - claimed; }
-                    else if (!done) avail = 0;
-                    if (avail > 0) {
-                        n = avail < AMP7_GN ? avail : AMP7_GN;
-                        if (atomic_cas(&ctrl[C7_GNEXT], claimed, claimed + n) == claimed) { at = claimed; break; }
-                        continue;
-                    }
-                    if (done) break;
-                    c_yield();
-                }
-            }
-            at = w_shfl(at, 0); n = w_shfl(n, 0);
-            if (at < 0) break;
-            fence_block();
-            if (lane < n) {
-                const int idx = at + lane;
-                uint32_t v;
-                if (idx < AMP7_GLCAP) { while ((v = (uint32_t)ld_vol(&ctrl[C7_GL + idx])) == 0u) c_yield(); }   // reserved but not yet written
-                else v = ld_cg_u32(&glist[idx - AMP7_GLCAP]);
-                gm.queue[lane] = v - 1u;
-            }
-            w_sync();
-            warp_generic_phase<WT>(P, gm, cnt, wt, wbase, n, n, lane, TRIM, PILE, parity, tk);
-        }
-    }
+    // ---- G: whatever is left of the list (entries in shared memory are taken while the list is still being filled, the
+    // overflow in global memory once every batch warp is done), then the parked insertion alleles
+    if (is_gwarp) while (generic_round(true)) {}
+    if (PILE) ins_drain(P, ctrl, lane);
     AMP7_TICK(tk, 6);
     AMP7_TDUMP(tk, 0);
     c_sync();
-    if (PILE) ins_drain(P, ctrl, tid, nthreads);                   // the parked insertion alleles, one thread each
+    if (PILE) ins_drain(P, ctrl, lane);                            // alleles parked by the last warps to finish
     if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);
 #if defined(__CUDA_ARCH__) && defined(AMP7_TIMING)
     if (tid == 0 && P.phase_cycles) {   // whole-CTA cycles: sum / min / max over CTAs
