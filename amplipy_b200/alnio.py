@@ -36,6 +36,9 @@ def hostio():
         lib.amp_bgzf_bound.restype = ctypes.c_longlong
         lib.amp_bgzf_deflate.restype = ctypes.c_longlong
         lib.amp_bam_rewrite.restype = ctypes.c_longlong
+        lib.amp_bgzf_deflate_blocks.restype = ctypes.c_longlong
+        lib.amp_bgzf_plan.restype = ctypes.c_longlong
+        lib.amp_bam_serialize.restype = ctypes.c_longlong
         _lib = lib
     return _lib
 
@@ -65,6 +68,83 @@ def bgzf_decompress(raw, threads=0):
     if lib.amp_bgzf_inflate(_p(src), _p(in_off), _p(out_len), _p(out_off), _ll(n), _ll(src.size), _p(out), threads):
         raise InputError("Corrupt BGZF block")
     return out[:int(out_off[-1])]
+
+
+def bgzf_blocks(raw):
+    """Block table of a BGZF file: {"in_off": int64[n] start of every block, "out_len": uint32[n] its ISIZE}."""
+    lib = hostio()
+    src = np.frombuffer(raw, dtype=np.uint8)
+    n = lib.amp_bgzf_scan(_p(src), _ll(src.size), None, None, _ll(0))
+    if n < 0:
+        raise InputError("Invalid BGZF stream")
+    in_off = np.empty(n, np.int64)
+    out_len = np.empty(n, np.uint32)
+    lib.amp_bgzf_scan(_p(src), _ll(src.size), _p(in_off), _p(out_len), _ll(n))
+    return {"in_off": in_off, "out_len": out_len}
+
+
+def bam_layout(raw):
+    """What the device-side decoder needs from the host, without inflating the records: the BGZF block table, the BAM header
+    (text + reference list, inflated from the first block(s)) and the offset of the first record in the inflated stream."""
+    import zlib
+    blocks = bgzf_blocks(raw)
+    in_off, out_len = blocks["in_off"], blocks["out_len"]
+    mv = memoryview(raw)
+    hdr = bytearray()
+    k = 0
+
+    def more():
+        nonlocal k
+        if k >= len(in_off):
+            raise InputError("Invalid BAM file")
+        a = int(in_off[k]); e = int(in_off[k + 1]) if k + 1 < len(in_off) else len(raw)
+        xlen = int(mv[a + 10]) | (int(mv[a + 11]) << 8)
+        try:
+            hdr.extend(zlib.decompress(bytes(mv[a + 12 + xlen:e - 8]), -15))
+        except zlib.error:
+            raise InputError("Corrupt BGZF block")
+        k += 1
+
+    def need(n):
+        while len(hdr) < n:
+            more()
+    need(12)
+    if bytes(hdr[:4]) != b"BAM\x01":
+        raise InputError("Invalid BAM file")
+    l_text = int.from_bytes(hdr[4:8], "little", signed=True)
+    if l_text < 0:
+        raise InputError("Invalid BAM file")
+    need(12 + l_text)
+    header_text = bytes(hdr[8:8 + l_text]).split(b"\0", 1)[0].decode()
+    p = 8 + l_text
+    n_ref = int.from_bytes(hdr[p:p + 4], "little", signed=True); p += 4
+    refs = []
+    for _ in range(max(n_ref, 0)):
+        need(p + 4)
+        l_name = int.from_bytes(hdr[p:p + 4], "little", signed=True); p += 4
+        if l_name < 1:
+            raise InputError("Invalid BAM file")
+        need(p + l_name + 4)
+        name = bytes(hdr[p:p + l_name - 1]).decode(); p += l_name
+        refs.append((name, int.from_bytes(hdr[p:p + 4], "little", signed=True))); p += 4
+    return {"in_off": in_off, "out_len": out_len, "body_off": p, "header_text": header_text, "refs": refs}
+
+
+def bgzf_compress_units(data, bounds, level=6, threads=0):
+    """BGZF the way htslib lays a BAM out: a block holds whole units (``bounds`` = sorted cut points from 0 to len(data), e.g.
+    header end + record starts) -- a record never straddles a block boundary (bgzf_flush_try in htslib's bam_write1)."""
+    lib = hostio()
+    src = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+    bounds = np.ascontiguousarray(bounds, np.int64)
+    assert bounds[0] == 0 and bounds[-1] == src.size
+    nb = int(lib.amp_bgzf_plan(_p(bounds), _ll(bounds.size), None, _ll(0)))
+    bstart = np.empty(nb + 1, np.int64)
+    assert lib.amp_bgzf_plan(_p(bounds), _ll(bounds.size), _p(bstart), _ll(nb)) == nb
+    out = np.empty(src.size + 64 * nb + 1024, np.uint8)
+    n = lib.amp_bgzf_deflate_blocks(_p(src), _p(bstart), _ll(nb), _p(out), level, threads)
+    if n < 0:
+        raise RuntimeError("BGZF deflate failed")
+    return out[:n].tobytes()
 
 
 def bgzf_compress(data, level=6, threads=0):
@@ -212,8 +292,17 @@ def check_output_path(path):
         raise InputError("%s: %s" % (ERROR_TEXT_INVALID_READ_EXTENSION, path))
 
 
-def write_alignments(path, aln, header_text, trim, threads=0, level=6):
+def default_bam_level():
+    """Deflate level of the BAM files written here: 6 like htslib's default; AMPLIPY_BAM_LEVEL overrides (1 = fastest)."""
+    try:
+        return max(0, min(9, int(os.environ.get("AMPLIPY_BAM_LEVEL", "6"))))
+    except ValueError:
+        return 6
+
+
+def write_alignments(path, aln, header_text, trim, threads=0, level=None):
     """Write the reads that pass the gate (AmpliPy.py:910-911) with their new pos / CIGAR."""
+    level = default_bam_level() if level is None else level
     sel = np.flatnonzero(trim.keep).astype(np.int64)
     to_sam = path.lower() == "stdout" or path.lower().endswith(".sam")
     if to_sam:
@@ -241,13 +330,37 @@ def write_alignments(path, aln, header_text, trim, threads=0, level=6):
         lib.amp_bam_rewrite(_p(aln.bam_buf), _p(aln.bam_rec_off), _p(sel), _ll(len(sel)), _p(trim.pos), _p(trim.ncig),
                             _p(b.cig_off), _p(trim.cigar), _p(body))
         body = body[:int(size)]
+        ooff = np.empty(len(sel) + 1, np.int64)
+        lib.amp_bam_rewrite_offsets(_p(aln.bam_buf), _p(aln.bam_rec_off), _p(sel), _ll(len(sel)), _p(trim.ncig), _p(ooff))
+        head = _bam_header_bytes(header_text, aln.refs)
+        hb = np.frombuffer(head, np.uint8)
+        bounds = np.unique(np.concatenate([[0], hb.size + ooff]).astype(np.int64))
+        with open(path, "wb") as f:
+            f.write(bgzf_compress_units(np.concatenate([hb, body]), bounds, level, threads))
+        return len(sel)
     else:
         body = np.frombuffer(b"".join(_sam_fields_to_bam(aln, int(i), int(trim.pos[i]), trim.cigartuples(int(i))) for i in sel),
                              np.uint8)
     head = _bam_header_bytes(header_text, aln.refs)
     with open(path, "wb") as f:
-        f.write(bgzf_compress(np.concatenate([np.frombuffer(head, np.uint8), body]), level, threads))
+        f.write(_bam_file_bytes(head, np.ascontiguousarray(body), level, threads))
     return len(sel)
+
+
+def _bam_file_bytes(head, body, level, threads):
+    """header + records as BGZF with htslib's layout: the header in blocks of its own, records never straddling a block"""
+    lib = hostio()
+    body = np.ascontiguousarray(body, np.uint8)
+    n = int(lib.amp_bam_scan(_p(body), _ll(body.size), _ll(0), None, None, None, _ll(0))) if body.size else 0
+    if n < 0:
+        raise RuntimeError("internal error: malformed BAM records")
+    rec_off = np.empty(max(n, 1), np.int64); ncig = np.empty(max(n, 1), np.int32); lseq = np.empty(max(n, 1), np.int32)
+    if n:
+        lib.amp_bam_scan(_p(body), _ll(body.size), _ll(0), _p(rec_off), _p(ncig), _p(lseq), _ll(n))
+    hb = np.frombuffer(head, np.uint8)
+    bounds = np.concatenate([[0], hb.size + rec_off[:n], [hb.size + body.size]]).astype(np.int64)
+    bounds = np.unique(bounds)
+    return bgzf_compress_units(np.concatenate([hb, body]), bounds, level, threads)
 
 
 def _bam_header_bytes(header_text, refs):
@@ -363,21 +476,20 @@ def _bam_tags_to_sam(b):
 
 
 def write_bam(path, header_text, refs, batch, names=None, mapq=60, threads=0, level=1):
-    """Serialise a ReadBatch as a BAM file (synthetic inputs for tests / benchmarks)."""
-    import struct
-    n = batch.n
-    parts = [_bam_header_bytes(header_text, refs)]
-    for i in range(n):
-        pos, flag, tlen, ops, seq, qual = batch.record(i)
-        name = (names[i] if names else "r%d" % i).encode() + b"\0"
-        rlen = sum(x for op, x in ops if op in (0, 2, 3, 7, 8))
-        if (flag & 4) or rlen == 0:
-            rlen = 1
-        a, c = int(batch.cig_off[i]), int(batch.cig_off[i + 1])
-        core = struct.pack("<iiBBHHHiiii", 0 if not (flag & 4) else -1, pos, len(name), mapq, _reg2bin(pos, pos + rlen), c - a, flag,
-                           len(seq), 0 if (flag & 1) else -1, max(pos + tlen, 0) if (flag & 1) else -1, tlen)
-        body = core + name + batch.cigar[a:c].tobytes() + batch.seq[int(batch.seq_off[i]):int(batch.seq_off[i + 1])].tobytes() + \
-            bytes(qual)
-        parts.append(struct.pack("<I", len(body)) + body)
+    """Serialise a ReadBatch as a BAM file (synthetic inputs for tests / benchmarks; read names r<i>)."""
+    lib = hostio()
+    b = batch
+    nblob = noff = None
+    if names is not None:
+        enc = [str(x).encode() + b"\0" for x in names]
+        assert len(enc) == b.n and all(len(e) <= 255 for e in enc)
+        noff = np.zeros(b.n + 1, np.int64)
+        np.cumsum([len(e) for e in enc], out=noff[1:])
+        nblob = np.frombuffer(b"".join(enc) + b"\0", np.uint8)
+    args = (_ll(b.n), _p(b.pos), _p(b.flag), _p(b.tlen), _p(b.cig_off), _p(b.cigar), _p(b.seq_off), _p(b.seq), _p(b.qual_off),
+            _p(b.qual), int(mapq), _p(nblob), _p(noff))
+    size = int(lib.amp_bam_serialize(*args, None, None))
+    body = np.empty(size + 8, np.uint8)
+    lib.amp_bam_serialize(*args, _p(body), None)
     with open(path, "wb") as f:
-        f.write(bgzf_compress(b"".join(parts), level, threads))
+        f.write(_bam_file_bytes(_bam_header_bytes(header_text, refs), body[:size], level, threads))

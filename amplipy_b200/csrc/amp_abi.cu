@@ -11,6 +11,7 @@
 
 #include "../../include/amplipy_b200.h"
 #include "amp_warp.cuh"
+#include "amp_bgzf.cuh"
 
 static_assert(AMP_F_TRIM_START == AMP_FLAG_TRIM_START && AMP_F_KEEP == AMP_FLAG_KEEP && AMP_F_SKIPPED == AMP_FLAG_SKIPPED &&
                   AMP_F_ERROR == AMP_FLAG_ERROR && AMP_E_ARENA_FULL == AMP_DEVERR_ARENA_FULL,
@@ -333,6 +334,79 @@ __global__ void amp_ins_merge_packed_kernel(amp::InsTable tab, const unsigned lo
     }
 }
 
+// ---- BGZF / BAM decode on the device (amp_bgzf.cuh) ------------------------------------------------------------------------
+#define AMPZ_WARPS 16
+__global__ void __launch_bounds__(AMPZ_WARPS * 32) amp_bgzf_inflate_kernel(const uint8_t* comp, long long comp_len, const long long* in_off,
+                                                                          const uint32_t* out_len, const long long* out_off, long long k0,
+                                                                          long long k1, uint8_t* raw, unsigned int* next, unsigned int* err) {
+    extern __shared__ __align__(16) unsigned char zsm[];
+    amp::InflateMem& M = ((amp::InflateMem*)zsm)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(next, 1u);
+        const long long k = k0 + (long long)__shfl_sync(0xFFFFFFFFu, t, 0);
+        if (k >= k1) break;
+        const uint8_t* b = comp + in_off[k];
+        const long long bend = in_off[k + 1];                 // (the table has one entry more: the end of the last block)
+        const long long xlen = (long long)b[10] | ((long long)b[11] << 8);
+        const long long clen = bend - in_off[k] - 12 - xlen - 8;
+        int e = 0;
+        if (clen < 0) e = AMPZ_E_DATA;
+        else if (out_len[k]) e = amp::inflate_block(b + 12 + xlen, clen, raw + out_off[k], (long long)out_len[k], M, lane);
+        if (e && lane == 0) atomicOr(err, (unsigned int)e);
+        __syncwarp();
+    }
+}
+__global__ void amp_bam_count_kernel(const uint8_t* raw, const long long* out_off, long long n_blocks, long long body_off,
+                                     amp::BamBlockTotals* tot, unsigned int* err) {
+    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= n_blocks) return;
+    long long lo = out_off[k]; const long long hi = out_off[k + 1];
+    if (lo < body_off) lo = body_off;
+    amp::BamBlockTotals t; t.n_rec = 0; t.n_cig = 0; t.n_seq = 0; t.n_qual = 0;
+    if (lo < hi && !amp::bam_chain_totals(raw, lo, hi, t)) { atomicOr(err, (unsigned int)AMPZ_E_ALIGN); t.n_rec = 0; t.n_cig = 0; t.n_seq = 0; t.n_qual = 0; }
+    tot[k] = t;
+}
+// exclusive prefix sums of the per-block totals (one CTA): prefix[c][k], c = records, CIGAR ops, seq bytes, qual bytes; prefix[c][n] = total
+__global__ void __launch_bounds__(1024) amp_bam_scan_kernel(const amp::BamBlockTotals* tot, long long n_blocks, unsigned long long* prefix) {
+    __shared__ unsigned long long part[4][1024];
+    const int t = threadIdx.x;
+    const long long per = (n_blocks + 1023) / 1024, lo = t * per, hi = lo + per < n_blocks ? lo + per : n_blocks;
+    unsigned long long s[4] = {0, 0, 0, 0};
+    for (long long k = lo; k < hi; ++k) { s[0] += tot[k].n_rec; s[1] += tot[k].n_cig; s[2] += tot[k].n_seq; s[3] += tot[k].n_qual; }
+    for (int c = 0; c < 4; ++c) part[c][t] = s[c];
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        unsigned long long v[4];
+        for (int c = 0; c < 4; ++c) v[c] = t >= d ? part[c][t - d] : 0ULL;
+        __syncthreads();
+        for (int c = 0; c < 4; ++c) part[c][t] += v[c];
+        __syncthreads();
+    }
+    unsigned long long run[4];
+    for (int c = 0; c < 4; ++c) run[c] = part[c][t] - s[c];
+    for (long long k = lo; k < hi; ++k) {
+        for (int c = 0; c < 4; ++c) prefix[(size_t)c * (n_blocks + 1) + k] = run[c];
+        run[0] += tot[k].n_rec; run[1] += tot[k].n_cig; run[2] += tot[k].n_seq; run[3] += tot[k].n_qual;
+    }
+    if (t == 1023) for (int c = 0; c < 4; ++c) prefix[(size_t)c * (n_blocks + 1) + n_blocks] = part[c][1023];
+}
+__global__ void __launch_bounds__(256) amp_bam_scatter_kernel(const uint8_t* raw, const long long* out_off, long long n_blocks, long long body_off,
+                                                             const unsigned long long* prefix, amp::BamSoa D) {
+    const long long k = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (k >= n_blocks) return;
+    long long lo = out_off[k]; const long long hi = out_off[k + 1];
+    if (lo < body_off) lo = body_off;
+    const size_t st = (size_t)(n_blocks + 1);
+    if (lo < hi) amp::bam_scatter_block(raw, lo, hi, D, prefix[k], prefix[st + k], prefix[2 * st + k], prefix[3 * st + k], lane);
+    if (k == n_blocks - 1 && lane == 0) {                     // the closing entries of the three offset arrays
+        const unsigned long long n = prefix[n_blocks];
+        D.cig_off[n] = (uint32_t)prefix[st + n_blocks]; D.seq_off[n] = (uint32_t)prefix[2 * st + n_blocks]; D.qual_off[n] = (uint32_t)prefix[3 * st + n_blocks];
+    }
+}
+
 struct DevChunk {   // device staging for one in-flight chunk of amp_process_host
     cudaStream_t stream = nullptr;
     int32_t* pos = nullptr; uint16_t* flag = nullptr; int32_t* tlen = nullptr;
@@ -362,6 +436,21 @@ struct amp_ctx {
     int last_launches = 0;
     size_t max_dyn_smem = 0;
     bool v7_attr = false;
+    // decoded file (amp_bam_decode_host): compressed bytes, inflated stream, block tables, struct-of-arrays batch, trim outputs
+    struct Decoded {
+        uint8_t* comp = nullptr; size_t cap_comp = 0;
+        uint8_t* raw = nullptr; size_t cap_raw = 0;
+        long long* in_off = nullptr; long long* out_off = nullptr; uint32_t* out_len = nullptr; amp::BamBlockTotals* tot = nullptr;
+        unsigned long long* prefix = nullptr; size_t cap_blocks = 0;
+        unsigned int* ctr = nullptr;                              // [0] block counter of the inflate kernel, [1] error bits
+        int32_t* pos = nullptr; uint16_t* flag = nullptr; int32_t* tlen = nullptr; uint32_t *cig_off = nullptr, *seq_off = nullptr, *qual_off = nullptr;
+        unsigned long long* rec_off = nullptr; int32_t* o_pos = nullptr; uint16_t* o_ncig = nullptr; uint8_t* o_flags = nullptr; size_t cap_reads = 0;
+        uint32_t* cigar = nullptr; size_t cap_cig = 0; uint8_t* seq = nullptr; size_t cap_seq = 0; uint8_t* qual = nullptr; size_t cap_qual = 0;
+        uint32_t* o_cigar = nullptr; size_t cap_ocig = 0; uint32_t* scratch = nullptr; size_t cap_scratch = 0;
+        long long n_reads = 0, sum_cig = 0, sum_seq = 0, sum_qual = 0, n_blocks = 0, raw_len = 0;
+        bool valid = false, z_attr = false;
+        cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    } dec;
     unsigned char* d_xbuf = nullptr; size_t xbuf_bytes = 0;   // scratch of amp_ins_export / amp_ins_merge (grown at high-water marks)
     unsigned char* d_ref = nullptr;     // reference characters (amp_set_reference)
     unsigned char* d_call = nullptr;    // calling outputs (one block, offsets below)
@@ -538,6 +627,13 @@ int amp_destroy(amp_ctx* c) {
     if (c->counts_owned) cudaFree(c->d_counts);
     cudaFree(c->tab.slots); cudaFree(c->tab.entries); cudaFree(c->tab.slot_entry); cudaFree(c->tab.arena); cudaFree(c->tab.cursor);
     cudaFree(c->d_err); cudaFree(c->d_heads); cudaFree(c->d_scratch); cudaFree(c->d_glist); cudaFree(c->d_ref); cudaFree(c->d_call); cudaFree(c->d_xbuf);
+    {
+        auto& d = c->dec;
+        void* ps[] = {d.comp, d.raw, d.in_off, d.out_off, d.out_len, d.tot, d.prefix, d.ctr, d.pos, d.flag, d.tlen, d.cig_off, d.seq_off, d.qual_off,
+                      d.rec_off, d.o_pos, d.o_ncig, d.o_flags, d.cigar, d.seq, d.qual, d.o_cigar, d.scratch};
+        for (void* q : ps) cudaFree(q);
+        for (auto& e : d.ev) if (e) cudaEventDestroy(e);
+    }
     for (auto& ch : c->chunk) {
         cudaFree(ch.pos); cudaFree(ch.flag); cudaFree(ch.tlen); cudaFree(ch.cig_off); cudaFree(ch.seq_off); cudaFree(ch.qual_off);
         cudaFree(ch.cigar); cudaFree(ch.seq); cudaFree(ch.qual); cudaFree(ch.o_pos); cudaFree(ch.o_ncig); cudaFree(ch.o_flags);
@@ -1023,6 +1119,174 @@ int amp_counts_copy_device(amp_ctx* c, int32_t* dev_dst, void* stream) {
     if (!c || !dev_dst) return fail(AMP_ERR_ARG, "amp_counts_copy_device: null argument");
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaMemcpyAsync(dev_dst, c->d_counts, (size_t)c->cfg.n_samples * AMP_NCH * c->Lpad * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return AMP_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// BAM on the device: the compressed file crosses PCIe as it is and is decoded in HBM (amp_bgzf.cuh)
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int amp_bam_decode_host(amp_ctx* c, const uint8_t* bgzf, int64_t n_bytes, const int64_t* block_off, const uint32_t* block_isize,
+                        int64_t n_blocks, int64_t body_off, amp_bam_info* info) {
+    if (!c || !bgzf || !block_off || !block_isize || !info || n_bytes < 0 || n_blocks < 0 || body_off < 0)
+        return fail(AMP_ERR_ARG, "amp_bam_decode_host: bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    auto& d = c->dec;
+    d.valid = false;
+    cudaStream_t sc = c->chunk[0].stream, sx = c->chunk[1].stream;    // compute / copy
+    CK(cudaStreamSynchronize(sc)); CK(cudaStreamSynchronize(sx));
+    // host-side tables: block ends, output offsets
+    std::vector<long long> in_off((size_t)n_blocks + 1), out_off((size_t)n_blocks + 1);
+    long long raw_len = 0;
+    for (int64_t k = 0; k < n_blocks; ++k) {
+        if (block_off[k] < 0 || block_off[k] + 28 > n_bytes || (k && block_off[k] <= block_off[k - 1])) return fail(AMP_ERR_ARG, "amp_bam_decode_host: bad block table");
+        in_off[k] = block_off[k]; out_off[k] = raw_len; raw_len += block_isize[k];
+    }
+    in_off[n_blocks] = n_bytes; out_off[n_blocks] = raw_len;
+    if (body_off > raw_len) return fail(AMP_ERR_ARG, "amp_bam_decode_host: body offset beyond the stream");
+    int rc;
+    if ((rc = dev_grow(&d.comp, &d.cap_comp, (size_t)n_bytes + 64))) return rc;
+    if ((rc = dev_grow(&d.raw, &d.cap_raw, (size_t)raw_len + 64))) return rc;
+    if ((size_t)n_blocks + 1 > d.cap_blocks) {
+        const size_t want = (size_t)n_blocks + 1 + 256;
+        cudaFree(d.in_off); cudaFree(d.out_off); cudaFree(d.out_len); cudaFree(d.tot); cudaFree(d.prefix);
+        d.in_off = d.out_off = nullptr; d.out_len = nullptr; d.tot = nullptr; d.prefix = nullptr; d.cap_blocks = 0;
+        CK(cudaMalloc((void**)&d.in_off, want * 8)); CK(cudaMalloc((void**)&d.out_off, want * 8)); CK(cudaMalloc((void**)&d.out_len, want * 4));
+        CK(cudaMalloc((void**)&d.tot, want * sizeof(amp::BamBlockTotals))); CK(cudaMalloc((void**)&d.prefix, want * 4 * 8));
+        d.cap_blocks = want;
+    }
+    if (!d.ctr) CK(cudaMalloc((void**)&d.ctr, 64));
+    for (auto& e : d.ev) if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!d.z_attr) {
+        CK(cudaFuncSetAttribute(amp_bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AMPZ_WARPS * sizeof(amp::InflateMem))));
+        d.z_attr = true;
+    }
+    CK(cudaMemcpyAsync(d.in_off, in_off.data(), ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, sx));
+    CK(cudaMemcpyAsync(d.out_off, out_off.data(), ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, sx));
+    CK(cudaMemcpyAsync(d.out_len, block_isize, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, sx));
+    CK(cudaMemsetAsync(d.ctr, 0, 64, sx));
+    // the compressed bytes in up to eight pieces on the copy stream; each piece is inflated as soon as it has landed
+    const int pieces = n_blocks >= 64 ? 8 : 1;
+    c->last_launches = 0;
+    for (int pi = 0; pi < pieces; ++pi) {
+        const long long k0 = n_blocks * pi / pieces, k1 = n_blocks * (pi + 1) / pieces;
+        if (k1 <= k0) continue;
+        const long long b0 = in_off[k0], b1 = in_off[k1];
+        CK(cudaMemcpyAsync(d.comp + b0, bgzf + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sx));
+        CK(cudaEventRecord(d.ev[pi], sx));
+        CK(cudaStreamWaitEvent(sc, d.ev[pi], 0));
+        CK(cudaMemsetAsync(d.ctr, 0, 4, sc));
+        const long long nb = k1 - k0;
+        const int grid = (int)std::min<long long>((nb + AMPZ_WARPS - 1) / AMPZ_WARPS, (long long)c->sm_count * 2);
+        amp_bgzf_inflate_kernel<<<grid, AMPZ_WARPS * 32, AMPZ_WARPS * sizeof(amp::InflateMem), sc>>>(d.comp, n_bytes, d.in_off, d.out_len, d.out_off, k0, k1, d.raw,
+                                                                                                  d.ctr, d.ctr + 1);
+        CK(cudaGetLastError());
+        c->last_launches += 1;
+    }
+    unsigned long long tot[4] = {0, 0, 0, 0};
+    unsigned int zerr = 0;
+    if (n_blocks > 0) {
+        amp_bam_count_kernel<<<(unsigned)((n_blocks + 127) / 128), 128, 0, sc>>>(d.raw, d.out_off, n_blocks, body_off, d.tot, d.ctr + 1);
+        CK(cudaGetLastError());
+        amp_bam_scan_kernel<<<1, 1024, 0, sc>>>(d.tot, n_blocks, d.prefix);
+        CK(cudaGetLastError());
+        c->last_launches += 2;
+        const size_t st = (size_t)n_blocks + 1;
+        for (int k = 0; k < 4; ++k) CK(cudaMemcpyAsync(&tot[k], d.prefix + k * st + n_blocks, 8, cudaMemcpyDeviceToHost, sc));
+        CK(cudaMemcpyAsync(&zerr, d.ctr + 1, 4, cudaMemcpyDeviceToHost, sc));
+    }
+    CK(cudaStreamSynchronize(sc));
+    if (zerr & (AMPZ_E_DATA | AMPZ_E_SIZE)) return fail(AMP_ERR_DATA, "amp_bam_decode_host: corrupt BGZF block");
+    if (zerr & AMPZ_E_ALIGN) return fail(AMP_ERR_DATA, "amp_bam_decode_host: a BAM record straddles a BGZF block boundary (not written by htslib?): use the host decoder");
+    if (tot[2] >= (1ULL << 32) || tot[3] >= (1ULL << 32) || tot[1] >= (1ULL << 32)) return fail(AMP_ERR_DATA, "amp_bam_decode_host: more than 4 GiB of bases in one batch; split the input");
+    const size_t n = (size_t)tot[0];
+    if (n + 1 > d.cap_reads) {
+        const size_t want = n + 1 + n / 8 + 64;
+        void** arrs[] = {(void**)&d.pos, (void**)&d.flag, (void**)&d.tlen, (void**)&d.cig_off, (void**)&d.seq_off, (void**)&d.qual_off,
+                         (void**)&d.rec_off, (void**)&d.o_pos, (void**)&d.o_ncig, (void**)&d.o_flags};
+        for (void** ap : arrs) { if (*ap) CK(cudaFree(*ap)); *ap = nullptr; CK(cudaMalloc(ap, want * 8)); }
+        d.cap_reads = want;
+    }
+    if ((rc = dev_grow(&d.cigar, &d.cap_cig, (size_t)tot[1] + 8))) return rc;
+    if ((rc = dev_grow(&d.seq, &d.cap_seq, (size_t)tot[2] + 64))) return rc;
+    if ((rc = dev_grow(&d.qual, &d.cap_qual, (size_t)tot[3] + 64))) return rc;
+    if (n_blocks > 0 && n > 0) {
+        amp::BamSoa D{d.pos, d.flag, d.tlen, d.cig_off, d.cigar, d.seq_off, d.seq, d.qual_off, d.qual, d.rec_off};
+        amp_bam_scatter_kernel<<<(unsigned)((n_blocks * 32 + 255) / 256), 256, 0, sc>>>(d.raw, d.out_off, n_blocks, body_off, d.prefix, D);
+        CK(cudaGetLastError());
+        c->last_launches += 1;
+    } else {
+        CK(cudaMemsetAsync(d.cig_off, 0, 4, sc)); CK(cudaMemsetAsync(d.seq_off, 0, 4, sc)); CK(cudaMemsetAsync(d.qual_off, 0, 4, sc));
+    }
+    d.n_reads = (long long)n; d.sum_cig = (long long)tot[1]; d.sum_seq = (long long)tot[2]; d.sum_qual = (long long)tot[3];
+    d.n_blocks = n_blocks; d.raw_len = raw_len; d.valid = true;
+    info->n_reads = d.n_reads; info->sum_cigar_ops = d.sum_cig; info->sum_seq_bytes = d.sum_seq; info->sum_qual_bytes = d.sum_qual;
+    info->raw_bytes = raw_len;
+    return AMP_OK;
+}
+
+int amp_process_decoded(amp_ctx* c, int mode, int sample, const amp_trim_out* host_out) {
+    if (!c) return fail(AMP_ERR_ARG, "amp_process_decoded: null context");
+    auto& d = c->dec;
+    if (!d.valid) return fail(AMP_ERR_STATE, "amp_process_decoded: no decoded batch (amp_bam_decode_host first)");
+    if (sample < 0 || sample >= c->cfg.n_samples) return fail(AMP_ERR_ARG, "amp_process_decoded: sample out of range");
+    if ((mode & AMP_MODE_TRIM) && !c->d_min_start) return fail(AMP_ERR_ARG, "amp_process_decoded: trimming needs primer tables");
+    if (!(mode & (AMP_MODE_TRIM | AMP_MODE_PILEUP))) return fail(AMP_ERR_ARG, "amp_process_decoded: empty mode");
+    CK(cudaSetDevice(c->cfg.device));
+    cudaStream_t sc = c->chunk[0].stream;
+    const bool trim = mode & AMP_MODE_TRIM;
+    const size_t n = (size_t)d.n_reads, orows = (size_t)d.sum_cig + 3 * n;
+    int rc;
+    if (trim) {
+        if ((rc = dev_grow(&d.o_cigar, &d.cap_ocig, orows + 8))) return rc;
+        if ((rc = dev_grow(&d.scratch, &d.cap_scratch, 2 * (orows + 8)))) return rc;
+    }
+    {
+        const size_t need = glist_words_for(c, (long long)n);
+        if (need > c->glist_words) {
+            if (c->d_glist) CK(cudaFree(c->d_glist));
+            c->d_glist = nullptr; c->glist_words = 0;
+            CK(cudaMalloc((void**)&c->d_glist, need * 4));
+            c->glist_words = need;
+        }
+    }
+    c->last_launches = 0;
+    amp::BatchPtrs bp{0, (long long)n, d.pos, d.flag, d.tlen, d.cig_off, d.cigar, d.seq_off, d.seq, d.qual_off, d.qual};
+    amp::TrimOut to{};
+    if (trim) { to.pos = d.o_pos; to.ncig = d.o_ncig; to.flags = d.o_flags; to.cigar = d.o_cigar; }
+    if ((rc = launch_process(c, bp, d.sum_cig, 0, d.sum_qual > 0 ? d.sum_qual : 1, mode, sample, to, trim ? d.scratch : nullptr, c->d_glist, sc))) return rc;
+    if (trim && host_out && n) {
+        if (host_out->pos) CK(cudaMemcpyAsync(host_out->pos, d.o_pos, n * 4, cudaMemcpyDeviceToHost, sc));
+        if (host_out->ncig) CK(cudaMemcpyAsync(host_out->ncig, d.o_ncig, n * 2, cudaMemcpyDeviceToHost, sc));
+        if (host_out->flags) CK(cudaMemcpyAsync(host_out->flags, d.o_flags, n, cudaMemcpyDeviceToHost, sc));
+        if (host_out->cigar) CK(cudaMemcpyAsync(host_out->cigar, d.o_cigar, orows * 4, cudaMemcpyDeviceToHost, sc));
+    }
+    CK(cudaStreamSynchronize(sc));
+    return AMP_OK;
+}
+
+// the decoded batch back on the host (parity tests, the command line's BAM writer): any pointer may be NULL
+int amp_decoded_copy_host(amp_ctx* c, const amp_batch_out* h, uint64_t* rec_off) {
+    if (!c || !h) return fail(AMP_ERR_ARG, "amp_decoded_copy_host: null argument");
+    auto& d = c->dec;
+    if (!d.valid) return fail(AMP_ERR_STATE, "amp_decoded_copy_host: no decoded batch");
+    CK(cudaSetDevice(c->cfg.device));
+    cudaStream_t sc = c->chunk[0].stream;
+    const size_t n = (size_t)d.n_reads;
+    if (h->pos) CK(cudaMemcpyAsync(h->pos, d.pos, n * 4, cudaMemcpyDeviceToHost, sc));
+    if (h->flag) CK(cudaMemcpyAsync(h->flag, d.flag, n * 2, cudaMemcpyDeviceToHost, sc));
+    if (h->tlen) CK(cudaMemcpyAsync(h->tlen, d.tlen, n * 4, cudaMemcpyDeviceToHost, sc));
+    if (h->cig_off) CK(cudaMemcpyAsync(h->cig_off, d.cig_off, (n + 1) * 4, cudaMemcpyDeviceToHost, sc));
+    if (h->seq_off) CK(cudaMemcpyAsync(h->seq_off, d.seq_off, (n + 1) * 4, cudaMemcpyDeviceToHost, sc));
+    if (h->qual_off) CK(cudaMemcpyAsync(h->qual_off, d.qual_off, (n + 1) * 4, cudaMemcpyDeviceToHost, sc));
+    if (h->cigar && d.sum_cig) CK(cudaMemcpyAsync(h->cigar, d.cigar, (size_t)d.sum_cig * 4, cudaMemcpyDeviceToHost, sc));
+    if (h->seq && d.sum_seq) CK(cudaMemcpyAsync(h->seq, d.seq, (size_t)d.sum_seq, cudaMemcpyDeviceToHost, sc));
+    if (h->qual && d.sum_qual) CK(cudaMemcpyAsync(h->qual, d.qual, (size_t)d.sum_qual, cudaMemcpyDeviceToHost, sc));
+    if (rec_off && n) CK(cudaMemcpyAsync(rec_off, d.rec_off, n * 8, cudaMemcpyDeviceToHost, sc));
+    CK(cudaStreamSynchronize(sc));
     return AMP_OK;
 }
 

@@ -1,0 +1,312 @@
+// amp_bgzf.cuh -- BGZF / BAM decode on the device (sm_100a): the step in front of the hot path.
+//
+// The reference gets its records from pysam / htslib (AmpliPy.py:296-360 create_AlignmentFile_objects, 896 iteration); here the
+// compressed file crosses PCIe as it is (about a fifth of the decoded struct-of-arrays bytes) and is decoded in HBM:
+//   inflate_block   one warp per BGZF block (RFC 1951): lane 0 reads bits and decodes Huffman symbols -- literals are stored as
+//                   they come -- and hands every match (length, distance) to the warp, whose lanes copy it together; the code
+//                   tables of a block (a 10-bit direct table + canonical lists for longer codes) live in the warp's shared memory
+//   bam_count       one thread per BGZF block walks its record chain: htslib never lets a record straddle a block boundary
+//                   (bgzf_flush_try in bam_write1), so every block starts on a record; a block that does not end on one raises an
+//                   error and the host falls back to its own decoder
+//   bam_scatter     one warp per block: records -> pos / flag / tlen / packed CIGAR / 4-bit seq / qual arrays at the offsets the
+//                   prefix sums over the per-block totals give
+// Written with the warp primitives of amp_warp.cuh so that tests/emu runs the same source on the CPU (against zlib).
+#pragma once
+#include "amp_warp.cuh"
+
+namespace amp {
+
+#define AMPZ_LBITS 10                 // direct table of the literal / length code
+#define AMPZ_DBITS 8                  // direct table of the distance code
+#define AMPZ_E_DATA 1                 // malformed deflate stream
+#define AMPZ_E_SIZE 2                 // output does not match ISIZE
+#define AMPZ_E_ALIGN 4                // a BAM record straddles a block boundary (or a record header does not fit its record)
+
+// RFC 1951 3.2.5: base values / extra bits of the length and distance symbols, order of the code-length code lengths
+#if defined(__CUDACC__)
+#define AMPZ_TABLE __device__ __constant__
+#else
+#define AMPZ_TABLE static const
+#endif
+AMPZ_TABLE uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+AMPZ_TABLE uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+AMPZ_TABLE uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+AMPZ_TABLE uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+AMPZ_TABLE uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct HuffLists { uint16_t count[16]; uint16_t symbol[288]; };          // canonical code: symbols ordered by (length, symbol)
+struct InflateMem {                                                       // per warp, in shared memory
+    uint16_t ltab[1 << AMPZ_LBITS];                                       // (symbol << 4) | length, 0 = longer than the table
+    uint16_t dtab[1 << AMPZ_DBITS];
+    HuffLists lit, dist;
+    uint8_t lens[320];
+};
+
+struct BitReader {
+    const uint32_t* wp;               // next aligned word
+    const uint32_t* wend;             // first word past the readable range
+    unsigned long long buf; int cnt;  // cnt valid bits in buf
+};
+AMP_WD void br_init(BitReader& b, const uint8_t* p, const uint8_t* end) {
+    const uintptr_t a = (uintptr_t)p;
+    b.wp = (const uint32_t*)(a & ~(uintptr_t)3);
+    b.wend = (const uint32_t*)(((uintptr_t)end + 3) & ~(uintptr_t)3);
+    const int skip = (int)(a & 3) * 8;
+    b.buf = (unsigned long long)(*b.wp++) >> skip; b.cnt = 32 - skip;
+}
+AMP_WD void br_refill(BitReader& b) {               // at least 32 valid bits afterwards (zeros past the end of the input)
+    if (b.cnt <= 32) {
+        const unsigned long long w = b.wp < b.wend ? (unsigned long long)*b.wp : 0ULL;
+        ++b.wp;
+        b.buf |= w << b.cnt; b.cnt += 32;
+    }
+}
+AMP_WD unsigned br_peek(const BitReader& b, int n) { return (unsigned)(b.buf & ((1ULL << n) - 1ULL)); }
+AMP_WD void br_skip(BitReader& b, int n) { b.buf >>= n; b.cnt -= n; }
+AMP_WD unsigned br_bits(BitReader& b, int n) { br_refill(b); const unsigned v = br_peek(b, n); br_skip(b, n); return v; }
+// bytes consumed so far (whole bytes; the bit position rounded up)
+AMP_WD long long br_bytes_used(const BitReader& b, const uint8_t* start) {
+    return (long long)((const uint8_t*)b.wp - start) - (b.cnt >> 3);
+}
+
+AMP_WD unsigned rev_bits(unsigned v, int n) {       // the low n bits of v in reverse order
+#if defined(__CUDA_ARCH__)
+    return __brev(v) >> (32 - n);
+#else
+    unsigned r = 0;
+    for (int i = 0; i < n; ++i) r |= ((v >> i) & 1u) << (n - 1 - i);
+    return r;
+#endif
+}
+
+// canonical lists from code lengths (lane 0); returns false for an over-subscribed or incomplete code (a single-code distance
+// tree is allowed, as zlib allows it)
+AMP_WD bool huff_lists(HuffLists& h, const uint8_t* len, int n) {
+    for (int l = 0; l < 16; ++l) h.count[l] = 0;
+    for (int s = 0; s < n; ++s) ++h.count[len[s]];
+    if (h.count[0] == n) return true;               // no codes at all: legal as long as none is used
+    int left = 1;
+    for (int l = 1; l < 16; ++l) { left <<= 1; left -= h.count[l]; if (left < 0) return false; }
+    uint16_t offs[16];
+    offs[1] = 0;
+    for (int l = 1; l < 15; ++l) offs[l + 1] = (uint16_t)(offs[l] + h.count[l]);
+    for (int s = 0; s < n; ++s) if (len[s]) h.symbol[offs[len[s]]++] = (uint16_t)s;
+    return left == 0 || (n - h.count[0] == 1);
+}
+// direct table from the lists, all lanes: entry of sorted position i = code first[len] + (i - offset[len]), bit-reversed, at stride 2^len
+AMP_WD void huff_table(uint16_t* tab, int tbits, const HuffLists& h, int lane) {
+    for (int i = lane; i < (1 << tbits); i += 32) tab[i] = 0;
+    w_sync();
+    int total = 0;
+    for (int l = 1; l < 16; ++l) total += h.count[l];
+    for (int i = lane; i < total; i += 32) {
+        int l = 1, off = 0, first = 0;
+        while (i >= off + h.count[l]) { off += h.count[l]; first = (first + h.count[l]) << 1; ++l; }
+        if (l > tbits) continue;
+        const unsigned code = (unsigned)(first + (i - off));
+        const uint16_t e = (uint16_t)((h.symbol[i] << 4) | l);
+        for (unsigned r = rev_bits(code, l); r < (1u << tbits); r += 1u << l) tab[r] = e;
+    }
+    w_sync();
+}
+// one symbol (lane 0): direct table, else the canonical walk bit by bit; -1 = invalid code
+AMP_WD int huff_decode(BitReader& b, const uint16_t* tab, int tbits, const HuffLists& h) {
+    br_refill(b);
+    const unsigned e = tab[br_peek(b, tbits)];
+    if (e) { br_skip(b, (int)(e & 15u)); return (int)(e >> 4); }
+    int code = 0, first = 0, index = 0;
+    unsigned long long bits = b.buf;
+    for (int l = 1; l < 16; ++l) {
+        code |= (int)(bits & 1ULL); bits >>= 1;
+        const int c = h.count[l];
+        if (code - c < first) { br_skip(b, l); return h.symbol[index + (code - first)]; }
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+// Inflate one raw deflate stream of in_len bytes into out[0, out_len) (one warp; every lane calls).  Returns AMPZ_E_* bits.
+// `in` must be readable up to the next 4-byte boundary past its end; `out` is written only inside [0, out_len).
+AMP_WD int inflate_block(const uint8_t* in, long long in_len, uint8_t* out, long long out_len, InflateMem& M, int lane) {
+    BitReader b; b.wp = b.wend = nullptr; b.buf = 0; b.cnt = 0;
+    if (lane == 0) br_init(b, in, in + in_len);
+    int o = 0;                                       // bytes written (lane 0's copy is authoritative, broadcast with every match)
+    int err = 0;
+    for (;;) {
+        // ---- block header (lane 0), tables (all lanes)
+        int last = 0, type = 0;
+        if (lane == 0) { last = (int)br_bits(b, 1); type = (int)br_bits(b, 2); }
+        last = w_shfl(last, 0); type = w_shfl(type, 0);
+        if (type == 3) { err |= AMPZ_E_DATA; break; }
+        if (type == 0) {                             // stored: LEN, NLEN, bytes (lane 0 copies; rare in BAM files)
+            int n = -1;
+            if (lane == 0) {
+                br_skip(b, b.cnt & 7);               // to the byte boundary
+                const unsigned len = br_bits(b, 16), nlen = br_bits(b, 16);
+                if ((len ^ nlen) == 0xFFFFu && (long long)o + (long long)len <= out_len) {
+                    n = (int)len;
+                    for (int i = 0; i < n; ++i) out[o + i] = (uint8_t)br_bits(b, 8);
+                }
+            }
+            n = w_shfl(n, 0);
+            if (n < 0) { err |= AMPZ_E_DATA; break; }
+            o += n;
+            if (last) break;
+            continue;
+        }
+        int ok = 1;
+        if (type == 1) {                             // fixed code (RFC 1951 3.2.6)
+            for (int s = lane; s < 288; s += 32) M.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
+            w_sync();
+            if (lane == 0) ok = huff_lists(M.lit, M.lens, 288);
+            w_sync();
+            for (int s = lane; s < 30; s += 32) M.lens[s] = 5;
+            w_sync();
+            if (lane == 0) { huff_lists(M.dist, M.lens, 30); ok = 1; }      // (30 of the 32 five-bit codes: incomplete by definition)
+        } else if (lane == 0) {                      // dynamic code: the code-length code first, then both length lists
+            const int nlen = (int)br_bits(b, 5) + 257, ndist = (int)br_bits(b, 5) + 1, ncode = (int)br_bits(b, 4) + 4;
+            if (nlen > 286 || ndist > 30) ok = 0;
+            for (int i = 0; i < 19; ++i) M.lens[i] = 0;
+            for (int i = 0; i < ncode; ++i) M.lens[kClOrder[i]] = (uint8_t)br_bits(b, 3);
+            if (ok) ok = huff_lists(M.lit, M.lens, 19) ? 1 : 0;        // (the literal list's storage doubles as the code-length code's)
+            if (ok) {
+                // the code-length code is decoded with the canonical walk only (no direct table: at most 316 symbols)
+                uint8_t* L = M.lens;                                  // overwritten in place once the 19 lengths are in the lists
+                int idx = 0;
+                HuffLists& cl = M.lit;
+                // copy the code-length lists aside: M.lit is rebuilt below
+                uint16_t ccount[16], csym[19];
+                for (int i = 0; i < 16; ++i) ccount[i] = cl.count[i];
+                for (int i = 0; i < 19; ++i) csym[i] = cl.symbol[i];
+                while (idx < nlen + ndist && ok) {
+                    br_refill(b);
+                    int code = 0, first = 0, index = 0, sym = -1;
+                    unsigned long long bits = b.buf;
+                    for (int l = 1; l < 8; ++l) {
+                        code |= (int)(bits & 1ULL); bits >>= 1;
+                        const int c = ccount[l];
+                        if (code - c < first) { br_skip(b, l); sym = csym[index + (code - first)]; break; }
+                        index += c; first += c; first <<= 1; code <<= 1;
+                    }
+                    if (sym < 0) { ok = 0; break; }
+                    if (sym < 16) L[idx++] = (uint8_t)sym;
+                    else {
+                        int rep, val = 0;
+                        if (sym == 16) { if (idx == 0) { ok = 0; break; } val = L[idx - 1]; rep = 3 + (int)br_bits(b, 2); }
+                        else if (sym == 17) rep = 3 + (int)br_bits(b, 3);
+                        else rep = 11 + (int)br_bits(b, 7);
+                        if (idx + rep > nlen + ndist) { ok = 0; break; }
+                        while (rep--) L[idx++] = (uint8_t)val;
+                    }
+                }
+                if (ok && L[256] == 0) ok = 0;                         // no end-of-block code
+                if (ok) {
+                    uint8_t dl[30];
+                    for (int i = 0; i < ndist; ++i) dl[i] = L[nlen + i];
+                    ok = huff_lists(M.lit, L, nlen) ? 1 : 0;
+                    if (ok) ok = huff_lists(M.dist, dl, ndist) ? 1 : 0;
+                }
+            }
+        }
+        ok = w_shfl(ok, 0);
+        if (!ok) { err |= AMPZ_E_DATA; break; }
+        w_sync();
+        huff_table(M.ltab, AMPZ_LBITS, M.lit, lane);
+        huff_table(M.dtab, AMPZ_DBITS, M.dist, lane);
+        // ---- symbols: lane 0 stores literals as they come and stops at every match / end of block / error
+        for (;;) {
+            int len = 0, dist = 0;                   // len > 0: match; len == 0: end of block; len < 0: error
+            if (lane == 0) {
+                for (;;) {
+                    const int sym = huff_decode(b, M.ltab, AMPZ_LBITS, M.lit);
+                    if (sym < 0) { len = -1; break; }
+                    if (sym < 256) {
+                        if ((long long)o >= out_len) { len = -1; break; }
+                        out[o++] = (uint8_t)sym;
+                        continue;
+                    }
+                    if (sym == 256) break;
+                    if (sym > 285) { len = -1; break; }
+                    len = kLenBase[sym - 257] + (int)br_bits(b, kLenExtra[sym - 257]);
+                    const int ds = huff_decode(b, M.dtab, AMPZ_DBITS, M.dist);
+                    if (ds < 0 || ds > 29) { len = -1; break; }
+                    dist = kDistBase[ds] + (int)br_bits(b, kDistExtra[ds]);
+                    if (dist > o || (long long)o + len > out_len) len = -1;
+                    break;
+                }
+            }
+            {   // length and distance in one word
+                const int ld = w_shfl(len > 0 ? (len << 16) | dist : len, 0);
+                len = ld > 0 ? ld >> 16 : ld; dist = ld & 0xFFFF;
+            }
+            if (len <= 0) { if (len < 0) err |= AMPZ_E_DATA; break; }
+            o = w_shfl(o, 0);
+            // out[o + i] = out[o - dist + i mod dist]: the source stretch [o - dist, o) is complete (periodic extension)
+            const uint8_t* src = out + o - dist;
+            for (int i = lane; i < len; i += 32) out[o + i] = src[dist >= len ? i : i % dist];
+            w_sync();
+            o += len;
+        }
+        if (err || last) break;
+    }
+    o = w_shfl(o, 0);
+    err = w_shfl(err, 0) | err;
+    if (!err && (long long)o != out_len) err |= AMPZ_E_SIZE;
+    return err;
+}
+
+// ---- BAM record chains -------------------------------------------------------------------------------------------------------
+// record (after the 4-byte block_size): refID, pos, l_read_name(u8), mapq(u8), bin(u16), n_cigar(u16), flag(u16), l_seq, next_refID,
+// next_pos, tlen, read_name, cigar, seq, qual, tags
+AMP_HD uint32_t ld_u32u(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+AMP_HD uint32_t ld_u16u(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+struct BamBlockTotals { unsigned int n_rec, n_cig; unsigned long long n_seq, n_qual; };   // per BGZF block
+
+// one thread: records of raw[lo, hi); false when the chain does not end exactly at hi or a header does not fit its record
+AMP_HD bool bam_chain_totals(const uint8_t* raw, long long lo, long long hi, BamBlockTotals& t) {
+    t.n_rec = 0; t.n_cig = 0; t.n_seq = 0; t.n_qual = 0;
+    long long p = lo;
+    while (p < hi) {
+        if (p + 36 > hi) return false;
+        const long long bs = ld_u32u(raw + p);
+        const uint8_t* r = raw + p + 4;
+        const long long lname = r[8], nc = ld_u16u(r + 12), ls = (int)ld_u32u(r + 16);
+        if (bs < 32 || p + 4 + bs > hi || ls < 0 || 32 + lname + 4 * nc + (ls + 1) / 2 + ls > bs) return false;
+        ++t.n_rec; t.n_cig += (unsigned int)nc; t.n_seq += (unsigned long long)((ls + 1) / 2); t.n_qual += (unsigned long long)ls;
+        p += 4 + bs;
+    }
+    return p == hi;
+}
+
+struct BamSoa {       // destination arrays (device), indexed with global read indices / offsets
+    int32_t* pos; uint16_t* flag; int32_t* tlen; uint32_t* cig_off; uint32_t* cigar; uint32_t* seq_off; uint8_t* seq;
+    uint32_t* qual_off; uint8_t* qual; unsigned long long* rec_off;   // rec_off: offset of the record's block_size word in the raw stream
+};
+// one warp: the records of raw[lo, hi) into the arrays, starting at read r0 / CIGAR op c0 / seq byte s0 / qual byte q0
+AMP_WD void bam_scatter_block(const uint8_t* raw, long long lo, long long hi, const BamSoa& D, unsigned long long r0, unsigned long long c0,
+                              unsigned long long s0, unsigned long long q0, int lane) {
+    long long p = lo;
+    unsigned long long ri = r0, ci = c0, si = s0, qi = q0;
+    while (p < hi) {
+        const uint8_t* r = raw + p + 4;
+        const long long bs = ld_u32u(raw + p);
+        const uint32_t lname = r[8], nc = ld_u16u(r + 12), ls = ld_u32u(r + 16);
+        if (lane == 0) {
+            D.pos[ri] = (int32_t)ld_u32u(r + 4); D.flag[ri] = (uint16_t)ld_u16u(r + 14); D.tlen[ri] = (int32_t)ld_u32u(r + 28);
+            D.cig_off[ri] = (uint32_t)ci; D.seq_off[ri] = (uint32_t)si; D.qual_off[ri] = (uint32_t)qi;
+            D.rec_off[ri] = (unsigned long long)p;
+        }
+        const uint8_t* c = r + 32 + lname;
+        for (uint32_t k = lane; k < nc; k += 32) D.cigar[ci + k] = ld_u32u(c + 4 * k);
+        const uint8_t* s = c + 4 * (size_t)nc;
+        const uint32_t nsb = (ls + 1) / 2;
+        for (uint32_t k = lane; k < nsb; k += 32) D.seq[si + k] = s[k];
+        const uint8_t* q = s + nsb;
+        for (uint32_t k = lane; k < ls; k += 32) D.qual[qi + k] = q[k];
+        ++ri; ci += nc; si += nsb; qi += ls;
+        p += 4 + bs;
+    }
+}
+
+}  // namespace amp

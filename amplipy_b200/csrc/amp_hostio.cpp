@@ -8,6 +8,7 @@
 //     `reference_start` does to a pysam segment); everything else is copied byte for byte.
 // Build: g++ -O2 -fPIC -shared -fopenmp amp_hostio.cpp -lz
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
@@ -78,9 +79,9 @@ int amp_bgzf_inflate(const uint8_t* in, const long long* in_off, const uint32_t*
 // Deflate `len` bytes into BGZF blocks of <= 0xff00 payload bytes each, in parallel, plus the EOF block.
 // out capacity must be >= amp_bgzf_bound(len).  Returns bytes written or -1.
 long long amp_bgzf_bound(long long len) { return (len / 0xff00 + 2) * (0xff00 + 1024) + 28; }
-long long amp_bgzf_deflate(const uint8_t* in, long long len, uint8_t* out, int level, int n_threads) {
+// Deflate in[bstart[k], bstart[k+1]) as BGZF block k (each at most 0xff00 bytes), in parallel, plus the EOF block.
+long long amp_bgzf_deflate_blocks(const uint8_t* in, const long long* bstart, long long nb, uint8_t* out, int level, int n_threads) {
     const long long BS = 0xff00;
-    const long long nb = (len + BS - 1) / BS;
     const long long slot = BS + 1024;
     uint32_t* clen = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(nb + 1));
     uint8_t* tmp = (uint8_t*)malloc((size_t)(nb ? nb : 1) * (size_t)slot);
@@ -90,8 +91,10 @@ long long amp_bgzf_deflate(const uint8_t* in, long long len, uint8_t* out, int l
 #endif
 #pragma omp parallel for schedule(dynamic, 8) reduction(| : bad)
     for (long long k = 0; k < nb; ++k) {
-        const uint8_t* src = in + k * BS;
-        const uInt n = (uInt)((k == nb - 1) ? (len - k * BS) : BS);
+        const uint8_t* src = in + bstart[k];
+        const long long n64 = bstart[k + 1] - bstart[k];
+        if (n64 < 0 || n64 > BS) { bad |= 1; continue; }
+        const uInt n = (uInt)n64;
         uint8_t* dst = tmp + k * slot;
         z_stream zs; memset(&zs, 0, sizeof zs);
         if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad |= 1; continue; }
@@ -116,6 +119,41 @@ long long amp_bgzf_deflate(const uint8_t* in, long long len, uint8_t* out, int l
     }
     free(clen); free(tmp);
     return bad ? -1 : o;
+}
+long long amp_bgzf_deflate(const uint8_t* in, long long len, uint8_t* out, int level, int n_threads) {
+    const long long BS = 0xff00;
+    const long long nb = (len + BS - 1) / BS;
+    long long* bstart = (long long*)malloc(sizeof(long long) * (size_t)(nb + 1));
+    for (long long k = 0; k <= nb; ++k) bstart[k] = k * BS < len ? k * BS : len;
+    const long long r = amp_bgzf_deflate_blocks(in, bstart, nb, out, level, n_threads);
+    free(bstart);
+    return r;
+}
+// Block starts the way htslib lays a BAM out (bgzf_flush after the header, bgzf_flush_try per record): a block holds whole
+// units -- bounds[0..n_bounds) are the cut points (sorted, bounds[0] = 0, the last one = the length) -- up to 0xff00 bytes; a
+// unit longer than that is split.  Returns the number of blocks (bstart gets one entry more); call with bstart = NULL to count.
+long long amp_bgzf_plan(const long long* bounds, long long n_bounds, long long* bstart, long long max_blocks) {
+    const long long BS = 0xff00;
+    long long nb = 0, cur = 0;                                  // cur = start of the open block
+    if (n_bounds < 2) { if (bstart && max_blocks >= 0) bstart[0] = 0; return 0; }
+    for (long long i = 1; i < n_bounds; ++i) {
+        const long long end = bounds[i];
+        if (end - cur <= BS) continue;                          // unit i fits the open block
+        if (bounds[i - 1] > cur) {                              // close the open block in front of unit i
+            if (bstart) { if (nb >= max_blocks) return -1; bstart[nb] = cur; }
+            ++nb; cur = bounds[i - 1];
+        }
+        while (end - cur > BS) {                                // a unit longer than a block
+            if (bstart) { if (nb >= max_blocks) return -1; bstart[nb] = cur; }
+            ++nb; cur += BS;
+        }
+    }
+    if (bounds[n_bounds - 1] > cur) {
+        if (bstart) { if (nb >= max_blocks) return -1; bstart[nb] = cur; }
+        ++nb;
+    }
+    if (bstart) bstart[nb] = bounds[n_bounds - 1];
+    return nb;
 }
 
 // ---- BAM records -> struct of arrays ------------------------------------------------------------------
@@ -164,6 +202,50 @@ void amp_bam_fill(const uint8_t* buf, const long long* rec_off, long long n, int
     }
 }
 
+static inline int reg2bin(int64_t beg, int64_t end);
+// A ReadBatch as BAM records (names from a blob of NUL-terminated strings, or r<i>; refID 0, mates on the same reference):
+// synthetic inputs for tests and benchmarks.
+// rec_off gets n + 1 offsets; pass out = NULL to get the size.
+long long amp_bam_serialize(long long n, const int32_t* pos, const uint16_t* flag, const int32_t* tlen, const uint32_t* cig_off,
+                            const uint32_t* cigar, const uint32_t* seq_off, const uint8_t* seq, const uint32_t* qual_off,
+                            const uint8_t* qual, int mapq, const char* names, const long long* name_off, uint8_t* out, long long* rec_off) {
+    long long o = 0;
+    for (long long i = 0; i < n; ++i) {
+        char nbuf[32];
+        const char* name = nbuf;
+        int lname;
+        if (names) { name = names + name_off[i]; lname = (int)(name_off[i + 1] - name_off[i]); }     // NUL-terminated, <= 255 bytes
+        else lname = snprintf(nbuf, sizeof nbuf, "r%lld", i) + 1;
+        const uint32_t nc = cig_off[i + 1] - cig_off[i], ls = qual_off[i + 1] - qual_off[i], nsb = seq_off[i + 1] - seq_off[i];
+        const uint32_t bs = 32 + (uint32_t)lname + 4 * nc + nsb + ls;
+        if (rec_off) rec_off[i] = o;
+        if (out) {
+            uint8_t* w = out + o;
+            memcpy(w, &bs, 4);
+            const uint32_t* cg = cigar + cig_off[i];
+            int64_t rlen = 0;
+            for (uint32_t c = 0; c < nc; ++c) { const uint32_t op = cg[c] & 15; if ((0x18Du >> op) & 1) rlen += cg[c] >> 4; }
+            const uint16_t fl = flag[i];
+            if ((fl & 4) || rlen == 0) rlen = 1;
+            const int32_t rid = (fl & 4) ? -1 : 0, p = pos[i], nrid = (fl & 1) ? 0 : -1;
+            int32_t npos = (fl & 1) ? p + tlen[i] : -1; if ((fl & 1) && npos < 0) npos = 0;
+            const uint16_t bin = (uint16_t)reg2bin(p, p + rlen), ncw = (uint16_t)nc;
+            const uint8_t ln = (uint8_t)lname, mq = (uint8_t)mapq;
+            const int32_t lsi = (int32_t)ls, tl = tlen[i];
+            memcpy(w + 4, &rid, 4); memcpy(w + 8, &p, 4); w[12] = ln; w[13] = mq; memcpy(w + 14, &bin, 2); memcpy(w + 16, &ncw, 2);
+            memcpy(w + 18, &fl, 2); memcpy(w + 20, &lsi, 4); memcpy(w + 24, &nrid, 4); memcpy(w + 28, &npos, 4); memcpy(w + 32, &tl, 4);
+            memcpy(w + 36, name, (size_t)lname);
+            uint8_t* q = w + 36 + lname;
+            memcpy(q, cg, 4 * (size_t)nc); q += 4 * (size_t)nc;
+            memcpy(q, seq + seq_off[i], nsb); q += nsb;
+            memcpy(q, qual + qual_off[i], ls);
+        }
+        o += 4 + bs;
+    }
+    if (rec_off) rec_off[n] = o;
+    return o;
+}
+
 static inline int reg2bin(int64_t beg, int64_t end) {   // SAM spec 5.3
     --end;
     if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
@@ -179,15 +261,27 @@ static inline int reg2bin(int64_t beg, int64_t end) {   // SAM spec 5.3
 long long amp_bam_rewrite(const uint8_t* buf, const long long* rec_off, const long long* sel, long long n_sel,
                           const int32_t* new_pos, const uint16_t* new_ncig, const uint32_t* cig_off, const uint32_t* new_cigar,
                           uint8_t* out) {
+    // sizes first (one pass), then the records in parallel at their offsets
+    long long* ooff = (long long*)malloc(sizeof(long long) * (size_t)(n_sel + 1));
     long long o = 0;
     for (long long k = 0; k < n_sel; ++k) {
         const long long i = sel[k];
         const uint8_t* r = buf + rec_off[i] + 4;
         const uint32_t bs = rd32(buf + rec_off[i]);
-        const uint32_t lname = r[8], nc_old = rd16(r + 12), nc_new = new_ncig[i];
-        const uint32_t nbs = bs - 4 * nc_old + 4 * nc_new;
-        if (out) {
-            uint8_t* w = out + o;
+        const uint32_t nc_old = rd16(r + 12), nc_new = new_ncig[i];
+        ooff[k] = o;
+        o += 4 + (long long)(bs - 4 * nc_old + 4 * nc_new);
+    }
+    ooff[n_sel] = o;
+    if (out) {
+#pragma omp parallel for schedule(static)
+        for (long long k = 0; k < n_sel; ++k) {
+            const long long i = sel[k];
+            const uint8_t* r = buf + rec_off[i] + 4;
+            const uint32_t bs = rd32(buf + rec_off[i]);
+            const uint32_t lname = r[8], nc_old = rd16(r + 12), nc_new = new_ncig[i];
+            const uint32_t nbs = bs - 4 * nc_old + 4 * nc_new;
+            uint8_t* w = out + ooff[k];
             memcpy(w, &nbs, 4);
             memcpy(w + 4, r, 32 + lname);
             const int32_t p = new_pos[i]; memcpy(w + 4 + 4, &p, 4);
@@ -202,9 +296,22 @@ long long amp_bam_rewrite(const uint8_t* buf, const long long* rec_off, const lo
             const uint32_t rest = bs - 32 - lname - 4 * nc_old;
             memcpy(w + 4 + 32 + lname + 4 * (size_t)nc_new, r + 32 + lname + 4 * (size_t)nc_old, rest);
         }
-        o += 4 + nbs;
     }
+    free(ooff);
     return o;
+}
+// offsets of the records written by amp_bam_rewrite (n_sel + 1 entries): the block planner's cut points
+void amp_bam_rewrite_offsets(const uint8_t* buf, const long long* rec_off, const long long* sel, long long n_sel,
+                             const uint16_t* new_ncig, long long* ooff) {
+    long long o = 0;
+    for (long long k = 0; k < n_sel; ++k) {
+        const long long i = sel[k];
+        const uint32_t bs = rd32(buf + rec_off[i]);
+        const uint32_t nc_old = rd16(buf + rec_off[i] + 4 + 12), nc_new = new_ncig[i];
+        ooff[k] = o;
+        o += 4 + (long long)(bs - 4 * nc_old + 4 * nc_new);
+    }
+    ooff[n_sel] = o;
 }
 
 int amp_hostio_threads(void) {

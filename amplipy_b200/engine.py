@@ -37,7 +37,8 @@ EXPORTED_SYMBOLS = [
     "amp_bind_counts", "amp_counts_host", "amp_ins_count", "amp_ins_export", "amp_ins_merge", "amp_call",
     "amp_host_alloc", "amp_host_free", "amp_reset_async", "amp_set_reference", "amp_call_device",
     "amp_nccl_unique_id", "amp_nccl_comm_init", "amp_nccl_comm_destroy", "amp_nccl_allgather", "amp_allreduce_counts",
-    "amp_ins_slot_bytes", "amp_ins_pack_device", "amp_ins_merge_packed", "amp_reserve", "amp_counts_copy_device"]
+    "amp_ins_slot_bytes", "amp_ins_pack_device", "amp_ins_merge_packed", "amp_reserve", "amp_counts_copy_device",
+    "amp_bam_decode_host", "amp_process_decoded", "amp_decoded_copy_host"]
 
 
 class AmpConfig(ctypes.Structure):
@@ -56,6 +57,17 @@ class AmpBatch(ctypes.Structure):
 class AmpTrimOut(ctypes.Structure):
     _fields_ = [("pos", ctypes.c_void_p), ("ncig", ctypes.c_void_p), ("flags", ctypes.c_void_p),
                 ("cigar", ctypes.c_void_p)]
+
+
+class AmpBamInfo(ctypes.Structure):
+    _fields_ = [("n_reads", ctypes.c_int64), ("sum_cigar_ops", ctypes.c_int64), ("sum_seq_bytes", ctypes.c_int64),
+                ("sum_qual_bytes", ctypes.c_int64), ("raw_bytes", ctypes.c_int64)]
+
+
+class AmpBatchOut(ctypes.Structure):
+    _fields_ = [("pos", ctypes.c_void_p), ("flag", ctypes.c_void_p), ("tlen", ctypes.c_void_p), ("cig_off", ctypes.c_void_p),
+                ("cigar", ctypes.c_void_p), ("seq_off", ctypes.c_void_p), ("seq", ctypes.c_void_p), ("qual_off", ctypes.c_void_p),
+                ("qual", ctypes.c_void_p)]
 
 
 class AmpCallParams(ctypes.Structure):
@@ -350,6 +362,52 @@ class Engine:
         chars = np.ascontiguousarray(chars, np.uint8) if len(chars) else np.zeros(1, np.uint8)
         _check(self.lib.amp_ins_merge(self._ctx, ctypes.c_int64(len(pos)), _ptr(sample), _ptr(pos), _ptr(count),
                                       _ptr(str_off), _ptr(chars)), "amp_ins_merge")
+
+    # ---------------------------------------------------------------- BAM decoded on the device
+    def decode_bam(self, raw, layout):
+        """H2D of the compressed file as it is + inflate / record scan / scatter on the device (amp_bam_decode_host).
+        ``raw``: the file's bytes (bytes or a uint8 array; page-locked memory makes the copy asynchronous), ``layout``:
+        alnio.bam_layout(raw).  Returns the batch's totals; the batch itself stays in HBM for process_decoded()."""
+        src = raw if isinstance(raw, np.ndarray) else np.frombuffer(raw, np.uint8)
+        in_off = np.ascontiguousarray(layout["in_off"], np.int64)
+        out_len = np.ascontiguousarray(layout["out_len"], np.uint32)
+        info = AmpBamInfo()
+        _check(self.lib.amp_bam_decode_host(self._ctx, _ptr(src), ctypes.c_int64(src.size), _ptr(in_off), _ptr(out_len),
+                                            ctypes.c_int64(in_off.size), ctypes.c_int64(int(layout["body_off"])), ctypes.byref(info)),
+               "amp_bam_decode_host")
+        self.launches += int(self.lib.amp_last_launches(self._ctx))
+        self._decoded = {"n": int(info.n_reads), "sum_cig": int(info.sum_cigar_ops), "sum_seq": int(info.sum_seq_bytes),
+                         "sum_qual": int(info.sum_qual_bytes), "raw_bytes": int(info.raw_bytes)}
+        return dict(self._decoded)
+
+    def alloc_decoded_trim_out(self):
+        n, sc = self._decoded["n"], self._decoded["sum_cig"]
+        return (np.zeros(n, np.int32), np.zeros(n, np.uint16), np.zeros(n, np.uint8), np.zeros(sc + 3 * n, np.uint32))
+
+    def process_decoded(self, trim=True, pileup=True, sample=0, out=None):
+        """Fused kernel on the batch decode_bam left in HBM; trim outputs copied to ``out`` (alloc_decoded_trim_out)."""
+        mode = (MODE_TRIM if trim else 0) | (MODE_PILEUP if pileup else 0)
+        to = None
+        if trim:
+            if out is None:
+                out = self.alloc_decoded_trim_out()
+            to = AmpTrimOut(_ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]))
+        _check(self.lib.amp_process_decoded(self._ctx, mode, sample, ctypes.byref(to) if to else None), "amp_process_decoded")
+        self.launches += int(self.lib.amp_last_launches(self._ctx))
+        return out
+
+    def decoded_batch(self):
+        """The decoded batch copied back to the host as a ReadBatch, plus the offset of every record in the inflated stream."""
+        d = self._decoded
+        n = d["n"]
+        b = ReadBatch(np.empty(n, np.int32), np.empty(n, np.uint16), np.empty(n, np.int32), np.empty(n + 1, np.uint32),
+                      np.empty(d["sum_cig"], np.uint32), np.empty(n + 1, np.uint32), np.empty(d["sum_seq"], np.uint8),
+                      np.empty(n + 1, np.uint32), np.empty(d["sum_qual"], np.uint8))
+        rec_off = np.empty(n, np.uint64)
+        bo = AmpBatchOut(_ptr(b.pos), _ptr(b.flag), _ptr(b.tlen), _ptr(b.cig_off), _ptr(b.cigar), _ptr(b.seq_off), _ptr(b.seq),
+                         _ptr(b.qual_off), _ptr(b.qual))
+        _check(self.lib.amp_decoded_copy_host(self._ctx, ctypes.byref(bo), _ptr(rec_off)), "amp_decoded_copy_host")
+        return b, rec_off
 
     # ---------------------------------------------------------------- deep-sample exchange (dist.py)
     def reserve(self, max_reads, max_cigar_ops):

@@ -34,6 +34,7 @@ extern "C" {
 #define AMP_ERR_ARG (-2)
 #define AMP_ERR_NOMEM (-3)
 #define AMP_ERR_STATE (-4)
+#define AMP_ERR_DATA (-5)     /* malformed input data (message says what) */
 
 /* out_flags bits per read (AmpliPy.py:443-447 return tuple of trim_read + write gate 910 + skip 902) */
 #define AMP_FLAG_TRIM_START 1
@@ -177,6 +178,27 @@ int amp_ins_merge_packed(amp_ctx* ctx, const void* dev_slots, int n_ranks, int m
 int amp_reserve(amp_ctx* ctx, int64_t max_reads, int64_t max_cigar_ops);
 /* device-to-device copy of the count matrices into a caller-owned buffer of the same shape */
 int amp_counts_copy_device(amp_ctx* ctx, int32_t* dev_dst, void* stream);
+
+/* ---- BAM on the device (replaces pysam's record iteration, AmpliPy.py:296-360 + 896, in front of the path).
+ * The compressed file crosses PCIe as it is (about a fifth of the decoded arrays) and is decoded in HBM: one warp inflates one
+ * BGZF block (RFC 1951), one thread per block walks its BAM record chain, one warp per block scatters the records into the
+ * struct-of-arrays batch the kernels read.  Requires what htslib guarantees for the files it writes: no record straddles a BGZF
+ * block boundary; otherwise AMP_ERR_DATA is returned and the caller uses its host decoder.  CRC32 of the blocks is not checked
+ * on the device (ISIZE is).
+ *   bgzf, n_bytes      the file's bytes (page-locked memory makes the copy asynchronous)
+ *   block_off[n_blocks], block_isize[n_blocks]   start of every BGZF block in `bgzf` and its ISIZE (a host-side header scan)
+ *   body_off           offset of the first alignment record in the inflated stream (= size of the BAM header)
+ * amp_process_decoded runs the fused kernel on the decoded batch and copies the trim outputs (rows as in amp_trim_out,
+ * sized from amp_bam_info) to host_out; host_out may be NULL.  amp_decoded_copy_host hands the decoded arrays back. */
+typedef struct { int64_t n_reads, sum_cigar_ops, sum_seq_bytes, sum_qual_bytes, raw_bytes; } amp_bam_info;
+typedef struct {
+    int32_t* pos; uint16_t* flag; int32_t* tlen; uint32_t* cig_off; uint32_t* cigar; uint32_t* seq_off; uint8_t* seq;
+    uint32_t* qual_off; uint8_t* qual;
+} amp_batch_out;
+int amp_bam_decode_host(amp_ctx* ctx, const uint8_t* bgzf, int64_t n_bytes, const int64_t* block_off, const uint32_t* block_isize,
+                        int64_t n_blocks, int64_t body_off, amp_bam_info* info);
+int amp_process_decoded(amp_ctx* ctx, int mode, int sample, const amp_trim_out* host_out);
+int amp_decoded_copy_host(amp_ctx* ctx, const amp_batch_out* host_arrays, uint64_t* rec_off);
 
 /* pinned host memory helpers for callers that want full-speed amp_process_host */
 int amp_host_alloc(void** p, int64_t bytes);

@@ -13,6 +13,7 @@
 #include <cstdio>
 
 #include "../../amplipy_b200/csrc/amp_warp.cuh"
+#include "../../amplipy_b200/csrc/amp_bgzf.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Fiber runtime for the warp-autonomous kernel: every CUDA thread of one CTA is a ucontext fiber; warp collectives
@@ -326,6 +327,39 @@ void emu_call(void* h, const char* ref_seq, int mdc, double mfc, int mdv, double
     P.ins_alt = ins_alt;
     static const unsigned char syms[8] = {'A', 'C', 'G', 'T', 'N', '-', 0, 0};
     for (long long gp = 0; gp < (long long)c->n_samples * c->L; ++gp) amp::call_position(P, syms, gp);
+}
+
+
+// ---- BGZF / BAM decode kernels (amp_bgzf.cuh): one warp of fibers per BGZF block ------------------------------------------------
+struct InflateJob { const uint8_t* in; long long in_len; uint8_t* out; long long out_len; amp::InflateMem* mem; int err; };
+static void inflate_body(void* a) {
+    InflateJob* j = (InflateJob*)a;
+    const int e = amp::inflate_block(j->in, j->in_len, j->out, j->out_len, *j->mem, amp::c_tid() & 31);
+    if ((amp::c_tid() & 31) == 0) j->err = e;
+}
+// raw deflate stream -> out; returns the AMPZ_E_* bits
+int emu_inflate(const uint8_t* in, long long in_len, uint8_t* out, long long out_len) {
+    amp::InflateMem mem;
+    InflateJob j{in, in_len, out, out_len, &mem, 0};
+    run_cta(0, 32, inflate_body, &j);
+    return j.err;
+}
+// BAM records of raw[lo, hi) (block-aligned chain) -> totals; returns 0 when the chain is not aligned
+int emu_bam_totals(const uint8_t* raw, long long lo, long long hi, unsigned long long* out4) {
+    amp::BamBlockTotals t;
+    const bool ok = amp::bam_chain_totals(raw, lo, hi, t);
+    out4[0] = t.n_rec; out4[1] = t.n_cig; out4[2] = t.n_seq; out4[3] = t.n_qual;
+    return ok ? 1 : 0;
+}
+struct ScatterJob { const uint8_t* raw; long long lo, hi; amp::BamSoa D; };
+static void scatter_body(void* a) {
+    ScatterJob* j = (ScatterJob*)a;
+    amp::bam_scatter_block(j->raw, j->lo, j->hi, j->D, 0, 0, 0, 0, amp::c_tid() & 31);
+}
+void emu_bam_scatter(const uint8_t* raw, long long lo, long long hi, int32_t* pos, uint16_t* flag, int32_t* tlen, uint32_t* cig_off,
+                     uint32_t* cigar, uint32_t* seq_off, uint8_t* seq, uint32_t* qual_off, uint8_t* qual, unsigned long long* rec_off) {
+    ScatterJob j{raw, lo, hi, amp::BamSoa{pos, flag, tlen, cig_off, cigar, seq_off, seq, qual_off, qual, rec_off}};
+    run_cta(0, 32, scatter_body, &j);
 }
 
 }  // extern "C"

@@ -19,7 +19,8 @@ def build(asan=False):
     so = os.path.join(_DIR, name)
     srcs = [os.path.join(_DIR, "amp_emu.cpp"), os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_core.cuh"),
             os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_kernels.cuh"),
-            os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_warp.cuh")]
+            os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_warp.cuh"),
+            os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_bgzf.cuh")]
     if not os.path.isfile(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         gxx = "/usr/bin/g++" if os.path.isfile("/usr/bin/g++") else "g++"
         flags = ["-O1", "-g", "-fsanitize=address,undefined"] if asan else ["-O2"]

@@ -395,3 +395,77 @@ def test_plate_384_samples_cfg5():
         fixed = sres.top_id < 6                                       # insertion ids are table-order dependent
         assert np.array_equal(pres.top_id[sl][fixed], sres.top_id[fixed])
     assert plate.error_flags() == 0
+
+
+# ---- BAM decoded on the device (amp_bam_decode_host / amp_process_decoded) -------------------------------------------------------
+def _bam_bytes(tmp_path, b, L, level=6):
+    import os
+    from amplipy_b200 import alnio
+    path = os.path.join(str(tmp_path), "in_%d.bam" % level)
+    alnio.write_bam(path, "@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:ref\tLN:%d\n@PG\tID:synth\tPN:synth\n" % L, [("ref", L)], b, level=level)
+    return open(path, "rb").read()
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_device_bam_decode_equals_host_decoder(tmp_path, level):
+    """Byte-equal struct-of-arrays batch (and record offsets) from the device-side inflate + record scatter and from the host
+    decoder (zlib + amp_bam_fill), on Illumina-like and ONT-like records, at several deflate levels."""
+    from amplipy_b200 import alnio
+    g, prim, amps = _scheme(L=6000, n_amp=18)
+    for b in (synth.illumina_batch(g, amps, 30_000, seed=51, p_ins=0.1, p_del=0.1), synth.ont_batch(g, amps, 2_000, seed=52)):
+        raw = _bam_bytes(tmp_path, b, 6000, level)
+        a = alnio._read_bam(raw)
+        eng = make_engine(ref_len=6000)
+        info = eng.decode_bam(raw, alnio.bam_layout(raw))
+        assert info["n"] == b.n and info["sum_cig"] == int(b.cig_off[-1]) and info["sum_qual"] == int(b.qual_off[-1])
+        got, rec_off = eng.decoded_batch()
+        for f in ("pos", "flag", "tlen", "cig_off", "cigar", "seq_off", "seq", "qual_off", "qual"):
+            assert np.array_equal(getattr(got, f), getattr(a.batch, f)), f
+            assert np.array_equal(getattr(got, f), getattr(b, f)), f
+        assert np.array_equal(rec_off.astype(np.int64), a.bam_rec_off)
+
+
+def test_device_bam_path_vs_oracle(oracle_lib, tmp_path):
+    """File bytes -> device decode -> fused kernel -> calling, against the oracle on the same reads."""
+    from amplipy_b200 import alnio
+    g, prim, amps = _scheme()
+    b = synth.illumina_batch(g, amps, 120_000, seed=53, snvs=[(1000, "T", 0.5)])
+    raw = _bam_bytes(tmp_path, b, len(g))
+
+    class BamEngine:
+        def __init__(self, **kw):
+            self.e = make_engine(**kw)
+
+        def process(self, batch, trim=True, pileup=True, sample=0):
+            from amplipy_b200.engine import TrimResult
+            self.e.decode_bam(raw, alnio.bam_layout(raw))
+            out = self.e.process_decoded(trim=trim, pileup=pileup, sample=sample)
+            return TrimResult(batch, *out) if trim else None
+
+        def __getattr__(self, k):
+            return getattr(self.e, k)
+    parity.check_against_oracle(BamEngine, oracle_lib, b, g, prim)
+
+
+def test_device_bam_decode_rejects_bad_input(tmp_path):
+    from amplipy_b200 import alnio
+    from amplipy_b200.engine import AmpError
+    g, prim, amps = _scheme(L=6000, n_amp=18)
+    b = synth.illumina_batch(g, amps, 5_000, seed=54)
+    raw = _bam_bytes(tmp_path, b, 6000)
+    lay = alnio.bam_layout(raw)
+    eng = make_engine(ref_len=6000)
+    bad = bytearray(raw)
+    k = len(lay["in_off"]) // 2
+    a = int(lay["in_off"][k])
+    for i in range(a + 40, a + 60):
+        bad[i] ^= 0x5A                                    # garble one block's deflate stream
+    with pytest.raises(AmpError):
+        eng.decode_bam(bytes(bad), lay)
+    # records straddling block boundaries (plain 0xff00-byte blocks, as a non-htslib writer may produce them)
+    payload = alnio.bgzf_decompress(raw).tobytes()
+    raw2 = alnio.bgzf_compress(payload)
+    with pytest.raises(AmpError):
+        eng.decode_bam(raw2, alnio.bam_layout(raw2))
+    info = eng.decode_bam(raw, lay)                       # the context is still usable
+    assert info["n"] == b.n
