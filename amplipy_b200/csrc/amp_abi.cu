@@ -1169,7 +1169,7 @@ int amp_bam_decode_host(amp_ctx* c, const uint8_t* bgzf, int64_t n_bytes, const 
     CK(cudaMemcpyAsync(d.out_len, block_isize, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, sx));
     CK(cudaMemsetAsync(d.ctr, 0, 64, sx));
     // the compressed bytes in up to eight pieces on the copy stream; each piece is inflated as soon as it has landed
-    const int pieces = n_blocks >= 64 ? 8 : 1;
+    const int pieces = 1;   // (one launch: a block's inflate is latency-bound on one warp, so every block should be in flight at once)
     c->last_launches = 0;
     for (int pi = 0; pi < pieces; ++pi) {
         const long long k0 = n_blocks * pi / pieces, k1 = n_blocks * (pi + 1) / pieces;
@@ -1180,7 +1180,7 @@ int amp_bam_decode_host(amp_ctx* c, const uint8_t* bgzf, int64_t n_bytes, const 
         CK(cudaStreamWaitEvent(sc, d.ev[pi], 0));
         CK(cudaMemsetAsync(d.ctr, 0, 4, sc));
         const long long nb = k1 - k0;
-        const int grid = (int)std::min<long long>((nb + AMPZ_WARPS - 1) / AMPZ_WARPS, (long long)c->sm_count * 2);
+        const int grid = (int)std::min<long long>((nb + AMPZ_WARPS - 1) / AMPZ_WARPS, (long long)c->sm_count * 3);
         amp_bgzf_inflate_kernel<<<grid, AMPZ_WARPS * 32, AMPZ_WARPS * sizeof(amp::InflateMem), sc>>>(d.comp, n_bytes, d.in_off, d.out_len, d.out_off, k0, k1, d.raw,
                                                                                                   d.ctr, d.ctr + 1);
         CK(cudaGetLastError());

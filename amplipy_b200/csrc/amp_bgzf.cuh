@@ -69,6 +69,13 @@ AMP_WD long long br_bytes_used(const BitReader& b, const uint8_t* start) {
     return (long long)((const uint8_t*)b.wp - start) - (b.cnt >> 3);
 }
 
+AMP_WD uint8_t ld_cg_u8(const uint8_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
 AMP_WD unsigned rev_bits(unsigned v, int n) {       // the low n bits of v in reverse order
 #if defined(__CUDA_ARCH__)
     return __brev(v) >> (32 - n);
@@ -242,8 +249,9 @@ AMP_WD int inflate_block(const uint8_t* in, long long in_len, uint8_t* out, long
             if (len <= 0) { if (len < 0) err |= AMPZ_E_DATA; break; }
             o = w_shfl(o, 0);
             // out[o + i] = out[o - dist + i mod dist]: the source stretch [o - dist, o) is complete (periodic extension)
+            // (read through L2: the L1 may hold a line of `out` from before these bytes were written)
             const uint8_t* src = out + o - dist;
-            for (int i = lane; i < len; i += 32) out[o + i] = src[dist >= len ? i : i % dist];
+            for (int i = lane; i < len; i += 32) out[o + i] = ld_cg_u8(src + (dist >= len ? i : i % dist));
             w_sync();
             o += len;
         }
