@@ -12,6 +12,7 @@
 #include "../../include/amplipy_b200.h"
 #include "amp_warp.cuh"
 #include "amp_bgzf.cuh"
+#include "amp_ont.cuh"
 
 static_assert(AMP_F_TRIM_START == AMP_FLAG_TRIM_START && AMP_F_KEEP == AMP_FLAG_KEEP && AMP_F_SKIPPED == AMP_FLAG_SKIPPED &&
                   AMP_F_ERROR == AMP_FLAG_ERROR && AMP_E_ARENA_FULL == AMP_DEVERR_ARENA_FULL,
@@ -64,6 +65,13 @@ template <bool TRIM, bool PILE>
 __global__ void __launch_bounds__(AMP7_WARPS * 32, 1) amp_trim_pileup_warp_kernel(const __grid_constant__ amp::KParams P) {
     extern __shared__ __align__(128) unsigned char smem7[];
     amp::cta_trim_pileup_v9<TRIM, PILE, AMP7_WT>(P, smem7, AMP7_GWARPS, AMP7_DWARPS);
+}
+
+// warp-per-read kernel for indel-rich batches (amp_ont.cuh): one CTA per SM, AMPO_WARPS warps
+template <bool TRIM, bool PILE>
+__global__ void __launch_bounds__(AMPO_WARPS * 32, 1) amp_trim_pileup_ont_kernel(const __grid_constant__ amp::KParams P) {
+    extern __shared__ __align__(128) unsigned char smem_o[];
+    amp::cta_trim_pileup_ont<TRIM, PILE, AMPO_WT>(P, smem_o, AMPO_GWARPS);
 }
 
 __device__ const unsigned char kFixedSyms[8] = {'A', 'C', 'G', 'T', 'N', '-', 0, 0};
@@ -435,7 +443,7 @@ struct amp_ctx {
     DevChunk chunk[3];
     int last_launches = 0;
     size_t max_dyn_smem = 0;
-    bool v7_attr = false;
+    bool v7_attr = false, ont_attr = false;
     // decoded file (amp_bam_decode_host): compressed bytes, inflated stream, block tables, struct-of-arrays batch, trim outputs
     struct Decoded {
         uint8_t* comp = nullptr; size_t cap_comp = 0;
@@ -534,6 +542,30 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
             fprintf(stderr, "[cycles per CTA] mean %.0f  min %lld  max %lld\n", (double)h[8] / grid, h[9], h[10]);
         }
 #endif
+        c->last_launches += 1;
+        return AMP_OK;
+    }
+    // indel-rich batches: the warp-per-read kernel.  AMP_KERNEL=tile forces the older CTA-phased kernel (A/B experiments).
+    if (t.direct && !force_tile && b.n < (1LL << 31)) {
+        P.wt = AMPO_WT; P.reads_per_tile = 1;
+        P.ntiles = (int)b.n;
+        int grid = std::max(1, std::min(P.ntiles, c->sm_count));
+        P.tiles_per_cta = (P.ntiles + grid - 1) / grid;
+        grid = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
+        const size_t smem = amp::smem_bytes_ont(P.wt, AMPO_WARPS, AMPO_GWARPS);
+        if (!c->ont_attr) {
+            CK(cudaFuncSetAttribute(amp_trim_pileup_ont_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_ont_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(amp_trim_pileup_ont_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            c->ont_attr = true;
+        }
+        P.gcap = P.tiles_per_cta;
+        P.glist = glist;
+        const bool tr = mode & AMP_MODE_TRIM, pl = mode & AMP_MODE_PILEUP;
+        if (tr && pl) amp_trim_pileup_ont_kernel<true, true><<<grid, AMPO_WARPS * 32, smem, st>>>(P);
+        else if (tr) amp_trim_pileup_ont_kernel<true, false><<<grid, AMPO_WARPS * 32, smem, st>>>(P);
+        else amp_trim_pileup_ont_kernel<false, true><<<grid, AMPO_WARPS * 32, smem, st>>>(P);
+        CK(cudaGetLastError());
         c->last_launches += 1;
         return AMP_OK;
     }

@@ -14,6 +14,7 @@
 
 #include "../../amplipy_b200/csrc/amp_warp.cuh"
 #include "../../amplipy_b200/csrc/amp_bgzf.cuh"
+#include "../../amplipy_b200/csrc/amp_ont.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Fiber runtime for the warp-autonomous kernel: every CUDA thread of one CTA is a ucontext fiber; warp collectives
@@ -245,6 +246,48 @@ int emu_process_v7(void* h, long long first, long long n, const int32_t* pos, co
     const int dwarps = warps >= 3 ? 1 : 0;              // one dedicated list warp when there are warps to spare
     V7Launch v{&P, sbase, mode, gwarps, dwarps};
     for (int b = 0; b < grid; ++b) run_cta(b, warps * 32, v9_body, &v);
+    return 0;
+}
+
+// the warp-per-read kernel for indel-rich batches (amp_ont.cuh)
+struct OntLaunch { const amp::KParams* P; unsigned char* smem; int mode, gwarps; };
+static void ont_body(void* a) {
+    OntLaunch* v = (OntLaunch*)a;
+    if (v->mode == 3) amp::cta_trim_pileup_ont<true, true, 0>(*v->P, v->smem, v->gwarps);
+    else if (v->mode == 1) amp::cta_trim_pileup_ont<true, false, 0>(*v->P, v->smem, v->gwarps);
+    else amp::cta_trim_pileup_ont<false, true, 0>(*v->P, v->smem, v->gwarps);
+}
+int emu_process_ont(void* h, long long first, long long n, const int32_t* pos, const uint16_t* flag, const int32_t* tlen,
+                    const uint32_t* cig_off, const uint32_t* cigar, const uint32_t* seq_off, const uint8_t* seq,
+                    const uint32_t* qual_off, const uint8_t* qual, int mode, int sample, int32_t* o_pos, uint16_t* o_ncig,
+                    uint8_t* o_flags, uint32_t* o_cigar, int grid_override, int warps, int wt_override) {
+    EmuCtx* c = (EmuCtx*)h;
+    if (n <= 0) return 0;
+    amp::KParams P{};
+    P.b = amp::BatchPtrs{first, n, pos, flag, tlen, cig_off, cigar, seq_off, seq, qual_off, qual};
+    P.o = amp::TrimOut{o_pos, o_ncig, o_flags, o_cigar};
+    P.tp = c->tp; P.mode = mode;
+    P.counts = c->counts.data() + (size_t)sample * AMP_NCH * c->Lpad; P.Lpad = c->Lpad; P.gpos_base = sample * c->Lpad;
+    P.tab = c->tab; P.err = &c->err;
+    const long long sum_cig = cig_off[first + n] - cig_off[first];
+    std::vector<uint32_t> scratch(2 * (size_t)(sum_cig + 3 * n) + 8);
+    P.scratch = scratch.data() - ((size_t)cig_off[first] + 3 * (size_t)first);
+    P.scratch_half = sum_cig + 3 * n;
+    P.wt = wt_override ? wt_override : AMPO_WT;
+    P.reads_per_tile = 1; P.ntiles = (int)n;
+    int grid = std::max(1, std::min(grid_override ? grid_override : 148, P.ntiles));
+    P.tiles_per_cta = (P.ntiles + grid - 1) / grid;
+    grid = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
+    if (!warps) warps = 4;
+    const int gwarps = std::max(1, std::min(warps, AMPO_GWARPS));
+    std::vector<unsigned char> smem(amp::smem_bytes_ont(P.wt, warps, gwarps) + 64);
+    unsigned char* sbase = smem.data();
+    sbase += (16 - ((uintptr_t)sbase & 15)) & 15;
+    P.gcap = P.tiles_per_cta;
+    std::vector<uint32_t> glist((size_t)grid * P.gcap + 1);
+    P.glist = glist.data();
+    OntLaunch v{&P, sbase, mode, gwarps};
+    for (int b = 0; b < grid; ++b) run_cta(b, warps * 32, ont_body, &v);
     return 0;
 }
 

@@ -20,7 +20,8 @@ def build(asan=False):
     srcs = [os.path.join(_DIR, "amp_emu.cpp"), os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_core.cuh"),
             os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_kernels.cuh"),
             os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_warp.cuh"),
-            os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_bgzf.cuh")]
+            os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_bgzf.cuh"),
+            os.path.join(_HERE, "..", "amplipy_b200", "csrc", "amp_ont.cuh")]
     if not os.path.isfile(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         gxx = "/usr/bin/g++" if os.path.isfile("/usr/bin/g++") else "g++"
         flags = ["-O1", "-g", "-fsanitize=address,undefined"] if asan else ["-O2"]
@@ -88,6 +89,13 @@ class EmuEngine:
         # the staging loops read 16-byte vectors from 16-byte aligned addresses: keep numpy buffers aligned
         qual = _aligned(batch.qual)
         seq = _aligned(batch.seq)
+        if self.kernel == "ont":
+            g, w, br, wt = self.v7_knobs
+            lib().emu_process_ont(self._h, ctypes.c_longlong(first), ctypes.c_longlong(n), _p(batch.pos), _p(batch.flag),
+                                  _p(batch.tlen), _p(batch.cig_off), _p(batch.cigar), _p(batch.seq_off), _p(seq),
+                                  _p(batch.qual_off), _p(qual), mode, sample, _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
+                                  g, w, wt)
+            return TrimResult(batch, *out) if trim else None
         if self.kernel == "v7":
             g, w, br, wt = self.v7_knobs
             lib().emu_process_v7(self._h, ctypes.c_longlong(first), ctypes.c_longlong(n), _p(batch.pos), _p(batch.flag),
