@@ -1212,7 +1212,7 @@ int amp_bam_decode_host(amp_ctx* c, const uint8_t* bgzf, int64_t n_bytes, const 
         CK(cudaStreamWaitEvent(sc, d.ev[pi], 0));
         CK(cudaMemsetAsync(d.ctr, 0, 4, sc));
         const long long nb = k1 - k0;
-        const int grid = (int)std::min<long long>((nb + AMPZ_WARPS - 1) / AMPZ_WARPS, (long long)c->sm_count * 3);
+        const int grid = (int)std::min<long long>((nb + AMPZ_WARPS - 1) / AMPZ_WARPS, (long long)c->sm_count * 2);
         amp_bgzf_inflate_kernel<<<grid, AMPZ_WARPS * 32, AMPZ_WARPS * sizeof(amp::InflateMem), sc>>>(d.comp, n_bytes, d.in_off, d.out_len, d.out_off, k0, k1, d.raw,
                                                                                                   d.ctr, d.ctr + 1);
         CK(cudaGetLastError());

@@ -35,39 +35,49 @@ AMPZ_TABLE uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6
 AMPZ_TABLE uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 struct HuffLists { uint16_t count[16]; uint16_t symbol[288]; };          // canonical code: symbols ordered by (length, symbol)
+#define AMPZ_RING 64                  // words of the compressed stream kept in shared memory ahead of the bit reader
+#define AMPZ_WIN 2048                 // bytes of output kept in shared memory (circular): source of the near matches
 struct InflateMem {                                                       // per warp, in shared memory
     uint16_t ltab[1 << AMPZ_LBITS];                                       // (symbol << 4) | length, 0 = longer than the table
     uint16_t dtab[1 << AMPZ_DBITS];
     HuffLists lit, dist;
     uint8_t lens[320];
+    uint32_t ring[AMPZ_RING];
+    uint8_t win[AMPZ_WIN];
 };
 
+// Bit reader of lane 0.  Words come from the ring in shared memory when they are there (the warp keeps it ahead of the reader at
+// every point where its lanes meet) and from global memory otherwise, so correctness never depends on the ring.
 struct BitReader {
-    const uint32_t* wp;               // next aligned word
-    const uint32_t* wend;             // first word past the readable range
+    const uint32_t* words;            // the stream's aligned words in global memory
+    const uint32_t* ring;
+    int nwords;                       // words that hold stream bytes
+    int widx;                         // next word to take
+    int ring_hi;                      // the ring holds words [ring_hi - AMPZ_RING, ring_hi)
     unsigned long long buf; int cnt;  // cnt valid bits in buf
 };
-AMP_WD void br_init(BitReader& b, const uint8_t* p, const uint8_t* end) {
-    const uintptr_t a = (uintptr_t)p;
-    b.wp = (const uint32_t*)(a & ~(uintptr_t)3);
-    b.wend = (const uint32_t*)(((uintptr_t)end + 3) & ~(uintptr_t)3);
-    const int skip = (int)(a & 3) * 8;
-    b.buf = (unsigned long long)(*b.wp++) >> skip; b.cnt = 32 - skip;
+AMP_WD uint32_t br_word(const BitReader& b, int idx) {
+    if (idx >= b.nwords) return 0u;                                       // zeros past the end of the input
+    if (idx < b.ring_hi && idx >= b.ring_hi - AMPZ_RING) return b.ring[idx & (AMPZ_RING - 1)];
+    return b.words[idx];
 }
-AMP_WD void br_refill(BitReader& b) {               // at least 32 valid bits afterwards (zeros past the end of the input)
+AMP_WD void br_init(BitReader& b, const uint8_t* p, const uint8_t* end, const uint32_t* ring) {
+    const uintptr_t a = (uintptr_t)p;
+    b.words = (const uint32_t*)(a & ~(uintptr_t)3);
+    b.ring = ring; b.ring_hi = 0;
+    b.nwords = (int)((((uintptr_t)end + 3) & ~(uintptr_t)3) - (a & ~(uintptr_t)3)) >> 2;
+    const int skip = (int)(a & 3) * 8;
+    b.buf = (unsigned long long)(b.nwords > 0 ? b.words[0] : 0u) >> skip; b.cnt = 32 - skip; b.widx = 1;
+}
+AMP_WD void br_refill(BitReader& b) {               // at least 32 valid bits afterwards
     if (b.cnt <= 32) {
-        const unsigned long long w = b.wp < b.wend ? (unsigned long long)*b.wp : 0ULL;
-        ++b.wp;
-        b.buf |= w << b.cnt; b.cnt += 32;
+        b.buf |= (unsigned long long)br_word(b, b.widx) << b.cnt;
+        ++b.widx; b.cnt += 32;
     }
 }
 AMP_WD unsigned br_peek(const BitReader& b, int n) { return (unsigned)(b.buf & ((1ULL << n) - 1ULL)); }
 AMP_WD void br_skip(BitReader& b, int n) { b.buf >>= n; b.cnt -= n; }
 AMP_WD unsigned br_bits(BitReader& b, int n) { br_refill(b); const unsigned v = br_peek(b, n); br_skip(b, n); return v; }
-// bytes consumed so far (whole bytes; the bit position rounded up)
-AMP_WD long long br_bytes_used(const BitReader& b, const uint8_t* start) {
-    return (long long)((const uint8_t*)b.wp - start) - (b.cnt >> 3);
-}
 
 AMP_WD uint8_t ld_cg_u8(const uint8_t* p) {
 #if defined(__CUDA_ARCH__)
@@ -134,11 +144,30 @@ AMP_WD int huff_decode(BitReader& b, const uint16_t* tab, int tbits, const HuffL
 
 // Inflate one raw deflate stream of in_len bytes into out[0, out_len) (one warp; every lane calls).  Returns AMPZ_E_* bits.
 // `in` must be readable up to the next 4-byte boundary past its end; `out` is written only inside [0, out_len).
+// Output bytes go to the circular window in shared memory first and reach `out` in stretches copied by all lanes; a match whose
+// source still lies in the window is copied inside shared memory, a farther one is read back from `out` (through L2).
 AMP_WD int inflate_block(const uint8_t* in, long long in_len, uint8_t* out, long long out_len, InflateMem& M, int lane) {
-    BitReader b; b.wp = b.wend = nullptr; b.buf = 0; b.cnt = 0;
-    if (lane == 0) br_init(b, in, in + in_len);
-    int o = 0;                                       // bytes written (lane 0's copy is authoritative, broadcast with every match)
+    BitReader b; b.words = nullptr; b.ring = M.ring; b.nwords = 0; b.widx = 0; b.ring_hi = 0; b.buf = 0; b.cnt = 0;
+    br_init(b, in, in + in_len, M.ring);            // every lane keeps the geometry; only lane 0's reader advances
+    int o = 0;                                       // bytes produced (lane 0's copy is authoritative, broadcast where the lanes meet)
+    int flushed = 0;                                 // bytes of the window already copied to `out`
+    int wlo = 0;                                     // the window is valid for positions >= wlo (and >= o - AMPZ_WIN)
     int err = 0;
+    // keep the ring ahead of the reader / copy finished output: all lanes, at points where they meet (widx, o are uniform then)
+    auto top_up = [&](int widx) {
+        while (b.ring_hi < b.nwords && b.ring_hi - widx < AMPZ_RING - 32) {
+            const int idx = b.ring_hi + lane;
+            if (idx < b.nwords) M.ring[idx & (AMPZ_RING - 1)] = b.words[idx];
+            b.ring_hi += 32;
+        }
+        w_sync();
+    };
+    auto flush_to = [&](int upto) {
+        for (int p = flushed + lane; p < upto; p += 32) out[p] = M.win[p & (AMPZ_WIN - 1)];
+        flushed = upto;
+        w_sync();
+    };
+    top_up(1);
     for (;;) {
         // ---- block header (lane 0), tables (all lanes)
         int last = 0, type = 0;
@@ -146,6 +175,7 @@ AMP_WD int inflate_block(const uint8_t* in, long long in_len, uint8_t* out, long
         last = w_shfl(last, 0); type = w_shfl(type, 0);
         if (type == 3) { err |= AMPZ_E_DATA; break; }
         if (type == 0) {                             // stored: LEN, NLEN, bytes (lane 0 copies; rare in BAM files)
+            flush_to(o);
             int n = -1;
             if (lane == 0) {
                 br_skip(b, b.cnt & 7);               // to the byte boundary
@@ -157,7 +187,8 @@ AMP_WD int inflate_block(const uint8_t* in, long long in_len, uint8_t* out, long
             }
             n = w_shfl(n, 0);
             if (n < 0) { err |= AMPZ_E_DATA; break; }
-            o += n;
+            o += n; flushed = o; wlo = o;            // these bytes are in `out` only
+            top_up(w_shfl(b.widx, 0));
             if (last) break;
             continue;
         }
@@ -220,16 +251,19 @@ AMP_WD int inflate_block(const uint8_t* in, long long in_len, uint8_t* out, long
         w_sync();
         huff_table(M.ltab, AMPZ_LBITS, M.lit, lane);
         huff_table(M.dtab, AMPZ_DBITS, M.dist, lane);
-        // ---- symbols: lane 0 stores literals as they come and stops at every match / end of block / error
+        top_up(w_shfl(b.widx, 0));
+        // ---- symbols: lane 0 puts literals into the window as they come and stops at every match / end of block / error, and
+        // when the ring runs low or the window fills up (len = -2: the lanes only top up / flush and it goes on)
         for (;;) {
-            int len = 0, dist = 0;                   // len > 0: match; len == 0: end of block; len < 0: error
+            int len = 0, dist = 0;                   // len > 0: match; len == 0: end of block; len == -1: error; -2: service stop
             if (lane == 0) {
                 for (;;) {
+                    if ((b.ring_hi < b.nwords && b.ring_hi - b.widx < 4) || o - flushed > AMPZ_WIN - 320) { len = -2; break; }
                     const int sym = huff_decode(b, M.ltab, AMPZ_LBITS, M.lit);
                     if (sym < 0) { len = -1; break; }
                     if (sym < 256) {
                         if ((long long)o >= out_len) { len = -1; break; }
-                        out[o++] = (uint8_t)sym;
+                        M.win[o & (AMPZ_WIN - 1)] = (uint8_t)sym; ++o;
                         continue;
                     }
                     if (sym == 256) break;
@@ -246,19 +280,30 @@ AMP_WD int inflate_block(const uint8_t* in, long long in_len, uint8_t* out, long
                 const int ld = w_shfl(len > 0 ? (len << 16) | dist : len, 0);
                 len = ld > 0 ? ld >> 16 : ld; dist = ld & 0xFFFF;
             }
-            if (len <= 0) { if (len < 0) err |= AMPZ_E_DATA; break; }
+            if (len == -1) { err |= AMPZ_E_DATA; break; }
             o = w_shfl(o, 0);
-            // out[o + i] = out[o - dist + i mod dist]: the source stretch [o - dist, o) is complete (periodic extension)
-            // (read through L2: the L1 may hold a line of `out` from before these bytes were written)
-            const uint8_t* src = out + o - dist;
-            for (int i = lane; i < len; i += 32) out[o + i] = ld_cg_u8(src + (dist >= len ? i : i % dist));
-            w_sync();
-            o += len;
+            const int widx = w_shfl(b.widx, 0);
+            if (len == 0) { top_up(widx); break; }
+            if (len > 0) {
+                // window[o + i] = byte at o - dist + (i mod dist): the stretch [o - dist, o) is complete (periodic extension)
+                const int s0 = o - dist;
+                if (s0 >= wlo && dist <= AMPZ_WIN - 258) {
+                    for (int i = lane; i < len; i += 32) M.win[(o + i) & (AMPZ_WIN - 1)] = M.win[(s0 + (dist >= len ? i : i % dist)) & (AMPZ_WIN - 1)];
+                } else {                             // far source: everything before o is in `out` after the flush (read through L2)
+                    flush_to(o);
+                    for (int i = lane; i < len; i += 32) M.win[(o + i) & (AMPZ_WIN - 1)] = ld_cg_u8(out + s0 + (dist >= len ? i : i % dist));
+                }
+                w_sync();
+                o += len;
+            }
+            if (o - flushed >= 512) flush_to(o);
+            top_up(widx);
         }
         if (err || last) break;
     }
     o = w_shfl(o, 0);
     err = w_shfl(err, 0) | err;
+    if (!err) flush_to(o);
     if (!err && (long long)o != out_len) err |= AMPZ_E_SIZE;
     return err;
 }

@@ -293,7 +293,7 @@ AMP_HD void ins_commit(const KParams& P, const uint8_t* seq_read, int pos, int b
     TileSink::Text t; t.seq = seq_read; t.b = b;
     ins_table_add(P.tab, P.gpos_base + pos, n, t, 1);
 }
-AMP_WD void ins_defer(const KParams& P, int* ctrl, uint32_t so0, int pos, int b, int n) {   // so0: the read's offset in P.b.seq
+AMP_WD_COLD void ins_defer(const KParams& P, int* ctrl, uint32_t so0, int pos, int b, int n) {   // so0: the read's offset in P.b.seq
     if (b < 65536 && n > 0 && n < 65536) {
         const int idx = atomic_add(&ctrl[C7_NEV], 1);
         if (idx < AMP7_EVCAP) {      // the third word (never 0) is written last: it tells a draining warp that the entry is complete
