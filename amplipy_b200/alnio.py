@@ -127,7 +127,23 @@ def bam_layout(raw):
         need(p + l_name + 4)
         name = bytes(hdr[p:p + l_name - 1]).decode(); p += l_name
         refs.append((name, int.from_bytes(hdr[p:p + 4], "little", signed=True))); p += 4
-    return {"in_off": in_off, "out_len": out_len, "body_off": p, "header_text": header_text, "refs": refs}
+    # a look at the first records (CIGAR ops per read): callers size the insertion table for indel-rich data before decoding
+    ops_per_read = 0.0
+    try:
+        while len(hdr) < p + 36 and k < len(in_off):
+            more()
+        q, nrec, nops = p, 0, 0
+        while q + 36 <= len(hdr) and nrec < 256:
+            bs = int.from_bytes(hdr[q:q + 4], "little")
+            if bs < 32 or q + 4 + bs > len(hdr):
+                break
+            nops += int.from_bytes(hdr[q + 16:q + 18], "little"); nrec += 1
+            q += 4 + bs
+        ops_per_read = nops / nrec if nrec else 0.0
+    except InputError:
+        pass
+    return {"in_off": in_off, "out_len": out_len, "body_off": p, "header_text": header_text, "refs": refs,
+            "ops_per_read": ops_per_read}
 
 
 def bgzf_compress_units(data, bounds, level=6, threads=0):

@@ -207,35 +207,79 @@ def _run(untrimmed_reads_fn, primer_fn, reference_fn, trimmed_reads_fn, variants
     if variants_fn is not None:
         print_log("Output variants VCF: %s" % variants_fn)
         vcf.check_output_path(variants_fn)
+    import threading
     import time as _time
     tm = {}
-    _t = _time.perf_counter()
-    aln = alnio.read_alignments(in_fn)
-    tm["decode"] = _time.perf_counter() - _t
-    out_header = alnio.header_with_pg(aln.header_text, argv) if run_trim else None
+    from .engine import AmpError, Engine, TrimResult
 
-    from .engine import Engine
-    indel_rich = aln.n and (aln.batch.cigar.size / aln.n) > 8
-    eng = Engine(ref_len=L, primer_tables=tables, max_primer_len=mpl,
-                 min_quality=DEFAULT_MIN_QUALITY if min_quality is None else min_quality,
-                 sliding_window_width=DEFAULT_SLIDING_WINDOW_WIDTH if sliding_window_width is None else sliding_window_width,
-                 min_length=DEFAULT_MIN_LENGTH if min_length is None else min_length,
-                 include_no_primer=bool(include_no_primer), device=device,
-                 ins_slots=(1 << 24) if indel_rich else 0, ins_arena_bytes=(1 << 30) if indel_rich else 0)
-    print_log("Processing reads...")
+    def make_engine(indel_rich):
+        return Engine(ref_len=L, primer_tables=tables, max_primer_len=mpl,
+                      min_quality=DEFAULT_MIN_QUALITY if min_quality is None else min_quality,
+                      sliding_window_width=DEFAULT_SLIDING_WINDOW_WIDTH if sliding_window_width is None else sliding_window_width,
+                      min_length=DEFAULT_MIN_LENGTH if min_length is None else min_length,
+                      include_no_primer=bool(include_no_primer), device=device,
+                      ins_slots=(1 << 24) if indel_rich else 0, ins_arena_bytes=(1 << 30) if indel_rich else 0)
     pile = run_variants or run_consensus
     _t = _time.perf_counter()
-    trim = eng.process(aln.batch, trim=run_trim, pileup=pile)
-    eng.raise_on_device_errors()
-    tm["gpu_process"] = _time.perf_counter() - _t
+    aln = eng = trim = None
+    n_reads = 0
+    if (in_fn.lower().endswith(".bam") and os.path.isfile(in_fn) and not os.environ.get("AMPLIPY_HOST_DECODE") and
+            hasattr(Engine, "decode_bam")):
+        # BAM: the compressed file goes to the GPU as it is and is decoded there (amp_bam_decode_host); the host inflates it too,
+        # at the same time, only when the records are needed for the trimmed output
+        with open(in_fn, "rb") as f:
+            raw = f.read()
+        layout = alnio.bam_layout(raw)
+        box = {}
+        host = None
+        if run_trim:
+            def _host_decode():
+                try:
+                    box["aln"] = alnio._read_bam(raw)
+                except BaseException as e:
+                    box["err"] = e
+            host = threading.Thread(target=_host_decode)
+            host.start()
+        out_header = alnio.header_with_pg(layout["header_text"], argv) if run_trim else None
+        eng = make_engine(layout["ops_per_read"] > 8)
+        print_log("Processing reads...")
+        try:
+            info = eng.decode_bam(raw, layout)
+            outs = eng.process_decoded(trim=run_trim, pileup=pile)
+            n_reads = info["n"]
+        except AmpError:
+            eng.close()
+            eng = None                       # e.g. records straddling BGZF blocks (not written by htslib): host decoder below
+        tm["gpu_decode_process"] = _time.perf_counter() - _t
+        if host is not None:
+            host.join()
+            if "err" in box:
+                raise box["err"]
+            aln = box["aln"]
+            if eng is not None:
+                trim = TrimResult(aln.batch, *outs)
+        tm["decode"] = _time.perf_counter() - _t
+        if eng is not None:
+            eng.raise_on_device_errors()
+    if eng is None:
+        aln = aln or alnio.read_alignments(in_fn)
+        tm["decode"] = _time.perf_counter() - _t
+        out_header = alnio.header_with_pg(aln.header_text, argv) if run_trim else None
+        indel_rich = aln.n and (aln.batch.cigar.size / aln.n) > 8
+        eng = make_engine(indel_rich)
+        print_log("Processing reads...")
+        _t = _time.perf_counter()
+        trim = eng.process(aln.batch, trim=run_trim, pileup=pile)
+        eng.raise_on_device_errors()
+        tm["gpu_process"] = _time.perf_counter() - _t
+        n_reads = aln.n
     # the reference reports its progress every PROGRESS_NUM_READS reads of its loop (AmpliPy.py:19, 898-899); the reads
     # are processed as one batch here, so the same lines are written once the batch is through
-    for k in range(PROGRESS_NUM_READS, aln.n, PROGRESS_NUM_READS):
+    for k in range(PROGRESS_NUM_READS, n_reads, PROGRESS_NUM_READS):
         print_log("Processed %d reads..." % k)
     writer = None
     if run_trim:
         # the trimmed reads are encoded (record rewrite + BGZF deflate, both outside the GIL) while calling and the text outputs run
-        import threading
         def _write():
             t0 = _time.perf_counter()
             try:
@@ -275,7 +319,7 @@ def _run(untrimmed_reads_fn, primer_fn, reference_fn, trimmed_reads_fn, variants
         import json
         with open(os.environ["AMP_CLI_TIMINGS"], "w") as f:
             json.dump({k: round(v, 4) for k, v in tm.items()}, f)
-    print_log("Finished Processing %d reads" % max(aln.n - 1, 0))
+    print_log("Finished Processing %d reads" % max(n_reads - 1, 0))
     return eng
 
 

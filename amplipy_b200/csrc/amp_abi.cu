@@ -855,6 +855,17 @@ int amp_counts_host(amp_ctx* c, int sample, int32_t* host) {
     return AMP_OK;
 }
 
+// the inverse of amp_counts_host: replace count matrix `sample` by host values (function-level drop-ins, tests)
+int amp_counts_upload(amp_ctx* c, int sample, const int32_t* host) {
+    if (!c || !host || sample < 0 || sample >= c->cfg.n_samples) return fail(AMP_ERR_ARG, "amp_counts_upload: bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaDeviceSynchronize());
+    const size_t L = (size_t)c->cfg.ref_len;
+    CK(cudaMemset(c->d_counts + (size_t)sample * AMP_NCH * c->Lpad, 0, (size_t)AMP_NCH * c->Lpad * 4));
+    CK(cudaMemcpy2D(c->d_counts + (size_t)sample * AMP_NCH * c->Lpad, (size_t)c->Lpad * 4, host, L * 4, L * 4, AMP_NCH, cudaMemcpyHostToDevice));
+    return AMP_OK;
+}
+
 int amp_ins_count(amp_ctx* c, int64_t* n_alleles, int64_t* n_chars) {
     if (!c || !n_alleles || !n_chars) return fail(AMP_ERR_ARG, "amp_ins_count: null argument");
     CK(cudaSetDevice(c->cfg.device));

@@ -288,7 +288,9 @@ AMP_WD int inflate_block(const uint8_t* in, long long in_len, uint8_t* out, long
                 // window[o + i] = byte at o - dist + (i mod dist): the stretch [o - dist, o) is complete (periodic extension)
                 const int s0 = o - dist;
                 if (s0 >= wlo && dist <= AMPZ_WIN - 258) {
-                    for (int i = lane; i < len; i += 32) M.win[(o + i) & (AMPZ_WIN - 1)] = M.win[(s0 + (dist >= len ? i : i % dist)) & (AMPZ_WIN - 1)];
+                    if (dist >= len) { for (int i = lane; i < len; i += 32) M.win[(o + i) & (AMPZ_WIN - 1)] = M.win[(s0 + i) & (AMPZ_WIN - 1)]; }
+                    else if (dist == 1) { const uint8_t v = M.win[s0 & (AMPZ_WIN - 1)]; for (int i = lane; i < len; i += 32) M.win[(o + i) & (AMPZ_WIN - 1)] = v; }
+                    else for (int i = lane; i < len; i += 32) M.win[(o + i) & (AMPZ_WIN - 1)] = M.win[(s0 + i % dist) & (AMPZ_WIN - 1)];
                 } else {                             // far source: everything before o is in `out` after the flush (read through L2)
                     flush_to(o);
                     for (int i = lane; i < len; i += 32) M.win[(o + i) & (AMPZ_WIN - 1)] = ld_cg_u8(out + s0 + (dist >= len ? i : i % dist));

@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "amp_host_alloc", "amp_host_free", "amp_reset_async", "amp_set_reference", "amp_call_device",
     "amp_nccl_unique_id", "amp_nccl_comm_init", "amp_nccl_comm_destroy", "amp_nccl_allgather", "amp_allreduce_counts",
     "amp_ins_slot_bytes", "amp_ins_pack_device", "amp_ins_merge_packed", "amp_reserve", "amp_counts_copy_device",
-    "amp_bam_decode_host", "amp_process_decoded", "amp_decoded_copy_host"]
+    "amp_bam_decode_host", "amp_process_decoded", "amp_decoded_copy_host", "amp_counts_upload"]
 
 
 class AmpConfig(ctypes.Structure):
@@ -310,6 +310,12 @@ class Engine:
         out = np.empty((6, self.L), np.int32)
         _check(self.lib.amp_counts_host(self._ctx, sample, _ptr(out)), "amp_counts_host")
         return out
+
+    def upload_counts(self, counts, sample=0):
+        """Replace count matrix ``sample`` by the host array counts[6, L] (A C G T N '-')."""
+        a = np.ascontiguousarray(counts, np.int32)
+        assert a.shape == (6, self.L)
+        _check(self.lib.amp_counts_upload(self._ctx, sample, _ptr(a)), "amp_counts_upload")
 
     def counts_device_ptr(self):
         p = ctypes.c_void_p()

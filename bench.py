@@ -260,8 +260,7 @@ def file_to_file(args, g, prim, b, runs=3):
         t_decode = time.perf_counter() - t0
         assert a.batch.n == b.n
         del a
-        times, splits = [], []
-        for r in range(runs):
+        def one_run():
             for f in ("trimmed.bam", "variants.vcf", "consensus.fas", "timings.json"):
                 if os.path.exists(j(f)):
                     os.remove(j(f))
@@ -269,16 +268,28 @@ def file_to_file(args, g, prim, b, runs=3):
             t0 = time.perf_counter()
             cli.main(["aio", "-i", j("in.bam"), "-p", j("primers.bed"), "-r", j("ref.fas"), "-ot", j("trimmed.bam"),
                       "-ov", j("variants.vcf"), "-oc", j("consensus.fas")])
-            times.append(time.perf_counter() - t0)
+            dt = time.perf_counter() - t0
             try:
-                splits.append(json.load(open(j("timings.json"))))
+                sp = json.load(open(j("timings.json")))
             except Exception:
-                splits.append(None)
+                sp = None
+            return dt, sp
+        times, splits = [], []
+        for r in range(runs):
+            dt, sp = one_run()
+            times.append(dt); splits.append(sp)
+        size6 = os.path.getsize(j("trimmed.bam"))
+        os.environ["AMPLIPY_BAM_LEVEL"] = "1"           # the trimmed BAM deflated at level 1 instead of htslib's default 6
+        fast = [one_run() for _ in range(2)]
+        os.environ.pop("AMPLIPY_BAM_LEVEL", None)
+        kf = int(np.argmin([x[0] for x in fast]))
+        fast_obj = {"value": b.n / fast[kf][0], "unit": "reads/s", "seconds": fast[kf][0], "split_s": fast[kf][1],
+                    "trimmed_bam_bytes": os.path.getsize(j("trimmed.bam")), "note": "AMPLIPY_BAM_LEVEL=1"}
         os.environ.pop("AMP_CLI_TIMINGS", None)
         k = int(np.argmin(times))
         return {"value": b.n / times[k], "unit": "reads/s", "seconds": times[k], "runs_s": times, "split_s": splits[k],
                 "bam_decode_only_reads_per_s": b.n / t_decode,
-                "bam_bytes": os.path.getsize(j("in.bam")), "trimmed_bam_bytes": os.path.getsize(j("trimmed.bam")),
+                "bam_bytes": os.path.getsize(j("in.bam")), "trimmed_bam_bytes": size6, "deflate_level_1": fast_obj,
                 "note": "python -m amplipy_b200 aio on files in a temp directory (page cache warm), best of %d; "
                         "the reference's counterpart is AmpliPy.py aio with pysam I/O" % runs}
     finally:

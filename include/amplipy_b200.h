@@ -134,6 +134,7 @@ int amp_last_launches(amp_ctx* ctx);                  /* kernels launched by the
 int amp_counts_device(amp_ctx* ctx, int32_t** dev_counts);
 int amp_bind_counts(amp_ctx* ctx, int32_t* dev_counts);          /* use a caller-owned device buffer (e.g. a torch tensor for NCCL) */
 int amp_counts_host(amp_ctx* ctx, int sample, int32_t* host_counts /* [6][L] */);
+int amp_counts_upload(amp_ctx* ctx, int sample, const int32_t* host_counts /* [6][L] */);   /* replace a sample's matrix */
 
 /* insertion alleles (the non-fixed keys of symbol_counts_at_ref_pos, AmpliPy.py:745-748) */
 int amp_ins_count(amp_ctx* ctx, int64_t* n_alleles, int64_t* n_chars);

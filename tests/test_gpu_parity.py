@@ -469,3 +469,49 @@ def test_device_bam_decode_rejects_bad_input(tmp_path):
         eng.decode_bam(raw2, alnio.bam_layout(raw2))
     info = eng.decode_bam(raw, lay)                       # the context is still usable
     assert info["n"] == b.n
+
+
+# ---- function-level drop-ins with the reference's signatures (amplipy_b200/compat.py) -------------------------------------------
+class _Seg:
+    """The pysam.AlignedSegment attributes the reference's functions touch."""
+
+    def __init__(self, rec):
+        pos, flag, tlen, ops, seq, qual = rec
+        self.reference_start, self.flag, self.template_length = pos, flag, tlen
+        self.cigartuples, self.query_sequence, self.query_qualities = [tuple(x) for x in ops], seq, list(qual)
+
+
+def test_function_level_dropins_match_the_golden_quirks():
+    """trim_read(s, ...), update_base_counts(counts, s, mq), alleles_from_counts(dict) with the reference's signatures, read by
+    read, against the quirk vectors produced by the unmodified reference (tests/golden/quirks.npz)."""
+    from amplipy_b200 import compat
+    b, meta, arr = golden_io.load_case("quirks")
+    p = meta["params"]
+    L = meta["L"]
+    prim = [tuple(x) for x in meta["primers"]]
+    mn, mx = compat.find_overlapping_primers(L, prim, p["offset"])
+    counts = [{'A': 0, 'C': 0, 'G': 0, 'T': 0, 'N': 0, '-': 0} for _ in range(L)]
+    mpl = max(e - s for s, e in prim)
+    for i in range(b.n):
+        s = _Seg(b.record(i))
+        if (s.flag & 4) or not s.cigartuples:
+            continue
+        ts, te, tq = compat.trim_read(s, mn, mx, mpl, p["min_quality"], p["window"])
+        fl = int(arr["t_flags"][i])
+        assert (ts, te, tq) == (bool(fl & 1), bool(fl & 2), bool(fl & 4)), i
+        assert s.reference_start == int(arr["t_pos"][i])
+        a = int(b.cig_off[i]) + 3 * i
+        assert [((n << 4) | op) for op, n in s.cigartuples] == arr["t_cigar"][a:a + int(arr["t_ncig"][i])].tolist(), i
+        compat.update_base_counts(counts, s, p["min_quality"])
+    want = arr["counts_aio"]
+    for ch in range(6):
+        assert [counts[q]["ACGTN-"[ch]] for q in range(L)] == want[ch].tolist()
+    got_ins = {(q, k): v for q in range(L) for k, v in counts[q].items() if not (len(k) == 1 and k in "ACGTN-")}
+    assert got_ins == golden_io.ins_from_meta(meta)
+    al_off = arr["al_off"]
+    for q in range(L):
+        total, al = compat.alleles_from_counts(counts[q])
+        a0, a1 = int(al_off[q]), int(al_off[q + 1])
+        assert total == int(arr["depth_aio"][q])
+        assert [x[2] for x in al] == meta["al_sym"][a0:a1] and [x[0] for x in al] == arr["al_count"][a0:a1].tolist()
+        assert [x[1] for x in al] == arr["al_freq"][a0:a1].tolist()
