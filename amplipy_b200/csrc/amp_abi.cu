@@ -109,7 +109,7 @@ __device__ __noinline__ void call_long_list(const amp::CallParams& P, long long 
 #pragma unroll
     for (int o = 0; o < AMP_NCH; ++o) { cfix[o] = cnt[(size_t)o * P.Lpad + p]; total += cfix[o]; }
     for (int t = head; t >= 0;) { const amp::InsSlot sl = P.slots[t]; total += sl.count; t = sl.next; }
-    const unsigned char refsym = P.ref_seq[p];
+    const unsigned char refsym = P.ref_seq[(size_t)sample * (size_t)P.ref_stride + p];
     int n_alt = 0, alt_fixed = 0;
     int top_id = -1, top_c = 0;                 // set by the lane that owns the first allele of the order
     int ref_key = -1, refc = 0; double reff = 0.0;   // 936-937: the last match in visiting order wins
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) amp_call_kernel(const __grid_constant__ a
     int total = c;
 #pragma unroll
     for (int d = 1; d < G; d <<= 1) total += __shfl_xor_sync(gmask, total, d);
-    const unsigned char refsym = P.ref_seq[p];
+    const unsigned char refsym = P.ref_seq[(size_t)sample * (size_t)P.ref_stride + p];
     const double f = c ? (double)c / (double)total : 0.0;
     // index in the sorted allele list = number of alleles that are greater
     int rank = 0;
@@ -433,6 +433,10 @@ struct amp_ctx {
     amp_config cfg;
     int Lpad = 0, sm_count = 0, max_primer_len = 0;
     int32_t *d_min_start = nullptr, *d_max_end = nullptr;
+    // samples with a primer scheme / reference of their own (amp_set_scheme / amp_set_sample_reference)
+    struct Scheme { int32_t* d_min = nullptr; int32_t* d_max = nullptr; int L = 0, mpl = 0; };
+    std::vector<Scheme> scheme;
+    bool ref_per_sample = false;
     int* d_counts = nullptr; bool counts_owned = true;
     amp::InsTable tab{};
     unsigned long long nslots = 0;
@@ -478,6 +482,10 @@ int dev_grow(T** p, size_t* cap, size_t need) {
     return AMP_OK;
 }
 
+bool has_scheme(const amp_ctx* c, int sample) {
+    return c->d_min_start || (sample >= 0 && (size_t)sample < c->scheme.size() && c->scheme[sample].L > 0);
+}
+
 // words of the per-CTA generic-read lists + their counters for a launch over n reads
 size_t glist_words_for(const amp_ctx* c, long long n) { return (size_t)n + 33 * ((size_t)c->sm_count + 1) + (size_t)c->sm_count + 64; }
 
@@ -487,7 +495,11 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
     amp::KParams P{};
     P.b = b; P.o = o;
     P.tp.L = c->cfg.ref_len; P.tp.min_primer_start = c->d_min_start; P.tp.max_primer_end = c->d_max_end;
-    P.tp.max_primer_len = c->max_primer_len; P.tp.min_quality = c->cfg.min_quality; P.tp.window = c->cfg.sliding_window;
+    P.tp.max_primer_len = c->max_primer_len;
+    if ((size_t)sample < c->scheme.size() && c->scheme[sample].L > 0) {       // this sample's own scheme
+        const auto& sc = c->scheme[sample];
+        P.tp.L = sc.L; P.tp.min_primer_start = sc.d_min; P.tp.max_primer_end = sc.d_max; P.tp.max_primer_len = sc.mpl;
+    } P.tp.min_quality = c->cfg.min_quality; P.tp.window = c->cfg.sliding_window;
     P.tp.min_length = c->cfg.min_length; P.tp.include_no_primer = c->cfg.include_no_primer;
     P.mode = mode;
     P.counts = c->d_counts + (size_t)sample * AMP_NCH * c->Lpad;
@@ -656,6 +668,7 @@ int amp_destroy(amp_ctx* c) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     cudaFree(c->d_min_start); cudaFree(c->d_max_end);
+    for (auto& sc : c->scheme) { cudaFree(sc.d_min); cudaFree(sc.d_max); }
     if (c->counts_owned) cudaFree(c->d_counts);
     cudaFree(c->tab.slots); cudaFree(c->tab.entries); cudaFree(c->tab.slot_entry); cudaFree(c->tab.arena); cudaFree(c->tab.cursor);
     cudaFree(c->d_err); cudaFree(c->d_heads); cudaFree(c->d_scratch); cudaFree(c->d_glist); cudaFree(c->d_ref); cudaFree(c->d_call); cudaFree(c->d_xbuf);
@@ -717,7 +730,7 @@ int amp_process_device(amp_ctx* c, const amp_batch* b, int64_t sum_cigar_ops, in
                        const amp_trim_out* o, void* stream) {
     if (!c || !b) return fail(AMP_ERR_ARG, "amp_process_device: null argument");
     if (sample < 0 || sample >= c->cfg.n_samples) return fail(AMP_ERR_ARG, "amp_process_device: sample out of range");
-    if ((mode & AMP_MODE_TRIM) && (!o || !c->d_min_start)) return fail(AMP_ERR_ARG, "amp_process_device: trimming needs primer tables and an output block");
+    if ((mode & AMP_MODE_TRIM) && (!o || !has_scheme(c, sample))) return fail(AMP_ERR_ARG, "amp_process_device: trimming needs primer tables and an output block");
     if (!(mode & (AMP_MODE_TRIM | AMP_MODE_PILEUP))) return fail(AMP_ERR_ARG, "amp_process_device: empty mode");
     CK(cudaSetDevice(c->cfg.device));
     c->last_launches = 0;
@@ -760,7 +773,7 @@ int amp_process_device(amp_ctx* c, const amp_batch* b, int64_t sum_cigar_ops, in
 int amp_process_host(amp_ctx* c, const amp_batch* b, int mode, int sample, const amp_trim_out* o) {
     if (!c || !b) return fail(AMP_ERR_ARG, "amp_process_host: null argument");
     if (sample < 0 || sample >= c->cfg.n_samples) return fail(AMP_ERR_ARG, "amp_process_host: sample out of range");
-    if ((mode & AMP_MODE_TRIM) && (!o || !c->d_min_start)) return fail(AMP_ERR_ARG, "amp_process_host: trimming needs primer tables and an output block");
+    if ((mode & AMP_MODE_TRIM) && (!o || !has_scheme(c, sample))) return fail(AMP_ERR_ARG, "amp_process_host: trimming needs primer tables and an output block");
     if (!(mode & (AMP_MODE_TRIM | AMP_MODE_PILEUP))) return fail(AMP_ERR_ARG, "amp_process_host: empty mode");
     CK(cudaSetDevice(c->cfg.device));
     c->last_launches = 0;
@@ -939,6 +952,7 @@ int amp_ins_merge(amp_ctx* c, int64_t n, const int32_t* sample, const int32_t* p
 int amp_set_reference(amp_ctx* c, const char* ref_seq) {
     if (!c || !ref_seq) return fail(AMP_ERR_ARG, "amp_set_reference: null argument");
     CK(cudaSetDevice(c->cfg.device));
+    if (c->ref_per_sample) { CK(cudaFree(c->d_ref)); c->d_ref = nullptr; c->ref_per_sample = false; }
     if (!c->d_ref) CK(cudaMalloc((void**)&c->d_ref, (size_t)c->cfg.ref_len + 16));
     CK(cudaMemcpy(c->d_ref, ref_seq, (size_t)c->cfg.ref_len, cudaMemcpyHostToDevice));
     return AMP_OK;
@@ -967,6 +981,7 @@ int amp_call_device(amp_ctx* c, const amp_call_params* p, void* stream) {
     amp::CallParams P{};
     P.L = (int)L; P.Lpad = c->Lpad; P.n_samples = (int)S; P.counts = c->d_counts; P.slots = c->tab.slots;
     P.slot_entry = c->tab.slot_entry; P.arena = c->tab.arena; P.heads = c->d_heads; P.ref_seq = c->d_ref;
+    P.ref_stride = c->ref_per_sample ? (long long)c->cfg.ref_len : 0;
     P.min_depth_consensus = p->min_depth_consensus; P.min_freq_consensus = p->min_freq_consensus;
     P.min_depth_variants = p->min_depth_variants; P.min_freq_variants = p->min_freq_variants;
     P.depth = (int*)(blk + c->o_depth); P.top_id = (int*)(blk + c->o_top); P.top_count = (int*)(blk + c->o_topc);
@@ -1141,7 +1156,7 @@ int amp_reserve(amp_ctx* c, int64_t max_reads, int64_t max_cigar_ops) {
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaDeviceSynchronize());
     const size_t need_s = 2 * ((size_t)max_cigar_ops + 3 * (size_t)max_reads);
-    if (c->d_min_start && need_s > c->scratch_words) {
+    if (need_s > c->scratch_words) {
         if (c->d_scratch) CK(cudaFree(c->d_scratch));
         c->d_scratch = nullptr; c->scratch_words = 0;
         CK(cudaMalloc((void**)&c->d_scratch, need_s * 4));
@@ -1276,7 +1291,7 @@ int amp_process_decoded(amp_ctx* c, int mode, int sample, const amp_trim_out* ho
     auto& d = c->dec;
     if (!d.valid) return fail(AMP_ERR_STATE, "amp_process_decoded: no decoded batch (amp_bam_decode_host first)");
     if (sample < 0 || sample >= c->cfg.n_samples) return fail(AMP_ERR_ARG, "amp_process_decoded: sample out of range");
-    if ((mode & AMP_MODE_TRIM) && !c->d_min_start) return fail(AMP_ERR_ARG, "amp_process_decoded: trimming needs primer tables");
+    if ((mode & AMP_MODE_TRIM) && !has_scheme(c, sample)) return fail(AMP_ERR_ARG, "amp_process_decoded: trimming needs primer tables");
     if (!(mode & (AMP_MODE_TRIM | AMP_MODE_PILEUP))) return fail(AMP_ERR_ARG, "amp_process_decoded: empty mode");
     CK(cudaSetDevice(c->cfg.device));
     cudaStream_t sc = c->chunk[0].stream;
@@ -1330,6 +1345,84 @@ int amp_decoded_copy_host(amp_ctx* c, const amp_batch_out* h, uint64_t* rec_off)
     if (h->qual && d.sum_qual) CK(cudaMemcpyAsync(h->qual, d.qual, (size_t)d.sum_qual, cudaMemcpyDeviceToHost, sc));
     if (rec_off && n) CK(cudaMemcpyAsync(rec_off, d.rec_off, n * 8, cudaMemcpyDeviceToHost, sc));
     CK(cudaStreamSynchronize(sc));
+    return AMP_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// heterogeneous plates: a primer scheme / reference per sample, tables built on the device
+// ---------------------------------------------------------------------------------------------------
+// find_overlapping_primers (AmpliPy.py:174-209) as its covering-set definition: position p takes the smallest start / largest
+// end over the primers with start - offset <= p < end + offset (the offset widens the coverage only); -1 = uncovered
+__global__ void amp_primer_tables_kernel(int L, const int32_t* start, const int32_t* end, int n, int offset, int32_t* mn, int32_t* mx) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= L) return;
+    int lo = 0x7FFFFFFF, hi = -1;
+    for (int k = 0; k < n; ++k) {
+        const int s = start[k], e = end[k];
+        if (s - offset <= p && p < e + offset) { lo = s < lo ? s : lo; hi = e > hi ? e : hi; }
+    }
+    mn[p] = hi < 0 ? -1 : lo; mx[p] = hi;
+}
+
+extern "C" {
+
+int amp_set_scheme(amp_ctx* c, int sample, int32_t ref_len, const int32_t* primer_start, const int32_t* primer_end, int32_t n_primers,
+                   int32_t offset) {
+    if (!c || sample < 0 || sample >= c->cfg.n_samples || ref_len < 1 || ref_len > c->cfg.ref_len || n_primers < 0 || offset < 0 ||
+        (n_primers && (!primer_start || !primer_end)))
+        return fail(AMP_ERR_ARG, "amp_set_scheme: bad argument (the sample's reference must not be longer than the context's ref_len)");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaDeviceSynchronize());
+    if (c->scheme.size() < (size_t)c->cfg.n_samples) c->scheme.resize((size_t)c->cfg.n_samples);
+    auto& sc = c->scheme[sample];
+    if (!sc.d_min) { CK(cudaMalloc((void**)&sc.d_min, (size_t)c->cfg.ref_len * 4)); CK(cudaMalloc((void**)&sc.d_max, (size_t)c->cfg.ref_len * 4)); }
+    int32_t *d_s = nullptr, *d_e = nullptr;
+    int mpl = 0;
+    for (int k = 0; k < n_primers; ++k) mpl = std::max(mpl, primer_end[k] - primer_start[k]);
+    {
+        int rc = dev_grow(&c->d_xbuf, &c->xbuf_bytes, (size_t)n_primers * 8 + 64);
+        if (rc) return rc;
+    }
+    d_s = (int32_t*)c->d_xbuf; d_e = d_s + n_primers;
+    if (n_primers) {
+        CK(cudaMemcpy(d_s, primer_start, (size_t)n_primers * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_e, primer_end, (size_t)n_primers * 4, cudaMemcpyHostToDevice));
+    }
+    amp_primer_tables_kernel<<<(ref_len + 255) / 256, 256>>>(ref_len, d_s, d_e, n_primers, offset, sc.d_min, sc.d_max);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    sc.L = ref_len; sc.mpl = mpl;
+    return AMP_OK;
+}
+
+// the tables of a sample's scheme back on the host (tests: the device-side build against find_overlapping_primers)
+int amp_get_scheme(amp_ctx* c, int sample, int32_t* min_primer_start, int32_t* max_primer_end, int32_t* max_primer_len) {
+    if (!c || sample < 0 || (size_t)sample >= c->scheme.size() || c->scheme[sample].L < 1) return fail(AMP_ERR_ARG, "amp_get_scheme: no scheme for this sample");
+    CK(cudaSetDevice(c->cfg.device));
+    const auto& sc = c->scheme[sample];
+    if (min_primer_start) CK(cudaMemcpy(min_primer_start, sc.d_min, (size_t)sc.L * 4, cudaMemcpyDeviceToHost));
+    if (max_primer_end) CK(cudaMemcpy(max_primer_end, sc.d_max, (size_t)sc.L * 4, cudaMemcpyDeviceToHost));
+    if (max_primer_len) *max_primer_len = sc.mpl;
+    return AMP_OK;
+}
+
+// a reference of its own for one sample (at most ref_len characters; positions past its end are called as 'N' with depth 0)
+int amp_set_sample_reference(amp_ctx* c, int sample, const char* ref_seq, int32_t len) {
+    if (!c || !ref_seq || sample < 0 || sample >= c->cfg.n_samples || len < 1 || len > c->cfg.ref_len) return fail(AMP_ERR_ARG, "amp_set_sample_reference: bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaDeviceSynchronize());
+    const size_t L = (size_t)c->cfg.ref_len, S = (size_t)c->cfg.n_samples;
+    if (!c->ref_per_sample) {
+        unsigned char* nr = nullptr;
+        CK(cudaMalloc((void**)&nr, S * L + 16));
+        CK(cudaMemset(nr, 'N', S * L));
+        if (c->d_ref) { for (size_t k = 0; k < S; ++k) CK(cudaMemcpy(nr + k * L, c->d_ref, L, cudaMemcpyDeviceToDevice)); CK(cudaFree(c->d_ref)); }
+        c->d_ref = nr; c->ref_per_sample = true;
+    }
+    CK(cudaMemset(c->d_ref + (size_t)sample * L, 'N', L));
+    CK(cudaMemcpy(c->d_ref + (size_t)sample * L, ref_seq, (size_t)len, cudaMemcpyHostToDevice));
     return AMP_OK;
 }
 

@@ -660,7 +660,8 @@ struct CallParams {
     const int* slot_entry;             // slot -> dense allele index k (amp_ins_export order)
     const unsigned char* arena;
     const int* heads;                  // [n_samples * Lpad] slot index of the first insertion allele, -1 = none
-    const unsigned char* ref_seq;      // [L] raw FASTA characters
+    const unsigned char* ref_seq;      // raw FASTA characters: [L], or [n_samples][ref_stride] when samples have references of their own
+    long long ref_stride;              // 0: one reference for every sample
     int min_depth_consensus; double min_freq_consensus;
     int min_depth_variants; double min_freq_variants;
     // outputs
@@ -721,7 +722,7 @@ AMP_HD void call_position_impl(const CallParams& P, const unsigned char* fixed_s
     P.depth[gp] = (int)total;
     int best_id = -1, best_c = 0; Sym best_s; best_s.p = fixed_syms; best_s.len = 0;
     int refc = 0; double reff = 0.0; unsigned alt = 0; int n_alt = 0;
-    const unsigned char refsym = P.ref_seq[p];
+    const unsigned char refsym = P.ref_seq[(size_t)(gp / P.L) * (size_t)P.ref_stride + p];
     for (int ch = 0; ch < AMP_NCH; ++ch) {
         double f = total ? (double)c[ch] / (double)total : 0.0;
         P.fixed_freq[gp * AMP_NCH + ch] = f;

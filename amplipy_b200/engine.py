@@ -38,7 +38,8 @@ EXPORTED_SYMBOLS = [
     "amp_host_alloc", "amp_host_free", "amp_reset_async", "amp_set_reference", "amp_call_device",
     "amp_nccl_unique_id", "amp_nccl_comm_init", "amp_nccl_comm_destroy", "amp_nccl_allgather", "amp_allreduce_counts",
     "amp_ins_slot_bytes", "amp_ins_pack_device", "amp_ins_merge_packed", "amp_reserve", "amp_counts_copy_device",
-    "amp_bam_decode_host", "amp_process_decoded", "amp_decoded_copy_host", "amp_counts_upload"]
+    "amp_bam_decode_host", "amp_process_decoded", "amp_decoded_copy_host", "amp_counts_upload",
+    "amp_set_scheme", "amp_get_scheme", "amp_set_sample_reference"]
 
 
 class AmpConfig(ctypes.Structure):
@@ -197,6 +198,27 @@ class Engine:
         ref = ref_seq.encode("latin-1") if isinstance(ref_seq, str) else bytes(ref_seq)
         assert len(ref) == self.L
         _check(self.lib.amp_set_reference(self._ctx, ctypes.c_char_p(ref)), "amp_set_reference")
+
+    # ---------------------------------------------------------------- heterogeneous plates: a scheme / reference per sample
+    def set_scheme(self, sample, primers, offset=0, ref_len=None):
+        """Primer scheme of one sample: [(start, end)] sorted as load_primers returns them; the two per-position tables are
+        built on the device (find_overlapping_primers, AmpliPy.py:174-209)."""
+        st = np.ascontiguousarray([p[0] for p in primers], np.int32)
+        en = np.ascontiguousarray([p[1] for p in primers], np.int32)
+        _check(self.lib.amp_set_scheme(self._ctx, int(sample), int(self.L if ref_len is None else ref_len), _ptr(st), _ptr(en),
+                                       int(st.size), int(offset)), "amp_set_scheme")
+        self.has_primers = True
+
+    def get_scheme(self, sample, ref_len=None):
+        n = int(self.L if ref_len is None else ref_len)
+        mn, mx = np.empty(n, np.int32), np.empty(n, np.int32)
+        mpl = ctypes.c_int32(0)
+        _check(self.lib.amp_get_scheme(self._ctx, int(sample), _ptr(mn), _ptr(mx), ctypes.byref(mpl)), "amp_get_scheme")
+        return mn, mx, int(mpl.value)
+
+    def set_sample_reference(self, sample, ref_seq):
+        ref = ref_seq.encode("latin-1") if isinstance(ref_seq, str) else bytes(ref_seq)
+        _check(self.lib.amp_set_sample_reference(self._ctx, int(sample), ctypes.c_char_p(ref), len(ref)), "amp_set_sample_reference")
 
     def call_device(self, min_depth_consensus=10, min_freq_consensus=0.0, min_depth_variants=1, min_freq_variants=0.03,
                     stream=None):

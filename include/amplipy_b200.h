@@ -201,6 +201,15 @@ int amp_bam_decode_host(amp_ctx* ctx, const uint8_t* bgzf, int64_t n_bytes, cons
 int amp_process_decoded(amp_ctx* ctx, int mode, int sample, const amp_trim_out* host_out);
 int amp_decoded_copy_host(amp_ctx* ctx, const amp_batch_out* host_arrays, uint64_t* rec_off);
 
+/* ---- heterogeneous plates: a primer scheme and / or a reference of its own for one sample of the context.
+ * amp_set_scheme builds the two per-position tables of find_overlapping_primers (AmpliPy.py:174-209) on the device from the
+ * sorted primer list (start, end) and the offset; ref_len <= the context's ref_len.  amp_process_* of that sample then trims
+ * against these tables, amp_call calls it against its own reference; one calling launch still covers the whole plate. */
+int amp_set_scheme(amp_ctx* ctx, int sample, int32_t ref_len, const int32_t* primer_start, const int32_t* primer_end,
+                   int32_t n_primers, int32_t offset);
+int amp_get_scheme(amp_ctx* ctx, int sample, int32_t* min_primer_start, int32_t* max_primer_end, int32_t* max_primer_len);
+int amp_set_sample_reference(amp_ctx* ctx, int sample, const char* ref_seq, int32_t len);
+
 /* pinned host memory helpers for callers that want full-speed amp_process_host */
 int amp_host_alloc(void** p, int64_t bytes);
 int amp_host_free(void* p);

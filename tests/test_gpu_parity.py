@@ -515,3 +515,56 @@ def test_function_level_dropins_match_the_golden_quirks():
         assert total == int(arr["depth_aio"][q])
         assert [x[2] for x in al] == meta["al_sym"][a0:a1] and [x[0] for x in al] == arr["al_count"][a0:a1].tolist()
         assert [x[1] for x in al] == arr["al_freq"][a0:a1].tolist()
+
+
+# ---- heterogeneous plates: a primer scheme / reference per sample in one context ---------------------------------
+def test_device_primer_tables_equal_find_overlapping_primers():
+    rng = np.random.default_rng(17)
+    L = 5000
+    eng = make_engine(ref_len=L, n_samples=4)
+    for smp, (n, off) in enumerate([(40, 0), (200, 3), (1, 10), (0, 0)]):
+        st = np.sort(rng.integers(0, L - 40, n))
+        prim = [(int(s), int(s + rng.integers(15, 35))) for s in st]
+        eng.set_scheme(smp, prim, off)
+        mn, mx, mpl = eng.get_scheme(smp)
+        wmn, wmx = find_overlapping_primers(L, prim, off) if n else (np.full(L, -1, np.int32), np.full(L, -1, np.int32))
+        assert np.array_equal(mn, wmn) and np.array_equal(mx, wmx)
+        assert mpl == (max_primer_len(prim) if n else 0)
+
+
+def test_mixed_plate_in_one_context_equals_solo_runs():
+    """Three samples with different primer schemes, offsets, references and reference lengths in ONE context: per-sample trim
+    outputs, counts, insertions and calling results equal those of a context of their own; one calling launch covers the plate."""
+    specs = [(29903, 98, 2, 0, 61), (12000, 40, 3, 2, 62), (29903, 98, 4, 0, 63)]
+    Lmax = max(s[0] for s in specs)
+    plate = make_engine(ref_len=Lmax, n_samples=len(specs))
+    solo_res = []
+    batches = []
+    for smp, (L, n_amp, seed, off, bseed) in enumerate(specs):
+        g = synth.random_genome(L, 10 + smp)
+        primers, amps = synth.make_scheme(L, n_amp, seed=seed)
+        prim = [(s, e) for s, e, _ in primers]
+        b = synth.illumina_batch(g, amps, 30_000, seed=bseed, p_ins=0.05, snvs=[(L // 3, "T", 0.4)])
+        batches.append((b, g, prim, off, L))
+        solo = make_engine(ref_len=L, primer_tables=find_overlapping_primers(L, prim, off), max_primer_len=max_primer_len(prim))
+        t = solo.process(b)
+        ins = solo.insertions()
+        res = solo.call(g)
+        solo_res.append((t, solo.counts(), ins.as_dict(), calling.consensus_string(res, ins), calling.variant_records(res, ins, g, solo.counts())))
+        plate.set_scheme(smp, prim, off, ref_len=L)
+        plate.set_sample_reference(smp, g)
+    outs = [plate.process(b, sample=smp) for smp, (b, g, prim, off, L) in enumerate(batches)]
+    assert plate.error_flags() == 0
+    ins = plate.insertions()
+    res = plate.call(None)
+    for smp, (b, g, prim, off, L) in enumerate(batches):
+        t, counts, insd, cons, recs = solo_res[smp]
+        assert np.array_equal(outs[smp].pos, t.pos) and np.array_equal(outs[smp].flags, t.flags) and np.array_equal(outs[smp].ncig, t.ncig)
+        assert np.array_equal(plate.counts(smp)[:, :L], counts)
+        mine = {(int(p), s): int(c) for sm, p, c, s in zip(ins.sample, ins.pos, ins.count, ins.strs) if sm == smp}
+        assert mine == insd
+        assert calling.consensus_string(res, ins, smp)[:L] == cons
+        got = calling.variant_records(res, ins, g + "N" * (Lmax - L), plate.counts(smp), smp)
+        assert len(got) == len(recs)
+        for a, c in zip(got, recs):
+            assert tuple(a[:6]) == tuple(c[:6]) and a[6] == c[6] and a[7] == c[7] and tuple(a[8]) == tuple(c[8])
