@@ -365,7 +365,7 @@ def deep_leg(args, rank, world, local_rank, stream):
     eng.set_reference(g)
     d = eng.upload(mine)
     eng.reserve(mine.n, int(mine.cig_off[-1]))
-    ex = adist.DeepExchange(eng, cap_entries=1 << 17, cap_arena_bytes=8 << 20)
+    ex = adist.DeepExchange(eng, cap_entries=1 << 15, cap_arena_bytes=2 << 20)
     s = stream.cuda_stream
     steps = max(3, min(args.steps, 20))
 
@@ -449,7 +449,7 @@ def main():
     ap.add_argument("--no-file-e2e", action="store_true", help="skip the file-to-file command line leg (N=1)")
     ap.add_argument("--file-e2e", action="store_true", help="(kept for compatibility: the leg runs by default at N=1)")
     ap.add_argument("--no-ont", action="store_true", help="skip the ONT-like sub-object (N=1)")
-    ap.add_argument("--ont-reads", type=int, default=100_000)
+    ap.add_argument("--ont-reads", type=int, default=300_000)
     ap.add_argument("--no-deep", action="store_true", help="skip the deep-sample sub-object (N>1)")
     ap.add_argument("--deep-copies", type=int, default=8)
     ap.add_argument("--lean", action="store_true", help="headline numbers only (tuning runs): no cpu baseline, ont, file or deep legs")
