@@ -15,10 +15,11 @@
 // offset-induced targets in front of the read, rows too long for the staging buffers) is appended to the CTA's list and takes the
 // loop-for-loop generic path of amp_warp.cuh afterwards.
 //
-// update_base_counts (690-753) then runs per op: a lane counts the bases of its M/=/X op or the positions of its D/N op into the
-// CTA's tile, and resolves the insertion state machine (730-748) of its I op from the op itself and the kind of its successor
+// update_base_counts (690-753): the aligned bases of the kept query range are dealt out evenly over the lanes (a lane finds the
+// op of its first base by binary search on the prefix sums); then lane per op: the positions of a D/N op into the CTA's tile,
+// and an I op resolves the insertion state machine (730-748) of its I op from the op itself and the kind of its successor
 // (exit A: a match follows, B: a deletion follows -- the key runs to the end of the read, C: the trailing clip follows, D: a
-// low-quality inserted base).  Insertion alleles are parked in the CTA's list (amp_warp.cuh) and added one thread each.
+// low-quality inserted base).  Insertion alleles are parked in the warp's own list and added to the table a lane each.
 #pragma once
 #include "amp_warp.cuh"
 

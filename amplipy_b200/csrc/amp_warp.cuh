@@ -2,11 +2,11 @@
 //
 // One CTA per SM owns a contiguous chunk of the (coordinate-sorted) reads and one privatised count tile over the
 // reference window of that chunk, indexed directly by the BAM base nibble (18 rows x WT: rows 1,2,4,8,15 = A,C,G,T,N;
-// row 16 = '-'; row 17 = sink for masked bases; any other row only raises the KeyError flag at the flush).  The warps are
+// row 16 = sink for masked bases, never read; row 17 = '-'; any other row only raises the KeyError flag at the flush).  The warps are
 // autonomous: no block barrier between set-up and the final flush.
 //
 // Batch warps loop over batches of up to 32 consecutive reads, software-pipelined over the batches:
-//   A  lane per read : [S]M[S] classification and the closed form of the two primer clips (trim_read,
+//   A  lane per read : [H][S]M[(I|D)M][S][H] classification (Shape5, amp_core.cuh) and the closed form of the two primer clips (trim_read,
 //                      AmpliPy.py:450-558) from metadata / CIGAR words loaded one batch ahead; lane 0 starts one bulk async
 //                      copy (cp.async.bulk, completion on an mbarrier) per array that drops the batch's contiguous quality /
 //                      sequence byte ranges into the warp's staging buffers.
@@ -16,7 +16,7 @@
 //   B2 pileup        : (update_base_counts, 718 + 752-753) the 8-base chunks of the batch's aligned runs are dealt out
 //                      evenly over the 32 lanes; per chunk a SIMD byte compare q >= minq, per base one byte permute (row
 //                      offset), one select (sink row for masked bases), one add, one shared-memory atomic.
-//   G  every read that is not [S]M[S] (indels, hard clips, corner cases the closed form declines) goes to the CTA's list.
+//   G  every read the closed form declines (three or more alignment ops, odd clips, equal neighbours) goes to the CTA's list.
 //      When the batches are done the generic-capable warps work through it (AMP7_DWARPS > 0: that many warps do nothing
 //      else from the start; measured no better): rows staged with one bulk copy per lane, the loop-for-loop generic path
 //      lane per read (trim_read + plan_read of amp_core.cuh on CIGAR rows in shared memory), runs counted with the
