@@ -551,7 +551,8 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
             fprintf(stderr, "[cycles per warp] prologue %.0f  A %.0f  bulk-wait %.0f  window+trim %.0f  count %.0f  (barrier issue %.0f)  wait+generic %.0f\n",
                     h[0] / wf, h[1] / wf, h[2] / wf, h[3] / wf, h[4] / wf, h[5] / wf, h[6] / wf);
             fprintf(stderr, "[generic phase, cycles summed over its warp-rounds / 1000] load+copy %lld  trim_read %lld  outputs %lld  plan_read %lld\n", h[360] / 1000, h[361] / 1000, h[362] / 1000, h[363] / 1000);
-            fprintf(stderr, "[cycles per CTA] mean %.0f  min %lld  max %lld\n", (double)h[8] / grid, h[9], h[10]);
+            fprintf(stderr, "[cycles per CTA] mean %.0f  min %lld  max %lld   set-up %.0f  last barrier (per warp) %.0f  drain+flush %.0f\n", (double)h[8] / grid, h[9], h[10],
+                    (double)h[11] / grid, h[12] / wf, (double)h[13] / grid);
         }
 #endif
         c->last_launches += 1;

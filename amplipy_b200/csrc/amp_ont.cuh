@@ -67,7 +67,7 @@ AMP_HD WarpMem7 carve_ont_generic(unsigned char* base, int wt, int warps, int g)
     m.qbuf = b; b += AMP7_QBUF;
     m.sbuf = b; b += AMP7_SBUF;
     m.par = (Par4*)b; b += 32 * 32;
-    m.own = b; b += 32;
+    m.own = (uint16_t*)b; b += 64;
     m.bar = (unsigned long long*)b; b += 16;
     m.runs = (Seg*)b; b += AMP7_RUNCAP * 16;
     m.queue = (uint32_t*)b; b += AMP7_QCAP * 4;

@@ -142,6 +142,9 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 #endif
 #define AMP7_PRAGMA_(x) _Pragma(#x)
 #define AMP7_UNROLL(n) AMP7_PRAGMA_(unroll n)
+#ifndef AMP7_COUNT_UNROLL
+#define AMP7_COUNT_UNROLL 1     // the count loop as it is: unrolled by the compiler it measured no faster and is twice the code
+#endif
 
 // ---- shared-memory layout ------------------------------------------------------------------------------------------
 #ifndef AMP7_WARPS
@@ -193,18 +196,20 @@ AMP_HD size_t tile_bytes_v7(int wt) { return ((size_t)(AMP7_SINK_ROW + 2) * wt +
 AMP_HD size_t smem_bytes_v9(int wt, int warps, int gwarps);   // below
 
 // One aligned run of the count pass, fully decoded by its owner lane so that switching runs inside the chunk loop is cheap:
-//   a = aligned qbuf offset of chunk 0 | aligned sbuf offset << 16
-//   b = tile position of chunk 0 | chunks << 16 | odd first nibble << 24
-//   s = quality funnel shift (bits) | sequence funnel shift << 8,  w = first chunk in the batch's concatenation
+//   qoff / soff = byte offset, from the start of the count tile, of the aligned quality / sequence word of chunk 0
+//   toff = the same of the tile element (row 0) of chunk 0's first base
+//   k = quality funnel shift (bits) | sequence funnel shift << 8 | chunks << 16 | odd first nibble << 24
 //   mka/mkb = byte masks of the last chunk's bases 0,2,4,6 / 1,3,5,7, mfa/mfb = of the first chunk's (phi bases in front)
-struct Par4 { unsigned a, b, s, w, mka, mkb, mfa, mfb; };
-AMP_WD Par4 make_par(int a0, int n0, int m, int phi, int z, int w) {   // a0 / n0 / z: of the first of the m bases (incl. phi in front)
+// Everything a lane needs when it moves on to the next run is a plain copy of these words (the switch sits in the count loop and
+// runs in almost every iteration for some lane of the warp, so each of its instructions counts like one of the loop body).
+struct Par4 { unsigned qoff, soff, toff, k, mka, mkb, mfa, mfb; };
+AMP_WD Par4 make_par(unsigned qbase, unsigned sbase, int a0, int n0, int m, int phi, int z) {   // a0 / n0 / z: of the first of the m bases (incl. phi in front)
     Par4 p;
     const int sb = n0 >> 1, nch = (m + 7) >> 3;
-    p.a = (unsigned)(a0 & ~3) | ((unsigned)(sb & ~3) << 16);
-    p.b = (unsigned)z | ((unsigned)nch << 16) | ((unsigned)(n0 & 1) << 24);
-    p.s = (unsigned)((a0 & 3) << 3) | ((unsigned)((sb & 3) << 3) << 8);
-    p.w = (unsigned)w;
+    p.qoff = qbase + (unsigned)(a0 & ~3);
+    p.soff = sbase + (unsigned)(sb & ~3);
+    p.toff = 4u * (unsigned)z;
+    p.k = (unsigned)((a0 & 3) << 3) | ((unsigned)((sb & 3) << 3) << 8) | ((unsigned)nch << 16) | ((unsigned)(n0 & 1) << 24);
     const int left = m - 8 * (nch - 1);              // bases of the last chunk, 1 .. 8
     const unsigned mk0 = left >= 4 ? 0xFFFFFFFFu : (1u << (8 * left)) - 1u;
     const unsigned mk1 = left >= 8 ? 0xFFFFFFFFu : (left > 4 ? (1u << (8 * (left - 4))) - 1u : 0u);
@@ -226,8 +231,8 @@ inline V7Cfg pick_v7_cfg(long long n, long long sum_qual, int sm_count) {
 }
 
 // fast kernel: per-warp staging buffers, the per-run parameters of the count pass, and the bulk-copy barrier
-#define AMP7_FAST_BYTES (AMP7_QBUF + AMP7_SBUF + 32 * 32 + 32 + 16)
-struct FastMem { uint8_t* qbuf; uint8_t* sbuf; Par4* par; uint8_t* own; unsigned long long* bar; };
+#define AMP7_FAST_BYTES (AMP7_QBUF + AMP7_SBUF + 32 * 32 + 64 + 16)
+struct FastMem { uint8_t* qbuf; uint8_t* sbuf; Par4* par; uint16_t* own; unsigned long long* bar; };
 AMP_HD size_t smem_bytes_fast(int wt, int warps) { return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_FAST_BYTES; }
 AMP_HD FastMem carve_fast(unsigned char* base, int wt, int w) {
     unsigned char* b = base + tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)w * AMP7_FAST_BYTES;
@@ -235,14 +240,14 @@ AMP_HD FastMem carve_fast(unsigned char* base, int wt, int w) {
     m.qbuf = b; b += AMP7_QBUF;
     m.sbuf = b; b += AMP7_SBUF;
     m.par = (Par4*)b; b += 32 * 32;
-    m.own = b; b += 32;
+    m.own = (uint16_t*)b; b += 64;
     m.bar = (unsigned long long*)b;
     return m;
 }
 
 struct WarpMem7 {
     uint8_t* qbuf; uint8_t* sbuf; Seg* runs; uint32_t* queue; int* ctr; unsigned long long* bar; uint32_t* cig;
-    Par4* par; uint8_t* own; int* ctrl;
+    Par4* par; uint16_t* own; int* ctrl;
 };
 AMP_HD size_t smem_bytes_v9(int wt, int warps, int gwarps) {
     return tile_bytes_v7(wt) + C7_WORDS * 4 + (size_t)warps * AMP7_FAST_BYTES + (size_t)gwarps * AMP7_GEXTRA_BYTES;
@@ -264,22 +269,23 @@ AMP_HD WarpMem7 carve_warp7(unsigned char* base, int wt, int warps, int gwarps, 
 // channel of a nibble row, -1 = not a countable base
 AMP_HD int row_channel(int row) { return nib_channel((uint32_t)row); }
 
-// tile -> global count matrix; rows that are no base only raise the KeyError flag (AmpliPy.py:753)
+// tile -> global count matrix; rows that are no base only raise the KeyError flag (AmpliPy.py:753).  A thread per position: all
+// its loads are independent (one round trip to shared memory instead of one per row).
 AMP_HD void flush_tile7(const KParams& P, const int* cnt, int wbase, int tid, int nthreads) {
-    for (int row = 0; row < AMP7_SINK_ROW; ++row) {
-        const int ch = row_channel(row);
-        for (int w = tid; w < P.wt; w += nthreads) {
-            const int v = cnt[row * P.wt + w];
-            if (v) {
-                if (ch >= 0) atomic_add(&P.counts[(size_t)ch * P.Lpad + wbase + w], v);
-                else atomic_or(P.err, AMP_E_BASE);
-            }
-        }
-    }
-    const int* del = cnt + del_row_off(P.wt);
-    for (int w = tid; w < P.wt; w += nthreads) {
-        const int v = del[w];
-        if (v) atomic_add(&P.counts[(size_t)5 * P.Lpad + wbase + w], v);
+    const int wt = P.wt;
+    const int* del = cnt + del_row_off(wt);
+    for (int w = tid; w < wt; w += nthreads) {
+        const int a = cnt[1 * wt + w], c = cnt[2 * wt + w], g = cnt[4 * wt + w], t = cnt[8 * wt + w], n = cnt[15 * wt + w], d = del[w];
+        int bad = cnt[w] | cnt[3 * wt + w];
+        for (int row = 5; row < 15; ++row) if (row != 8) bad |= cnt[row * wt + w];
+        int* out = P.counts + wbase + w;
+        if (a) atomic_add(out, a);
+        if (c) atomic_add(out + (size_t)1 * P.Lpad, c);
+        if (g) atomic_add(out + (size_t)2 * P.Lpad, g);
+        if (t) atomic_add(out + (size_t)3 * P.Lpad, t);
+        if (n) atomic_add(out + (size_t)4 * P.Lpad, n);
+        if (d) atomic_add(out + (size_t)5 * P.Lpad, d);
+        if (bad) atomic_or(P.err, AMP_E_BASE);
     }
 }
 
@@ -346,32 +352,34 @@ AMP_WD void ins_drain(const KParams& P, int* ctrl, int lane) {
 // with the same start hit the same address and are merged by the hardware (ATOMS.POPC.INC).
 //
 // The chunks of all runs of a batch are dealt out evenly: this lane walks chunks [g0, g1) of their concatenation,
-// starting inside run rr0 (par[] lists the decoded runs, .w = first chunk) and
-// moving on to the next run inside the loop, so every lane of the warp executes the same number of iterations.
+// starting at chunk c0 of run rr0 (par[] lists the runs) and moving on to the next run inside the loop, so every lane of the
+// warp executes the same number of iterations.
 template <int WT>
-AMP_WD void count_chunks_v9(int* cnt, int wt, const uint8_t* qbuf, const uint8_t* sbuf, const Par4* par, int rr0, int g0, int g1,
-                            unsigned minq4) {
-    int rr = rr0 - 1, rem = 0;                               // rem = chunks of the current run still to do
-    const uint32_t* A = nullptr; const uint32_t* S = nullptr;
-    unsigned sh = 0, ssh = 0, qa = 0, sa = 0, x = 0, mka = 0, mkb = 0, ma = 0xFFFFFFFFu, mb = 0xFFFFFFFFu;
-    bool odd = false;
-    int* tl = cnt;
+AMP_WD void count_chunks_v9(int* cnt, int wt, const Par4* par, int rr0, int c0, int g0, int g1, unsigned minq4) {
+    const char* base = (const char*)cnt;
+    const Par4* pp = par + rr0;
+    const Par4 p0 = *pp;
+    int rem = (int)((p0.k >> 16) & 0xFFu) - c0;              // chunks of the current run still to do (>= 1)
+    const uint32_t* A = (const uint32_t*)(base + p0.qoff) + 2 * c0;
+    const uint32_t* S = (const uint32_t*)(base + p0.soff) + c0;
+    unsigned sh = p0.k, ssh = p0.k >> 8;                     // (funnel shifts use the low five bits)
+    bool odd = (p0.k >> 24) != 0;
+    unsigned qa = A[0], sa = S[1], x = funnel_r(S[0], sa, ssh);
+    int* tl = (int*)(base + p0.toff) + 8 * c0;
+    unsigned mka = p0.mka, mkb = p0.mkb, ma = c0 == 0 ? p0.mfa : 0xFFFFFFFFu, mb = c0 == 0 ? p0.mfb : 0xFFFFFFFFu;
     const unsigned nminq4 = 0u - minq4;
 #if defined(__CUDA_ARCH__) && defined(AMP7_COUNT_UNROLL)
     AMP7_UNROLL(AMP7_COUNT_UNROLL)
 #endif
     for (int g = g0; g < g1; ++g) {
-        if (rem == 0) {                                      // next run: chunk g is its chunk g - w (0 unless it is the lane's first run)
-            const Par4 pr = par[++rr];
-            const int c = g - (int)pr.w;
-            rem = (int)((pr.b >> 16) & 0xFFu) - c;
-            A = (const uint32_t*)(qbuf + (pr.a & 0xFFFFu)) + 2 * c; sh = pr.s;          // (funnel shifts use the low five bits)
-            S = (const uint32_t*)(sbuf + (pr.a >> 16)) + c; ssh = pr.s >> 8;
-            odd = (pr.b >> 24) != 0;
+        if (rem == 0) {                                      // next run, from its chunk 0
+            const Par4 pr = *++pp;
+            rem = (int)((pr.k >> 16) & 0xFFu);
+            A = (const uint32_t*)(base + pr.qoff); S = (const uint32_t*)(base + pr.soff);
+            sh = pr.k; ssh = pr.k >> 8; odd = (pr.k >> 24) != 0;
             qa = A[0]; sa = S[1]; x = funnel_r(S[0], sa, ssh);
-            tl = cnt + (pr.b & 0xFFFFu) + 8 * c;
-            mka = pr.mka; mkb = pr.mkb;
-            ma = c == 0 ? pr.mfa : 0xFFFFFFFFu; mb = c == 0 ? pr.mfb : 0xFFFFFFFFu;
+            tl = (int*)(base + pr.toff);
+            mka = pr.mka; mkb = pr.mkb; ma = pr.mfa; mb = pr.mfb;
         }
         const unsigned q1 = A[1], q2 = A[2];
         const unsigned v0 = funnel_r(qa, q1, sh), v1 = funnel_r(q1, q2, sh);
@@ -415,7 +423,7 @@ AMP_WD void count_chunks_v9(int* cnt, int wt, const uint8_t* qbuf, const uint8_t
 // amplicon data most runs of a batch start at the same position, and lanes that are at different chunks of such runs would
 // otherwise all fall into the same four banks of the tile (phi <= w0: never in front of the tile).
 template <int WT>
-AMP_WD void count_runs_balanced(int* cnt, int wt, const uint8_t* qbuf, const uint8_t* sbuf, Par4* par, uint8_t* own, int lane, bool has,
+AMP_WD void count_runs_balanced(int* cnt, int wt, const uint8_t* qbuf, const uint8_t* sbuf, Par4* par, uint16_t* own, int lane, bool has,
                                 int a0, int n0, int m, int w0, unsigned minq4) {
     const unsigned hmask = w_ballot(has);                                      // the runs, in lane order
     if (!hmask) return;                                                        // uniform
@@ -426,13 +434,13 @@ AMP_WD void count_runs_balanced(int* cnt, int wt, const uint8_t* qbuf, const uin
     const int start = incl - nchk, total = w_shfl(incl, 31);
     const int q = (total + 31) >> 5;
     if (has) {
-        par[rank] = make_par(a0 - phi, n0 - phi, m + phi, phi, w0 - phi, start);
+        par[rank] = make_par((unsigned)(qbuf - (const uint8_t*)cnt), (unsigned)(sbuf - (const uint8_t*)cnt), a0 - phi, n0 - phi, m + phi, phi, w0 - phi);
         const int l_hi = (start + nchk + q - 1) / q;
-        for (int ll = (start + q - 1) / q; ll < l_hi && ll < 32; ++ll) own[ll] = (uint8_t)rank;   // lanes that start in this run
+        for (int ll = (start + q - 1) / q; ll < l_hi && ll < 32; ++ll) own[ll] = (uint16_t)(rank | ((ll * q - start) << 8));   // lanes that start in this run, and at which chunk
     }
     w_sync();
     const int g0 = lane * q, g1 = g0 + q < total ? g0 + q : total;
-    if (g0 < g1) count_chunks_v9<WT>(cnt, wt, qbuf, sbuf, par, own[lane], g0, g1, minq4);
+    if (g0 < g1) { const int o = own[lane]; count_chunks_v9<WT>(cnt, wt, par, o & 0xFF, o >> 8, g0, g1, minq4); }
     w_sync();                                                                  // par / own may be rewritten
 }
 
@@ -665,37 +673,32 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
     const long long n_end = P.b.first + P.b.n;
     uint32_t* glist = P.glist + (size_t)block * P.gcap;          // overflow of the shared-memory list
 
+    // Set-up.  The loads it depends on (start positions of the chunk's first reads for the window base, below the metadata of each
+    // warp's first batch) are issued first, so that their latency overlaps the clearing of the tile and the two barriers.
+    const int nwarps = nthreads >> 5, n_fast = nwarps - dwarps;     // warps [0, n_fast) take batches, the rest only the list
+    int wmin0 = 0x7FFFFFFF;
+    if (n_batches > 0 && tid < 64) {
+        const long long i = P.b.first + g_lo * BR + tid;
+        if (i < n_end) { const int p0 = P.b.pos[i]; if (p0 >= 0 && !(P.b.flag[i] & 4)) wmin0 = p0; }
+    }
     if (PILE) {                                                   // the sink row is never read
         for (int i = tid; i < AMP7_SINK_ROW * wt; i += nthreads) cnt[i] = 0;
         for (int i = tid; i < wt; i += nthreads) cnt[del_row_off(wt) + i] = 0;
     }
-    if (tid == 0) { ctrl[C7_NEXT] = 0; ctrl[C7_NGEN] = 0; ctrl[C7_GNEXT] = 0; ctrl[C7_FASTDONE] = 0; ctrl[C7_NEV] = 0; ctrl[C7_EVDONE] = 0; }
+    if (tid == 0) {
+        ctrl[C7_NEXT] = n_fast;                                   // batch w is warp w's first one
+        ctrl[C7_NGEN] = 0; ctrl[C7_GNEXT] = 0; ctrl[C7_FASTDONE] = 0; ctrl[C7_NEV] = 0; ctrl[C7_EVDONE] = 0; ctrl[C7_TMIN] = 0x7FFFFFFF;
+    }
     for (int k = tid; k < AMP7_GLCAP; k += nthreads) ctrl[C7_GL + k] = 0;   // list entries: 0 = not written yet
     for (int k = tid; k < AMP7_EVCAP; k += nthreads) ctrl[C7_EV + 3 * k + 2] = 0;
-    const int nwarps = nthreads >> 5, n_fast = nwarps - dwarps;     // warps [0, n_fast) take batches, the rest only the list
     if (lane == 0) mbar_init(wm.bar);
-    const int wb = chunk_window_base(P, ctrl, P.b.first + g_lo * BR, n_end, tid, n_batches > 0);
-    const int wbase = PILE ? wb : -1;
-    // the stretch of the two primer tables this chunk looks at (from its window base), for phase A
-    TrimParams tps = P.tp;
-    const int pbase = wb >= 0 ? wb : 0;
-    if (TRIM) {
-        int* ptab = ctrl + C7_PTAB;
-        for (int k = tid; k < 2 * AMP7_PSLICE; k += nthreads) {
-            const int p = pbase + (k < AMP7_PSLICE ? k : k - AMP7_PSLICE);
-            ptab[k] = p < P.tp.L ? (k < AMP7_PSLICE ? P.tp.min_primer_start[p] : P.tp.max_primer_end[p]) : -1;
-        }
-        tps.min_primer_start = ptab - pbase; tps.max_primer_end = ptab + AMP7_PSLICE - pbase;
-        c_sync();
-    }
-
+    c_sync();
+    if (wmin0 != 0x7FFFFFFF) atomic_min(&ctrl[C7_TMIN], wmin0);
     const int minq = P.tp.min_quality;
     // the word-wise passes need the default window and a quality threshold that fits the SIMD byte compare
     const bool fast_ok = minq >= 0 && minq <= 127 && (!TRIM || P.tp.window == 4);
     const unsigned minq4 = (unsigned)minq * 0x01010101u;
     uint32_t parity = 0;
-    AMP7_T0(tk);
-    AMP7_TICK(tk, 0);
 
     // Software pipeline over the warp's batches: the per-read metadata of the next batch is loaded while the current one is
     // in its window pass, its first CIGAR words (and an L2 prefetch of its rows) while the current one is being counted.
@@ -727,6 +730,31 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
         M.g3 = nc > 3 ? P.b.cigar[M.c0 + 3] : 0u;
         M.g4 = nc > 4 ? P.b.cigar[M.c0 + 4] : 0u;
     };
+    Meta M, Mn;
+    M.c0 = M.c1 = M.qo0 = M.qo1 = M.so0 = M.so1 = M.g0 = M.g1 = M.g2 = M.g3 = M.g4 = 0; M.flag = M.pos = M.tlen = 0;
+    Mn = M;
+    int bi = warp < n_fast ? warp : n_batches;
+    if (bi < n_batches) { load_meta(bi, M); load_cigar5(M); }
+    c_sync();
+    const int wb = ctrl[C7_TMIN] != 0x7FFFFFFF ? (ctrl[C7_TMIN] & ~31) : -1;
+    const int wbase = PILE ? wb : -1;
+    // the stretch of the two primer tables this chunk looks at (from its window base), for phase A
+    TrimParams tps = P.tp;
+    const int pbase = wb >= 0 ? wb : 0;
+    if (TRIM) {
+        int* ptab = ctrl + C7_PTAB;
+        for (int k = tid; k < 2 * AMP7_PSLICE; k += nthreads) {
+            const int p = pbase + (k < AMP7_PSLICE ? k : k - AMP7_PSLICE);
+            ptab[k] = p < P.tp.L ? (k < AMP7_PSLICE ? P.tp.min_primer_start[p] : P.tp.max_primer_end[p]) : -1;
+        }
+        tps.min_primer_start = ptab - pbase; tps.max_primer_end = ptab + AMP7_PSLICE - pbase;
+        c_sync();
+    }
+#if defined(__CUDA_ARCH__) && defined(AMP7_TIMING)
+    if (tid == 0 && P.phase_cycles) atomicAdd((unsigned long long*)&P.phase_cycles[11], (unsigned long long)(clock64() - t_cta0));   // set-up
+#endif
+    AMP7_T0(tk);
+    AMP7_TICK(tk, 0);
     // One round of the generic phase: up to AMP7_GN listed reads, taken by a generic-capable warp between two of its batches
     // (wait = false: only what is there) or when its batches are done (wait = true: until the list is complete and empty).
     const bool is_gwarp = warp >= nwarps - gwarps;
@@ -763,11 +791,6 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
         warp_generic_phase<WT>(P, gm, cnt, wt, wbase, n, n, lane, TRIM, PILE, parity, tk);
         return true;
     };
-    Meta M, Mn;
-    M.c0 = M.c1 = M.qo0 = M.qo1 = M.so0 = M.so1 = M.g0 = M.g1 = M.g2 = M.g3 = M.g4 = 0; M.flag = M.pos = M.tlen = 0;
-    Mn = M;
-    int bi = warp < n_fast ? claim() : n_batches;
-    if (bi < n_batches) { load_meta(bi, M); load_cigar5(M); }
     while (bi < n_batches) {
         const long long t0 = P.b.first + (g_lo + bi) * BR;
         long long t1 = t0 + BR; if (t1 > n_end) t1 = n_end;
@@ -915,12 +938,20 @@ AMP_WD void cta_trim_pileup_v9(const KParams& P, unsigned char* smem_base, int g
     if (PILE) ins_drain(P, ctrl, lane);
     AMP7_TICK(tk, 6);
     AMP7_TDUMP(tk, 0);
+#if defined(__CUDA_ARCH__) && defined(AMP7_TIMING)
+    const long long t_bar0 = clock64();
+#endif
     c_sync();
+#if defined(__CUDA_ARCH__) && defined(AMP7_TIMING)
+    const long long t_bar1 = clock64();
+    if (lane == 0 && P.phase_cycles) atomicAdd((unsigned long long*)&P.phase_cycles[12], (unsigned long long)(t_bar1 - t_bar0));     // wait at the last barrier, per warp
+#endif
     if (PILE) ins_drain(P, ctrl, lane);                            // alleles parked by the last warps to finish
     if (PILE && wbase >= 0) flush_tile7(P, cnt, wbase, tid, nthreads);
 #if defined(__CUDA_ARCH__) && defined(AMP7_TIMING)
     if (tid == 0 && P.phase_cycles) {   // whole-CTA cycles: sum / min / max over CTAs
         const long long tot = clock64() - t_cta0;
+        atomicAdd((unsigned long long*)&P.phase_cycles[13], (unsigned long long)(clock64() - t_bar1));                               // drain + flush (thread 0's view)
         atomicAdd((unsigned long long*)&P.phase_cycles[8], (unsigned long long)tot);
         atomicMin((long long*)&P.phase_cycles[9], tot);
         atomicMax((long long*)&P.phase_cycles[10], tot);
