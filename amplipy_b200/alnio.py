@@ -146,9 +146,10 @@ def bam_layout(raw):
             "ops_per_read": ops_per_read}
 
 
-def bgzf_compress_units(data, bounds, level=6, threads=0):
+def bgzf_compress_units(data, bounds, level=6, threads=0, deflater=None):
     """BGZF the way htslib lays a BAM out: a block holds whole units (``bounds`` = sorted cut points from 0 to len(data), e.g.
-    header end + record starts) -- a record never straddles a block boundary (bgzf_flush_try in htslib's bam_write1)."""
+    header end + record starts) -- a record never straddles a block boundary (bgzf_flush_try in htslib's bam_write1).
+    ``deflater(data, block_starts)``: compress the planned blocks elsewhere (Engine.bgzf_deflate: on the GPU) instead of zlib here."""
     lib = hostio()
     src = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
     bounds = np.ascontiguousarray(bounds, np.int64)
@@ -156,6 +157,8 @@ def bgzf_compress_units(data, bounds, level=6, threads=0):
     nb = int(lib.amp_bgzf_plan(_p(bounds), _ll(bounds.size), None, _ll(0)))
     bstart = np.empty(nb + 1, np.int64)
     assert lib.amp_bgzf_plan(_p(bounds), _ll(bounds.size), _p(bstart), _ll(nb)) == nb
+    if deflater is not None:
+        return deflater(src, bstart)
     out = np.empty(src.size + 64 * nb + 1024, np.uint8)
     n = lib.amp_bgzf_deflate_blocks(_p(src), _p(bstart), _ll(nb), _p(out), level, threads)
     if n < 0:
@@ -316,8 +319,9 @@ def default_bam_level():
         return 6
 
 
-def write_alignments(path, aln, header_text, trim, threads=0, level=None):
-    """Write the reads that pass the gate (AmpliPy.py:910-911) with their new pos / CIGAR."""
+def write_alignments(path, aln, header_text, trim, threads=0, level=None, deflater=None):
+    """Write the reads that pass the gate (AmpliPy.py:910-911) with their new pos / CIGAR.  ``deflater``: see bgzf_compress_units
+    (BAM output of BAM input only)."""
     level = default_bam_level() if level is None else level
     sel = np.flatnonzero(trim.keep).astype(np.int64)
     to_sam = path.lower() == "stdout" or path.lower().endswith(".sam")
@@ -352,7 +356,7 @@ def write_alignments(path, aln, header_text, trim, threads=0, level=None):
         hb = np.frombuffer(head, np.uint8)
         bounds = np.unique(np.concatenate([[0], hb.size + ooff]).astype(np.int64))
         with open(path, "wb") as f:
-            f.write(bgzf_compress_units(np.concatenate([hb, body]), bounds, level, threads))
+            f.write(bgzf_compress_units(np.concatenate([hb, body]), bounds, level, threads, deflater))
         return len(sel)
     else:
         body = np.frombuffer(b"".join(_sam_fields_to_bam(aln, int(i), int(trim.pos[i]), trim.cigartuples(int(i))) for i in sel),

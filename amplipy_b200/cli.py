@@ -232,7 +232,11 @@ def _run(untrimmed_reads_fn, primer_fn, reference_fn, trimmed_reads_fn, variants
         layout = alnio.bam_layout(raw)
         box = {}
         host = None
-        if run_trim:
+        # BAM in -> BAM out: the trimmed records are rebuilt and compressed on the device as well (amp_decoded_write_bam), unless a
+        # zlib level is asked for (AMPLIPY_BAM_LEVEL; 6 = what htslib writes)
+        dev_bam_out = (run_trim and trimmed_reads_fn.lower().endswith(".bam") and "AMPLIPY_BAM_LEVEL" not in os.environ and
+                       hasattr(Engine, "decoded_write_bam"))
+        if run_trim and not dev_bam_out:
             def _host_decode():
                 try:
                     box["aln"] = alnio._read_bam(raw)
@@ -245,11 +249,12 @@ def _run(untrimmed_reads_fn, primer_fn, reference_fn, trimmed_reads_fn, variants
         print_log("Processing reads...")
         try:
             info = eng.decode_bam(raw, layout)
-            outs = eng.process_decoded(trim=run_trim, pileup=pile)
+            outs = eng.process_decoded(trim=run_trim, pileup=pile, download=not dev_bam_out)
             n_reads = info["n"]
         except AmpError:
             eng.close()
             eng = None                       # e.g. records straddling BGZF blocks (not written by htslib): host decoder below
+            dev_bam_out = False
         tm["gpu_decode_process"] = _time.perf_counter() - _t
         if host is not None:
             host.join()
@@ -261,6 +266,8 @@ def _run(untrimmed_reads_fn, primer_fn, reference_fn, trimmed_reads_fn, variants
         tm["decode"] = _time.perf_counter() - _t
         if eng is not None:
             eng.raise_on_device_errors()
+    else:
+        dev_bam_out = False
     if eng is None:
         aln = aln or alnio.read_alignments(in_fn)
         tm["decode"] = _time.perf_counter() - _t
@@ -283,7 +290,14 @@ def _run(untrimmed_reads_fn, primer_fn, reference_fn, trimmed_reads_fn, variants
         def _write():
             t0 = _time.perf_counter()
             try:
-                alnio.write_alignments(trimmed_reads_fn, aln, out_header, trim)
+                if dev_bam_out:
+                    data, _ = eng.decoded_write_bam(alnio._bam_header_bytes(out_header, layout["refs"]))
+                    with open(trimmed_reads_fn, "wb") as f:
+                        f.write(data)
+                else:
+                    # BGZF deflate on the GPU unless a zlib level is asked for
+                    on_gpu = "AMPLIPY_BAM_LEVEL" not in os.environ and hasattr(eng, "bgzf_deflate")
+                    alnio.write_alignments(trimmed_reads_fn, aln, out_header, trim, deflater=eng.bgzf_deflate if on_gpu else None)
             except BaseException as e:      # re-raised on the main thread
                 tm["_write_error"] = e
             tm["encode_bam"] = _time.perf_counter() - t0

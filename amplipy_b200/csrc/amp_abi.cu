@@ -13,6 +13,7 @@
 #include "amp_warp.cuh"
 #include "amp_bgzf.cuh"
 #include "amp_ont.cuh"
+#include "amp_deflate.cuh"
 
 static_assert(AMP_F_TRIM_START == AMP_FLAG_TRIM_START && AMP_F_KEEP == AMP_FLAG_KEEP && AMP_F_SKIPPED == AMP_FLAG_SKIPPED &&
                   AMP_F_ERROR == AMP_FLAG_ERROR && AMP_E_ARENA_FULL == AMP_DEVERR_ARENA_FULL,
@@ -342,6 +343,134 @@ __global__ void amp_ins_merge_packed_kernel(amp::InsTable tab, const unsigned lo
     }
 }
 
+// ---- BGZF deflate on the device (amp_deflate.cuh) --------------------------------------------------------------------------
+#define AMPD_WARPS 16
+// block k = in[bstart[k], bstart[k + 1]) -> a deflate stream in slot k (clen[k] = its bytes, 0xFFFFFFFF: did not shrink, to be stored)
+// and its CRC-32; the warps take blocks from a counter
+__global__ void __launch_bounds__(AMPD_WARPS * 32) amp_bgzf_deflate_kernel(const uint8_t* in, const long long* bstart, long long nb, uint8_t* slots,
+                                                                          uint32_t* clen, uint32_t* crc, unsigned int* next) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    amp::DeflateTables& T = *(amp::DeflateTables*)dsm;
+    amp::DeflateMem& M = ((amp::DeflateMem*)(dsm + ((sizeof(amp::DeflateTables) + 15) & ~(size_t)15)))[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    amp::deflate_tables_init(T, (int)threadIdx.x, (int)blockDim.x);
+    __syncthreads();
+    const uint32_t mcol = amp::crc_shift_column(T, lane);
+    for (;;) {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(next, 1u);
+        const long long k = (long long)__shfl_sync(0xFFFFFFFFu, t, 0);
+        if (k >= nb) break;
+        const uint8_t* src = in + bstart[k];
+        const int n = (int)(bstart[k + 1] - bstart[k]);
+        const int cap_words = (n + 3) / 4;                                // "does not shrink" = would need more words than the input has
+        int bytes = n >= 16 ? amp::deflate_block(src, n, M, T, (uint32_t*)(slots + (size_t)k * AMPD_SLOT), cap_words, lane) : -1;
+        if (bytes >= n + 5) bytes = -1;
+        const uint32_t cr = amp::crc32_block(src, n, T, mcol, lane);
+        if (lane == 0) { clen[k] = bytes < 0 ? 0xFFFFFFFFu : (uint32_t)bytes; crc[k] = cr; }
+        __syncwarp();
+    }
+}
+// the BGZF blocks themselves: 18-byte header, the deflate stream (or the data as one stored block), CRC-32, ISIZE, at off[k]
+__global__ void __launch_bounds__(256) amp_bgzf_pack_kernel(const uint8_t* in, const long long* bstart, long long nb, const uint8_t* slots,
+                                                           const uint32_t* clen, const uint32_t* crc, const long long* off, uint8_t* out) {
+    const int lane = threadIdx.x & 31;
+    const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= nb) return;
+    const uint32_t n = (uint32_t)(bstart[k + 1] - bstart[k]);
+    const bool stored = clen[k] == 0xFFFFFFFFu;
+    const uint32_t payload = stored ? n + 5u : clen[k], bsize = payload + 26u;
+    uint8_t* dst = out + off[k];
+    if (lane < 18) {
+        const uint8_t hdr[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, (uint8_t)((bsize - 1u) & 0xFFu), (uint8_t)((bsize - 1u) >> 8)};
+        dst[lane] = hdr[lane];
+    }
+    uint8_t* pay = dst + 18;
+    if (stored) {
+        if (lane == 0) { pay[0] = 1; pay[1] = (uint8_t)(n & 0xFFu); pay[2] = (uint8_t)(n >> 8); pay[3] = (uint8_t)(~n & 0xFFu); pay[4] = (uint8_t)((~n >> 8) & 0xFFu); }
+        const uint8_t* src = in + bstart[k];
+        for (uint32_t i = lane; i < n; i += 32) pay[5 + i] = src[i];
+    } else {
+        const uint8_t* src = slots + (size_t)k * AMPD_SLOT;
+        for (uint32_t i = lane; i < payload; i += 32) pay[i] = src[i];
+    }
+    if (lane < 8) { const uint32_t v = lane < 4 ? crc[k] : n; pay[payload + lane] = (uint8_t)(v >> (8 * (lane & 3))); }
+}
+
+// ---- trimmed BAM records rebuilt on the device (what assigning cigartuples / reference_start does to a pysam segment before
+// out_aln.write, AmpliPy.py:463-514, 591-658, 911): everything but pos / bin / n_cigar / CIGAR is copied byte for byte ------------------
+__device__ __forceinline__ uint32_t ld_le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+__device__ __forceinline__ uint32_t ld_le16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+// size of read i's record in the output (0: the read does not pass the write gate, AmpliPy.py:910)
+__global__ void amp_bam_newsize_kernel(const uint8_t* raw, const unsigned long long* rec_off, long long n, const uint16_t* o_ncig, const uint8_t* o_flags,
+                                       uint32_t* sizes) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t sz = 0;
+    if (o_flags[i] & AMP_F_KEEP) {
+        const uint8_t* r = raw + rec_off[i];
+        sz = 4u + ld_le32(r) - 4u * ld_le16(r + 4 + 12) + 4u * (uint32_t)o_ncig[i];
+    }
+    sizes[i] = sz;
+}
+// exclusive prefix sums of n 32-bit sizes (64-bit results, n + 1 of them), one CTA
+__global__ void __launch_bounds__(1024) amp_scan_sizes_kernel(const uint32_t* sizes, long long n, unsigned long long* off) {
+    __shared__ unsigned long long part[1024];
+    const int t = threadIdx.x;
+    const long long per = (n + 1023) / 1024, lo = t * per, hi = lo + per < n ? lo + per : n;
+    unsigned long long s = 0;
+    for (long long k = lo; k < hi; ++k) s += sizes[k];
+    part[t] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const unsigned long long v = t >= d ? part[t - d] : 0ULL;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned long long run = part[t] - s;
+    for (long long k = lo; k < hi; ++k) { off[k] = run; run += sizes[k]; }
+    if (t == 1023) off[n] = part[1023];
+}
+__device__ __forceinline__ int reg2bin_dev(long long beg, long long end) {   // SAM spec 5.3
+    --end;
+    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+    return 0;
+}
+// one warp per kept read: the record with its new block_size / pos / bin / n_cigar / CIGAR at out + off[i]
+__global__ void __launch_bounds__(256) amp_bam_rewrite_kernel(const uint8_t* raw, const unsigned long long* rec_off, long long n, const uint32_t* cig_off,
+                                                             const int32_t* o_pos, const uint16_t* o_ncig, const uint32_t* o_cigar,
+                                                             const unsigned long long* off, uint8_t* out) {
+    const int lane = threadIdx.x & 31;
+    const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n || off[i + 1] == off[i]) return;
+    const uint8_t* r = raw + rec_off[i] + 4;
+    const uint32_t bs = ld_le32(r - 4), lname = r[8], nc_old = ld_le16(r + 12), nc_new = o_ncig[i], flag = ld_le16(r + 14);
+    const uint32_t nbs = bs - 4u * nc_old + 4u * nc_new;
+    uint8_t* w = out + off[i];
+    const uint32_t* cg = o_cigar + (size_t)cig_off[i] + 3 * (size_t)i;
+    const uint32_t head = 32u + lname, rest = bs - head - 4u * nc_old;
+    const uint8_t* tail = r + head + 4u * nc_old;
+    uint8_t* wt = w + 4 + head + 4u * nc_new;
+    for (uint32_t k = lane; k < head; k += 32) w[4 + k] = r[k];
+    for (uint32_t k = lane; k < rest; k += 32) wt[k] = tail[k];
+    for (uint32_t k = lane; k < 4u * nc_new; k += 32) w[4 + head + k] = (uint8_t)(cg[k >> 2] >> (8 * (k & 3)));
+    __syncwarp();
+    if (lane == 0) {
+        long long rlen = 0;
+        for (uint32_t c = 0; c < nc_new; ++c) { const uint32_t op = cg[c] & 15u; if ((0x18Du >> op) & 1u) rlen += cg[c] >> 4; }
+        if ((flag & 4u) || rlen == 0) rlen = 1;                                // htslib bam_endpos
+        const int32_t p = o_pos[i];
+        const uint32_t bin = (uint32_t)reg2bin_dev(p, p + rlen);
+        for (int b = 0; b < 4; ++b) { w[b] = (uint8_t)(nbs >> (8 * b)); w[8 + b] = (uint8_t)((uint32_t)p >> (8 * b)); }
+        w[14] = (uint8_t)bin; w[15] = (uint8_t)(bin >> 8); w[16] = (uint8_t)nc_new; w[17] = (uint8_t)(nc_new >> 8);
+    }
+}
+
 // ---- BGZF / BAM decode on the device (amp_bgzf.cuh) ------------------------------------------------------------------------
 #define AMPZ_WARPS 16
 __global__ void __launch_bounds__(AMPZ_WARPS * 32) amp_bgzf_inflate_kernel(const uint8_t* comp, long long comp_len, const long long* in_off,
@@ -460,9 +589,16 @@ struct amp_ctx {
         uint32_t* cigar = nullptr; size_t cap_cig = 0; uint8_t* seq = nullptr; size_t cap_seq = 0; uint8_t* qual = nullptr; size_t cap_qual = 0;
         uint32_t* o_cigar = nullptr; size_t cap_ocig = 0; uint32_t* scratch = nullptr; size_t cap_scratch = 0;
         long long n_reads = 0, sum_cig = 0, sum_seq = 0, sum_qual = 0, n_blocks = 0, raw_len = 0;
-        bool valid = false, z_attr = false;
+        bool valid = false, z_attr = false, trimmed = false;             // trimmed: o_* hold the trim outputs of this batch
+        uint32_t* w_sizes = nullptr; size_t cap_wsizes = 0; unsigned long long* w_off = nullptr; size_t cap_woff = 0; uint8_t* w_stream = nullptr; size_t cap_wstream = 0;
         cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     } dec;
+    struct Deflater {                                            // amp_bgzf_deflate_host (grown at high-water marks)
+        uint8_t* in = nullptr; size_t cap_in = 0; uint8_t* slots = nullptr; size_t cap_slots = 0; uint8_t* out = nullptr; size_t cap_out = 0;
+        long long* bstart = nullptr; size_t cap_bstart = 0; long long* off = nullptr; size_t cap_off = 0;
+        uint32_t* clen = nullptr; size_t cap_clen = 0; uint32_t* crc = nullptr; size_t cap_crc = 0; unsigned int* ctr = nullptr;
+        bool attr = false; cudaStream_t stream = nullptr;            // its own stream: a writer thread may call it while the context calls
+    } defl;
     unsigned char* d_xbuf = nullptr; size_t xbuf_bytes = 0;   // scratch of amp_ins_export / amp_ins_merge (grown at high-water marks)
     unsigned char* d_ref = nullptr;     // reference characters (amp_set_reference)
     unsigned char* d_call = nullptr;    // calling outputs (one block, offsets below)
@@ -553,6 +689,7 @@ int launch_process(amp_ctx* c, const amp::BatchPtrs& b, long long sum_cig, long 
             fprintf(stderr, "[generic phase, cycles summed over its warp-rounds / 1000] load+copy %lld  trim_read %lld  outputs %lld  plan_read %lld\n", h[360] / 1000, h[361] / 1000, h[362] / 1000, h[363] / 1000);
             fprintf(stderr, "[cycles per CTA] mean %.0f  min %lld  max %lld   set-up %.0f  last barrier (per warp) %.0f  drain+flush %.0f\n", (double)h[8] / grid, h[9], h[10],
                     (double)h[11] / grid, h[12] / wf, (double)h[13] / grid);
+            fprintf(stderr, "[runs counted outside the tile] %lld\n", h[14]);
         }
 #endif
         c->last_launches += 1;
@@ -672,11 +809,13 @@ int amp_destroy(amp_ctx* c) {
     for (auto& sc : c->scheme) { cudaFree(sc.d_min); cudaFree(sc.d_max); }
     if (c->counts_owned) cudaFree(c->d_counts);
     cudaFree(c->tab.slots); cudaFree(c->tab.entries); cudaFree(c->tab.slot_entry); cudaFree(c->tab.arena); cudaFree(c->tab.cursor);
+    if (c->defl.stream) cudaStreamDestroy(c->defl.stream);
+    cudaFree(c->defl.in); cudaFree(c->defl.slots); cudaFree(c->defl.out); cudaFree(c->defl.bstart); cudaFree(c->defl.off); cudaFree(c->defl.clen); cudaFree(c->defl.crc); cudaFree(c->defl.ctr);
     cudaFree(c->d_err); cudaFree(c->d_heads); cudaFree(c->d_scratch); cudaFree(c->d_glist); cudaFree(c->d_ref); cudaFree(c->d_call); cudaFree(c->d_xbuf);
     {
         auto& d = c->dec;
         void* ps[] = {d.comp, d.raw, d.in_off, d.out_off, d.out_len, d.tot, d.prefix, d.ctr, d.pos, d.flag, d.tlen, d.cig_off, d.seq_off, d.qual_off,
-                      d.rec_off, d.o_pos, d.o_ncig, d.o_flags, d.cigar, d.seq, d.qual, d.o_cigar, d.scratch};
+                      d.rec_off, d.o_pos, d.o_ncig, d.o_flags, d.cigar, d.seq, d.qual, d.o_cigar, d.scratch, d.w_sizes, d.w_off, d.w_stream};
         for (void* q : ps) cudaFree(q);
         for (auto& e : d.ev) if (e) cudaEventDestroy(e);
     }
@@ -1025,6 +1164,123 @@ int amp_call(amp_ctx* c, const char* ref_seq, const amp_call_params* p, const am
     return AMP_OK;
 }
 
+// The blocks of a byte stream that is already in device memory (readable up to d_in + n_bytes + 8): deflate + pack kernels, then the
+// BGZF blocks and the EOF block to the host.  Returns the bytes written to out or a negative error code.
+static int64_t deflate_device(amp_ctx* c, const uint8_t* d_in, int64_t n_bytes, const int64_t* bstart, int64_t n_blocks, uint8_t* out, int64_t out_cap,
+                              cudaStream_t st) {
+    static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (bstart[0] != 0 || bstart[n_blocks] != n_bytes) return fail(AMP_ERR_ARG, "BGZF deflate: the block table does not cover the data");
+    for (int64_t k = 0; k < n_blocks; ++k)
+        if (bstart[k + 1] < bstart[k] || bstart[k + 1] - bstart[k] > AMPD_MAXBLOCK) return fail(AMP_ERR_ARG, "BGZF deflate: a block is longer than 0xff00 bytes");
+    if (n_blocks == 0) { if (out_cap < 28) return fail(AMP_ERR_ARG, "BGZF deflate: output buffer too small"); memcpy(out, eof, 28); return 28; }
+    auto& d = c->defl;
+    int rc;
+    if ((rc = dev_grow(&d.slots, &d.cap_slots, (size_t)n_blocks * AMPD_SLOT))) return rc;
+    if ((rc = dev_grow(&d.bstart, &d.cap_bstart, (size_t)n_blocks + 1))) return rc;
+    if ((rc = dev_grow(&d.off, &d.cap_off, (size_t)n_blocks + 1))) return rc;
+    if ((rc = dev_grow(&d.clen, &d.cap_clen, (size_t)n_blocks))) return rc;
+    if ((rc = dev_grow(&d.crc, &d.cap_crc, (size_t)n_blocks))) return rc;
+    if (!d.ctr) CK(cudaMalloc((void**)&d.ctr, 16));
+    const size_t smem = ((sizeof(amp::DeflateTables) + 15) & ~(size_t)15) + (size_t)AMPD_WARPS * sizeof(amp::DeflateMem);
+    if (!d.attr) { CK(cudaFuncSetAttribute(amp_bgzf_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); d.attr = true; }
+    CK(cudaMemcpyAsync(d.bstart, bstart, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d.ctr, 0, 16, st));
+    const int grid = (int)std::min<int64_t>((n_blocks + AMPD_WARPS - 1) / AMPD_WARPS, (int64_t)c->sm_count);
+    amp_bgzf_deflate_kernel<<<grid, AMPD_WARPS * 32, smem, st>>>(d_in, d.bstart, n_blocks, d.slots, d.clen, d.crc, d.ctr);
+    CK(cudaGetLastError());
+    std::vector<uint32_t> clen((size_t)n_blocks);
+    CK(cudaMemcpyAsync(clen.data(), d.clen, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<long long> off((size_t)n_blocks + 1);
+    long long total = 0;
+    for (int64_t k = 0; k < n_blocks; ++k) {
+        off[(size_t)k] = total;
+        total += 26 + (clen[(size_t)k] == 0xFFFFFFFFu ? (bstart[k + 1] - bstart[k]) + 5 : (long long)clen[(size_t)k]);
+    }
+    off[(size_t)n_blocks] = total;
+    if (total + 28 > out_cap) return fail(AMP_ERR_ARG, "BGZF deflate: output buffer too small");
+    if ((rc = dev_grow(&d.out, &d.cap_out, (size_t)total + 64))) return rc;
+    CK(cudaMemcpyAsync(d.off, off.data(), ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
+    amp_bgzf_pack_kernel<<<(unsigned)((n_blocks + 7) / 8), 256, 0, st>>>(d_in, d.bstart, n_blocks, d.slots, d.clen, d.crc, d.off, d.out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d.out, (size_t)total, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(out + total, eof, 28);
+    return total + 28;
+}
+
+// BGZF-compress host data on the device: in[bstart[k], bstart[k + 1]) becomes block k (each at most 0xff00 bytes; the caller cuts
+// at record boundaries the way htslib does), then the EOF block.  Returns the bytes written to out, or a negative error code.
+int64_t amp_bgzf_deflate_host(amp_ctx* c, const uint8_t* in, int64_t n_bytes, const int64_t* bstart, int64_t n_blocks, uint8_t* out, int64_t out_cap) {
+    if (!c || !in || !bstart || !out || n_bytes < 0 || n_blocks < 0) return fail(AMP_ERR_ARG, "amp_bgzf_deflate_host: bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    auto& d = c->defl;
+    if (!d.stream) CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    int rc;
+    if ((rc = dev_grow(&d.in, &d.cap_in, (size_t)n_bytes + 64))) return rc;
+    CK(cudaMemcpyAsync(d.in, in, (size_t)n_bytes, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemsetAsync(d.in + n_bytes, 0, 64, d.stream));
+    return deflate_device(c, d.in, n_bytes, bstart, n_blocks, out, out_cap, d.stream);
+}
+
+// The trimmed BAM file of the batch amp_bam_decode_host decoded and amp_process_decoded trimmed, built entirely on the device: the
+// reads that pass the write gate (AmpliPy.py:910), their records rebuilt with the new pos / bin / n_cigar / CIGAR in the inflated
+// input stream that is still in HBM, cut into BGZF blocks at record boundaries (as htslib's bam_write1 does), compressed, and copied to
+// the host once.  header = the BAM header (magic, text, references) the file starts with.
+int64_t amp_decoded_write_bam(amp_ctx* c, const uint8_t* header, int64_t header_bytes, uint8_t* out, int64_t out_cap, int64_t* n_records) {
+    if (!c || !header || !out || header_bytes < 12) return fail(AMP_ERR_ARG, "amp_decoded_write_bam: bad argument");
+    auto& d = c->dec;
+    if (!d.valid || !d.trimmed) return fail(AMP_ERR_STATE, "amp_decoded_write_bam: no trimmed batch (amp_bam_decode_host + amp_process_decoded with AMP_MODE_TRIM first)");
+    CK(cudaSetDevice(c->cfg.device));
+    if (!c->defl.stream) CK(cudaStreamCreateWithFlags(&c->defl.stream, cudaStreamNonBlocking));
+    cudaStream_t st = c->defl.stream;
+    const long long n = d.n_reads;
+    int rc;
+    if ((rc = dev_grow(&d.w_sizes, &d.cap_wsizes, (size_t)n + 1))) return rc;
+    if ((rc = dev_grow(&d.w_off, &d.cap_woff, (size_t)n + 2))) return rc;
+    std::vector<unsigned long long> off((size_t)n + 1, 0ULL);
+    if (n) {
+        amp_bam_newsize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.raw, d.rec_off, n, d.o_ncig, d.o_flags, d.w_sizes);
+        CK(cudaGetLastError());
+        amp_scan_sizes_kernel<<<1, 1024, 0, st>>>(d.w_sizes, n, d.w_off);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(off.data(), d.w_off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    const long long total = header_bytes + (long long)off[(size_t)n];
+    // block starts: htslib's layout (whole records per block, up to 0xff00 bytes; the header may share the first block)
+    std::vector<int64_t> bstart;
+    long long kept = 0;
+    {
+        const long long BS = AMPD_MAXBLOCK;
+        long long cur = 0, prev = 0;
+        auto unit = [&](long long end) {                        // a unit [prev, end) joins the open block or starts the next one
+            if (end - cur > BS) {
+                if (prev > cur) { bstart.push_back(cur); cur = prev; }
+                while (end - cur > BS) { bstart.push_back(cur); cur += BS; }
+            }
+            prev = end;
+        };
+        unit(header_bytes);
+        for (long long i = 0; i < n; ++i) {
+            if (off[(size_t)i + 1] == off[(size_t)i]) continue;
+            ++kept;
+            unit(header_bytes + (long long)off[(size_t)i + 1]);
+        }
+        if (total > cur) bstart.push_back(cur);
+        bstart.push_back(total);
+    }
+    if (n_records) *n_records = kept;
+    if ((rc = dev_grow(&d.w_stream, &d.cap_wstream, (size_t)total + 64))) return rc;
+    CK(cudaMemcpyAsync(d.w_stream, header, (size_t)header_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d.w_stream + total, 0, 64, st));
+    if (n) {
+        amp_bam_rewrite_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d.raw, d.rec_off, n, d.cig_off, d.o_pos, d.o_ncig, d.o_cigar, d.w_off, d.w_stream + header_bytes);
+        CK(cudaGetLastError());
+    }
+    return deflate_device(c, d.w_stream, total, bstart.data(), (int64_t)bstart.size() - 1, out, out_cap, st);
+}
+
 int amp_host_alloc(void** p, int64_t bytes) {
     if (!p || bytes < 0) return fail(AMP_ERR_ARG, "amp_host_alloc: bad argument");
     CK(cudaHostAlloc(p, (size_t)std::max<int64_t>(bytes, 16), cudaHostAllocDefault));
@@ -1194,7 +1450,7 @@ int amp_bam_decode_host(amp_ctx* c, const uint8_t* bgzf, int64_t n_bytes, const 
         return fail(AMP_ERR_ARG, "amp_bam_decode_host: bad argument");
     CK(cudaSetDevice(c->cfg.device));
     auto& d = c->dec;
-    d.valid = false;
+    d.valid = false; d.trimmed = false;
     cudaStream_t sc = c->chunk[0].stream, sx = c->chunk[1].stream;    // compute / copy
     CK(cudaStreamSynchronize(sc)); CK(cudaStreamSynchronize(sx));
     // host-side tables: block ends, output offsets
@@ -1317,6 +1573,7 @@ int amp_process_decoded(amp_ctx* c, int mode, int sample, const amp_trim_out* ho
     amp::TrimOut to{};
     if (trim) { to.pos = d.o_pos; to.ncig = d.o_ncig; to.flags = d.o_flags; to.cigar = d.o_cigar; }
     if ((rc = launch_process(c, bp, d.sum_cig, 0, d.sum_qual > 0 ? d.sum_qual : 1, mode, sample, to, trim ? d.scratch : nullptr, c->d_glist, sc))) return rc;
+    if (trim) d.trimmed = true;
     if (trim && host_out && n) {
         if (host_out->pos) CK(cudaMemcpyAsync(host_out->pos, d.o_pos, n * 4, cudaMemcpyDeviceToHost, sc));
         if (host_out->ncig) CK(cudaMemcpyAsync(host_out->ncig, d.o_ncig, n * 2, cudaMemcpyDeviceToHost, sc));

@@ -619,6 +619,9 @@ AMP_WD_COLD void warp_generic_phase(const KParams& P, const WarpMem7& wm, int* c
 AMP_WD_COLD void count_run_slow(const KParams& P, int* cnt, int wbase, const uint8_t* qrun, const uint8_t* sbuf, int nb0, int rpos, int m) {
     const int minq = P.tp.min_quality;
     unsigned errs = 0;
+#if defined(__CUDA_ARCH__) && defined(AMP7_TIMING)
+    if (P.phase_cycles) atomicAdd((unsigned long long*)&P.phase_cycles[14], 1ULL);        // runs outside the tile
+#endif
     for (int t = 0; t < m; ++t) {
         if (qrun[t] < minq) continue;                                              // 718
         const uint32_t nb = (uint32_t)(nb0 + t);

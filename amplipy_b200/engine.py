@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "amp_host_alloc", "amp_host_free", "amp_reset_async", "amp_set_reference", "amp_call_device",
     "amp_nccl_unique_id", "amp_nccl_comm_init", "amp_nccl_comm_destroy", "amp_nccl_allgather", "amp_allreduce_counts",
     "amp_ins_slot_bytes", "amp_ins_pack_device", "amp_ins_merge_packed", "amp_reserve", "amp_counts_copy_device",
-    "amp_bam_decode_host", "amp_process_decoded", "amp_decoded_copy_host", "amp_counts_upload",
+    "amp_bam_decode_host", "amp_process_decoded", "amp_decoded_copy_host", "amp_counts_upload", "amp_bgzf_deflate_host", "amp_decoded_write_bam",
     "amp_set_scheme", "amp_get_scheme", "amp_set_sample_reference"]
 
 
@@ -412,11 +412,12 @@ class Engine:
         n, sc = self._decoded["n"], self._decoded["sum_cig"]
         return (np.zeros(n, np.int32), np.zeros(n, np.uint16), np.zeros(n, np.uint8), np.zeros(sc + 3 * n, np.uint32))
 
-    def process_decoded(self, trim=True, pileup=True, sample=0, out=None):
-        """Fused kernel on the batch decode_bam left in HBM; trim outputs copied to ``out`` (alloc_decoded_trim_out)."""
+    def process_decoded(self, trim=True, pileup=True, sample=0, out=None, download=True):
+        """Fused kernel on the batch decode_bam left in HBM; trim outputs copied to ``out`` (alloc_decoded_trim_out), or left on the
+        device only (``download=False``: decoded_write_bam is their consumer)."""
         mode = (MODE_TRIM if trim else 0) | (MODE_PILEUP if pileup else 0)
         to = None
-        if trim:
+        if trim and download:
             if out is None:
                 out = self.alloc_decoded_trim_out()
             to = AmpTrimOut(_ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]))
@@ -436,6 +437,35 @@ class Engine:
                          _ptr(b.qual_off), _ptr(b.qual))
         _check(self.lib.amp_decoded_copy_host(self._ctx, ctypes.byref(bo), _ptr(rec_off)), "amp_decoded_copy_host")
         return b, rec_off
+
+    def decoded_write_bam(self, header_bytes):
+        """The trimmed BAM file (uint8 array) of the batch decode_bam + process_decoded(trim=True) left in HBM, and the number of
+        records in it (amp_decoded_write_bam); ``header_bytes``: the BAM header the file starts with."""
+        hb = np.frombuffer(header_bytes, np.uint8) if not isinstance(header_bytes, np.ndarray) else header_bytes
+        raw = int(self._decoded["raw_bytes"])
+        out = np.empty(hb.size + raw + raw // 1000 + 4 * int(self._decoded["sum_cig"]) + 12 * int(self._decoded["n"]) + 4096, np.uint8)
+        nrec = ctypes.c_int64(0)
+        self.lib.amp_decoded_write_bam.restype = ctypes.c_int64
+        r = int(self.lib.amp_decoded_write_bam(self._ctx, _ptr(hb), ctypes.c_int64(hb.size), _ptr(out), ctypes.c_int64(out.size), ctypes.byref(nrec)))
+        if r < 0:
+            _check(r, "amp_decoded_write_bam")
+        self.launches += 5
+        return out[:r], int(nrec.value)
+
+    def bgzf_deflate(self, data, bstart):
+        """BGZF blocks (+ EOF block) of ``data`` cut at ``bstart`` (n_blocks + 1 offsets, each block <= 0xff00 bytes), compressed
+        on the device (amp_bgzf_deflate_host).  Returns a uint8 array."""
+        src = np.ascontiguousarray(data, np.uint8)
+        bs = np.ascontiguousarray(bstart, np.int64)
+        nb = bs.size - 1
+        out = np.empty(src.size + 31 * max(nb, 0) + 28, np.uint8)
+        self.lib.amp_bgzf_deflate_host.restype = ctypes.c_int64
+        r = int(self.lib.amp_bgzf_deflate_host(self._ctx, _ptr(src), ctypes.c_int64(src.size), _ptr(bs), ctypes.c_int64(nb), _ptr(out),
+                                               ctypes.c_int64(out.size)))
+        if r < 0:
+            _check(r, "amp_bgzf_deflate_host")
+        self.launches += 2
+        return out[:r]
 
     # ---------------------------------------------------------------- deep-sample exchange (dist.py)
     def reserve(self, max_reads, max_cigar_ops):

@@ -242,9 +242,9 @@ def parity_on_sample(eng, oracle, sb, g, prim, tables, mpl, pouts, sample):
 
 
 def file_to_file(args, g, prim, b, runs=3):
-    """`aio` through the command line on files: BAM decode (host, multi-threaded BGZF) -> GPU path -> BAM encode + VCF +
-    FASTA.  Reported next to the kernel numbers because this is where a real run is bounded (host I/O).  Warm: the CUDA
-    context and the libraries are up; best of `runs`."""
+    """`aio` through the command line on files: BAM bytes -> GPU (inflate, trim + pileup, calling, record rebuild, deflate) -> trimmed
+    BAM + VCF + FASTA.  Reported next to the kernel numbers because this is what a real run sees.  Warm: the CUDA context and the
+    libraries are up; best of `runs`."""
     import shutil
     import tempfile
     from amplipy_b200 import alnio, cli, synth
@@ -278,19 +278,20 @@ def file_to_file(args, g, prim, b, runs=3):
         for r in range(runs):
             dt, sp = one_run()
             times.append(dt); splits.append(sp)
-        size6 = os.path.getsize(j("trimmed.bam"))
-        os.environ["AMPLIPY_BAM_LEVEL"] = "1"           # the trimmed BAM deflated at level 1 instead of htslib's default 6
-        fast = [one_run() for _ in range(2)]
+        size_dev = os.path.getsize(j("trimmed.bam"))
+        os.environ["AMPLIPY_BAM_LEVEL"] = "6"           # the trimmed BAM rebuilt and deflated on the host with zlib at htslib's default level
+        slow = [one_run() for _ in range(2)]
         os.environ.pop("AMPLIPY_BAM_LEVEL", None)
-        kf = int(np.argmin([x[0] for x in fast]))
-        fast_obj = {"value": b.n / fast[kf][0], "unit": "reads/s", "seconds": fast[kf][0], "split_s": fast[kf][1],
-                    "trimmed_bam_bytes": os.path.getsize(j("trimmed.bam")), "note": "AMPLIPY_BAM_LEVEL=1"}
+        kf = int(np.argmin([x[0] for x in slow]))
+        host_obj = {"value": b.n / slow[kf][0], "unit": "reads/s", "seconds": slow[kf][0], "split_s": slow[kf][1],
+                    "trimmed_bam_bytes": os.path.getsize(j("trimmed.bam")), "note": "AMPLIPY_BAM_LEVEL=6: host inflate + record rewrite + zlib"}
         os.environ.pop("AMP_CLI_TIMINGS", None)
         k = int(np.argmin(times))
         return {"value": b.n / times[k], "unit": "reads/s", "seconds": times[k], "runs_s": times, "split_s": splits[k],
                 "bam_decode_only_reads_per_s": b.n / t_decode,
-                "bam_bytes": os.path.getsize(j("in.bam")), "trimmed_bam_bytes": size6, "deflate_level_1": fast_obj,
-                "note": "python -m amplipy_b200 aio on files in a temp directory (page cache warm), best of %d; "
+                "bam_bytes": os.path.getsize(j("in.bam")), "trimmed_bam_bytes": size_dev, "host_zlib_level_6": host_obj,
+                "note": "python -m amplipy_b200 aio on files in a temp directory (page cache warm), best of %d: the BAM is inflated, "
+                        "trimmed, rebuilt and deflated on the GPU (fixed-Huffman deflate, about the size of zlib level 1); "
                         "the reference's counterpart is AmpliPy.py aio with pysam I/O" % runs}
     finally:
         shutil.rmtree(d, ignore_errors=True)

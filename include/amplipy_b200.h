@@ -201,6 +201,24 @@ int amp_bam_decode_host(amp_ctx* ctx, const uint8_t* bgzf, int64_t n_bytes, cons
 int amp_process_decoded(amp_ctx* ctx, int mode, int sample, const amp_trim_out* host_out);
 int amp_decoded_copy_host(amp_ctx* ctx, const amp_batch_out* host_arrays, uint64_t* rec_off);
 
+/* ---- BGZF deflate on the device (replaces the zlib deflate behind out_aln.write, AmpliPy.py:911).
+ * host data -> BGZF blocks: block k = in[bstart[k], bstart[k + 1]) (bstart has n_blocks + 1 entries, bstart[0] = 0, the last one =
+ * n_bytes, every block at most 0xff00 bytes -- the caller cuts at record boundaries as htslib does), followed by the EOF block.
+ * One warp per block: LZ77 (4-byte hash + run candidate) and the fixed Huffman code, CRC-32 and ISIZE in the footer; a block that
+ * does not shrink is stored.  Any inflater reads the result; it is about the size of zlib level 1.
+ * out must hold n_bytes + 31 * n_blocks + 28 bytes.  Returns the number of bytes written, or a negative AMP_ERR_* code. */
+int64_t amp_bgzf_deflate_host(amp_ctx* ctx, const uint8_t* in, int64_t n_bytes, const int64_t* bstart, int64_t n_blocks, uint8_t* out,
+                              int64_t out_cap);
+
+/* The trimmed BAM file of the decoded batch, built on the device (replaces the cigartuples / reference_start assignments and
+ * out_aln.write of AmpliPy.py:463-658, 910-911 for BAM input): after amp_bam_decode_host + amp_process_decoded(AMP_MODE_TRIM) the
+ * inflated input and the trim outputs are both in HBM; the records of the reads that pass the write gate are rebuilt there (new
+ * block_size / pos / bin / n_cigar / CIGAR, the rest byte for byte), cut into BGZF blocks at record boundaries, compressed
+ * (amp_bgzf_deflate_host's kernels) and copied to the host once.  header = the BAM header the file starts with (magic, l_text,
+ * text, references).  out must hold header_bytes + the inflated input + 31 bytes per 64 KB + 28.  Returns the size of the file
+ * or a negative AMP_ERR_* code; *n_records = the number of records written. */
+int64_t amp_decoded_write_bam(amp_ctx* ctx, const uint8_t* header, int64_t header_bytes, uint8_t* out, int64_t out_cap, int64_t* n_records);
+
 /* ---- heterogeneous plates: a primer scheme and / or a reference of its own for one sample of the context.
  * amp_set_scheme builds the two per-position tables of find_overlapping_primers (AmpliPy.py:174-209) on the device from the
  * sorted primer list (start, end) and the offset; ref_len <= the context's ref_len.  amp_process_* of that sample then trims

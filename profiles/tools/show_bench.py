@@ -11,6 +11,7 @@ if "cpu_baseline" in d:
 if "ont" in d:
     o = d["ont"]; print("ont      %d reads kernel %.4f ms frac %.4f step %.4f ms err %s" % (o["reads"], o["kernel_ms"], o["frac"], o["ms_per_step"], o["device_error_flags"]))
 if "file_e2e" in d:
-    f = d["file_e2e"]; print("file     %.2f M reads/s (%.3f s) split %s | level 1: %.2f M reads/s split %s" % (f["value"] / 1e6, f["seconds"], f["split_s"], f["deflate_level_1"]["value"] / 1e6, f["deflate_level_1"]["split_s"]))
+    f = d["file_e2e"]; h = f.get("host_zlib_level_6") or f.get("deflate_level_1")
+    print("file     %.2f M reads/s (%.3f s, %d bytes) split %s | host zlib: %.2f M reads/s (%d bytes) split %s" % (f["value"] / 1e6, f["seconds"], f["trimmed_bam_bytes"], f["split_s"], h["value"] / 1e6, h["trimmed_bam_bytes"], h["split_s"]))
 if "deep" in d:
     x = d["deep"]; print("deep     %d reads on %d ranks: %.3f ms/step = %.2f G reads/s; kernel %.3f allreduce %.3f ins %.3f call %.3f ms; parity %s" % (x["reads"], x["ranks"], x["ms_per_step"], x["reads_per_s"] / 1e9, x["kernel_ms"], x["allreduce_ms"], x["ins_exchange_ms"], x["call_ms"], x["deep_parity"]))

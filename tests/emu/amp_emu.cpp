@@ -15,6 +15,7 @@
 #include "../../amplipy_b200/csrc/amp_warp.cuh"
 #include "../../amplipy_b200/csrc/amp_bgzf.cuh"
 #include "../../amplipy_b200/csrc/amp_ont.cuh"
+#include "../../amplipy_b200/csrc/amp_deflate.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Fiber runtime for the warp-autonomous kernel: every CUDA thread of one CTA is a ucontext fiber; warp collectives
@@ -403,6 +404,28 @@ void emu_bam_scatter(const uint8_t* raw, long long lo, long long hi, int32_t* po
                      uint32_t* cigar, uint32_t* seq_off, uint8_t* seq, uint32_t* qual_off, uint8_t* qual, unsigned long long* rec_off) {
     ScatterJob j{raw, lo, hi, amp::BamSoa{pos, flag, tlen, cig_off, cigar, seq_off, seq, qual_off, qual, rec_off}};
     run_cta(0, 32, scatter_body, &j);
+}
+
+// ---- BGZF deflate kernel (amp_deflate.cuh): one warp of fibers per block ------------------------------------------------------------
+struct DeflateJob { const uint8_t* in; int n; uint32_t* out; int cap_words; amp::DeflateMem* mem; amp::DeflateTables* tab; int bytes; uint32_t crc; };
+static void deflate_body(void* a) {
+    DeflateJob* j = (DeflateJob*)a;
+    const int lane = amp::c_tid() & 31;
+    amp::deflate_tables_init(*j->tab, amp::c_tid(), amp::c_nthreads());
+    amp::c_sync();
+    const uint32_t mcol = amp::crc_shift_column(*j->tab, lane);
+    const int bytes = j->n >= 16 ? amp::deflate_block(j->in, j->n, *j->mem, *j->tab, j->out, j->cap_words, lane) : -1;
+    const uint32_t crc = amp::crc32_block(j->in, j->n, *j->tab, mcol, lane);
+    if (lane == 0) { j->bytes = bytes; j->crc = crc; }
+}
+// in[0, n) (readable up to in + n + 8) -> raw deflate stream in out (cap_words 32-bit words + 64 words of slack); returns its length
+// in bytes or -1 (does not fit / too short to bother); *crc = CRC-32 of the input
+int emu_deflate(const uint8_t* in, int n, uint32_t* out, int cap_words, uint32_t* crc) {
+    amp::DeflateMem mem; amp::DeflateTables tab;
+    DeflateJob j{in, n, out, cap_words, &mem, &tab, 0, 0};
+    run_cta(0, 32, deflate_body, &j);
+    *crc = j.crc;
+    return j.bytes;
 }
 
 }  // extern "C"

@@ -568,3 +568,92 @@ def test_mixed_plate_in_one_context_equals_solo_runs():
         assert len(got) == len(recs)
         for a, c in zip(got, recs):
             assert tuple(a[:6]) == tuple(c[:6]) and a[6] == c[6] and a[7] == c[7] and tuple(a[8]) == tuple(c[8])
+
+
+# ---- BGZF deflate on the device (amp_bgzf_deflate_host) ----------------------------------------------------------------------------
+def _bgzf_members(buf):
+    """(payload bytes, isize) of every BGZF block of buf, checking the fixed header fields"""
+    out, o = [], 0
+    while o < len(buf):
+        assert buf[o:o + 4] == b"\x1f\x8b\x08\x04" and buf[o + 12:o + 16] == b"BC\x02\x00"
+        bsize = int.from_bytes(buf[o + 16:o + 18], "little") + 1
+        out.append((buf[o + 18:o + bsize - 8], int.from_bytes(buf[o + bsize - 4:o + bsize], "little")))
+        o += bsize
+    assert o == len(buf)
+    return out
+
+
+@pytest.mark.gpu
+def test_device_bgzf_deflate_round_trip(tmp_path):
+    """Whatever the device compressor writes is a BGZF file: every block a gzip member with the right CRC-32 / ISIZE (Python's gzip
+    checks both), the EOF block at the end, blocks cut where the caller said; incompressible blocks come back stored."""
+    import gzip
+    from amplipy_b200 import alnio
+    g, prim, amps = _scheme(L=6000, n_amp=18)
+    b = synth.illumina_batch(g, amps, 40_000, seed=61, p_ins=0.05, p_del=0.05)
+    raw = _bam_bytes(tmp_path, b, 6000)
+    data = alnio.bgzf_decompress(raw)
+    rng = np.random.default_rng(5)
+    noise = rng.integers(0, 256, 200_000, dtype=np.uint8)
+    eng = make_engine(ref_len=6000)
+    for payload, step in ((data, 0xff00), (data[:1_000_003], 40_000), (noise, 0xff00), (np.concatenate([data[:100_000], noise, data[:70_001]]), 65_000),
+                          (data[:10], 0xff00), (data[:0], 0xff00)):
+        bstart = np.unique(np.concatenate([np.arange(0, payload.size, step), [payload.size]])).astype(np.int64)
+        if payload.size == 0:
+            bstart = np.zeros(1, np.int64)
+        out = eng.bgzf_deflate(payload, bstart).tobytes()
+        assert out.endswith(bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0]))
+        assert gzip.decompress(out) == payload.tobytes()
+        members = _bgzf_members(out)
+        assert [m[1] for m in members[:-1]] == list(np.diff(bstart)) and members[-1][1] == 0
+        assert alnio.bgzf_decompress(out).tobytes() == payload.tobytes()           # the repo's own host inflater
+    # compressible data does get smaller, noise does not grow by more than the block overhead
+    bs = np.unique(np.concatenate([np.arange(0, data.size, 0xff00), [data.size]])).astype(np.int64)
+    assert eng.bgzf_deflate(data, bs).size < 0.45 * data.size
+    bn = np.unique(np.concatenate([np.arange(0, noise.size, 0xff00), [noise.size]])).astype(np.int64)
+    assert eng.bgzf_deflate(noise, bn).size <= noise.size + 31 * (bn.size - 1) + 28
+    # and the device decoder reads it back: file bytes -> amp_bam_decode_host -> the same batch
+    cuts = np.unique(np.concatenate([[0], np.cumsum(alnio.bam_layout(raw)["out_len"].astype(np.int64))]))     # the record-aligned blocks of the input
+    out = eng.bgzf_deflate(data, cuts).tobytes()
+    info = eng.decode_bam(out, alnio.bam_layout(out))
+    got, _ = eng.decoded_batch()
+    assert info["n"] == b.n
+    for f in ("pos", "flag", "tlen", "cig_off", "cigar", "seq_off", "seq", "qual_off", "qual"):
+        assert np.array_equal(getattr(got, f), getattr(b, f)), f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["illumina", "ont", "nothing_kept"])
+def test_cli_bam_output_device_vs_zlib(tmp_path, monkeypatch, kind):
+    """`trim` BAM -> BAM with the records rebuilt and compressed on the device (default: amp_decoded_write_bam) and on the host with
+    zlib level 6 (AMPLIPY_BAM_LEVEL): the same records, byte for byte."""
+    import os
+    from amplipy_b200 import alnio, cli
+    g, prim, amps = _scheme(L=6000, n_amp=18)
+    if kind == "ont":
+        b = synth.ont_batch(g, amps, 6_000, seed=63)
+    else:
+        b = synth.illumina_batch(g, amps, 60_000 if kind == "illumina" else 3_000, seed=62, p_ins=0.05, p_del=0.05)
+    d = str(tmp_path)
+    open(os.path.join(d, "in.bam"), "wb").write(_bam_bytes(tmp_path, b, 6000))
+    with open(os.path.join(d, "p.bed"), "w") as f:
+        for k, (s, e) in enumerate(prim):
+            f.write("ref\t%d\t%d\tp%d\n" % (s, e, k))
+    with open(os.path.join(d, "ref.fas"), "w") as f:
+        f.write(">ref\n%s\n" % g)
+    j = lambda n: os.path.join(d, n)
+    monkeypatch.delenv("AMPLIPY_BAM_LEVEL", raising=False)
+    extra = ["-ml", "100000"] if kind == "nothing_kept" else []                      # a minimum length no read reaches: nothing passes the gate
+    cli.main(["trim", "-i", j("in.bam"), "-p", j("p.bed"), "-r", j("ref.fas"), "-o", j("dev.bam")] + extra)
+    monkeypatch.setenv("AMPLIPY_BAM_LEVEL", "6")
+    cli.main(["trim", "-i", j("in.bam"), "-p", j("p.bed"), "-r", j("ref.fas"), "-o", j("zlib.bam")] + extra)
+    a, z = alnio.read_alignments(j("dev.bam")), alnio.read_alignments(j("zlib.bam"))
+    assert a.n == z.n and (a.n > 0) == (kind != "nothing_kept") and a.header_text.splitlines()[:-1] == z.header_text.splitlines()[:-1]   # (@PG quotes the command)
+    for f in ("pos", "flag", "tlen", "cig_off", "cigar", "seq_off", "seq", "qual_off", "qual"):
+        assert np.array_equal(getattr(a.batch, f), getattr(z.batch, f)), f
+    import gzip
+    ra, rz = gzip.decompress(open(j("dev.bam"), "rb").read()), gzip.decompress(open(j("zlib.bam"), "rb").read())
+    assert ra[alnio.bam_layout(open(j("dev.bam"), "rb").read())["body_off"]:] == rz[alnio.bam_layout(open(j("zlib.bam"), "rb").read())["body_off"]:]
+    assert os.path.getsize(j("dev.bam")) < 2 * os.path.getsize(j("zlib.bam")) + 200
+    eng_cls = __import__("amplipy_b200.engine", fromlist=["Engine"]).Engine
+    assert hasattr(eng_cls, "decoded_write_bam")
