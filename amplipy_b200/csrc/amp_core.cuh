@@ -75,23 +75,11 @@ AMP_HD unsigned long long atomic_add64_warp(unsigned long long* p, unsigned long
     const unsigned m = __activemask();
     const int lane = (int)(threadIdx.x & 31u), leader = __ffs((int)m) - 1;
     unsigned long long pre = 0, tot = 0;
-    if (__any_sync(m, (v >> 20) != 0ULL)) {                    // (never in practice: a lane at a time)
-        for (unsigned r = m; r; r &= r - 1u) {
-            const int l = __ffs((int)r) - 1;
-            const unsigned long long x = __shfl_sync(m, v, l);
-            if (l < lane) pre += x;
-            tot += x;
-        }
-    } else {
-        // the requests are small (1 for the entry cursor, the words of one arena record): prefix sums over the arriving lanes one
-        // bit plane at a time -- a ballot and two population counts per plane that is in use
-        const unsigned lower = m & ((1u << lane) - 1u);
-        for (unsigned planes = __reduce_or_sync(m, (unsigned)v); planes; planes &= planes - 1u) {
-            const int b = __ffs((int)planes) - 1;
-            const unsigned bal = __ballot_sync(m, (unsigned)(v >> b) & 1u);
-            pre += (unsigned long long)__popc(bal & lower) << b;
-            tot += (unsigned long long)__popc(bal) << b;
-        }
+    for (unsigned r = m; r; r &= r - 1u) {     // (summing the requests a bit plane at a time with ballots measured slower: 1.25 vs 1.09 ms on the ONT batch)
+        const int l = __ffs((int)r) - 1;
+        const unsigned long long x = __shfl_sync(m, v, l);
+        if (l < lane) pre += x;
+        tot += x;
     }
     unsigned long long base = 0;
     if (lane == leader) base = atomicAdd(p, tot);

@@ -9,7 +9,9 @@ ncu --set full --clock-control none --import-source on -k regex:amp_trim_pileup_
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_ont_launches.csv python bench.py --lean --workload ont --reads 300000 --steps 2 --warmup 3 --e2e-steps 1 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:amp_trim_pileup_ont -s 3 -c 1 -f -o gpurun_out/r02_ont python bench.py --lean --workload ont --reads 300000 --steps 2 --warmup 3 --e2e-steps 1 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:amp_bgzf_inflate -s 1 -c 1 -f -o gpurun_out/r02_inflate python profiles/tools/bam_step.py 1000000 3 > /dev/null 2>&1
-for r in warp ont inflate; do
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_write_launches.csv python profiles/tools/prof_write.py > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:amp_bgzf_deflate_kernel -s 1 -c 1 -f -o gpurun_out/r02_deflate python profiles/tools/prof_write.py > /dev/null 2>&1
+for r in warp ont inflate deflate; do
   ncu -i gpurun_out/r02_$r.ncu-rep --page raw --csv > gpurun_out/r02_${r}_raw.csv 2>/dev/null
   ncu -i gpurun_out/r02_$r.ncu-rep --page details > gpurun_out/r02_${r}_details.txt 2>/dev/null
 done
