@@ -344,19 +344,20 @@ def write_alignments(path, aln, header_text, trim, threads=0, level=None, deflat
     if aln.fmt == "bam":
         lib = hostio()
         b = aln.batch
-        size = lib.amp_bam_rewrite(_p(aln.bam_buf), _p(aln.bam_rec_off), _p(sel), _ll(len(sel)), _p(trim.pos), _p(trim.ncig),
-                                   _p(b.cig_off), _p(trim.cigar), None)
-        body = np.empty(int(size) + 8, np.uint8)
-        lib.amp_bam_rewrite(_p(aln.bam_buf), _p(aln.bam_rec_off), _p(sel), _ll(len(sel)), _p(trim.pos), _p(trim.ncig),
-                            _p(b.cig_off), _p(trim.cigar), _p(body))
-        body = body[:int(size)]
         ooff = np.empty(len(sel) + 1, np.int64)
         lib.amp_bam_rewrite_offsets(_p(aln.bam_buf), _p(aln.bam_rec_off), _p(sel), _ll(len(sel)), _p(trim.ncig), _p(ooff))
         head = _bam_header_bytes(header_text, aln.refs)
         hb = np.frombuffer(head, np.uint8)
-        bounds = np.unique(np.concatenate([[0], hb.size + ooff]).astype(np.int64))
+        size = int(ooff[-1])
+        data = np.empty(hb.size + size + 8, np.uint8)               # header and records in one buffer: the stream to compress
+        data[:hb.size] = hb
+        lib.amp_bam_rewrite(_p(aln.bam_buf), _p(aln.bam_rec_off), _p(sel), _ll(len(sel)), _p(trim.pos), _p(trim.ncig),
+                            _p(b.cig_off), _p(trim.cigar), ctypes.c_void_p(data.ctypes.data + hb.size))
+        bounds = np.empty(len(sel) + 2, np.int64)                   # cut points: header end, record starts (increasing), end
+        bounds[0] = 0
+        bounds[1:] = ooff + hb.size
         with open(path, "wb") as f:
-            f.write(bgzf_compress_units(np.concatenate([hb, body]), bounds, level, threads, deflater))
+            f.write(bgzf_compress_units(data[:hb.size + size], bounds, level, threads, deflater))
         return len(sel)
     else:
         body = np.frombuffer(b"".join(_sam_fields_to_bam(aln, int(i), int(trim.pos[i]), trim.cigartuples(int(i))) for i in sel),

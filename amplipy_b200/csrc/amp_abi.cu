@@ -344,7 +344,7 @@ __global__ void amp_ins_merge_packed_kernel(amp::InsTable tab, const unsigned lo
 }
 
 // ---- BGZF deflate on the device (amp_deflate.cuh) --------------------------------------------------------------------------
-#define AMPD_WARPS 16
+#define AMPD_WARPS 24
 // block k = in[bstart[k], bstart[k + 1]) -> a deflate stream in slot k (clen[k] = its bytes, 0xFFFFFFFF: did not shrink, to be stored)
 // and its CRC-32; the warps take blocks from a counter
 __global__ void __launch_bounds__(AMPD_WARPS * 32) amp_bgzf_deflate_kernel(const uint8_t* in, const long long* bstart, long long nb, uint8_t* slots,
