@@ -96,7 +96,11 @@ def load_library():
         lib.amp_last_error.restype = ctypes.c_char_p
         lib.amp_ins_slot_bytes.restype = ctypes.c_int64
         for name in EXPORTED_SYMBOLS:
-            getattr(lib, name)   # AttributeError if the build is stale
+            try:
+                getattr(lib, name)   # AttributeError if the build is stale
+            except AttributeError:
+                if not (os.environ.get("AMP_LIB_OVERRIDE") and os.environ.get("AMP_LIB_ALLOW_MISSING")):   # A/B runs against older kernels
+                    raise
         _lib = lib
     return _lib
 
