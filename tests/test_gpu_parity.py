@@ -657,3 +657,37 @@ def test_cli_bam_output_device_vs_zlib(tmp_path, monkeypatch, kind):
     assert os.path.getsize(j("dev.bam")) < 2 * os.path.getsize(j("zlib.bam")) + 200
     eng_cls = __import__("amplipy_b200.engine", fromlist=["Engine"]).Engine
     assert hasattr(eng_cls, "decoded_write_bam")
+
+
+@pytest.mark.gpu
+def test_device_writer_error_paths(tmp_path):
+    """Argument and state errors of the two output entry points come back as AmpError, and the context stays usable."""
+    from amplipy_b200 import alnio
+    from amplipy_b200.engine import AmpError
+    g, prim, amps = _scheme(L=6000, n_amp=18)
+    b = synth.illumina_batch(g, amps, 4_000, seed=71)
+    raw = _bam_bytes(tmp_path, b, 6000)
+    lay = alnio.bam_layout(raw)
+    head = alnio._bam_header_bytes(lay["header_text"], lay["refs"])
+    from amplipy_b200.primers import find_overlapping_primers, max_primer_len
+    eng = make_engine(ref_len=6000, primer_tables=find_overlapping_primers(6000, prim, 0), max_primer_len=max_primer_len(prim))
+    with pytest.raises(AmpError):
+        eng._decoded = {"n": 0, "sum_cig": 0, "sum_seq": 0, "sum_qual": 0, "raw_bytes": 0}
+        eng.decoded_write_bam(head)                                   # nothing decoded yet
+    eng.decode_bam(raw, lay)
+    with pytest.raises(AmpError):
+        eng.decoded_write_bam(head)                                   # decoded but not trimmed
+    eng.process_decoded(trim=False, pileup=True)
+    with pytest.raises(AmpError):
+        eng.decoded_write_bam(head)                                   # pileup only: still no trim outputs
+    eng.process_decoded(trim=True, pileup=False, download=False)
+    data, nrec = eng.decoded_write_bam(head)
+    got = alnio._read_bam(data.tobytes())
+    assert got.n == nrec and 0 < nrec <= b.n
+    payload = np.arange(200_000, dtype=np.uint8)
+    with pytest.raises(AmpError):
+        eng.bgzf_deflate(payload, np.array([0, 100_000, 200_000], np.int64))          # blocks longer than 0xff00
+    with pytest.raises(AmpError):
+        eng.bgzf_deflate(payload, np.array([0, 50_000, 100_000], np.int64))           # table does not cover the data
+    out = eng.bgzf_deflate(payload, np.array([0, 50_000, 100_000, 150_000, 200_000], np.int64))
+    assert alnio.bgzf_decompress(out.tobytes()).tobytes() == payload.tobytes()
