@@ -399,19 +399,12 @@ __global__ void __launch_bounds__(256) amp_bgzf_pack_kernel(const uint8_t* in, c
 
 // ---- trimmed BAM records rebuilt on the device (what assigning cigartuples / reference_start does to a pysam segment before
 // out_aln.write, AmpliPy.py:463-514, 591-658, 911): everything but pos / bin / n_cigar / CIGAR is copied byte for byte ------------------
-__device__ __forceinline__ uint32_t ld_le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
-__device__ __forceinline__ uint32_t ld_le16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 // size of read i's record in the output (0: the read does not pass the write gate, AmpliPy.py:910)
 __global__ void amp_bam_newsize_kernel(const uint8_t* raw, const unsigned long long* rec_off, long long n, const uint16_t* o_ncig, const uint8_t* o_flags,
                                        uint32_t* sizes) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t sz = 0;
-    if (o_flags[i] & AMP_F_KEEP) {
-        const uint8_t* r = raw + rec_off[i];
-        sz = 4u + ld_le32(r) - 4u * ld_le16(r + 4 + 12) + 4u * (uint32_t)o_ncig[i];
-    }
-    sizes[i] = sz;
+    sizes[i] = (o_flags[i] & AMP_F_KEEP) ? amp::bam_new_record_size(raw, rec_off[i], (uint32_t)o_ncig[i]) : 0u;
 }
 // exclusive prefix sums of n 32-bit sizes (64-bit results, n + 1 of them), one CTA
 __global__ void __launch_bounds__(1024) amp_scan_sizes_kernel(const uint32_t* sizes, long long n, unsigned long long* off) {
@@ -432,15 +425,6 @@ __global__ void __launch_bounds__(1024) amp_scan_sizes_kernel(const uint32_t* si
     for (long long k = lo; k < hi; ++k) { off[k] = run; run += sizes[k]; }
     if (t == 1023) off[n] = part[1023];
 }
-__device__ __forceinline__ int reg2bin_dev(long long beg, long long end) {   // SAM spec 5.3
-    --end;
-    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
-    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
-    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
-    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
-    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
-    return 0;
-}
 // one warp per kept read: the record with its new block_size / pos / bin / n_cigar / CIGAR at out + off[i]
 __global__ void __launch_bounds__(256) amp_bam_rewrite_kernel(const uint8_t* raw, const unsigned long long* rec_off, long long n, const uint32_t* cig_off,
                                                              const int32_t* o_pos, const uint16_t* o_ncig, const uint32_t* o_cigar,
@@ -448,27 +432,7 @@ __global__ void __launch_bounds__(256) amp_bam_rewrite_kernel(const uint8_t* raw
     const int lane = threadIdx.x & 31;
     const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n || off[i + 1] == off[i]) return;
-    const uint8_t* r = raw + rec_off[i] + 4;
-    const uint32_t bs = ld_le32(r - 4), lname = r[8], nc_old = ld_le16(r + 12), nc_new = o_ncig[i], flag = ld_le16(r + 14);
-    const uint32_t nbs = bs - 4u * nc_old + 4u * nc_new;
-    uint8_t* w = out + off[i];
-    const uint32_t* cg = o_cigar + (size_t)cig_off[i] + 3 * (size_t)i;
-    const uint32_t head = 32u + lname, rest = bs - head - 4u * nc_old;
-    const uint8_t* tail = r + head + 4u * nc_old;
-    uint8_t* wt = w + 4 + head + 4u * nc_new;
-    for (uint32_t k = lane; k < head; k += 32) w[4 + k] = r[k];
-    for (uint32_t k = lane; k < rest; k += 32) wt[k] = tail[k];
-    for (uint32_t k = lane; k < 4u * nc_new; k += 32) w[4 + head + k] = (uint8_t)(cg[k >> 2] >> (8 * (k & 3)));
-    __syncwarp();
-    if (lane == 0) {
-        long long rlen = 0;
-        for (uint32_t c = 0; c < nc_new; ++c) { const uint32_t op = cg[c] & 15u; if ((0x18Du >> op) & 1u) rlen += cg[c] >> 4; }
-        if ((flag & 4u) || rlen == 0) rlen = 1;                                // htslib bam_endpos
-        const int32_t p = o_pos[i];
-        const uint32_t bin = (uint32_t)reg2bin_dev(p, p + rlen);
-        for (int b = 0; b < 4; ++b) { w[b] = (uint8_t)(nbs >> (8 * b)); w[8 + b] = (uint8_t)((uint32_t)p >> (8 * b)); }
-        w[14] = (uint8_t)bin; w[15] = (uint8_t)(bin >> 8); w[16] = (uint8_t)nc_new; w[17] = (uint8_t)(nc_new >> 8);
-    }
+    amp::bam_rewrite_record(raw, rec_off[i], o_pos[i], o_cigar + (size_t)cig_off[i] + 3 * (size_t)i, (uint32_t)o_ncig[i], out + off[i], lane);
 }
 
 // ---- BGZF / BAM decode on the device (amp_bgzf.cuh) ------------------------------------------------------------------------

@@ -364,4 +364,42 @@ AMP_WD void bam_scatter_block(const uint8_t* raw, long long lo, long long hi, co
     }
 }
 
+// ---- trimmed BAM records rebuilt from the inflated input (what assigning cigartuples / reference_start does to a pysam segment
+// before out_aln.write, AmpliPy.py:463-514, 591-658, 911): everything but block_size / pos / bin / n_cigar / CIGAR byte for byte ----
+AMP_HD int bam_reg2bin(long long beg, long long end) {   // SAM spec 5.3
+    --end;
+    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+    return 0;
+}
+// size of the record at raw + rec (its block_size word) once its CIGAR has nc_new ops
+AMP_HD uint32_t bam_new_record_size(const uint8_t* raw, unsigned long long rec, uint32_t nc_new) {
+    const uint8_t* r = raw + rec;
+    return 4u + ld_u32u(r) - 4u * ld_u16u(r + 4 + 12) + 4u * nc_new;
+}
+// one warp: the record at raw + rec with position new_pos and CIGAR cg[0, nc_new) written to w
+AMP_WD void bam_rewrite_record(const uint8_t* raw, unsigned long long rec, int32_t new_pos, const uint32_t* cg, uint32_t nc_new, uint8_t* w, int lane) {
+    const uint8_t* r = raw + rec + 4;
+    const uint32_t bs = ld_u32u(r - 4), lname = r[8], nc_old = ld_u16u(r + 12), flag = ld_u16u(r + 14);
+    const uint32_t nbs = bs - 4u * nc_old + 4u * nc_new;
+    const uint32_t head = 32u + lname, rest = bs - head - 4u * nc_old;
+    const uint8_t* tail = r + head + 4u * nc_old;
+    uint8_t* wt = w + 4 + head + 4u * nc_new;
+    for (uint32_t k = lane; k < head; k += 32) w[4 + k] = r[k];
+    for (uint32_t k = lane; k < rest; k += 32) wt[k] = tail[k];
+    for (uint32_t k = lane; k < 4u * nc_new; k += 32) w[4 + head + k] = (uint8_t)(cg[k >> 2] >> (8 * (k & 3)));
+    w_sync();
+    if (lane == 0) {
+        long long rlen = 0;
+        for (uint32_t c = 0; c < nc_new; ++c) { const uint32_t op = cg[c] & 15u; if ((0x18Du >> op) & 1u) rlen += cg[c] >> 4; }
+        if ((flag & 4u) || rlen == 0) rlen = 1;                                // htslib bam_endpos
+        const uint32_t bin = (uint32_t)bam_reg2bin(new_pos, new_pos + rlen);
+        for (int b = 0; b < 4; ++b) { w[b] = (uint8_t)(nbs >> (8 * b)); w[8 + b] = (uint8_t)((uint32_t)new_pos >> (8 * b)); }
+        w[14] = (uint8_t)bin; w[15] = (uint8_t)(bin >> 8); w[16] = (uint8_t)nc_new; w[17] = (uint8_t)(nc_new >> 8);
+    }
+}
+
 }  // namespace amp

@@ -406,6 +406,30 @@ void emu_bam_scatter(const uint8_t* raw, long long lo, long long hi, int32_t* po
     run_cta(0, 32, scatter_body, &j);
 }
 
+// ---- trimmed BAM records rebuilt (amp_bgzf.cuh bam_rewrite_record): one warp of fibers, the selected records one after the other ----
+struct RewriteJob { const uint8_t* raw; const unsigned long long* rec_off; const long long* sel; long long n_sel; const int32_t* new_pos;
+                    const uint16_t* new_ncig; const uint32_t* cig_off; const uint32_t* new_cigar; uint8_t* out; long long total; };
+static void rewrite_body(void* a) {
+    RewriteJob* j = (RewriteJob*)a;
+    const int lane = amp::c_tid() & 31;
+    long long o = 0;
+    for (long long k = 0; k < j->n_sel; ++k) {
+        const long long i = j->sel[k];
+        const uint32_t sz = amp::bam_new_record_size(j->raw, j->rec_off[i], j->new_ncig[i]);
+        if (j->out) amp::bam_rewrite_record(j->raw, j->rec_off[i], j->new_pos[i], j->new_cigar + (size_t)j->cig_off[i] + 3 * (size_t)i, j->new_ncig[i], j->out + o, lane);
+        o += sz;
+        amp::w_sync();
+    }
+    if (lane == 0) j->total = o;
+}
+// same contract as amp_bam_rewrite of amp_hostio.cpp (out = NULL: size only)
+long long emu_bam_rewrite(const uint8_t* raw, const unsigned long long* rec_off, const long long* sel, long long n_sel, const int32_t* new_pos,
+                          const uint16_t* new_ncig, const uint32_t* cig_off, const uint32_t* new_cigar, uint8_t* out) {
+    RewriteJob j{raw, rec_off, sel, n_sel, new_pos, new_ncig, cig_off, new_cigar, out, 0};
+    run_cta(0, 32, rewrite_body, &j);
+    return j.total;
+}
+
 // ---- BGZF deflate kernel (amp_deflate.cuh): one warp of fibers per block ------------------------------------------------------------
 struct DeflateJob { const uint8_t* in; int n; uint32_t* out; int cap_words; amp::DeflateMem* mem; amp::DeflateTables* tab; int bytes; uint32_t crc; };
 static void deflate_body(void* a) {

@@ -131,3 +131,36 @@ def test_bam_chain_and_scatter_match_the_host_decoder(tmp_path):
     for f in ("pos", "flag", "tlen", "cig_off", "cigar", "seq_off", "seq", "qual_off", "qual"):
         assert np.array_equal(got[f], getattr(a.batch, f)), f
     assert np.array_equal(got["rec_off"].astype(np.int64), a.bam_rec_off)
+
+
+def test_record_rewrite_matches_the_host_writer(oracle_lib, tmp_path):
+    """bam_rewrite_record (what amp_decoded_write_bam runs a warp per kept read) against amp_bam_rewrite of the host codec: trimmed
+    positions / CIGARs from the oracle patched into the records of a BAM stream, byte for byte."""
+    import os
+    from oracle import oracle
+    from amplipy_b200.primers import find_overlapping_primers, max_primer_len
+    L = 3000
+    g = synth.random_genome(L, 3)
+    primers, amps = synth.make_scheme(L, 8, seed=2)
+    prim = [(s, e) for s, e, _ in primers]
+    lib = emu_driver.lib()
+    lib.emu_bam_rewrite.restype = ctypes.c_longlong
+    host = alnio.hostio()
+    for b in (synth.illumina_batch(g, amps, 600, seed=8, p_ins=0.2, p_del=0.2, p_clip=0.3, p_hard=0.2), synth.ont_batch(g, amps, 60, seed=9)):
+        path = os.path.join(str(tmp_path), "x%d.bam" % b.n)
+        alnio.write_bam(path, "@HD\tVN:1.6\n@SQ\tSN:ref\tLN:%d\n@PG\tID:s\tPN:s\n" % L, [("ref", L)], b)
+        a = alnio._read_bam(open(path, "rb").read())
+        mn, mx = oracle.find_overlapping_primers(L, prim, 0)
+        t = oracle.trim_batch(b, L, mn, mx, max_primer_len(prim))
+        keep = (t["flags"] & 8) != 0
+        sel = np.flatnonzero(keep).astype(np.int64)
+        assert 0 < sel.size < b.n
+        p = lambda x: ctypes.c_void_p(x.ctypes.data)
+        pos, ncig, cig = np.ascontiguousarray(t["pos"], np.int32), np.ascontiguousarray(t["ncig"], np.uint16), np.ascontiguousarray(t["cigar"], np.uint32)
+        size = host.amp_bam_rewrite(p(a.bam_buf), p(a.bam_rec_off), p(sel), ctypes.c_longlong(sel.size), p(pos), p(ncig), p(b.cig_off), p(cig), None)
+        want = np.zeros(size + 8, np.uint8)
+        host.amp_bam_rewrite(p(a.bam_buf), p(a.bam_rec_off), p(sel), ctypes.c_longlong(sel.size), p(pos), p(ncig), p(b.cig_off), p(cig), p(want))
+        rec_off = a.bam_rec_off.astype(np.uint64)
+        got = np.full(size + 8, 0xEE, np.uint8)
+        n = lib.emu_bam_rewrite(p(a.bam_buf), p(rec_off), p(sel), ctypes.c_longlong(sel.size), p(pos), p(ncig), p(b.cig_off), p(cig), p(got))
+        assert n == size and np.array_equal(got[:size], want[:size]) and (got[size:] == 0xEE).all()
