@@ -691,3 +691,46 @@ def test_device_writer_error_paths(tmp_path):
         eng.bgzf_deflate(payload, np.array([0, 50_000, 100_000], np.int64))           # table does not cover the data
     out = eng.bgzf_deflate(payload, np.array([0, 50_000, 100_000, 150_000, 200_000], np.int64))
     assert alnio.bgzf_decompress(out.tobytes()).tobytes() == payload.tobytes()
+
+
+@pytest.mark.gpu
+def test_device_bam_with_a_header_longer_than_a_block(tmp_path, monkeypatch):
+    """4,000 reference sequences: the BAM header spans two BGZF blocks, the first record starts in the middle of one.  Device
+    decode == host decode, and the device writer's file (header cut across blocks again) reads back with the same records."""
+    import os
+    from amplipy_b200 import alnio, cli
+    g, prim, amps = _scheme(L=6000, n_amp=18)
+    b = synth.illumina_batch(g, amps, 20_000, seed=81)
+    refs = [("ref", 6000)] + [("decoy_%05d_with_a_long_name" % k, 1000 + k) for k in range(4000)]
+    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % r for r in refs) + "@PG\tID:synth\tPN:synth\n"
+    d = str(tmp_path)
+    j = lambda n: os.path.join(d, n)
+    alnio.write_bam(j("in.bam"), text, refs, b)
+    raw = open(j("in.bam"), "rb").read()
+    lay = alnio.bam_layout(raw)
+    assert lay["body_off"] > 0xff00 and len(lay["refs"]) == 4001
+    a = alnio._read_bam(raw)
+    eng = make_engine(ref_len=6000)
+    info = eng.decode_bam(raw, lay)
+    got, rec_off = eng.decoded_batch()
+    assert info["n"] == b.n
+    for f in ("pos", "flag", "tlen", "cig_off", "cigar", "seq_off", "seq", "qual_off", "qual"):
+        assert np.array_equal(getattr(got, f), getattr(a.batch, f)), f
+    assert np.array_equal(rec_off.astype(np.int64), a.bam_rec_off)
+    with open(j("p.bed"), "w") as f:
+        for k, (s, e) in enumerate(prim):
+            f.write("ref\t%d\t%d\tp%d\n" % (s, e, k))
+    with open(j("ref.fas"), "w") as f:
+        f.write(">ref\n%s\n" % g)
+    monkeypatch.delenv("AMPLIPY_BAM_LEVEL", raising=False)
+    cli.main(["trim", "-i", j("in.bam"), "-p", j("p.bed"), "-r", j("ref.fas"), "-o", j("dev.bam")])
+    monkeypatch.setenv("AMPLIPY_BAM_LEVEL", "6")
+    cli.main(["trim", "-i", j("in.bam"), "-p", j("p.bed"), "-r", j("ref.fas"), "-o", j("zlib.bam")])
+    x, z = alnio.read_alignments(j("dev.bam")), alnio.read_alignments(j("zlib.bam"))
+    assert x.n == z.n and x.n > 0 and x.refs == z.refs and len(x.refs) == 4001
+    for f in ("pos", "flag", "tlen", "cig_off", "cigar", "seq_off", "seq", "qual_off", "qual"):
+        assert np.array_equal(getattr(x.batch, f), getattr(z.batch, f)), f
+    # and the device decoder reads the device writer's file
+    out = open(j("dev.bam"), "rb").read()
+    info2 = eng.decode_bam(out, alnio.bam_layout(out))
+    assert info2["n"] == x.n
