@@ -344,11 +344,11 @@ __global__ void amp_ins_merge_packed_kernel(amp::InsTable tab, const unsigned lo
 }
 
 // ---- BGZF deflate on the device (amp_deflate.cuh) --------------------------------------------------------------------------
-#define AMPD_WARPS 24
+#define AMPD_WARPS 20
 // block k = in[bstart[k], bstart[k + 1]) -> a deflate stream in slot k (clen[k] = its bytes, 0xFFFFFFFF: did not shrink, to be stored)
 // and its CRC-32; the warps take blocks from a counter
 __global__ void __launch_bounds__(AMPD_WARPS * 32) amp_bgzf_deflate_kernel(const uint8_t* in, const long long* bstart, long long nb, uint8_t* slots,
-                                                                          uint32_t* clen, uint32_t* crc, unsigned int* next) {
+                                                                          uint32_t* clen, uint32_t* crc, unsigned int* next, uint32_t* toks) {
     extern __shared__ __align__(16) unsigned char dsm[];
     amp::DeflateTables& T = *(amp::DeflateTables*)dsm;
     amp::DeflateMem& M = ((amp::DeflateMem*)(dsm + ((sizeof(amp::DeflateTables) + 15) & ~(size_t)15)))[threadIdx.x >> 5];
@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(AMPD_WARPS * 32) amp_bgzf_deflate_kernel(const
         const uint8_t* src = in + bstart[k];
         const int n = (int)(bstart[k + 1] - bstart[k]);
         const int cap_words = (n + 3) / 4;                                // "does not shrink" = would need more words than the input has
-        int bytes = n >= 16 ? amp::deflate_block(src, n, M, T, (uint32_t*)(slots + (size_t)k * AMPD_SLOT), cap_words, lane) : -1;
+        uint32_t* tok = toks + ((size_t)blockIdx.x * AMPD_WARPS + (threadIdx.x >> 5)) * AMPD_TOKCAP;
+        int bytes = n >= 16 ? amp::deflate_block(src, n, M, T, (uint32_t*)(slots + (size_t)k * AMPD_SLOT), cap_words, tok, lane) : -1;
         if (bytes >= n + 5) bytes = -1;
         const uint32_t cr = amp::crc32_block(src, n, T, mcol, lane);
         if (lane == 0) { clen[k] = bytes < 0 ? 0xFFFFFFFFu : (uint32_t)bytes; crc[k] = cr; }
@@ -562,6 +563,7 @@ struct amp_ctx {
         uint8_t* in = nullptr; size_t cap_in = 0; uint8_t* slots = nullptr; size_t cap_slots = 0; uint8_t* out = nullptr; size_t cap_out = 0;
         long long* bstart = nullptr; size_t cap_bstart = 0; long long* off = nullptr; size_t cap_off = 0;
         uint32_t* clen = nullptr; size_t cap_clen = 0; uint32_t* crc = nullptr; size_t cap_crc = 0; unsigned int* ctr = nullptr;
+        uint32_t* toks = nullptr; size_t cap_toks = 0;           // token scratch of the deflate kernel's warps
         bool attr = false; cudaStream_t stream = nullptr;            // its own stream: a writer thread may call it while the context calls
     } defl;
     unsigned char* d_xbuf = nullptr; size_t xbuf_bytes = 0;   // scratch of amp_ins_export / amp_ins_merge (grown at high-water marks)
@@ -775,7 +777,7 @@ int amp_destroy(amp_ctx* c) {
     if (c->counts_owned) cudaFree(c->d_counts);
     cudaFree(c->tab.slots); cudaFree(c->tab.entries); cudaFree(c->tab.slot_entry); cudaFree(c->tab.arena); cudaFree(c->tab.cursor);
     if (c->defl.stream) cudaStreamDestroy(c->defl.stream);
-    cudaFree(c->defl.in); cudaFree(c->defl.slots); cudaFree(c->defl.out); cudaFree(c->defl.bstart); cudaFree(c->defl.off); cudaFree(c->defl.clen); cudaFree(c->defl.crc); cudaFree(c->defl.ctr);
+    cudaFree(c->defl.in); cudaFree(c->defl.slots); cudaFree(c->defl.out); cudaFree(c->defl.bstart); cudaFree(c->defl.off); cudaFree(c->defl.clen); cudaFree(c->defl.crc); cudaFree(c->defl.ctr); cudaFree(c->defl.toks);
     cudaFree(c->d_err); cudaFree(c->d_heads); cudaFree(c->d_scratch); cudaFree(c->d_glist); cudaFree(c->d_ref); cudaFree(c->d_call); cudaFree(c->d_xbuf);
     {
         auto& d = c->dec;
@@ -1152,7 +1154,8 @@ static int64_t deflate_device(amp_ctx* c, const uint8_t* d_in, int64_t n_bytes, 
     CK(cudaMemcpyAsync(d.bstart, bstart, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d.ctr, 0, 16, st));
     const int grid = (int)std::min<int64_t>((n_blocks + AMPD_WARPS - 1) / AMPD_WARPS, (int64_t)c->sm_count);
-    amp_bgzf_deflate_kernel<<<grid, AMPD_WARPS * 32, smem, st>>>(d_in, d.bstart, n_blocks, d.slots, d.clen, d.crc, d.ctr);
+    if ((rc = dev_grow(&d.toks, &d.cap_toks, (size_t)grid * AMPD_WARPS * AMPD_TOKCAP))) return rc;
+    amp_bgzf_deflate_kernel<<<grid, AMPD_WARPS * 32, smem, st>>>(d_in, d.bstart, n_blocks, d.slots, d.clen, d.crc, d.ctr, d.toks);
     CK(cudaGetLastError());
     std::vector<uint32_t> clen((size_t)n_blocks);
     CK(cudaMemcpyAsync(clen.data(), d.clen, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, st));

@@ -22,9 +22,19 @@ namespace amp {
 #define AMPD_MAXBLOCK 0xff00          // BGZF payload limit used by htslib
 #define AMPD_SLOT (AMPD_MAXBLOCK + 256)   // bytes of scratch per block for the compressed stream (multiple of 4)
 
-struct DeflateMem { int htab[1 << AMPD_HBITS]; };               // per warp: most recent position of a hash within the block
+#define AMPD_TOKCAP 8192              // tokens of one deflate block (a BGZF block becomes a few of them, each with its own code)
+struct DeflateMem {                                             // per warp
+    int htab[1 << AMPD_HBITS];                                  // most recent position of a hash within the BGZF block
+    uint32_t work[288];                                         // code construction: frequencies -> lengths in place; then the codes (u16)
+    uint16_t lfreq[288], dfreq[32];                             // symbol frequencies of the open deflate block
+    uint16_t order[288];                                        // symbols by ascending frequency
+    uint8_t llen[288], dlen[32], clen[20];                      // code lengths: literal / length, distance, code-length code
+    uint16_t cfreq[20];                                         // frequencies of the code lengths themselves
+};
+// token: literal = the byte; match = 1 << 31 | length symbol index << 26 | distance symbol << 21 | length extra << 16 | distance extra
 struct DeflateTables {                                          // per CTA
     uint32_t len_code[260];           // [len 3..258]: fixed code of the length symbol + its extra bits (LSB first) | bit count << 16
+    uint16_t len_info[260];           // [len 3..258]: index of the length symbol (0..28) | its extra-bit value << 8
     uint32_t crc_tab[256];
     uint16_t lit_code[256];           // bit-reversed fixed code of a literal (8 bits below 144, 9 from there)
 };
@@ -48,7 +58,8 @@ AMP_WD void deflate_tables_init(DeflateTables& T, int tid, int nthreads) {
             const int nb = sym <= 279 ? 7 : 8;
             const uint32_t code = sym <= 279 ? bit_reverse((uint32_t)(sym - 256), 7) : bit_reverse(0xC0u + (uint32_t)(sym - 280), 8);
             v = (code | ((uint32_t)(len - kLenBase[idx]) << nb)) | ((uint32_t)(nb + eb) << 16);
-        }
+            T.len_info[len] = (uint16_t)(idx | ((len - kLenBase[idx]) << 8));
+        } else T.len_info[len] = 0;
         T.len_code[len] = v;
     }
 }
@@ -78,14 +89,143 @@ AMP_WD int match_length(const uint8_t* in, int c, int p, int n) {
     return k < maxl ? k : maxl;
 }
 
-// One block by one warp: in[0, n) (n <= AMPD_MAXBLOCK, readable up to in + n + 8) -> a complete deflate stream (one final block,
-// fixed Huffman) in out32[0 ...]; returns its length in bytes, or -1 when it would not fit cap_words 32-bit words.
-AMP_WD int deflate_block(const uint8_t* in, int n, DeflateMem& M, const DeflateTables& T, uint32_t* out32, int cap_words, int lane) {
+// ---- code construction ---------------------------------------------------------------------------------------------------------
+// Code lengths (at most maxlen) of the symbols with freq[i] > 0 among n_sym, into len[] (0 = unused); at least two symbols get a
+// code (as zlib does, so that no special cases are left for the decoder).  All lanes call; freq / len / M in shared memory.
+// Ranking by (frequency, symbol) across the lanes, then the in-place minimum-redundancy algorithm of Moffat and Katajainen on the
+// sorted frequencies by lane 0; a code that comes out too long is recomputed from halved frequencies.
+AMP_WD void huff_lengths(uint16_t* freq, int n_sym, int maxlen, uint8_t* len, DeflateMem& M, int lane) {
+    if (lane == 0) {
+        int used = 0, which = -1;
+        for (int i = 0; i < n_sym; ++i) if (freq[i]) { ++used; which = i; }
+        if (used == 0) { freq[0] = 1; freq[1] = 1; }
+        else if (used == 1) freq[which == 0 ? 1 : 0] = 1;
+    }
+    w_sync();
+    int mine = 0;
+    for (int i = lane; i < n_sym; i += 32) {
+        len[i] = 0;
+        const unsigned f = freq[i];
+        if (!f) continue;
+        int rank = 0;
+        for (int j = 0; j < n_sym; ++j) { const unsigned g = freq[j]; if (g && (g < f || (g == f && j < i))) ++rank; }
+        M.order[rank] = (uint16_t)i;
+        ++mine;
+    }
+    const int n = w_add(mine);
+    w_sync();
+    if (lane == 0) {
+        uint32_t* A = M.work;
+        for (int shift = 0;; ++shift) {
+            for (int k = 0; k < n; ++k) { const uint32_t f = (uint32_t)freq[M.order[k]] >> shift; A[k] = f ? f : 1u; }
+            // first pass, left to right: parent pointers
+            A[0] += A[1];
+            int root = 0, leaf = 2;
+            for (int next = 1; next < n - 1; ++next) {
+                if (leaf >= n || A[root] < A[leaf]) { A[next] = A[root]; A[root++] = (uint32_t)next; } else A[next] = A[leaf++];
+                if (leaf >= n || (root < next && A[root] < A[leaf])) { A[next] += A[root]; A[root++] = (uint32_t)next; } else A[next] += A[leaf++];
+            }
+            // second pass, right to left: depths of the internal nodes
+            A[n - 2] = 0;
+            for (int next = n - 3; next >= 0; --next) A[next] = A[A[next]] + 1;
+            // third pass, right to left: depths of the leaves
+            int avbl = 1, used = 0, dpth = 0, next = n - 1;
+            root = n - 2;
+            while (avbl > 0) {
+                while (root >= 0 && (int)A[root] == dpth) { ++used; --root; }
+                while (avbl > used) { A[next--] = (uint32_t)dpth; --avbl; }
+                avbl = 2 * used; ++dpth; used = 0;
+            }
+            if ((int)A[0] <= maxlen) break;
+        }
+        for (int k = 0; k < n; ++k) len[M.order[k]] = (uint8_t)A[k];
+    }
+    w_sync();
+}
+// canonical codes of the lengths len[0, n), bit-reversed (deflate packs codes starting from their most significant bit); lane 0
+AMP_WD void huff_codes(const uint8_t* len, int n, uint16_t* code) {
+    int count[16], next[16];
+    for (int l = 0; l < 16; ++l) count[l] = 0;
+    for (int i = 0; i < n; ++i) ++count[len[i] & 15];
+    count[0] = 0;
+    int c = 0;
+    for (int l = 1; l < 16; ++l) { c = (c + count[l - 1]) << 1; next[l] = c; }
+    for (int i = 0; i < n; ++i) code[i] = len[i] ? (uint16_t)bit_reverse((uint32_t)next[len[i]]++, len[i]) : (uint16_t)0;
+}
+
+// The open deflate block (ntok tokens in tok[], their frequencies in M) written out: the code is built from the frequencies, or the
+// fixed code of RFC 1951 3.2.6 is used where that is shorter; `last` sets BFINAL.  xbits = extra bits of the tokens.  All lanes call;
+// returns false (warp-uniform) when the block does not fit cap_words.  Leaves the frequencies cleared.
+AMP_WD bool deflate_flush(DeflateMem& M, const uint32_t* tok, int ntok, int xbits, bool last, BitWriter& bw, int cap_words, int lane) {
+    if (lane == 0) ++M.lfreq[256];                                             // end of block
+    w_sync();
+    huff_lengths(M.lfreq, 286, 15, M.llen, M, lane);
+    huff_lengths(M.dfreq, 30, 15, M.dlen, M, lane);
+    int hlit = 0, hdist = 0;
+    bool dyn = false, fits = true;
+    if (lane == 0) {
+        hlit = 286; while (hlit > 257 && !M.llen[hlit - 1]) --hlit;
+        hdist = 30; while (hdist > 1 && !M.dlen[hdist - 1]) --hdist;
+        for (int v = 0; v < 19; ++v) M.cfreq[v] = 0;
+        for (int i = 0; i < hlit; ++i) ++M.cfreq[M.llen[i]];
+        for (int i = 0; i < hdist; ++i) ++M.cfreq[M.dlen[i]];
+    }
+    w_sync();
+    huff_lengths(M.cfreq, 19, 7, M.clen, M, lane);
+    if (lane == 0) {
+        long long cdyn = 3 + 14 + 19 * 3, cfix = 3;
+        for (int v = 0; v < 19; ++v) cdyn += (long long)M.cfreq[v] * M.clen[v];
+        for (int i = 0; i < 286; ++i) { cdyn += (long long)M.lfreq[i] * M.llen[i]; cfix += (long long)M.lfreq[i] * (i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8); }
+        for (int i = 0; i < 30; ++i) { cdyn += (long long)M.dfreq[i] * M.dlen[i]; cfix += (long long)M.dfreq[i] * 5; }
+        dyn = cdyn < cfix;
+        const long long bits = (dyn ? cdyn : cfix) + xbits;
+        fits = 4LL * bw.w + (bits >> 3) + 64 <= 4LL * cap_words;
+        if (fits) {
+            uint16_t* lcode = (uint16_t*)M.work; uint16_t* dcode = lcode + 288; uint16_t* ccode = dcode + 32;
+            bw_put(bw, last ? 1u : 0u, 1);
+            if (dyn) {
+                M.llen[286] = 0; M.llen[287] = 0; M.dlen[30] = 0; M.dlen[31] = 0;     // (symbols that cannot occur; huff_lengths leaves them alone)
+                bw_put(bw, 2u, 2);
+                bw_put(bw, (uint32_t)(hlit - 257), 5); bw_put(bw, (uint32_t)(hdist - 1), 5); bw_put(bw, 15u, 4);
+                for (int k = 0; k < 19; ++k) bw_put(bw, M.clen[kClOrder[k]], 3);
+                huff_codes(M.clen, 19, ccode);
+                for (int i = 0; i < hlit; ++i) bw_put(bw, ccode[M.llen[i]], M.clen[M.llen[i]]);
+                for (int i = 0; i < hdist; ++i) bw_put(bw, ccode[M.dlen[i]], M.clen[M.dlen[i]]);
+            } else {
+                bw_put(bw, 1u, 2);
+                for (int i = 0; i < 288; ++i) M.llen[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
+                for (int i = 0; i < 32; ++i) M.dlen[i] = 5;
+            }
+            huff_codes(M.llen, 288, lcode);
+            huff_codes(M.dlen, 32, dcode);
+            for (int t = 0; t < ntok; ++t) {
+                const uint32_t k = tok[t];
+                if (!(k >> 31)) { bw_put(bw, lcode[k], M.llen[k]); continue; }
+                const uint32_t idx = (k >> 26) & 31u, ds = (k >> 21) & 31u, lx = (k >> 16) & 31u, dx = k & 0x1FFFu;
+                const int ll = M.llen[257 + idx], dl = M.dlen[ds];
+                bw_put(bw, lcode[257 + idx] | (lx << ll), ll + kLenExtra[idx]);
+                bw_put(bw, dcode[ds] | (dx << dl), dl + (ds < 4u ? 0 : (int)(ds >> 1) - 1));
+            }
+            bw_put(bw, lcode[256], M.llen[256]);
+        }
+    }
+    w_sync();
+    for (int i = lane; i < 288; i += 32) M.lfreq[i] = 0;
+    if (lane < 32) M.dfreq[lane] = 0;
+    w_sync();
+    return w_shfl(fits ? 1 : 0, 0) != 0;
+}
+
+// One BGZF block by one warp: in[0, n) (n <= AMPD_MAXBLOCK, readable up to in + n + 8) -> a complete deflate stream in out32[0 ...]
+// (deflate blocks of up to AMPD_TOKCAP tokens, each with the shorter of its own and the fixed code); tok = AMPD_TOKCAP words of
+// scratch in global memory.  Returns the stream's length in bytes, or -1 when it would not fit cap_words 32-bit words.
+AMP_WD int deflate_block(const uint8_t* in, int n, DeflateMem& M, const DeflateTables& T, uint32_t* out32, int cap_words, uint32_t* tok, int lane) {
     for (int i = lane; i < (1 << AMPD_HBITS); i += 32) M.htab[i] = 0;
+    for (int i = lane; i < 288; i += 32) M.lfreq[i] = 0;
+    M.dfreq[lane] = 0;
     w_sync();
     BitWriter bw; bw.acc = 0; bw.n = 0; bw.out = out32; bw.w = 0;
-    if (lane == 0) { bw_put(bw, 1u, 1); bw_put(bw, 1u, 2); }                 // BFINAL = 1, BTYPE = 01
-    int cursor = 0;
+    int cursor = 0, ntok = 0, xbits = 0;
     for (int base = 0; base < n; base += 32) {
         const int p = base + lane;
         int L = 0, D = 0;
@@ -104,7 +244,7 @@ AMP_WD int deflate_block(const uint8_t* in, int n, DeflateMem& M, const DeflateT
                 if (l1 > L) { L = l1; D = 1; }
             }
         }
-        // greedy selection over the group, in order; lane 0 writes the tokens
+        // greedy selection over the group, in order; lane 0 records the tokens
         int s = cursor - base;
         const int lim = n - base < 32 ? n - base : 32;
         while (s < lim) {
@@ -112,26 +252,30 @@ AMP_WD int deflate_block(const uint8_t* in, int n, DeflateMem& M, const DeflateT
             if (Ls >= 4) {
                 const int Ds = w_shfl(D, s);
                 if (lane == 0) {
-                    const uint32_t lc = T.len_code[Ls];
-                    bw_put(bw, lc & 0xFFFFu, (int)(lc >> 16));
+                    const uint32_t info = T.len_info[Ls], idx = info & 0xFFu, lx = info >> 8;
                     const uint32_t d = (uint32_t)Ds - 1u;
                     uint32_t sym = d, extra = 0; int eb = 0;
                     if (d >= 4u) { const int t = msb32(d); eb = t - 1; sym = 2u * (uint32_t)t + ((d >> eb) & 1u); extra = d & ((1u << eb) - 1u); }
-                    bw_put(bw, bit_reverse(sym, 5) | (extra << 5), 5 + eb);
+                    tok[ntok++] = 0x80000000u | (idx << 26) | (sym << 21) | (lx << 16) | extra;
+                    ++M.lfreq[257 + idx]; ++M.dfreq[sym];
+                    xbits += kLenExtra[idx] + eb;
                 }
                 s += Ls;
             } else {
                 const int b = w_shfl((int)(w & 0xFFu), s);
-                if (lane == 0) bw_put(bw, T.lit_code[b], b < 144 ? 8 : 9);
+                if (lane == 0) { tok[ntok++] = (uint32_t)b; ++M.lfreq[b]; }
                 s += 1;
             }
         }
         cursor = base + s;
-        if (w_shfl(bw.w, 0) + 40 > cap_words) return -1;                       // a group writes at most 32 tokens of <= 31 bits
+        if (w_shfl(ntok, 0) > AMPD_TOKCAP - 32) {                              // (a group adds at most 32 tokens)
+            if (!deflate_flush(M, tok, ntok, xbits, false, bw, cap_words, lane)) return -1;
+            ntok = 0; xbits = 0;
+        }
     }
+    if (!deflate_flush(M, tok, ntok, xbits, true, bw, cap_words, lane)) return -1;
     int bytes = 0;
     if (lane == 0) {
-        bw_put(bw, 0u, 7);                                                     // end of block (symbol 256)
         bytes = 4 * bw.w + ((bw.n + 7) >> 3);
         if (bw.n > 0) bw.out[bw.w] = (uint32_t)bw.acc;
     }

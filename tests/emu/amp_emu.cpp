@@ -438,7 +438,8 @@ static void deflate_body(void* a) {
     amp::deflate_tables_init(*j->tab, amp::c_tid(), amp::c_nthreads());
     amp::c_sync();
     const uint32_t mcol = amp::crc_shift_column(*j->tab, lane);
-    const int bytes = j->n >= 16 ? amp::deflate_block(j->in, j->n, *j->mem, *j->tab, j->out, j->cap_words, lane) : -1;
+    static uint32_t tok[AMPD_TOKCAP];
+    const int bytes = j->n >= 16 ? amp::deflate_block(j->in, j->n, *j->mem, *j->tab, j->out, j->cap_words, tok, lane) : -1;
     const uint32_t crc = amp::crc32_block(j->in, j->n, *j->tab, mcol, lane);
     if (lane == 0) { j->bytes = bytes; j->crc = crc; }
 }
@@ -446,6 +447,7 @@ static void deflate_body(void* a) {
 // in bytes or -1 (does not fit / too short to bother); *crc = CRC-32 of the input
 int emu_deflate(const uint8_t* in, int n, uint32_t* out, int cap_words, uint32_t* crc) {
     amp::DeflateMem mem; amp::DeflateTables tab;
+    memset(&mem, 0xAB, sizeof mem); memset(&tab, 0xAB, sizeof tab);     // shared memory starts out with whatever the last kernel left
     DeflateJob j{in, n, out, cap_words, &mem, &tab, 0, 0};
     run_cta(0, 32, deflate_body, &j);
     *crc = j.crc;
