@@ -5,12 +5,14 @@
 //   deflate_block   LZ77 with a 4-byte hash (most recent occurrence per hash -- atomicMax, so the result does not depend on which lane
 //                   wins a collision -- 8 KB of shared memory per warp) plus the distance-1
 //                   candidate (runs); the lanes test 32 consecutive positions at a time, each extending its own match word-wise;
-//                   the greedy selection then walks the group (warp-uniform) and lane 0 emits the tokens with the FIXED Huffman
-//                   code of RFC 1951 3.2.6 (no code construction; tables of ready-made, bit-reversed codes in shared memory)
+//                   the greedy selection then walks the group (warp-uniform) and lane 0 records the tokens; every AMPD_TOKCAP tokens
+//                   become one deflate block with a Huffman code of their own (huff_lengths: frequency ranking across the lanes, then
+//                   the in-place minimum-redundancy algorithm, length-limited by halving) or the fixed code of RFC 1951 3.2.6,
+//                   whichever is shorter
 //   crc32_block     the CRC-32 of the BGZF footer: the lanes take 2 KB segments, the segment CRCs are combined with the
 //                   "advance by 2 KB of zeros" operator, whose 32 columns the lanes compute once per warp
 // The output is any valid deflate stream (RFC 1951 leaves the choice of matches to the compressor): larger than zlib level 6,
-// about the size of level 1, at a small fraction of its time.  A block that does not shrink is stored (BTYPE 00) by the caller.
+// a little smaller than level 1, at a small fraction of its time.  A block that does not shrink is stored (BTYPE 00) by the caller.
 // Written with the warp primitives of amp_warp.cuh so that tests/emu runs the same source on the CPU (checked against zlib).
 #pragma once
 #include "amp_bgzf.cuh"

@@ -291,7 +291,7 @@ def file_to_file(args, g, prim, b, runs=3):
                 "bam_decode_only_reads_per_s": b.n / t_decode,
                 "bam_bytes": os.path.getsize(j("in.bam")), "trimmed_bam_bytes": size_dev, "host_zlib_level_6": host_obj,
                 "note": "python -m amplipy_b200 aio on files in a temp directory (page cache warm), best of %d: the BAM is inflated, "
-                        "trimmed, rebuilt and deflated on the GPU (fixed-Huffman deflate, about the size of zlib level 1); "
+                        "trimmed, rebuilt and deflated on the GPU (the device compressor writes files a little smaller than zlib level 1); "
                         "the reference's counterpart is AmpliPy.py aio with pysam I/O" % runs}
     finally:
         shutil.rmtree(d, ignore_errors=True)

@@ -204,8 +204,9 @@ int amp_decoded_copy_host(amp_ctx* ctx, const amp_batch_out* host_arrays, uint64
 /* ---- BGZF deflate on the device (replaces the zlib deflate behind out_aln.write, AmpliPy.py:911).
  * host data -> BGZF blocks: block k = in[bstart[k], bstart[k + 1]) (bstart has n_blocks + 1 entries, bstart[0] = 0, the last one =
  * n_bytes, every block at most 0xff00 bytes -- the caller cuts at record boundaries as htslib does), followed by the EOF block.
- * One warp per block: LZ77 (4-byte hash + run candidate) and the fixed Huffman code, CRC-32 and ISIZE in the footer; a block that
- * does not shrink is stored.  Any inflater reads the result; it is about the size of zlib level 1.
+ * One warp per block: LZ77 (4-byte hash + run candidate), a Huffman code built for every 8 k tokens (or the fixed code where that is
+ * shorter), CRC-32 and ISIZE in the footer; a block that does not shrink is stored.  Any inflater reads the result; it is a little
+ * smaller than zlib level 1 writes.
  * out must hold n_bytes + 31 * n_blocks + 28 bytes.  Returns the number of bytes written, or a negative AMP_ERR_* code. */
 int64_t amp_bgzf_deflate_host(amp_ctx* ctx, const uint8_t* in, int64_t n_bytes, const int64_t* bstart, int64_t n_blocks, uint8_t* out,
                               int64_t out_cap);
