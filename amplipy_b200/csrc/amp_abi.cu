@@ -344,7 +344,7 @@ __global__ void amp_ins_merge_packed_kernel(amp::InsTable tab, const unsigned lo
 }
 
 // ---- BGZF deflate on the device (amp_deflate.cuh) --------------------------------------------------------------------------
-#define AMPD_WARPS 20
+#define AMPD_WARPS 24
 // block k = in[bstart[k], bstart[k + 1]) -> a deflate stream in slot k (clen[k] = its bytes, 0xFFFFFFFF: did not shrink, to be stored)
 // and its CRC-32; the warps take blocks from a counter
 __global__ void __launch_bounds__(AMPD_WARPS * 32) amp_bgzf_deflate_kernel(const uint8_t* in, const long long* bstart, long long nb, uint8_t* slots,
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(AMPD_WARPS * 32) amp_bgzf_deflate_kernel(const
         const uint8_t* src = in + bstart[k];
         const int n = (int)(bstart[k + 1] - bstart[k]);
         const int cap_words = (n + 3) / 4;                                // "does not shrink" = would need more words than the input has
-        uint32_t* tok = toks + ((size_t)blockIdx.x * AMPD_WARPS + (threadIdx.x >> 5)) * AMPD_TOKCAP;
+        uint32_t* tok = toks + ((size_t)blockIdx.x * AMPD_WARPS + (threadIdx.x >> 5)) * AMPD_SCRATCH;
         int bytes = n >= 16 ? amp::deflate_block(src, n, M, T, (uint32_t*)(slots + (size_t)k * AMPD_SLOT), cap_words, tok, lane) : -1;
         if (bytes >= n + 5) bytes = -1;
         const uint32_t cr = amp::crc32_block(src, n, T, mcol, lane);
@@ -1154,7 +1154,7 @@ static int64_t deflate_device(amp_ctx* c, const uint8_t* d_in, int64_t n_bytes, 
     CK(cudaMemcpyAsync(d.bstart, bstart, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d.ctr, 0, 16, st));
     const int grid = (int)std::min<int64_t>((n_blocks + AMPD_WARPS - 1) / AMPD_WARPS, (int64_t)c->sm_count);
-    if ((rc = dev_grow(&d.toks, &d.cap_toks, (size_t)grid * AMPD_WARPS * AMPD_TOKCAP))) return rc;
+    if ((rc = dev_grow(&d.toks, &d.cap_toks, (size_t)grid * AMPD_WARPS * AMPD_SCRATCH))) return rc;
     amp_bgzf_deflate_kernel<<<grid, AMPD_WARPS * 32, smem, st>>>(d_in, d.bstart, n_blocks, d.slots, d.clen, d.crc, d.ctr, d.toks);
     CK(cudaGetLastError());
     std::vector<uint32_t> clen((size_t)n_blocks);

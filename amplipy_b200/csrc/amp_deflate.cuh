@@ -25,14 +25,14 @@ namespace amp {
 #define AMPD_SLOT (AMPD_MAXBLOCK + 256)   // bytes of scratch per block for the compressed stream (multiple of 4)
 
 #define AMPD_TOKCAP 8192              // tokens of one deflate block (a BGZF block becomes a few of them, each with its own code)
-struct DeflateMem {                                             // per warp
+#define AMPD_SCRATCH (AMPD_TOKCAP + 512)   // words of global scratch per warp: the tokens, then the code construction's work arrays
+struct DeflateMem {                                             // per warp (9.2 KB: 24 warps per SM)
     int htab[1 << AMPD_HBITS];                                  // most recent position of a hash within the BGZF block
-    uint32_t work[288];                                         // code construction: frequencies -> lengths in place; then the codes (u16)
-    uint16_t lfreq[288], dfreq[32];                             // symbol frequencies of the open deflate block
-    uint16_t order[288];                                        // symbols by ascending frequency
+    uint16_t lfreq[288], dfreq[32];                             // symbol frequencies of the open deflate block; its codes while it is written
     uint8_t llen[288], dlen[32], clen[20];                      // code lengths: literal / length, distance, code-length code
-    uint16_t cfreq[20];                                         // frequencies of the code lengths themselves
+    uint16_t cfreq[20];                                         // frequencies of the code lengths themselves; then the code-length code
 };
+struct HuffWork { uint32_t* a; uint16_t* order; };              // in the warp's global scratch: 288 words (frequencies -> lengths in place), 288 symbols by ascending frequency
 // token: literal = the byte; match = 1 << 31 | length symbol index << 26 | distance symbol << 21 | length extra << 16 | distance extra
 struct DeflateTables {                                          // per CTA
     uint32_t len_code[260];           // [len 3..258]: fixed code of the length symbol + its extra bits (LSB first) | bit count << 16
@@ -93,10 +93,11 @@ AMP_WD int match_length(const uint8_t* in, int c, int p, int n) {
 
 // ---- code construction ---------------------------------------------------------------------------------------------------------
 // Code lengths (at most maxlen) of the symbols with freq[i] > 0 among n_sym, into len[] (0 = unused); at least two symbols get a
-// code (as zlib does, so that no special cases are left for the decoder).  All lanes call; freq / len / M in shared memory.
+// code (as zlib does, so that no special cases are left for the decoder).  All lanes call; freq / len in shared memory, W in the
+// warp's global scratch (touched a few times per 8 k tokens).
 // Ranking by (frequency, symbol) across the lanes, then the in-place minimum-redundancy algorithm of Moffat and Katajainen on the
 // sorted frequencies by lane 0; a code that comes out too long is recomputed from halved frequencies.
-AMP_WD void huff_lengths(uint16_t* freq, int n_sym, int maxlen, uint8_t* len, DeflateMem& M, int lane) {
+AMP_WD void huff_lengths(uint16_t* freq, int n_sym, int maxlen, uint8_t* len, const HuffWork& W, int lane) {
     if (lane == 0) {
         int used = 0, which = -1;
         for (int i = 0; i < n_sym; ++i) if (freq[i]) { ++used; which = i; }
@@ -111,15 +112,15 @@ AMP_WD void huff_lengths(uint16_t* freq, int n_sym, int maxlen, uint8_t* len, De
         if (!f) continue;
         int rank = 0;
         for (int j = 0; j < n_sym; ++j) { const unsigned g = freq[j]; if (g && (g < f || (g == f && j < i))) ++rank; }
-        M.order[rank] = (uint16_t)i;
+        W.order[rank] = (uint16_t)i;
         ++mine;
     }
     const int n = w_add(mine);
     w_sync();
     if (lane == 0) {
-        uint32_t* A = M.work;
+        uint32_t* A = W.a;
         for (int shift = 0;; ++shift) {
-            for (int k = 0; k < n; ++k) { const uint32_t f = (uint32_t)freq[M.order[k]] >> shift; A[k] = f ? f : 1u; }
+            for (int k = 0; k < n; ++k) { const uint32_t f = (uint32_t)freq[W.order[k]] >> shift; A[k] = f ? f : 1u; }
             // first pass, left to right: parent pointers
             A[0] += A[1];
             int root = 0, leaf = 2;
@@ -140,7 +141,7 @@ AMP_WD void huff_lengths(uint16_t* freq, int n_sym, int maxlen, uint8_t* len, De
             }
             if ((int)A[0] <= maxlen) break;
         }
-        for (int k = 0; k < n; ++k) len[M.order[k]] = (uint8_t)A[k];
+        for (int k = 0; k < n; ++k) len[W.order[k]] = (uint8_t)A[k];
     }
     w_sync();
 }
@@ -158,11 +159,11 @@ AMP_WD void huff_codes(const uint8_t* len, int n, uint16_t* code) {
 // The open deflate block (ntok tokens in tok[], their frequencies in M) written out: the code is built from the frequencies, or the
 // fixed code of RFC 1951 3.2.6 is used where that is shorter; `last` sets BFINAL.  xbits = extra bits of the tokens.  All lanes call;
 // returns false (warp-uniform) when the block does not fit cap_words.  Leaves the frequencies cleared.
-AMP_WD bool deflate_flush(DeflateMem& M, const uint32_t* tok, int ntok, int xbits, bool last, BitWriter& bw, int cap_words, int lane) {
+AMP_WD bool deflate_flush(DeflateMem& M, const HuffWork& W, const uint32_t* tok, int ntok, int xbits, bool last, BitWriter& bw, int cap_words, int lane) {
     if (lane == 0) ++M.lfreq[256];                                             // end of block
     w_sync();
-    huff_lengths(M.lfreq, 286, 15, M.llen, M, lane);
-    huff_lengths(M.dfreq, 30, 15, M.dlen, M, lane);
+    huff_lengths(M.lfreq, 286, 15, M.llen, W, lane);
+    huff_lengths(M.dfreq, 30, 15, M.dlen, W, lane);
     int hlit = 0, hdist = 0;
     bool dyn = false, fits = true;
     if (lane == 0) {
@@ -173,7 +174,7 @@ AMP_WD bool deflate_flush(DeflateMem& M, const uint32_t* tok, int ntok, int xbit
         for (int i = 0; i < hdist; ++i) ++M.cfreq[M.dlen[i]];
     }
     w_sync();
-    huff_lengths(M.cfreq, 19, 7, M.clen, M, lane);
+    huff_lengths(M.cfreq, 19, 7, M.clen, W, lane);
     if (lane == 0) {
         long long cdyn = 3 + 14 + 19 * 3, cfix = 3;
         for (int v = 0; v < 19; ++v) cdyn += (long long)M.cfreq[v] * M.clen[v];
@@ -183,7 +184,7 @@ AMP_WD bool deflate_flush(DeflateMem& M, const uint32_t* tok, int ntok, int xbit
         const long long bits = (dyn ? cdyn : cfix) + xbits;
         fits = 4LL * bw.w + (bits >> 3) + 64 <= 4LL * cap_words;
         if (fits) {
-            uint16_t* lcode = (uint16_t*)M.work; uint16_t* dcode = lcode + 288; uint16_t* ccode = dcode + 32;
+            uint16_t* lcode = M.lfreq; uint16_t* dcode = M.dfreq; uint16_t* ccode = M.cfreq;     // the frequencies have served: their arrays hold the codes now
             bw_put(bw, last ? 1u : 0u, 1);
             if (dyn) {
                 M.llen[286] = 0; M.llen[287] = 0; M.dlen[30] = 0; M.dlen[31] = 0;     // (symbols that cannot occur; huff_lengths leaves them alone)
@@ -219,9 +220,10 @@ AMP_WD bool deflate_flush(DeflateMem& M, const uint32_t* tok, int ntok, int xbit
 }
 
 // One BGZF block by one warp: in[0, n) (n <= AMPD_MAXBLOCK, readable up to in + n + 8) -> a complete deflate stream in out32[0 ...]
-// (deflate blocks of up to AMPD_TOKCAP tokens, each with the shorter of its own and the fixed code); tok = AMPD_TOKCAP words of
+// (deflate blocks of up to AMPD_TOKCAP tokens, each with the shorter of its own and the fixed code); tok = AMPD_SCRATCH words of
 // scratch in global memory.  Returns the stream's length in bytes, or -1 when it would not fit cap_words 32-bit words.
 AMP_WD int deflate_block(const uint8_t* in, int n, DeflateMem& M, const DeflateTables& T, uint32_t* out32, int cap_words, uint32_t* tok, int lane) {
+    HuffWork W; W.a = tok + AMPD_TOKCAP; W.order = (uint16_t*)(tok + AMPD_TOKCAP + 288);
     for (int i = lane; i < (1 << AMPD_HBITS); i += 32) M.htab[i] = 0;
     for (int i = lane; i < 288; i += 32) M.lfreq[i] = 0;
     M.dfreq[lane] = 0;
@@ -271,11 +273,11 @@ AMP_WD int deflate_block(const uint8_t* in, int n, DeflateMem& M, const DeflateT
         }
         cursor = base + s;
         if (w_shfl(ntok, 0) > AMPD_TOKCAP - 32) {                              // (a group adds at most 32 tokens)
-            if (!deflate_flush(M, tok, ntok, xbits, false, bw, cap_words, lane)) return -1;
+            if (!deflate_flush(M, W, tok, ntok, xbits, false, bw, cap_words, lane)) return -1;
             ntok = 0; xbits = 0;
         }
     }
-    if (!deflate_flush(M, tok, ntok, xbits, true, bw, cap_words, lane)) return -1;
+    if (!deflate_flush(M, W, tok, ntok, xbits, true, bw, cap_words, lane)) return -1;
     int bytes = 0;
     if (lane == 0) {
         bytes = 4 * bw.w + ((bw.n + 7) >> 3);

@@ -438,7 +438,7 @@ static void deflate_body(void* a) {
     amp::deflate_tables_init(*j->tab, amp::c_tid(), amp::c_nthreads());
     amp::c_sync();
     const uint32_t mcol = amp::crc_shift_column(*j->tab, lane);
-    static uint32_t tok[AMPD_TOKCAP];
+    static uint32_t tok[AMPD_SCRATCH];
     const int bytes = j->n >= 16 ? amp::deflate_block(j->in, j->n, *j->mem, *j->tab, j->out, j->cap_words, tok, lane) : -1;
     const uint32_t crc = amp::crc32_block(j->in, j->n, *j->tab, mcol, lane);
     if (lane == 0) { j->bytes = bytes; j->crc = crc; }
