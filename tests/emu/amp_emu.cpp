@@ -443,6 +443,18 @@ static void deflate_body(void* a) {
     const uint32_t crc = amp::crc32_block(j->in, j->n, *j->tab, mcol, lane);
     if (lane == 0) { j->bytes = bytes; j->crc = crc; }
 }
+struct HuffJob { uint16_t* freq; int n; int maxlen; uint8_t* len; };
+static void huff_body(void* a) {
+    HuffJob* j = (HuffJob*)a;
+    static uint32_t work[288]; static uint16_t order[288];
+    amp::HuffWork W; W.a = work; W.order = order;
+    amp::huff_lengths(j->freq, j->n, j->maxlen, j->len, W, amp::c_tid() & 31);
+}
+// code lengths of deflate_flush's code construction (freq may get two forced entries)
+void emu_huff_lengths(uint16_t* freq, int n, int maxlen, uint8_t* len) {
+    HuffJob j{freq, n, maxlen, len};
+    run_cta(0, 32, huff_body, &j);
+}
 // in[0, n) (readable up to in + n + 8) -> raw deflate stream in out (cap_words 32-bit words + 64 words of slack); returns its length
 // in bytes or -1 (does not fit / too short to bother); *crc = CRC-32 of the input
 int emu_deflate(const uint8_t* in, int n, uint32_t* out, int cap_words, uint32_t* crc) {

@@ -106,3 +106,71 @@ def test_output_feeds_the_device_inflater():
     out = np.zeros(len(data) + 64, np.uint8)
     err = lib.emu_inflate(ctypes.c_void_p(src.ctypes.data), ctypes.c_longlong(len(comp)), ctypes.c_void_p(out.ctypes.data), ctypes.c_longlong(len(data)))
     assert err == 0 and out[:len(data)].tobytes() == data
+
+
+def test_skewed_and_degenerate_alphabets():
+    """Code construction corner cases: Fibonacci-like literal frequencies (an unlimited Huffman code would be 17 bits deep: the
+    frequencies are halved until 15 suffice), literals only (no distance code in use: two are forced), one literal repeated (runs),
+    every byte value once, and a stream long enough for several deflate blocks with different statistics."""
+    rng = np.random.default_rng(23)
+    fib = [1, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 377, 610, 987, 1597, 2584]
+    sym = np.repeat(np.arange(len(fib), dtype=np.uint8) * 7 + 3, fib)
+    for _ in range(50):                                    # break up the runs of the frequent symbols as well as chance allows
+        rng.shuffle(sym)
+    cases = {
+        "fibonacci": sym.tobytes(),
+        "literals_only": bytes(rng.permutation(256).astype(np.uint8)) * 1 + bytes(rng.permutation(256).astype(np.uint8))[::-1][:200],
+        "one_symbol": b"Q" * 5000,
+        "two_symbols": (b"A" + b"B" * 3) * 700,
+        "phases": bytes(rng.integers(0, 4, 30000, dtype=np.uint8)) + bytes(rng.integers(100, 228, 20000, dtype=np.uint8)) + b"xyz" * 5000,
+    }
+    for name, data in cases.items():
+        r, comp, crc = _deflate(data, cap_words=len(data) // 4 + 200)
+        assert crc == zlib.crc32(data), name
+        assert r > 0, name
+        d = zlib.decompressobj(-15)
+        assert d.decompress(comp) + d.flush() == data and d.eof, name
+
+
+def _huffman_cost(freq):
+    """(total bits, depth) of an optimal unlimited prefix code (the deepest among the optimal ones: ties merge the shallower trees last)"""
+    import heapq
+    h = [(int(f), 0) for f in freq if f]
+    if len(h) < 2:
+        return sum(f for f, _ in h), 1
+    heapq.heapify(h)
+    cost = 0
+    while len(h) > 1:
+        (a, da), (b, db) = heapq.heappop(h), heapq.heappop(h)
+        cost += a + b
+        heapq.heappush(h, (a + b, max(da, db) + 1))
+    return cost, h[0][1]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_code_lengths_are_optimal_complete_and_limited(seed):
+    """huff_lengths: a complete prefix code (Kraft sum exactly 1), optimal whenever the optimum fits the limit, never longer than
+    the limit otherwise (Fibonacci frequencies: depth 17 unlimited), at least two symbols coded."""
+    lib = emu_driver.lib()
+    rng = np.random.default_rng(seed)
+    fib = [1, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 377, 610, 987, 1597, 2584]
+    cases = [(rng.integers(0, 50, 286), 15), (rng.integers(0, 3, 286) * rng.integers(0, 3000, 286), 15), (np.array(fib + [0] * 268), 15),
+             (np.array(fib[:12] + [0] * 7), 7), (rng.integers(0, 40, 19), 7), (np.array([0] * 30), 15), (np.array([0] * 7 + [9] + [0] * 22), 15),
+             (rng.integers(0, 2000, 30), 15), (np.array([1] * 286), 15)]
+    for freq, limit in cases:
+        f = np.ascontiguousarray(freq, np.uint16)
+        n = f.size
+        out = np.full(n + 8, 0xAB, np.uint8)
+        lib.emu_huff_lengths(ctypes.c_void_p(f.ctypes.data), n, limit, ctypes.c_void_p(out.ctypes.data))
+        ln = out[:n].astype(int)
+        assert (out[n:] == 0xAB).all()
+        used = ln > 0
+        assert used.sum() >= 2 and ((f > 0) <= used).all() and ln.max() <= limit
+        assert sum(2.0 ** -l for l in ln[used]) == 1.0
+        cost = int((f.astype(int) * ln).sum())
+        best, depth = _huffman_cost(f)                      # (f: with the forced entries, if any)
+        assert cost >= best
+        if depth <= limit:                                  # where an unlimited optimum fits, the result must be optimal too
+            assert cost == best, (cost, best, limit, depth)
+        else:
+            assert cost <= 1.05 * best + 8                  # the halving heuristic stays close
