@@ -241,7 +241,7 @@ def parity_on_sample(eng, oracle, sb, g, prim, tables, mpl, pouts, sample):
     return all(ok.values()), ok
 
 
-def file_to_file(args, g, prim, b, runs=3):
+def file_to_file(args, g, prim, b, runs=5):
     """`aio` through the command line on files: BAM bytes -> GPU (inflate, trim + pileup, calling, record rebuild, deflate) -> trimmed
     BAM + VCF + FASTA.  Reported next to the kernel numbers because this is what a real run sees.  Warm: the CUDA context and the
     libraries are up; best of `runs`."""
