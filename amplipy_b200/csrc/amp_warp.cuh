@@ -148,10 +148,10 @@ static long long g_v7_stats[2];   // emulation only: reads finished on the coope
 
 // ---- shared-memory layout ------------------------------------------------------------------------------------------
 #ifndef AMP7_WARPS
-#define AMP7_WARPS 18            // warps per CTA of the fast kernel (112 registers per thread)
+#define AMP7_WARPS 20            // warps per CTA of the fast kernel (96 registers per thread; 20 warps + 2 generic-capable ones fill the 227 KB of shared memory)
 #endif
 #ifndef AMP7_GWARPS
-#define AMP7_GWARPS 4            // warps that can run the generic phase (their extra shared memory must fit): the last ones
+#define AMP7_GWARPS 2            // warps that can run the generic phase (their extra shared memory must fit): the last ones
 #endif
 #ifndef AMP7_DWARPS
 #define AMP7_DWARPS 0            // of those, warps that do nothing else (they work on the list while it is being filled)
