@@ -80,25 +80,35 @@ def variant_records(res: CallResult, ins: Insertions, ref_seq: str, counts: np.n
     by_pos = {}
     if ins.k:
         sel = np.flatnonzero((ins.sample == sample) & (res.ins_alt[:ins.k] != 0))
-        for k in sel:
-            by_pos.setdefault(int(ins.pos[k]), []).append(int(k))
+        for k, p in zip(sel.tolist(), ins.pos[sel].tolist()):
+            by_pos.setdefault(p, []).append(k)
+    # the emitting positions' values as plain Python lists (indexing numpy scalars one by one costs more than everything else here)
+    ge = emit + base
+    fl = flags[emit].tolist()
+    masks = res.alt_mask[ge].tolist()
+    ranks = res.fixed_rank[ge].tolist()
+    freqs = res.fixed_freq[ge].tolist()
+    cnts = np.ascontiguousarray(counts[:, emit].T).tolist()
+    refc = res.ref_count[ge].tolist()
+    depth = res.depth[ge].tolist()
+    ins_rank, ins_count, ins_freq = res.ins_rank, ins.count, res.ins_freq
     out = []
-    for p in emit:
-        p = int(p)
-        gp = base + p
+    for j, p in enumerate(emit.tolist()):
         alts = []   # (rank, symbol, count, freq)
-        m = int(res.alt_mask[gp])
-        for ch in range(6):
-            if m & (1 << ch):
-                alts.append((int(res.fixed_rank[gp, ch]), FIXED_SYMS[ch], int(counts[ch, p]), float(res.fixed_freq[gp, ch])))
+        m = masks[j]
+        if m:
+            rk, fq, ct = ranks[j], freqs[j], cnts[j]
+            for ch in range(6):
+                if m & (1 << ch):
+                    alts.append((rk[ch], FIXED_SYMS[ch], ct[ch], fq[ch]))
         for k in by_pos.get(p, ()):
-            alts.append((int(res.ins_rank[k]), ins.strs[k], int(ins.count[k]), float(res.ins_freq[k])))
-        alts.sort(key=lambda a: a[0])
-        rc = int(res.ref_count[gp])
+            alts.append((int(ins_rank[k]), ins.strs[k], int(ins_count[k]), float(ins_freq[k])))
+        if len(alts) > 1:
+            alts.sort(key=lambda a: a[0])
+        rc = refc[j]
         ch_ref = FIXED_SYMS.find(ref_seq[p])
-        rf = float(res.fixed_freq[gp, ch_ref]) if (rc and ch_ref >= 0) else (rc / int(res.depth[gp]) if rc else 0.0)
+        rf = freqs[j][ch_ref] if (rc and ch_ref >= 0) else (rc / depth[j] if rc else 0.0)
         n = len(alts)
-        gt = tuple(range(n + 1)) if (flags[p] & 4) else tuple(range(1, n + 1))
-        out.append((p, ref_seq[p], [a[1] for a in alts], int(res.depth[gp]), rc, [a[2] for a in alts], rf,
-                    [a[3] for a in alts], gt))
+        gt = tuple(range(n + 1)) if (fl[j] & 4) else tuple(range(1, n + 1))
+        out.append((p, ref_seq[p], [a[1] for a in alts], depth[j], rc, [a[2] for a in alts], rf, [a[3] for a in alts], gt))
     return out

@@ -41,18 +41,23 @@ def header_text(ref_genome_id, version, argv):
     return "\n".join(lines) + "\n"
 
 
+_F32 = struct.Struct("f")
+
+
 def _f32(x):
-    return "%g" % struct.unpack("f", struct.pack("f", float(x)))[0]
+    return "%g" % _F32.unpack(_F32.pack(x))[0]
 
 
 def record_line(ref_genome_id, rec):
     """rec = (pos0, ref, [alts], DP, REF_DP, [ALT_DP], REF_FREQ, [ALT_FREQ], GT) from calling.variant_records.
     ALT_FREQ uses python's repr of the float64, as ','.join(str(freq)) does in AmpliPy.py:946."""
     pos0, ref, alts, dp, ref_dp, alt_dp, ref_freq, alt_freq, gt = rec
+    if len(alts) == 1:          # the common case without the joins
+        return "%s\t%d\t.\t%s\t%s\t.\tPASS\tDP=%d;REF_DP=%d;ALT_DP=%d;REF_FREQ=%s;ALT_FREQ=%r\tGT\t%s" % (
+            ref_genome_id, pos0 + 1, ref, alts[0], dp, ref_dp, alt_dp[0], _f32(ref_freq), float(alt_freq[0]), "/".join(map(str, gt)))
     info = "DP=%d;REF_DP=%d;ALT_DP=%s;REF_FREQ=%s;ALT_FREQ=%s" % (
-        dp, ref_dp, ",".join(str(c) for c in alt_dp), _f32(ref_freq), ",".join(repr(float(f)) for f in alt_freq))
-    return "\t".join([ref_genome_id, str(pos0 + 1), ".", ref, ",".join(alts), ".", "PASS", info, "GT",
-                      "/".join(str(g) for g in gt)])
+        dp, ref_dp, ",".join(map(str, alt_dp)), _f32(ref_freq), ",".join([repr(float(f)) for f in alt_freq]))
+    return "\t".join([ref_genome_id, str(pos0 + 1), ".", ref, ",".join(alts), ".", "PASS", info, "GT", "/".join(map(str, gt))])
 
 
 def write_vcf(path, ref_genome_id, version, argv, records):
