@@ -194,6 +194,10 @@ __global__ void __launch_bounds__(256) amp_call_kernel(const __grid_constant__ a
     const int sample = (int)(gp / P.L), p = (int)(gp - (long long)sample * P.L);
     const int g0 = threadIdx.x & (32 - G) & 31;               // first lane of this group
     const unsigned gmask = (G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u) << g0);
+    // (the fixed symbols' counts and the reference base are independent of the insertion list: loaded first, so that the latencies overlap)
+    const int* cnt = P.counts + (size_t)sample * AMP_NCH * P.Lpad;
+    const int c_fixed = ch < AMP_NCH ? cnt[(size_t)ch * P.Lpad + p] : 0;
+    const unsigned char refsym = P.ref_seq[(size_t)sample * (size_t)P.ref_stride + p];
     // insertion alleles of the position: lane 6 + j takes the j-th entry of the list
     int slot = -1, s = P.heads[(size_t)sample * P.Lpad + p];
     for (int j = 0; j < NINS && s >= 0; ++j) {
@@ -204,30 +208,28 @@ __global__ void __launch_bounds__(256) amp_call_kernel(const __grid_constant__ a
         call_long_list(P, gp, sample, p, ch, g0, gmask);
         return;
     }
-    const int* cnt = P.counts + (size_t)sample * AMP_NCH * P.Lpad;
-    int c = 0;
+    int c = c_fixed;
     amp::Sym me; me.p = kFixedSyms + (ch < AMP_NCH ? ch : 7); me.len = 1;
-    if (ch < AMP_NCH) c = cnt[(size_t)ch * P.Lpad + p];
-    else if (slot >= 0) { c = P.slots[slot].count; me = amp::slot_sym(P, slot); }
+    if (ch >= AMP_NCH && slot >= 0) { c = P.slots[slot].count; me = amp::slot_sym(P, slot); }
     int total = c;
 #pragma unroll
     for (int d = 1; d < G; d <<= 1) total += __shfl_xor_sync(gmask, total, d);
-    const unsigned char refsym = P.ref_seq[(size_t)sample * (size_t)P.ref_stride + p];
     const double f = c ? (double)c / (double)total : 0.0;
-    // index in the sorted allele list = number of alleles that are greater
+    // index in the sorted allele list = number of alleles that are greater; only alleles that occur take part (one or two at most
+    // positions), so the group walks the set bits of its occupancy mask instead of all sixteen lanes
+    const unsigned lanes = G == 32 ? 0xFFFFFFFFu : (1u << G) - 1u;
     int rank = 0;
-#pragma unroll
-    for (int o = 0; o < G; ++o) {
+    for (unsigned occ = (__ballot_sync(gmask, c != 0) >> g0) & lanes; occ; occ &= occ - 1u) {
+        const int o = __ffs((int)occ) - 1;
         const int co = __shfl_sync(gmask, c, g0 + o);
         amp::Sym so;
         so.p = (const unsigned char*)__shfl_sync(gmask, (unsigned long long)me.p, g0 + o);
         so.len = __shfl_sync(gmask, me.len, g0 + o);
-        if (o != ch && co && c && amp::allele_greater(co, so, c, me)) ++rank;
+        if (o != ch && c && amp::allele_greater(co, so, c, me)) ++rank;
     }
     if (!c) rank = -1;
     const bool is_ref = c && me.len == 1 && me.p[0] == refsym;                     // 936-937
     const bool is_alt = c && !is_ref && f >= P.min_freq_variants;                  // 938-939
-    const unsigned lanes = G == 32 ? 0xFFFFFFFFu : (1u << G) - 1u;
     const unsigned top_m = (__ballot_sync(gmask, rank == 0) >> g0) & lanes;
     const unsigned ref_m = (__ballot_sync(gmask, is_ref) >> g0) & lanes;
     const unsigned alt_m = (__ballot_sync(gmask, is_alt) >> g0) & lanes;
